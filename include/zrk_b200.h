@@ -1,0 +1,296 @@
+/*
+ * zrk_b200.h — C ABI of the B200-native batched tick of Ollegorii/ZRK_modulation.
+ *
+ * The reference has no FFI: its seam is the Python class interface
+ * `BaseModel.step()` (modules/BaseModel.py:13-44) + `Manager`
+ * (modules/Manager.py:9-140).  This header is the boundary a host (ctypes, cgo,
+ * a PyTorch custom op ...) binds to replace the per-tick loop
+ * `Manager.run_simulation` (modules/Manager.py:111-140) and every `step()` it
+ * calls, for B independent scenarios at once.  Plain pointers and sizes only.
+ *
+ * The same structs are consumed by the CPU oracle under oracle/ (test
+ * infrastructure only) so that parity tests compare like with like.
+ *
+ * Entry point                      replaces (reference file:line)
+ * -------------------------------  -------------------------------------------
+ * zrk_create                       main.create_objects_from_config  main.py:35-149
+ * zrk_step                         Manager.run_simulation loop body Manager.py:116-140
+ *                                  (AirEnv.py:26-53, Radar.py:144-205,
+ *                                   MissileLauncher.py:82-138, CCP.py:368-431,
+ *                                   Missile.py:148-196, AirObject.py:39-42)
+ * zrk_sync                         (run_simulation returning)       Manager.py:111
+ * zrk_get_time                     Timer.get_time                   Timer.py:20-22
+ * zrk_read_messages                Manager.give_messages            Manager.py:60-70
+ * zrk_read_counts                  sum(len(messages))               main.py:171
+ * zrk_read_state                   model attributes (pos, prev_pos, current_azimuth,
+ *                                  _target_dict ...)                BaseModel.py:28-36, CCP.py:80-86
+ * zrk_read_status                  exception propagation            (CCP.py:259, CCP.py:107)
+ * zrk_destroy                      Python GC
+ */
+#ifndef ZRK_B200_H
+#define ZRK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZRK_ABI_VERSION 1
+
+/* Python `None` for id-valued fields (receiver_id, target_id, missile_id). */
+#define ZRK_NONE INT32_MIN
+
+/* modules/constants.py:36-38 */
+#define ZRK_CCP_ID 0
+#define ZRK_DRAWER_ID 1
+#define ZRK_MANAGER_ID 2
+/* modules/constants.py:31 POSSIBLE_TARGET_RADIUS */
+#define ZRK_POSSIBLE_TARGET_RADIUS 100
+
+/* MessageType, in the declaration order of modules/constants.py:3-21. */
+enum zrk_msg_type {
+    ZRK_MSG_LAUNCH_MISSILE = 0,
+    ZRK_MSG_LAUNCHED_MISSILE = 1,
+    ZRK_MSG_LAUNCH_COMMAND = 2,
+    ZRK_MSG_MISSILE_COUNT_REQUEST = 3,
+    ZRK_MSG_MISSILE_COUNT_RESPONSE = 4,
+    ZRK_MSG_ALL_OBJECTS = 5,
+    ZRK_MSG_FOUND_OBJECTS = 6,
+    ZRK_MSG_ACTIVE_OBJECTS = 7,
+    ZRK_MSG_CCP_UPDATE_TARGET = 8,
+    ZRK_MSG_UPDATE_TARGET = 9,      /* never emitted */
+    ZRK_MSG_MISSILE_GET_HIT = 10,   /* no class, no emitter */
+    ZRK_MSG_DESTROYED_MISSILE = 11,
+    ZRK_MSG_DRAW_OBJECTS = 12,
+    ZRK_MSG_MISSILE_POS = 13,
+    ZRK_MSG_MISSILE_DETONATE = 14,
+    ZRK_MSG_NEW_MISSILE = 15,
+    ZRK_MSG_LAUNCH_CANCELLED = 16,
+    ZRK_MSG_LAUNCH_SUCCESSFUL = 17,
+    ZRK_MSG_NTYPES = 18
+};
+
+/* TargetType (modules/utils.py:6-9) + the 'ЗУР' string CCP uses for missiles (CCP.py:247,400). */
+enum zrk_obj_type { ZRK_AIR_PLANE = 0, ZRK_HELICOPTER = 1, ZRK_ANOTHER = 2, ZRK_ZUR = 3 };
+
+/* scan_mode (Radar.py:26); anything else never moves the sector (Radar.py:100-117). */
+enum zrk_scan_mode { ZRK_SCAN_HORIZONTAL = 0, ZRK_SCAN_VERTICAL = 1, ZRK_SCAN_OTHER = 2 };
+
+/* Reason strings of the ValueErrors in Missile._calculate_trajectory_params (Missile.py:72-94). */
+enum zrk_cancel_reason {
+    ZRK_CANCEL_PARALLEL = 0,      /* Missile.py:74  */
+    ZRK_CANCEL_PAST = 1,          /* Missile.py:79  */
+    ZRK_CANCEL_NO_REAL_ROOT = 2,  /* Missile.py:83  */
+    ZRK_CANCEL_NOT_POSITIVE = 3,  /* Missile.py:90  */
+    ZRK_CANCEL_TOO_FAR = 4        /* Missile.py:94  */
+};
+
+/* Per-scenario status: the reference aborts the whole run on these exceptions; the batched
+ * tick freezes just that scenario at the faulting point and reports it. */
+enum zrk_fault {
+    ZRK_FAULT_NONE = 0,
+    ZRK_FAULT_ATTRIBUTE_ERROR_CCP259 = 1, /* 'Missile' object has no attribute 'type' (CCP.py:259) */
+    ZRK_FAULT_KEY_ERROR_CCP107 = 2,       /* _target_dict[missile.target.id] (CCP.py:107)          */
+    ZRK_FAULT_LOG_OVERFLOW = 64           /* not a reference fault: this scenario's log region is full */
+};
+
+/* Return codes (no exceptions cross the ABI). */
+enum zrk_rc {
+    ZRK_OK = 0,
+    ZRK_ERR_ARG = -1,
+    ZRK_ERR_CUDA = -2,
+    ZRK_ERR_NO_DEVICE = -3,
+    ZRK_ERR_NOMEM = -4,
+    ZRK_ERR_UNSUPPORTED = -5,
+    ZRK_ERR_CAPACITY = -6
+};
+
+/* Which message types are written as explicit records to the per-scenario log.
+ * ACTIVE/ALL/FOUND carry object lists and are never stored as records: they are rebuilt
+ * from the per-tick alive / visibility masks (ZRK_LOG_MASKS). */
+#define ZRK_TYPE_BIT(t) (1u << (t))
+#define ZRK_LOG_EVENTS                                                                          \
+    (ZRK_TYPE_BIT(ZRK_MSG_LAUNCH_MISSILE) | ZRK_TYPE_BIT(ZRK_MSG_LAUNCHED_MISSILE) |              \
+     ZRK_TYPE_BIT(ZRK_MSG_LAUNCH_COMMAND) | ZRK_TYPE_BIT(ZRK_MSG_MISSILE_COUNT_REQUEST) |         \
+     ZRK_TYPE_BIT(ZRK_MSG_MISSILE_COUNT_RESPONSE) | ZRK_TYPE_BIT(ZRK_MSG_DESTROYED_MISSILE) |     \
+     ZRK_TYPE_BIT(ZRK_MSG_MISSILE_DETONATE) | ZRK_TYPE_BIT(ZRK_MSG_NEW_MISSILE) |                 \
+     ZRK_TYPE_BIT(ZRK_MSG_LAUNCH_CANCELLED) | ZRK_TYPE_BIT(ZRK_MSG_LAUNCH_SUCCESSFUL))
+#define ZRK_LOG_BULK                                                                            \
+    (ZRK_TYPE_BIT(ZRK_MSG_CCP_UPDATE_TARGET) | ZRK_TYPE_BIT(ZRK_MSG_DRAW_OBJECTS) |               \
+     ZRK_TYPE_BIT(ZRK_MSG_MISSILE_POS))
+#define ZRK_LOG_MASKS 0x80000000u /* keep per-tick alive + per-radar visibility masks */
+#define ZRK_LOG_FULL (ZRK_LOG_EVENTS | ZRK_LOG_BULK | ZRK_LOG_MASKS)
+
+/*
+ * One message of the reference's log (modules/BaseMessage.py:12-17 + modules/Messages.py),
+ * flattened.  `tick` is send_time / time_step.  relevance is 3 for MISSILE_COUNT_REQUEST
+ * (Messages.py:63) and 1 otherwise.  Payload by type:
+ *   MISSILE_POS            a=missile_id
+ *   MISSILE_DETONATE       a=missile_id  b=target_id|NONE        flag=self_detonation
+ *   ACTIVE/ALL/FOUND       a=offset into the id pool, b=number of ids
+ *   DESTROYED_MISSILE      a=missile_id (the reference stores the 1-tuple (id,), Messages.py:160)  flag=self_detonation
+ *   LAUNCH_MISSILE         a=target.id
+ *   LAUNCH_SUCCESSFUL      a=missile.id  b=target_id  xyz=new trajectory velocity (launch_time = tick*dt/1000)
+ *   LAUNCH_CANCELLED       a=missile.id  b=zrk_cancel_reason
+ *   LAUNCHED_MISSILE       a=missile.id  b=target_id
+ *   NEW_MISSILE            a=missile.id
+ *   MISSILE_COUNT_RESPONSE b=count
+ *   LAUNCH_COMMAND         a=target.id   b=radar_id  xyz=target_position
+ *   CCP_UPDATE_TARGET      a=target.id   b=missile_id|NONE
+ *   DRAW_OBJECTS           a=obj_id      b=zrk_obj_type  flag=is_visible_by_radar  xyz=coordinates
+ */
+typedef struct zrk_msg {
+    int32_t tick;
+    uint8_t type;      /* zrk_msg_type */
+    uint8_t relevance;
+    uint8_t flag;
+    uint8_t pad;
+    int32_t sender;
+    int32_t receiver;  /* ZRK_NONE for None */
+    int32_t a;
+    int32_t b;
+    double xyz[3];
+} zrk_msg; /* 48 bytes */
+
+/*
+ * A batch of B scenarios in the schema of main.create_objects_from_config (main.py:35-149),
+ * as host structure-of-arrays padded to the batch maxima.  All pointers are host memory owned
+ * by the caller; zrk_create copies what it needs.
+ *
+ * Object identity: "static index" s = targets in config order (0..n_targets-1) followed by
+ * missiles in launcher-major config order (max_targets + m).  AirEnv "slots" are positions in
+ * AirEnv.__objects (AirEnv.py:24): targets first, missiles in NEW_MISSILE arrival order.
+ * Restrictions checked by zrk_create (ZRK_ERR_UNSUPPORTED): air-object ids unique within a
+ * scenario; launcher ids unique within a scenario.
+ */
+typedef struct zrk_batch_desc {
+    int32_t abi_version; /* ZRK_ABI_VERSION */
+    int32_t n_scenarios;
+    int32_t max_targets;
+    int32_t max_radars;
+    int32_t max_launchers;
+    int32_t max_missiles;       /* missile objects per scenario, all launchers together */
+    int32_t max_ccp_launchers;  /* entries of CCP.missile_launcher_coords (main.py:107-111) */
+    int32_t dt_ms;              /* simulation.time_step (main.py:42) */
+
+    /* per scenario [B]; NULL means "the max for every scenario" */
+    const int32_t *n_targets, *n_radars, *n_launchers, *n_missiles, *n_ccp_launchers;
+    const int32_t *airenv_id;  /* [B] air_environment.id */
+    const int32_t *ccp_id;     /* [B] combat_control_point.id, ZRK_NONE = no CCP module (main.py:104-105) */
+    const int32_t *tick_limit; /* [B] optional: scenario stops after this many ticks; NULL = never */
+
+    /* targets [B][max_targets] (main.py:128-147) */
+    const int32_t *target_id;
+    const int32_t *target_type;  /* zrk_obj_type */
+    const double *target_pos;    /* [..][3] */
+    const double *target_vel;    /* [..][3] */
+
+    /* radars [B][max_radars] (main.py:56-71) */
+    const int32_t *radar_id;
+    const double *radar_pos;     /* [..][3] */
+    const double *radar_par;     /* [..][8] azimuth_start, elevation_start, max_distance, azimuth_range,
+                                    elevation_range, azimuth_speed, elevation_speed, zrk_scan_mode */
+
+    /* launchers [B][max_launchers] (main.py:74-101) */
+    const int32_t *launcher_id;
+    const double *launcher_pos;  /* [..][3] */
+
+    /* missiles [B][max_missiles], launcher-major, only those MissileLauncher.add_missile accepted
+       (MissileLauncher.py:43-48) */
+    const int32_t *missile_id;
+    const int32_t *missile_launcher; /* index into this scenario's launchers */
+    const double *missile_v0;        /* velocity_module */
+    const double *missile_v0sq;      /* Python `v0 ** 2` (Missile.py:65); NULL = v0*v0 */
+    const double *missile_radius;    /* detonate_radius */
+    const double *missile_life;      /* detonate_period, seconds */
+
+    /* CCP launcher dict, in dict order [B][max_ccp_launchers] (main.py:107-111) */
+    const int32_t *ccp_launcher_id;
+    const double *ccp_launcher_pos;  /* [..][3] */
+
+    /* Radar measurement noise replacing np.random.normal in SectorRadar.smooth_objects
+       (Radar.py:138-142): noise[(tick % noise_period)][radar index][static index][3], added in
+       place to the object's position for every (radar, visible object).  NULL = no noise.
+       noise_scenario_stride (doubles) = 0 shares one table between all scenarios. */
+    const double *noise;
+    int32_t noise_period;
+    int32_t noise_radars;
+    int32_t noise_objects;
+    int64_t noise_scenario_stride;
+} zrk_batch_desc;
+
+typedef struct zrk_options {
+    int32_t device;            /* CUDA device ordinal */
+    uint32_t log_types;        /* ZRK_LOG_* */
+    int32_t log_capacity;      /* records per scenario; 0 = bound for ZRK_LOG_EVENTS computed from the batch */
+    int32_t mask_ticks;        /* ticks of mask history to keep when ZRK_LOG_MASKS (ring if smaller than the run) */
+    int32_t ticks_per_launch;  /* ticks fused into one kernel launch; 0 = library default */
+    int32_t reserved[3];
+} zrk_options;
+
+/* Caller-provided host buffers for zrk_read_state; any pointer may be NULL (skipped).
+ * NS = max_targets + max_missiles slots / static indices, E = NS track entries per dict. */
+typedef struct zrk_state_view {
+    /* AirEnv slots [B][NS] */
+    int32_t *slot_obj;    /* static index of the object in this slot, -1 = never filled */
+    uint8_t *slot_alive;  /* 1 = in AirEnv.__objects (not None) */
+    /* objects by static index [B][NS] */
+    double *pos;          /* [..][3] BaseModel.pos */
+    double *prev_pos;     /* [..][3] AirObject.prev_pos */
+    uint8_t *has_prev;    /* 0 = prev_pos is None */
+    /* radars [B][max_radars] */
+    double *radar_az, *radar_el;
+    /* missiles [B][max_missiles] */
+    uint8_t *missile_status;   /* 0 ready, 1 active, 2 detonated */
+    double *missile_period;    /* remaining detonate_period */
+    double *missile_vel;       /* [..][3] trajectory.velocity */
+    double *missile_t0;        /* trajectory.start_time, seconds */
+    int32_t *missile_target;   /* static index of Missile.target, -1 = None */
+    /* launchers [B][max_launchers] */
+    int32_t *launcher_count;   /* len(missiles) */
+    /* CCP [B] and [B][E] */
+    int32_t *ccp_n_targets, *ccp_n_missiles;
+    int32_t *ccp_t_key, *ccp_t_ref, *ccp_t_upd, *ccp_t_missile; /* ref = static index; upd = tick */
+    uint8_t *ccp_t_following;
+    int32_t *ccp_m_key, *ccp_m_ref, *ccp_m_upd, *ccp_m_target;
+    int32_t *ccp_capacity, *ccp_launched;  /* [B][max_ccp_launchers] */
+} zrk_state_view;
+
+typedef struct zrk_handle zrk_handle;
+
+/* Build the device state for a batch.  Returns ZRK_ERR_NO_DEVICE when no CUDA device is
+ * usable: there is no CPU fallback. */
+int zrk_create(const zrk_batch_desc *desc, const zrk_options *opt, zrk_handle **out);
+/* Advance every scenario n_ticks ticks.  Asynchronous until zrk_sync or a read. */
+int zrk_step(zrk_handle *h, int n_ticks);
+int zrk_sync(zrk_handle *h);
+/* Current tick index and Timer.get_time() = tick * dt_ms. */
+int zrk_get_time(zrk_handle *h, int64_t *tick, int64_t *time_ms);
+/* Per scenario: fault code (zrk_fault), tick of the fault, explicit records logged. */
+int zrk_read_status(zrk_handle *h, int32_t *fault_code, int32_t *fault_tick, int32_t *n_records);
+/* Messages emitted so far per scenario and type: counts[B][ZRK_MSG_NTYPES]. */
+int zrk_read_counts(zrk_handle *h, int64_t *counts);
+/* Copy the explicit records of scenarios [s0, s1) to host: recs[(s - s0) * cap + i] for
+ * i < n[s - s0], cap = zrk_log_capacity().  Records of one scenario are in emission order. */
+int zrk_read_records(zrk_handle *h, int s0, int s1, zrk_msg *recs, int32_t *n);
+int zrk_log_capacity(zrk_handle *h);
+/* The full message list of one scenario for ticks [tick0, tick1), in the reference's order
+ * (Manager.py:41-58), with ACTIVE/ALL/FOUND rebuilt from the masks.  Needs ZRK_LOG_FULL.
+ * Returns ZRK_ERR_CAPACITY (and the needed sizes) if a buffer is too small. */
+int zrk_read_messages(zrk_handle *h, int scenario, int tick0, int tick1, zrk_msg *msgs, size_t cap,
+                      size_t *n, int32_t *ids, size_t ids_cap, size_t *n_ids);
+int zrk_read_state(zrk_handle *h, const zrk_state_view *view);
+/* Device pointers for zero-copy consumers (torch): borrowed, valid until zrk_destroy. */
+int zrk_device_ptr(zrk_handle *h, const char *name, void **ptr, size_t *bytes);
+/* Kernel launches issued by this handle and device time spent in them (CUDA events), ms. */
+int zrk_launch_stats(zrk_handle *h, int64_t *n_launches, double *kernel_ms);
+const char *zrk_last_error(zrk_handle *h); /* h may be NULL: error of the last failed zrk_create */
+void zrk_destroy(zrk_handle *h);
+int zrk_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZRK_B200_H */

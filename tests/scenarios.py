@@ -1,0 +1,74 @@
+"""Random scenario generator (reference YAML schema) shared by the golden-fixture script and
+the parity tests.  Deterministic in `seed`; families stress different parts of the tick."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def random_config(seed: int, family: str = "mixed"):
+    rng = np.random.default_rng(seed)
+    u = rng.uniform
+    dense = family == "dense"
+    box = 1500.0 if dense else (6000.0 if family == "mid" else 20000.0)
+    n_targets = int(rng.integers(0, 3)) if family == "tiny" else int(rng.integers(2, 14))
+    n_radars = int(rng.integers(0, 4)) if family in ("mixed", "tiny") else int(rng.integers(1, 3))
+    n_launchers = int(rng.integers(0, 4))
+    dt = int(rng.choice([100, 200, 250, 500]))
+    ticks = int(rng.integers(40, 140))
+    cfg = {"simulation": {"time_step": dt, "duration": dt * ticks},
+           "air_environment": {"id": 999, "position": [0.0, 0.0, 0.0], "targets": []},
+           "radars": [], "missile_launchers": []}
+    for i in range(n_targets):
+        stationary = rng.random() < 0.04
+        vel = [0.0, 0.0, 0.0] if stationary else [float(u(-300, 300)), float(u(-300, 300)), float(u(-15, 15))]
+        z = float(u(-200, 200)) if rng.random() < 0.1 else float(u(300, 8000))
+        cfg["air_environment"]["targets"].append({
+            "id": 1000 + i, "type": str(rng.choice(["AIR_PLANE", "HELICOPTER", "ANOTHER"])),
+            "position": [float(u(-box, box)), float(u(-box, box)), z], "velocity": vel})
+    for r in range(n_radars):
+        kind = rng.integers(0, 4)
+        par = dict(azimuth_start=0.0, elevation_start=0.0, max_distance=float(u(8000, 60000)),
+                   azimuth_range=360.0, elevation_range=float(rng.choice([90.0, 180.0])),
+                   azimuth_speed=0.0, elevation_speed=0.0, scan_mode="horizontal")
+        if kind == 1:   # sweeping sector
+            w = float(rng.choice([30.0, 45.0, 90.0, 180.0]))
+            par.update(azimuth_range=w, azimuth_speed=float(rng.choice([w, w / 2, 10.0])),
+                       azimuth_start=float(rng.choice([0.0, 15.0, 90.0])))
+        elif kind == 2:  # vertical mode with elevation steps
+            par.update(scan_mode="vertical", elevation_range=float(rng.choice([30.0, 60.0])),
+                       elevation_speed=float(rng.choice([0.0, 15.0, 30.0])),
+                       azimuth_range=float(rng.choice([120.0, 360.0])), azimuth_speed=float(rng.choice([0.0, 60.0])))
+        elif kind == 3:  # horizontal with elevation stepping + unknown mode sometimes
+            par.update(azimuth_range=float(rng.choice([120.0, 200.0])), azimuth_speed=120.0,
+                       elevation_range=45.0, elevation_speed=float(rng.choice([0.0, 20.0, 45.0])),
+                       elevation_start=float(rng.choice([0.0, 10.0])),
+                       scan_mode=str(rng.choice(["horizontal", "horizontal", "spiral"])))
+        cfg["radars"].append({"id": 5 + r, "position": [float(u(-2000, 2000)), float(u(-2000, 2000)), float(u(0, 50))], **par})
+    mid = 0
+    for l in range(n_launchers):
+        n_m = int(rng.integers(0, 6))
+        lc = {"id": 100 + l, "position": [float(u(-3000, 3000)), float(u(-3000, 3000)), 0.0], "missiles": []}
+        if rng.random() < 0.5:
+            lc["max_missiles"] = int(rng.integers(1, 6))
+        for _ in range(n_m):
+            mc = {"id": 5000 + mid}
+            mid += 1
+            if rng.random() < 0.8:
+                mc["velocity"] = [1000, 800.0, 300, 1234.5, 250][int(rng.integers(0, 5))]
+            if rng.random() < 0.8:
+                mc["explosion_radius"] = [150, 50.0, 300, 20][int(rng.integers(0, 4))]
+            if rng.random() < 0.8:
+                mc["life_time"] = [60, 35, 6, 3, 12.5][int(rng.integers(0, 5))]
+            lc["missiles"].append(mc)
+        cfg["missile_launchers"].append(lc)
+    if rng.random() < 0.93:
+        ids = [100 + l for l in range(n_launchers)]
+        if ids and rng.random() < 0.2:
+            ids = ids[::-1]
+        if rng.random() < 0.1:
+            ids = ids + [424242]          # unknown id: dropped (main.py:110)
+        if n_radars and rng.random() < 0.1:
+            ids = ids + [5]               # a radar id in the launcher list: asked, never answers
+        cfg["combat_control_point"] = {"id": 0, "missile_launcher_ids": ids,
+                                       "radar_ids": [5 + r for r in range(n_radars)]}
+    return cfg

@@ -1,0 +1,14 @@
+"""zrk_modulation_b200 — B200-native batched tick of Ollegorii/ZRK_modulation.
+
+The hot path (Manager.run_simulation, modules/Manager.py:111-140, and every step() it calls)
+runs as hand-written sm_100a CUDA behind the C ABI of include/zrk_b200.h.  This package is the
+Python host side: the scenario compiler (reference YAML schema) and the mirror of the
+reference's BaseModel / Manager / message interface.  There is no CPU fallback.
+"""
+from ._cabi import (ZRK_NONE, LOG_EVENTS, LOG_BULK, LOG_MASKS, LOG_FULL, MSG_NAMES)  # noqa: F401
+from .scenario import (Batch, compile_batch, load_config, make_noise, synthetic_batch,  # noqa: F401
+                       batch_to_config)
+
+__all__ = ["Batch", "compile_batch", "load_config", "make_noise", "synthetic_batch",
+           "batch_to_config", "ZRK_NONE", "LOG_EVENTS", "LOG_BULK", "LOG_MASKS", "LOG_FULL",
+           "MSG_NAMES"]

@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py — object-updates/s of the batched tick on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference tick on the host CPU cores
+
+A "step" is one pass of the hot path over one batch: every scenario of this rank's shard is
+advanced `ticks` ticks (Manager.run_simulation, Manager.py:111-140) from its initial state.
+Workload (default `c5`): BASELINE.json config 5 sharded — 131072 scenarios per GPU x 32 object
+slots (24 targets + 2 launchers x 4 missiles, all of which fly), 1 radar, 250 ticks; at 8 GPUs
+this is exactly "1M scenarios x 32 objects".  Scenarios are independent, so ranks exchange
+nothing per tick; the only collective is the final statistics all-reduce (NCCL).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (scenarios per GPU, targets, radars, launchers, missiles per launcher, ticks)
+    "c5": (131072, 24, 1, 2, 4, 250),
+    "c3": (4096, 64, 1, 0, 0, 1000),
+    "c4": (8192, 256, 2, 0, 0, 200),
+    "c2": (1, 1000, 1, 0, 0, 10000),
+    "tiny": (256, 24, 1, 2, 4, 50),
+}
+BYTES_PER_OBJECT_UPDATE = 128  # fp64 layout, one tick per pass (DESIGN.md "Algorithmic bytes")
+
+
+def describe(name, n_gpus):
+    B, T, R, L, mpl, ticks = WORKLOADS[name]
+    return {"workload": f"{name}: {B} scenarios/GPU x {T + L * mpl} object slots ({T} targets + {L}x{mpl} missiles), "
+                        f"{R} radar(s), {ticks} ticks, dt=200ms; BASELINE config "
+                        f"{ {'c5': 5, 'c3': 3, 'c4': 4, 'c2': 2}.get(name, 0) } shape",
+            "scenarios_per_gpu": B, "object_slots": T + L * mpl, "ticks": ticks, "radars": R,
+            "total_scenarios": B * n_gpus, "parallelism": f"scenario-sharded x{n_gpus}, no per-tick exchange",
+            "cache": "state per GPU larger than L2 (inputs larger than L2)" if B * (T + L * mpl) * 128 > 126e6
+                     else "state fits L2; L2 flushed between timed steps"}
+
+
+def make_batch(name, rank, pinned=False):
+    from zrk_modulation_b200 import synthetic_batch
+    B, T, R, L, mpl, ticks = WORKLOADS[name]
+    b = synthetic_batch(B, T, n_radars=R, n_launchers=L, missiles_per_launcher=mpl, seed0=rank * B)
+    if pinned:
+        import torch
+        for f in ("target_pos", "target_vel", "target_id", "target_type"):
+            t = torch.from_numpy(getattr(b, f)).pin_memory()
+            setattr(b, f, t.numpy())
+            b._keep.append(t)
+    return b, ticks
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.strip().lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_throughput(name, n_scen_per_core, cores, ticks=None):
+    """The reference tick on the host: oracle/zrk_oracle.c (the C restatement of the reference,
+    pinned bit-exactly to it by tests/golden) on `cores` threads over a bounded sample of the
+    same synthetic scenarios.  Returns object-updates/s."""
+    from oracle import oracle as O
+    from zrk_modulation_b200 import synthetic_batch
+    B, T, R, L, mpl, wticks = WORKLOADS[name]
+    ticks = ticks or wticks
+    n = max(1, min(B, n_scen_per_core * cores))
+    b = synthetic_batch(n, T, n_radars=R, n_launchers=L, missiles_per_launcher=mpl, seed0=0)
+    O.load()
+    t0 = time.perf_counter()
+    O.run_batch(b, 0, n, ticks, n_threads=cores)
+    dt = time.perf_counter() - t0
+    return n * (T + L * mpl) * ticks / dt, n, ticks, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    B, T, R, L, mpl, ticks = WORKLOADS[args.workload]
+    slots = T + L * mpl
+    per_core = max(1, int(2.0e6 / (slots * min(ticks, 250) * (1 + slots / 32.0))))
+    sample_ticks = min(ticks, 250)
+    vals, times = [], []
+    for i in range(args.warmup + args.steps):
+        v, n, tk, dt = cpu_reference_throughput(args.workload, per_core, cores, sample_ticks)
+        if i >= args.warmup:
+            vals.append(v)
+            times.append(dt)
+    value = float(np.mean(vals))
+    line = {"impl": "reference", "metric": "object-updates/sec", "value": value, "unit": "object-updates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": describe(args.workload, args.gpus),
+            "cpu_baseline": {"value": value, "unit": "object-updates/s", "cores": cores, "kind": "port",
+                             "sample": f"{n} scenarios x {slots} slots x {tk} ticks per step, C restatement of the "
+                                       f"reference tick (oracle/zrk_oracle.c) on {cores} host threads"},
+            "e2e": {"value": value, "unit": "object-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "scenario_ticks_per_s": value / slots}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from zrk_modulation_b200 import _cabi
+    from zrk_modulation_b200.engine import Engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    _cabi.load()
+    batch, ticks = make_batch(args.workload, rank, pinned=True)
+    if args.ticks:
+        ticks = args.ticks
+    B, NS = batch.n_scenarios, batch.n_slots
+    units = B * NS * ticks
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident pass: state already in HBM when the timed region starts
+    kern_ms, launches = [], 0
+    sampler = None
+    for i in range(args.warmup + args.steps):
+        eng = Engine(batch, device=dev, ticks_per_launch=args.ticks_per_launch)
+        eng.sync()
+        flush.fill_(i & 0xff)  # evict the freshly written state from L2
+        if i == args.warmup and rank == 0:
+            sampler = ClockSampler(dev)
+        barrier()
+        n0, ms0 = eng.launch_stats()
+        eng.step(ticks)
+        eng.sync()
+        n1, ms1 = eng.launch_stats()  # CUDA events on the launch stream, per launch
+        barrier()
+        if i >= args.warmup:
+            kern_ms.append(ms1 - ms0)
+            launches += n1 - n0
+        if i == args.warmup + args.steps - 1:
+            counts = eng.counts()
+            fc, ft, nr = eng.status()
+        eng.close()
+    clocks = sampler.stop() if sampler else None
+    t_dev = torch.tensor([sum(kern_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    total_ms = float(t_dev.item())
+
+    # ---- end to end through the C ABI with host buffers: create (H2D) + step + read-back (D2H)
+    h2d = sum(getattr(batch, f).nbytes for f in (
+        "n_targets", "n_radars", "n_launchers", "n_missiles", "n_ccp_launchers", "airenv_id", "ccp_id", "target_id",
+        "target_type", "target_pos", "target_vel", "radar_id", "radar_pos", "radar_par", "launcher_id", "launcher_pos",
+        "missile_id", "missile_launcher", "missile_v0", "missile_v0sq", "missile_radius", "missile_life",
+        "ccp_launcher_id", "ccp_launcher_pos")) + (batch.noise.nbytes if batch.noise is not None else 0)
+    d2h = B * (16 + _cabi.ZRK_MSG_NTYPES) * 4
+    e2e_s = []
+    for i in range(args.warmup + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        eng = Engine(batch, device=dev, ticks_per_launch=args.ticks_per_launch)
+        eng.step(ticks)
+        c2 = eng.counts()  # per-scenario message counters + status: the step's result
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        barrier()
+        eng.close()
+        if i >= args.warmup:
+            e2e_s.append(t1 - t0)
+    t_e2e = torch.tensor([sum(e2e_s)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    assert np.array_equal(c2, counts), "end-to-end run disagrees with the device-resident run"
+
+    # ---- final statistics gather: the one collective of the path
+    stats = torch.from_numpy(np.concatenate([counts.sum(0), [(fc & 63 != 0).sum(), B]]).astype(np.int64)).cuda()
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    stats = stats.cpu().numpy()
+
+    if rank == 0:
+        value = units * world * args.steps / (total_ms * 1e-3)
+        e2e_value = units * world * args.steps / float(t_e2e.item())
+        peak, peak_src = measured_peak_gbs()
+        per_launch_ms = sum(kern_ms) / max(1, launches)
+        ticks_per_launch = ticks * args.steps / max(1, launches)
+        achieved = B * NS * ticks_per_launch * BYTES_PER_OBJECT_UPDATE / (per_launch_ms * 1e-3) / 1e9
+        line = {
+            "metric": "object-updates/sec", "value": value, "unit": "object-updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(describe(args.workload, world), ticks_per_launch=ticks_per_launch),
+            "scenario_ticks_per_s": value / NS,
+            "e2e": {"value": e2e_value, "unit": "object-updates/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t_e2e.item()) / args.steps * 1e3},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "zrk_tick_kernel",
+                         "bytes_per_object_update": BYTES_PER_OBJECT_UPDATE,
+                         "note": "algorithmic bytes of a one-tick-per-pass fp64 layout x object-updates per launch; "
+                                 "a launch fuses ticks_per_launch ticks with state in shared memory, so real DRAM "
+                                 "traffic is far lower (see profiles/)"},
+            "stats": {"messages_total": int(stats[:18].sum()), "missile_detonations": int(stats[_cabi.MSG_MISSILE_DETONATE]),
+                      "launches": int(stats[_cabi.MSG_LAUNCH_SUCCESSFUL]), "faulted_scenarios": int(stats[18]),
+                      "scenarios": int(stats[19])},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            v, n, tk, dt = cpu_reference_throughput(args.workload, 512, cores, min(ticks, 250))
+            line["cpu_baseline"] = {"value": v, "unit": "object-updates/s", "cores": cores, "kind": "port",
+                                    "sample": f"{n} scenarios x {NS} slots x {tk} ticks in {dt:.2f}s, "
+                                              f"oracle/zrk_oracle.c on {cores} host threads"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--ticks", type=int, default=0)
+    ap.add_argument("--ticks-per-launch", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

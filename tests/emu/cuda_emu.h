@@ -1,0 +1,148 @@
+// cuda_emu.h — a small fiber-based SIMT emulator.  TEST INFRASTRUCTURE ONLY.
+//
+// Lets tests/ compile zrk_modulation_b200/csrc/*.cu{h} with g++ (-DZRK_EMU) and run the very
+// same kernel source on the CPU so that the host-side logic (state build, log reconstruction,
+// the per-tick control flow) is covered by `pytest -m "not gpu"` in a container without a GPU.
+// Every CUDA thread is a ucontext fiber; barriers and warp collectives are cooperative yield
+// points.  It is never built into, loaded by, or a fallback for the product library.
+#ifndef ZRK_CUDA_EMU_H
+#define ZRK_CUDA_EMU_H
+
+#include <ucontext.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(x)
+#define __align__(x) alignas(x)
+
+struct uint4 {
+    unsigned x, y, z, w;
+};
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+
+namespace zrk_emu {
+
+struct Barrier {
+    int count = 0, gen = 0;
+};
+struct Warp {
+    Barrier bar;
+    uint64_t vals[32];
+};
+struct Block {
+    std::vector<ucontext_t> ctx;
+    std::vector<char *> stacks;
+    std::vector<char> done;
+    std::vector<Warp> warps;
+    Barrier named[17];
+    unsigned char *smem = nullptr;
+    int n_threads = 0, n_done = 0;
+    ucontext_t main_ctx;
+    int cur = 0;
+    const std::function<void()> *body = nullptr;
+};
+
+extern Block *g_block;
+extern dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
+
+inline void yield() {
+    Block *b = g_block;
+    swapcontext(&b->ctx[b->cur], &b->main_ctx);
+}
+inline void barrier_wait(Barrier &bar, int expected) {
+    int gen = bar.gen;
+    if (++bar.count >= expected) {
+        bar.count = 0;
+        bar.gen++;
+    } else {
+        while (bar.gen == gen) yield();
+    }
+}
+inline void named_barrier(int id, int n) { barrier_wait(g_block->named[id], n); }
+inline unsigned char *dyn_smem() { return g_block->smem; }
+inline Warp &my_warp() { return g_block->warps[g_block->cur >> 5]; }
+inline int my_lane() { return g_block->cur & 31; }
+
+void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body);
+
+}  // namespace zrk_emu
+
+#define threadIdx zrk_emu::g_threadIdx
+#define blockIdx zrk_emu::g_blockIdx
+#define blockDim zrk_emu::g_blockDim
+#define gridDim zrk_emu::g_gridDim
+
+inline void __syncthreads() {
+    zrk_emu::Block *b = zrk_emu::g_block;
+    zrk_emu::barrier_wait(b->named[0], b->n_threads - b->n_done);
+}
+inline void __syncwarp(unsigned = 0xffffffffu) { zrk_emu::barrier_wait(zrk_emu::my_warp().bar, 32); }
+
+template <typename T>
+inline T zrk_emu_exchange(T v, int src_lane) {
+    static_assert(sizeof(T) <= 8, "shuffle payload too large");
+    zrk_emu::Warp &w = zrk_emu::my_warp();
+    uint64_t raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    w.vals[zrk_emu::my_lane()] = raw;
+    zrk_emu::barrier_wait(w.bar, 32);
+    uint64_t got = w.vals[src_lane & 31];
+    zrk_emu::barrier_wait(w.bar, 32);
+    T out;
+    memcpy(&out, &got, sizeof(T));
+    return out;
+}
+template <typename T>
+inline T __shfl_sync(unsigned, T v, int src) {
+    return zrk_emu_exchange(v, src);
+}
+template <typename T>
+inline T __shfl_up_sync(unsigned, T v, unsigned d) {
+    int l = zrk_emu::my_lane();
+    T got = zrk_emu_exchange(v, l >= (int)d ? l - (int)d : l);
+    return l >= (int)d ? got : v;
+}
+template <typename T>
+inline T __shfl_xor_sync(unsigned, T v, int m) {
+    return zrk_emu_exchange(v, zrk_emu::my_lane() ^ m);
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+    zrk_emu::Warp &w = zrk_emu::my_warp();
+    w.vals[zrk_emu::my_lane()] = pred ? 1 : 0;
+    zrk_emu::barrier_wait(w.bar, 32);
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++) r |= (unsigned)(w.vals[i] & 1) << i;
+    zrk_emu::barrier_wait(w.bar, 32);
+    return r;
+}
+inline int atomicMin(int *p, int v) {
+    int o = *p;
+    if (v < o) *p = v;
+    return o;
+}
+inline int atomicAdd(int *p, int v) {
+    int o = *p;
+    *p = o + v;
+    return o;
+}
+inline int atomicOr(int *p, int v) {
+    int o = *p;
+    *p = o | v;
+    return o;
+}
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+
+#endif

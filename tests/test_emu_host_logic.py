@@ -1,0 +1,82 @@
+"""Host-side logic on the CPU: the product sources (zrk_host.cu + zrk_tick.cuh) compiled for the
+fiber SIMT emulator in tests/emu, compared with the oracle.  Covers state build, the C ABI reads,
+the message-log reconstruction and the per-tick control flow without a GPU.  The emulated build
+is test infrastructure only."""
+import numpy as np
+import pytest
+
+import emu_lib
+import parity
+from enginecheck import check_batch_counts, check_batch_full
+from scenarios import random_config
+from zrk_modulation_b200 import compile_batch, make_noise, synthetic_batch
+from zrk_modulation_b200.engine import Engine, ZrkError
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return emu_lib.load()
+
+
+@pytest.mark.parametrize("name", [n for n in parity.golden_names() if n.startswith("shipped") or n.endswith(("0", "4", "6"))])
+def test_emulated_tick_on_golden_scenarios(lib, name):
+    g = parity.load_golden(name)
+    b = compile_batch(g["cfg"], noise=g["noise"])
+    check_batch_full(b, b.n_ticks(0), lib=lib)
+
+
+@pytest.mark.parametrize("family,seed,tpl", [("mixed", 300, 1), ("dense", 301, 5), ("mid", 302, 0), ("tiny", 303, 3),
+                                             ("dense", 304, 0), ("mixed", 305, 16)])
+def test_emulated_tick_random(lib, family, seed, tpl):
+    cfg = random_config(seed, family)
+    b = compile_batch(cfg)
+    b.set_noise(make_noise(8, b.max_radars, b.n_slots, seed=seed))
+    check_batch_full(b, b.n_ticks(0), lib=lib, ticks_per_launch=tpl)
+
+
+def test_ragged_batch_and_chunked_steps(lib):
+    cfgs = [random_config(400 + i, "mixed") for i in range(5)]
+    for c in cfgs:
+        c["simulation"]["time_step"] = 200
+    b = compile_batch(cfgs)
+    b.set_noise(make_noise(8, b.max_radars, b.n_slots, seed=1))
+    check_batch_full(b, 40, lib=lib, step_chunks=[1, 2, 30, 7])
+
+
+def test_exact_only_kernel_agrees(lib):
+    cfg = random_config(410, "dense")
+    b = compile_batch(cfg)
+    b.set_noise(make_noise(8, b.max_radars, b.n_slots, seed=3))
+    check_batch_full(b, b.n_ticks(0), lib=lib, exact_only=True)
+
+
+def test_team_of_64_and_128(lib):
+    b = synthetic_batch(2, 40, n_radars=2, n_launchers=2, missiles_per_launcher=3, noise_period=8)
+    check_batch_full(b, 30, lib=lib)
+    b = synthetic_batch(1, 100, n_radars=1, n_launchers=1, missiles_per_launcher=4, noise_period=8, box_km=8.0)
+    check_batch_full(b, 12, lib=lib)
+
+
+def test_events_mode_counts(lib):
+    b = synthetic_batch(8, 24, n_radars=1, n_launchers=2, missiles_per_launcher=4, noise_period=8)
+    check_batch_counts(b, 40, lib=lib, n_threads=2, sample=4)
+
+
+def test_create_rejects_bad_input(lib):
+    b = synthetic_batch(2, 4, n_radars=1)
+    b.target_id[1, 1] = b.target_id[1, 0]
+    with pytest.raises(ZrkError) as e:
+        Engine(b, lib=lib)
+    assert e.value.rc == -5
+    b = synthetic_batch(1, 1100, n_radars=1, noise_period=0)
+    with pytest.raises(ZrkError) as e:
+        Engine(b, lib=lib)
+    assert e.value.rc == -5
+
+
+def test_read_messages_needs_full_log(lib):
+    b = synthetic_batch(1, 4, n_radars=1, noise_period=4)
+    with Engine(b, lib=lib) as eng:
+        eng.step(2)
+        with pytest.raises(ZrkError):
+            eng.messages(0)

@@ -1,0 +1,123 @@
+"""Parity of the CUDA path (libzrk_b200.so on a B200) with the oracle and with the reference's
+golden fixtures, through the C ABI.  fp64 throughout: messages, payload bits, faults and final
+state must be identical (tolerance: none), except against the *reference* fixtures where numpy's
+libm pow() in the launch solve allows the last bits of a missile velocity to differ
+(rtol 1e-12 on payloads there; decisions and ids exact)."""
+import numpy as np
+import pytest
+
+import parity
+from enginecheck import check_batch_counts, check_batch_full
+from oracle import oracle as O
+from scenarios import random_config
+from zrk_modulation_b200 import LOG_FULL, compile_batch, make_noise, synthetic_batch
+from zrk_modulation_b200.engine import Engine
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", parity.golden_names())
+def test_golden_fixture_through_cuda(name):
+    g = parity.load_golden(name)
+    b = compile_batch(g["cfg"], noise=g["noise"])
+    nt = b.n_ticks(0)
+    with Engine(b, log_types=LOG_FULL, log_capacity=(3 * b.n_slots + 24) * nt + 64, mask_ticks=nt + 1) as eng:
+        eng.step(nt)
+        msgs, ids = eng.messages(0, 0, nt)
+        fc, ft, _ = eng.status()
+        counts = eng.counts()
+    assert parity.diff_msgs(g["msgs"], g["ids"], msgs, ids, xyz_rtol=1e-12) == ""
+    assert (int(fc[0]) & 63, int(ft[0])) == (g["fault_code"], g["fault_tick"]), g["fault_where"]
+    assert np.array_equal(counts[0], g["counts"])
+    check_batch_full(b, nt)  # and bit-exact against the oracle
+
+
+@pytest.mark.parametrize("family", ["mixed", "dense", "mid", "tiny"])
+@pytest.mark.parametrize("tpl", [0, 1])
+def test_random_scenarios_full_log(family, tpl):
+    for seed in range(500, 512):
+        cfg = random_config(seed, family)
+        b = compile_batch(cfg)
+        b.set_noise(make_noise(8, b.max_radars, b.n_slots, seed=seed))
+        check_batch_full(b, b.n_ticks(0), ticks_per_launch=tpl)
+
+
+def test_ragged_batch_chunked():
+    cfgs = [random_config(600 + i, f) for i, f in enumerate(["mixed", "dense", "mid", "tiny"] * 8)]
+    for c in cfgs:
+        c["simulation"]["time_step"] = 200
+    b = compile_batch(cfgs)
+    b.set_noise(make_noise(8, b.max_radars, b.n_slots, seed=11))
+    check_batch_full(b, 60, step_chunks=[1, 2, 3, 50, 4])
+
+
+def test_exact_only_kernel():
+    for seed in (700, 701, 702):
+        cfg = random_config(seed, "dense")
+        b = compile_batch(cfg)
+        b.set_noise(make_noise(8, b.max_radars, b.n_slots, seed=seed))
+        check_batch_full(b, b.n_ticks(0), exact_only=True)
+
+
+@pytest.mark.parametrize("n_targets,radars,launchers,mpl,ticks,box", [
+    (24, 1, 2, 4, 250, 20.0),    # BASELINE config 5 shape (N = 32 slots, missiles in flight)
+    (64, 1, 0, 0, 60, 20.0),     # config 3 shape
+    (56, 2, 2, 4, 80, 12.0),     # team of 64 with launches, two radars (one sweeping)
+    (120, 2, 1, 8, 40, 20.0),    # team of 128
+    (256, 2, 0, 0, 12, 20.0),    # config 4 shape (team of 256)
+    (300, 1, 2, 8, 10, 20.0),    # team of 512
+])
+def test_synthetic_families_full_log(n_targets, radars, launchers, mpl, ticks, box):
+    b = synthetic_batch(6, n_targets, n_radars=radars, n_launchers=launchers, missiles_per_launcher=mpl,
+                        seed0=1000, noise_period=16, box_km=box)
+    check_batch_full(b, ticks)
+
+
+def test_config2_shape_1000_objects():
+    """BASELINE config 2: one scenario, one radar, 1000 air objects.  All-visible for the ticks
+    the oracle finishes in seconds, then a 30-degree sweeping sector for longer."""
+    b = synthetic_batch(1, 1000, n_radars=1, seed0=7, noise_period=8)
+    check_batch_full(b, 6)
+    b = synthetic_batch(1, 1000, n_radars=1, seed0=8, noise_period=8)
+    b.radar_par[0, 0] = [0.0, 0.0, 30000.0, 30.0, 90.0, 30.0, 0.0, 0.0]
+    check_batch_full(b, 40)
+
+
+def test_events_mode_large_batch():
+    """Events-only log at a batch that fills the GPU: counts, faults and sampled event records."""
+    b = synthetic_batch(4096, 24, n_radars=1, n_launchers=2, missiles_per_launcher=4, seed0=5000)
+    counts = check_batch_counts(b, 250, n_threads=8, sample=32)
+    from zrk_modulation_b200 import _cabi as A
+    assert counts[:, A.MSG_LAUNCH_COMMAND].sum() > 0 and counts[:, A.MSG_MISSILE_DETONATE].sum() > 0
+
+
+def test_config3_counts():
+    b = synthetic_batch(4096, 64, n_radars=1, seed0=9000)
+    check_batch_counts(b, 40, n_threads=8, sample=8)
+
+
+def test_properties_at_scale():
+    """Size-independent properties on a large batch (no oracle): step(a)+step(b) == step(a+b);
+    ticks_per_launch does not change results; replicated scenarios give identical results."""
+    b = synthetic_batch(8192, 24, n_radars=1, n_launchers=2, missiles_per_launcher=4, seed0=123)
+    # make the second half a replica of the first
+    for name in ("target_pos", "target_vel"):
+        getattr(b, name)[4096:] = getattr(b, name)[:4096]
+    res = []
+    for tpl, chunks in ((0, [120]), (1, [120]), (16, [50, 70])):
+        with Engine(b, ticks_per_launch=tpl) as eng:
+            for c in chunks:
+                eng.step(c)
+            res.append((eng.counts(), eng.status(), eng.state()))
+    c0, s0, st0 = res[0]
+    for c, s, st in res[1:]:
+        assert np.array_equal(c0, c)
+        assert all(np.array_equal(x, y) for x, y in zip(s0, s))
+        assert parity.same_f64(st0["pos"], st["pos"]) and np.array_equal(st0["ccp_t_key"], st["ccp_t_key"])
+    assert np.array_equal(c0[:4096], c0[4096:])
+    assert parity.same_f64(st0["pos"][:4096], st0["pos"][4096:])
+    # conservation: every detonation removes its missile; launched = detonated + in flight
+    from zrk_modulation_b200 import _cabi as A
+    assert (c0[:, A.MSG_NEW_MISSILE] == c0[:, A.MSG_LAUNCH_SUCCESSFUL]).all()
+    assert (c0[:, A.MSG_MISSILE_DETONATE] <= c0[:, A.MSG_NEW_MISSILE]).all()
+    assert (c0[:, A.MSG_ACTIVE_OBJECTS] == 120).all()

@@ -145,7 +145,15 @@ def load():
         raise RuntimeError(
             f"{path} is missing: build the CUDA library first (__graft_entry__.build()). "
             "zrk_modulation_b200 has no CPU fallback.")
-    lib = C.CDLL(path)
+    lib = declare(C.CDLL(path))
+    if lib.zrk_abi_version() != ZRK_ABI_VERSION:
+        raise RuntimeError("libzrk_b200.so ABI version mismatch; rebuild")
+    _LIB = lib
+    return lib
+
+
+def declare(lib):
+    """Attach the prototypes of include/zrk_b200.h to a loaded library."""
     H = C.c_void_p
     lib.zrk_create.argtypes = [C.POINTER(ZrkBatchDesc), C.POINTER(ZrkOptions), C.POINTER(H)]
     lib.zrk_step.argtypes = [H, C.c_int]
@@ -169,9 +177,6 @@ def load():
               "zrk_read_counts", "zrk_read_records", "zrk_log_capacity", "zrk_read_messages",
               "zrk_read_state", "zrk_device_ptr", "zrk_launch_stats", "zrk_abi_version"):
         getattr(lib, f).restype = C.c_int
-    if lib.zrk_abi_version() != ZRK_ABI_VERSION:
-        raise RuntimeError("libzrk_b200.so ABI version mismatch; rebuild")
-    _LIB = lib
     return lib
 
 

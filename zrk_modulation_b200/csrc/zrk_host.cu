@@ -1,0 +1,754 @@
+// zrk_host.cu — the C ABI of include/zrk_b200.h on top of the sm_100a tick kernel.
+//
+// zrk_create uploads the caller's structure-of-arrays scenario description as it is and builds
+// the device state with an init kernel (no per-scenario host loop); zrk_step launches the tick
+// kernel on the handle's stream; reads copy back and, for zrk_read_messages, merge the explicit
+// record log with the ACTIVE/ALL/FOUND lists rebuilt from the per-tick masks into the
+// reference's message order (Manager.py:41-58).
+#ifdef ZRK_EMU
+#include "cuda_runtime_shim.h"
+#define ZRK_LAUNCH(kern, grid, block, smem, stream, ...) \
+    zrk_emu::launch(dim3(grid), dim3(block), (smem), [&]() { kern(__VA_ARGS__); })
+#else
+#include <cuda_runtime.h>
+#define ZRK_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "zrk_tick.cuh"
+
+using namespace zrk;
+
+// ------------------------------------------------------------------ init kernel
+
+struct DevDesc {  // zrk_batch_desc with device pointers
+    int B, T, R, L, M, C;
+    const int *n_targets, *n_radars, *n_launchers, *n_missiles, *n_ccp_launchers, *airenv_id, *ccp_id, *tick_limit;
+    const int *target_id, *target_type;
+    const double *target_pos, *target_vel;
+    const int *radar_id;
+    const double *radar_pos, *radar_par;
+    const int *launcher_id;
+    const double *launcher_pos;
+    const int *missile_id, *missile_launcher;
+    const double *missile_v0, *missile_v0sq, *missile_radius, *missile_life;
+    const int *ccp_launcher_id;
+    const double *ccp_launcher_pos;
+};
+
+// One thread per scenario: main.create_objects_from_config (main.py:35-149) into the device layout.
+__global__ void zrk_init_kernel(const Params P, const DevDesc d, int *err) {
+    const Layout &o = P.lo;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= o.B) return;
+    const int NSP = o.NSP, MP = o.MP;
+    unsigned char *sm = P.dyn + (size_t)b * o.dyn_bytes;
+    unsigned char *cs = const_cast<unsigned char *>(P.cst) + (size_t)b * o.cst_bytes;
+    double *traj = P.traj + (size_t)b * 8 * NSP;
+    const int nT = d.n_targets ? d.n_targets[b] : d.T, nR = d.n_radars ? d.n_radars[b] : d.R;
+    const int nL = d.n_launchers ? d.n_launchers[b] : d.L, nM = d.n_missiles ? d.n_missiles[b] : d.M;
+    const int nC = d.n_ccp_launchers ? d.n_ccp_launchers[b] : d.C;
+    if (nT < 0 || nT > d.T || nR < 0 || nR > d.R || nL < 0 || nL > d.L || nM < 0 || nM > d.M || nC < 0 || nC > d.C) {
+        atomicOr(err, 1);
+        return;
+    }
+    int *hdr = (int *)(sm + o.hdr);
+    hdr[H_NSLOTS] = nT;
+    double *pos = (double *)(sm + o.pos), *speed = (double *)(sm + o.speed);
+    int *sid = (int *)(sm + o.sid), *sflags = (int *)(sm + o.sflags), *srf = (int *)(sm + o.srf);
+    for (int t = 0; t < nT; t++) {
+        size_t g = (size_t)b * d.T + t;
+        double vx = d.target_vel[3 * g], vy = d.target_vel[3 * g + 1], vz = d.target_vel[3 * g + 2];
+        double sp = sqrt(dot3(vx, vy, vz, vx, vy, vz));  // np.linalg.norm (AirObject.py:36)
+        for (int k = 0; k < 3; k++) {
+            pos[k * NSP + t] = d.target_pos[3 * g + k];
+            traj[k * NSP + t] = d.target_pos[3 * g + k];
+            traj[(4 + k) * NSP + t] = d.target_vel[3 * g + k];
+        }
+        traj[3 * NSP + t] = 0.0;
+        traj[7 * NSP + t] = sp;
+        speed[t] = sp;
+        sid[t] = d.target_id[g];
+        int tt = d.target_type ? d.target_type[g] : ZRK_ANOTHER;
+        sflags[t] = F_ALIVE | ((tt & 3) << F_TTYPE_SHIFT) | (t << F_STATIC_SHIFT);
+    }
+    for (int k = 0; k < NSP; k++) srf[k] = -1;
+    int *te_mid = (int *)(sm + o.te_mid);
+    for (int k = 0; k < NSP; k++) te_mid[k] = ZRK_NONE;
+    int *chdr = (int *)(cs + o.c_hdr);
+    chdr[C_NT] = nT; chdr[C_NR] = nR; chdr[C_NL] = nL; chdr[C_NM] = nM; chdr[C_NC] = nC;
+    chdr[C_AIRENV_ID] = d.airenv_id ? d.airenv_id[b] : 1;
+    chdr[C_CCP_ID] = d.ccp_id ? d.ccp_id[b] : 0;
+    chdr[C_TICK_LIMIT] = d.tick_limit ? d.tick_limit[b] : -1;
+    double *rad_cur = (double *)(sm + o.rad_cur);
+    int *c_rad_id = (int *)(cs + o.c_rad_id);
+    double *c_rad_pos = (double *)(cs + o.c_rad_pos), *c_rad_par = (double *)(cs + o.c_rad_par);
+    for (int r = 0; r < nR; r++) {
+        size_t g = (size_t)b * d.R + r;
+        c_rad_id[r] = d.radar_id[g];
+        for (int k = 0; k < 3; k++) c_rad_pos[3 * r + k] = d.radar_pos[3 * g + k];
+        for (int k = 0; k < 8; k++) c_rad_par[RAD_PAR_STRIDE * r + k] = d.radar_par[8 * g + k];
+        double md = d.radar_par[8 * g + 2], md2 = md * md;
+        c_rad_par[RAD_PAR_STRIDE * r + 8] = md >= 0 ? md2 * (1.0 - 1e-14) : -1.0;
+        c_rad_par[RAD_PAR_STRIDE * r + 9] = md >= 0 ? md2 * (1.0 + 1e-14) : -1.0;
+        rad_cur[2 * r] = d.radar_par[8 * g + 0];
+        rad_cur[2 * r + 1] = d.radar_par[8 * g + 1];
+    }
+    int *c_l_id = (int *)(cs + o.c_l_id);
+    double *c_l_pos = (double *)(cs + o.c_l_pos);
+    for (int l = 0; l < nL; l++) {
+        size_t g = (size_t)b * d.L + l;
+        c_l_id[l] = d.launcher_id[g];
+        for (int k = 0; k < 3; k++) c_l_pos[3 * l + k] = d.launcher_pos[3 * g + k];
+        for (int j = 0; j < l; j++)
+            if (c_l_id[j] == c_l_id[l]) atomicOr(err, 2);
+    }
+    int *st_n = (int *)(sm + o.st_n), *st = (int *)(sm + o.st);
+    int *m_status = (int *)(sm + o.m_status), *m_target = (int *)(sm + o.m_target), *m_slot = (int *)(sm + o.m_slot),
+        *m_birth = (int *)(sm + o.m_birth);
+    double *m_period = (double *)(sm + o.m_period);
+    int *c_m_id = (int *)(cs + o.c_m_id), *c_m_launcher = (int *)(cs + o.c_m_launcher);
+    double *c_m_v0 = (double *)(cs + o.c_m_v0), *c_m_v0sq = (double *)(cs + o.c_m_v0sq),
+           *c_m_radius = (double *)(cs + o.c_m_radius);
+    for (int m = 0; m < nM; m++) {
+        size_t g = (size_t)b * d.M + m;
+        int l = d.missile_launcher[g];
+        if (l < 0 || l >= nL) {
+            atomicOr(err, 1);
+            return;
+        }
+        c_m_id[m] = d.missile_id[g];
+        c_m_launcher[m] = l;
+        c_m_v0[m] = d.missile_v0[g];
+        c_m_v0sq[m] = d.missile_v0sq ? d.missile_v0sq[g] : d.missile_v0[g] * d.missile_v0[g];
+        c_m_radius[m] = d.missile_radius[g];
+        m_period[m] = d.missile_life[g];
+        m_status[m] = ST_READY;
+        m_target[m] = -1;
+        m_slot[m] = -1;
+        m_birth[m] = -1;
+        st[l * MP + st_n[l]++] = m;  // MissileLauncher.add_missile (MissileLauncher.py:36-48)
+    }
+    // air-object ids must be unique (the tick resolves object identity by slot)
+    for (int i = 0; i < nT + nM; i++) {
+        int a = i < nT ? sid[i] : c_m_id[i - nT];
+        for (int j = 0; j < i; j++) {
+            int c = j < nT ? sid[j] : c_m_id[j - nT];
+            if (a == c) atomicOr(err, 2);
+        }
+    }
+    int *c_cl_id = (int *)(cs + o.c_cl_id), *c_cl_launcher = (int *)(cs + o.c_cl_launcher);
+    double *c_cl_pos = (double *)(cs + o.c_cl_pos);
+    for (int c = 0; c < nC; c++) {
+        size_t g = (size_t)b * d.C + c;
+        c_cl_id[c] = d.ccp_launcher_id[g];
+        for (int k = 0; k < 3; k++) c_cl_pos[3 * c + k] = d.ccp_launcher_pos[3 * g + k];
+        int li = -1;
+        for (int l = 0; l < nL; l++)
+            if (c_l_id[l] == c_cl_id[c]) li = l;
+        c_cl_launcher[c] = li;
+    }
+}
+
+// Per-scenario header + message counters packed [B][H_WORDS + NTYPES] for cheap read-back.
+#define ZRK_SUMMARY_WORDS (H_WORDS + ZRK_MSG_NTYPES)
+__global__ void zrk_summary_kernel(const Params P, int *out) {
+    const Layout &o = P.lo;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)o.B * ZRK_SUMMARY_WORDS) return;
+    const int b = (int)(i / ZRK_SUMMARY_WORDS), w = (int)(i % ZRK_SUMMARY_WORDS);
+    const unsigned char *sm = P.dyn + (size_t)b * o.dyn_bytes;
+    out[i] = w < H_WORDS ? ((const int *)(sm + o.hdr))[w] : ((const int *)(sm + o.counts))[w - H_WORDS];
+}
+
+// ------------------------------------------------------------------ handle
+
+struct zrk_handle {
+    Params P{};
+    zrk_batch_desc hd{};  // scalar fields only are meaningful after create
+    int device = 0;
+    cudaStream_t stream{};
+    std::vector<void *> allocs;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;  // per-launch event pairs
+    std::vector<cudaEvent_t> free_events;
+    long long n_launches = 0;
+    double kernel_ms = 0;
+    int ticks_per_launch = 0;
+    long long tick = 0;  // ticks requested so far
+    bool fast = true;
+    std::string err;
+    size_t smem_bytes = 0;
+    int grid = 0, block = 0;
+    // host copies kept for reconstruction
+    std::vector<int> h_radar_id, h_n_radars, h_airenv_id;
+    int *d_summary = nullptr;
+    std::vector<int> h_summary;
+};
+
+static thread_local std::string g_create_err;
+
+#define CK(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                 \
+            return ZRK_ERR_CUDA;                                                         \
+        }                                                                                \
+    } while (0)
+
+template <typename T>
+static int dev_upload(zrk_handle *h, const T *src, size_t n, const T **dst) {
+    *dst = nullptr;
+    if (!src || !n) return ZRK_OK;
+    void *p = nullptr;
+    CK(cudaMalloc(&p, n * sizeof(T)));
+    h->allocs.push_back(p);
+    CK(cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    *dst = (const T *)p;
+    return ZRK_OK;
+}
+template <typename T>
+static int dev_alloc(zrk_handle *h, size_t n, T **dst, bool zero) {
+    void *p = nullptr;
+    CK(cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
+    h->allocs.push_back(p);
+    if (zero) CK(cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), h->stream));
+    *dst = (T *)p;
+    return ZRK_OK;
+}
+
+typedef void (*tick_fn)(const Params, int);
+
+template <int TEAM, int TPC>
+static tick_fn pick_fast(bool fast) {
+    return fast ? (tick_fn)zrk_tick_kernel<TEAM, TPC, true> : (tick_fn)zrk_tick_kernel<TEAM, TPC, false>;
+}
+static tick_fn pick_kernel(int team, bool fast) {
+    switch (team) {
+    case 32: return pick_fast<32, 4>(fast);
+    case 64: return pick_fast<64, 2>(fast);
+    case 128: return pick_fast<128, 1>(fast);
+    case 256: return pick_fast<256, 1>(fast);
+    case 512: return pick_fast<512, 1>(fast);
+    case 1024: return pick_fast<1024, 1>(fast);
+    }
+    return nullptr;
+}
+
+extern "C" int zrk_abi_version(void) { return ZRK_ABI_VERSION; }
+
+extern "C" const char *zrk_last_error(zrk_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+extern "C" void zrk_destroy(zrk_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto &pr : h->pending) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    for (auto e : h->free_events) cudaEventDestroy(e);
+    for (void *p : h->allocs) cudaFree(p);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options *opt) {
+    if (d->abi_version != ZRK_ABI_VERSION) {
+        h->err = "zrk_batch_desc.abi_version mismatch";
+        return ZRK_ERR_ARG;
+    }
+    const int B = d->n_scenarios, T = d->max_targets, R = d->max_radars, L = d->max_launchers, M = d->max_missiles,
+              C = d->max_ccp_launchers;
+    if (B <= 0 || T < 0 || R < 0 || L < 0 || M < 0 || C < 0 || d->dt_ms <= 0) {
+        h->err = "bad batch dimensions";
+        return ZRK_ERR_ARG;
+    }
+    if ((T && (!d->target_id || !d->target_pos || !d->target_vel)) || (R && (!d->radar_id || !d->radar_pos || !d->radar_par)) ||
+        (L && (!d->launcher_id || !d->launcher_pos)) ||
+        (M && (!d->missile_id || !d->missile_launcher || !d->missile_v0 || !d->missile_radius || !d->missile_life)) ||
+        (C && (!d->ccp_launcher_id || !d->ccp_launcher_pos))) {
+        h->err = "missing array in zrk_batch_desc";
+        return ZRK_ERR_ARG;
+    }
+    Layout lo = make_layout(B, T, M, R, L, C);
+    if (!lo.team || T + M > 1024 || M > 1023) {
+        h->err = "unsupported: more than 1024 air-object slots per scenario";
+        return ZRK_ERR_UNSUPPORTED;
+    }
+    if (d->noise && (d->noise_period <= 0 || d->noise_radars < R || d->noise_objects < T + M)) {
+        h->err = "noise table does not cover max_radars x (max_targets + max_missiles)";
+        return ZRK_ERR_ARG;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        h->err = "no CUDA device: zrk_b200 has no CPU fallback";
+        return ZRK_ERR_NO_DEVICE;
+    }
+    h->device = opt ? opt->device : 0;
+    if (h->device < 0 || h->device >= ndev) {
+        h->err = "bad device ordinal";
+        return ZRK_ERR_ARG;
+    }
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->hd = *d;
+    Params &P = h->P;
+    P.lo = lo;
+    P.dt_ms = d->dt_ms;
+    P.dt_s = (double)d->dt_ms / 1000.0;
+    P.range_step = ZRK_POSSIBLE_TARGET_RADIUS * P.dt_s;
+    P.log_types = opt ? opt->log_types : (unsigned)ZRK_LOG_EVENTS;
+    int cap = opt ? opt->log_capacity : 0;
+    if (cap <= 0) cap = 2 * C + M * (6 + R) + 4;  // every ZRK_LOG_EVENTS record a scenario can ever emit
+    P.log_cap = cap;
+    P.mask_words = (lo.NS + 31) / 32;
+    if (P.mask_words < 1) P.mask_words = 1;
+    P.mask_ticks = (P.log_types & ZRK_LOG_MASKS) ? ((opt && opt->mask_ticks > 0) ? opt->mask_ticks : 1024) : 0;
+    h->ticks_per_launch = (opt && opt->ticks_per_launch > 0) ? opt->ticks_per_launch : 256;
+    h->fast = !(opt && (opt->reserved[0] & 1));  // reserved[0] bit 0: exact-only kernel (no pre-filters)
+
+    DevDesc dd{};
+    dd.B = B; dd.T = T; dd.R = R; dd.L = L; dd.M = M; dd.C = C;
+    int rc;
+#define UP(field, n) if ((rc = dev_upload(h, d->field, (size_t)(n), &dd.field)) != ZRK_OK) return rc
+    UP(n_targets, B); UP(n_radars, B); UP(n_launchers, B); UP(n_missiles, B); UP(n_ccp_launchers, B);
+    UP(airenv_id, B); UP(ccp_id, B); UP(tick_limit, B);
+    UP(target_id, (size_t)B * T); UP(target_type, (size_t)B * T);
+    UP(target_pos, (size_t)B * T * 3); UP(target_vel, (size_t)B * T * 3);
+    UP(radar_id, (size_t)B * R); UP(radar_pos, (size_t)B * R * 3); UP(radar_par, (size_t)B * R * 8);
+    UP(launcher_id, (size_t)B * L); UP(launcher_pos, (size_t)B * L * 3);
+    UP(missile_id, (size_t)B * M); UP(missile_launcher, (size_t)B * M); UP(missile_v0, (size_t)B * M);
+    UP(missile_v0sq, (size_t)B * M); UP(missile_radius, (size_t)B * M); UP(missile_life, (size_t)B * M);
+    UP(ccp_launcher_id, (size_t)B * C); UP(ccp_launcher_pos, (size_t)B * C * 3);
+#undef UP
+    const size_t n_desc_allocs = h->allocs.size();
+    if (d->noise) {
+        P.noise_period = d->noise_period;
+        P.noise_radars = d->noise_radars;
+        P.noise_objects = d->noise_objects;
+        P.noise_stride = d->noise_scenario_stride;
+        size_t one = (size_t)d->noise_period * d->noise_radars * d->noise_objects * 3;
+        size_t n = d->noise_scenario_stride ? (size_t)d->noise_scenario_stride * (B - 1) + one : one;
+        if ((rc = dev_upload(h, d->noise, n, &P.noise)) != ZRK_OK) return rc;
+    }
+    if ((rc = dev_alloc(h, (size_t)B * 8 * lo.NSP, &P.traj, true)) != ZRK_OK) return rc;
+    if ((rc = dev_alloc(h, (size_t)B * lo.dyn_bytes, &P.dyn, true)) != ZRK_OK) return rc;
+    unsigned char *cst = nullptr;
+    if ((rc = dev_alloc(h, (size_t)B * lo.cst_bytes, &cst, true)) != ZRK_OK) return rc;
+    P.cst = cst;
+    if ((rc = dev_alloc(h, (size_t)B * P.log_cap, &P.rec, false)) != ZRK_OK) return rc;
+    if (P.mask_ticks) {
+        size_t n = (size_t)P.mask_ticks * B * (1 + lo.RP) * P.mask_words;
+        if ((rc = dev_alloc(h, n, &P.masks, true)) != ZRK_OK) return rc;
+    }
+    int *derr = nullptr;
+    if ((rc = dev_alloc(h, 1, &derr, true)) != ZRK_OK) return rc;
+    if ((rc = dev_alloc(h, (size_t)B * ZRK_SUMMARY_WORDS, &h->d_summary, false)) != ZRK_OK) return rc;
+    ZRK_LAUNCH(zrk_init_kernel, (B + 127) / 128, 128, 0, h->stream, P, dd, derr);
+    CK(cudaGetLastError());
+    int herr = 0;
+    CK(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    // the uploaded description is no longer needed on the device
+    for (size_t i = 0; i < n_desc_allocs; i++) cudaFree(h->allocs[i]);
+    h->allocs.erase(h->allocs.begin(), h->allocs.begin() + n_desc_allocs);
+    if (herr & 1) {
+        h->err = "per-scenario count exceeds the batch maximum, or missile_launcher out of range";
+        return ZRK_ERR_ARG;
+    }
+    if (herr & 2) {
+        h->err = "unsupported scenario: air-object ids and launcher ids must be unique within a scenario";
+        return ZRK_ERR_UNSUPPORTED;
+    }
+    // small host copies used by zrk_read_messages
+    h->h_radar_id.assign(d->radar_id ? d->radar_id : nullptr, d->radar_id ? d->radar_id + (size_t)B * R : nullptr);
+    h->h_n_radars.resize(B);
+    h->h_airenv_id.resize(B);
+    for (int b = 0; b < B; b++) {
+        h->h_n_radars[b] = d->n_radars ? d->n_radars[b] : R;
+        h->h_airenv_id[b] = d->airenv_id ? d->airenv_id[b] : 1;
+    }
+    h->block = lo.team * lo.teams_per_cta;
+    h->grid = (B + lo.teams_per_cta - 1) / lo.teams_per_cta;
+    h->smem_bytes = (size_t)lo.team_smem_bytes * lo.teams_per_cta;
+    if (h->smem_bytes > 227 * 1024) {
+        h->err = "unsupported: scenario state does not fit in shared memory";
+        return ZRK_ERR_UNSUPPORTED;
+    }
+    tick_fn fn = pick_kernel(lo.team, h->fast);
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    return ZRK_OK;
+}
+
+extern "C" int zrk_create(const zrk_batch_desc *desc, const zrk_options *opt, zrk_handle **out) {
+    if (!desc || !out) {
+        g_create_err = "null argument";
+        return ZRK_ERR_ARG;
+    }
+    *out = nullptr;
+    zrk_handle *h = new zrk_handle();
+    int rc = create_impl(h, desc, opt);
+    if (rc != ZRK_OK) {
+        g_create_err = h->err;
+        zrk_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return ZRK_OK;
+}
+
+static int resolve_events(zrk_handle *h) {
+    for (auto &pr : h->pending) {
+        float ms = 0;
+        CK(cudaEventSynchronize(pr.second));
+        CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        h->kernel_ms += ms;
+        h->free_events.push_back(pr.first);
+        h->free_events.push_back(pr.second);
+    }
+    h->pending.clear();
+    return ZRK_OK;
+}
+static int get_event(zrk_handle *h, cudaEvent_t *e) {
+    if (!h->free_events.empty()) {
+        *e = h->free_events.back();
+        h->free_events.pop_back();
+        return ZRK_OK;
+    }
+    CK(cudaEventCreate(e));
+    return ZRK_OK;
+}
+
+extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
+    if (!h || n_ticks < 0) return ZRK_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    tick_fn fn = pick_kernel(h->P.lo.team, h->fast);
+    if (h->pending.size() > 4096) {
+        int rc = resolve_events(h);
+        if (rc) return rc;
+    }
+    int left = n_ticks;
+    while (left > 0) {
+        int k = left < h->ticks_per_launch ? left : h->ticks_per_launch;
+        cudaEvent_t e0, e1;
+        int rc;
+        if ((rc = get_event(h, &e0)) || (rc = get_event(h, &e1))) return rc;
+        CK(cudaEventRecord(e0, h->stream));
+        ZRK_LAUNCH(fn, h->grid, h->block, h->smem_bytes, h->stream, h->P, k);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e1, h->stream));
+        h->pending.push_back({e0, e1});
+        h->n_launches++;
+        left -= k;
+    }
+    h->tick += n_ticks;
+    return ZRK_OK;
+}
+
+extern "C" int zrk_sync(zrk_handle *h) {
+    if (!h) return ZRK_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return resolve_events(h);
+}
+
+extern "C" int zrk_get_time(zrk_handle *h, int64_t *tick, int64_t *time_ms) {
+    if (!h) return ZRK_ERR_ARG;
+    if (tick) *tick = h->tick;
+    if (time_ms) *time_ms = h->tick * h->P.dt_ms;
+    return ZRK_OK;
+}
+
+extern "C" int zrk_launch_stats(zrk_handle *h, int64_t *n_launches, double *kernel_ms) {
+    if (!h) return ZRK_ERR_ARG;
+    int rc = zrk_sync(h);
+    if (rc) return rc;
+    if (n_launches) *n_launches = h->n_launches;
+    if (kernel_ms) *kernel_ms = h->kernel_ms;
+    return ZRK_OK;
+}
+
+extern "C" int zrk_log_capacity(zrk_handle *h) { return h ? h->P.log_cap : ZRK_ERR_ARG; }
+
+// copy the dyn blobs of scenarios [s0, s1) to host
+static int fetch_dyn(zrk_handle *h, int s0, int s1, std::vector<unsigned char> &out) {
+    int rc = zrk_sync(h);
+    if (rc) return rc;
+    const Layout &o = h->P.lo;
+    out.resize((size_t)(s1 - s0) * o.dyn_bytes);
+    if (s1 > s0)
+        CK(cudaMemcpy(out.data(), h->P.dyn + (size_t)s0 * o.dyn_bytes, out.size(), cudaMemcpyDeviceToHost));
+    return ZRK_OK;
+}
+
+static int fetch_summary(zrk_handle *h) {
+    const Layout &o = h->P.lo;
+    CK(cudaSetDevice(h->device));
+    const long long n = (long long)o.B * ZRK_SUMMARY_WORDS;
+    ZRK_LAUNCH(zrk_summary_kernel, (unsigned)((n + 255) / 256), 256, 0, h->stream, h->P, h->d_summary);
+    CK(cudaGetLastError());
+    h->h_summary.resize((size_t)n);
+    CK(cudaMemcpyAsync(h->h_summary.data(), h->d_summary, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    return zrk_sync(h);
+}
+
+extern "C" int zrk_read_status(zrk_handle *h, int32_t *fault_code, int32_t *fault_tick, int32_t *n_records) {
+    if (!h) return ZRK_ERR_ARG;
+    int rc = fetch_summary(h);
+    if (rc) return rc;
+    for (int s = 0; s < h->P.lo.B; s++) {
+        const int *hdr = h->h_summary.data() + (size_t)s * ZRK_SUMMARY_WORDS;
+        if (fault_code) fault_code[s] = hdr[H_FAULT];
+        if (fault_tick) fault_tick[s] = hdr[H_FAULT_TICK];
+        if (n_records) n_records[s] = hdr[H_NREC];
+    }
+    return ZRK_OK;
+}
+
+extern "C" int zrk_read_counts(zrk_handle *h, int64_t *counts) {
+    if (!h || !counts) return ZRK_ERR_ARG;
+    int rc = fetch_summary(h);
+    if (rc) return rc;
+    for (int s = 0; s < h->P.lo.B; s++) {
+        const unsigned *c = (const unsigned *)(h->h_summary.data() + (size_t)s * ZRK_SUMMARY_WORDS + H_WORDS);
+        for (int t = 0; t < ZRK_MSG_NTYPES; t++) counts[(size_t)s * ZRK_MSG_NTYPES + t] = c[t];
+    }
+    return ZRK_OK;
+}
+
+extern "C" int zrk_read_records(zrk_handle *h, int s0, int s1, zrk_msg *recs, int32_t *n) {
+    if (!h || s0 < 0 || s1 > h->P.lo.B || s0 > s1) return ZRK_ERR_ARG;
+    int rc = fetch_summary(h);
+    if (rc) return rc;
+    for (int s = s0; s < s1; s++) {
+        const int *hdr = h->h_summary.data() + (size_t)s * ZRK_SUMMARY_WORDS;
+        if (n) n[s - s0] = std::min(hdr[H_NREC], h->P.log_cap);
+    }
+    if (recs && s1 > s0)
+        CK(cudaMemcpy(recs, h->P.rec + (size_t)s0 * h->P.log_cap, (size_t)(s1 - s0) * h->P.log_cap * sizeof(zrk_msg),
+                      cudaMemcpyDeviceToHost));
+    return ZRK_OK;
+}
+
+extern "C" int zrk_read_messages(zrk_handle *h, int sc, int tick0, int tick1, zrk_msg *msgs, size_t cap, size_t *n_out,
+                                 int32_t *ids, size_t ids_cap, size_t *n_ids_out) {
+    if (!h || sc < 0 || sc >= h->P.lo.B || tick0 < 0 || tick1 < tick0) return ZRK_ERR_ARG;
+    const Params &P = h->P;
+    const Layout &o = P.lo;
+    if ((P.log_types & ZRK_LOG_FULL) != (unsigned)ZRK_LOG_FULL) {
+        h->err = "zrk_read_messages needs a handle created with ZRK_LOG_FULL";
+        return ZRK_ERR_UNSUPPORTED;
+    }
+    std::vector<unsigned char> dyn;
+    int rc = fetch_dyn(h, sc, sc + 1, dyn);
+    if (rc) return rc;
+    const int *hdr = (const int *)(dyn.data() + o.hdr);
+    const int *sid = (const int *)(dyn.data() + o.sid);
+    const int done = hdr[H_TICK] + ((hdr[H_FAULT] & 63) ? 1 : 0);  // the faulting tick's messages exist too
+    if (hdr[H_FAULT] & ZRK_FAULT_LOG_OVERFLOW) {
+        h->err = "record log overflow: raise zrk_options.log_capacity";
+        return ZRK_ERR_CAPACITY;
+    }
+    if (tick1 > done) tick1 = done;
+    if (done - tick0 > P.mask_ticks && tick0 < tick1) {
+        h->err = "mask history ring is shorter than the requested range: raise zrk_options.mask_ticks";
+        return ZRK_ERR_CAPACITY;
+    }
+    const int nrec = std::min(hdr[H_NREC], P.log_cap);
+    std::vector<zrk_msg> rec(nrec ? nrec : 1);
+    if (nrec) CK(cudaMemcpy(rec.data(), P.rec + (size_t)sc * P.log_cap, (size_t)nrec * sizeof(zrk_msg), cudaMemcpyDeviceToHost));
+    const int nR = h->h_n_radars[sc], W = P.mask_words, rows = (1 + o.RP) * W;
+    std::vector<unsigned> mask(rows);
+    std::vector<zrk_msg> out;
+    std::vector<int32_t> pool;
+    int ri = 0;
+    while (ri < nrec && rec[ri].tick < tick0) ri++;
+    int det_prev = 0;
+    if (tick0 > 0) {  // DESTROYED_MISSILE of tick0 answers the detonations of tick0 - 1
+        for (int j = 0; j < nrec && rec[j].tick < tick0; j++)
+            if (rec[j].tick == tick0 - 1 && rec[j].type == ZRK_MSG_MISSILE_DETONATE) det_prev++;
+    }
+    auto list_msg = [&](int tick, int type, int sender, int receiver, const unsigned *bits) {
+        zrk_msg m{};
+        m.tick = tick;
+        m.type = (uint8_t)type;
+        m.relevance = 1;
+        m.sender = sender;
+        m.receiver = receiver;
+        m.a = (int32_t)pool.size();
+        int cnt = 0;
+        for (int k = 0; k < o.NS; k++)
+            if (bits[k >> 5] >> (k & 31) & 1u) {
+                pool.push_back(sid[k]);
+                cnt++;
+            }
+        m.b = cnt;
+        out.push_back(m);
+    };
+    for (int t = tick0; t < tick1; t++) {
+        size_t first = out.size();
+        CK(cudaMemcpy(mask.data(), P.masks + ((size_t)(t % P.mask_ticks) * o.B + sc) * rows, rows * sizeof(unsigned),
+                      cudaMemcpyDeviceToHost));
+        int det_now = 0;
+        // AirEnv.step: MISSILE_POS / MISSILE_DETONATE in slot order, then ACTIVE_OBJECTS
+        while (ri < nrec && rec[ri].tick == t &&
+               (rec[ri].type == ZRK_MSG_MISSILE_POS || rec[ri].type == ZRK_MSG_MISSILE_DETONATE)) {
+            det_now += rec[ri].type == ZRK_MSG_MISSILE_DETONATE;
+            out.push_back(rec[ri++]);
+        }
+        list_msg(t, ZRK_MSG_ACTIVE_OBJECTS, h->h_airenv_id[sc], ZRK_NONE, mask.data());
+        // every radar: ALL_OBJECTS, FOUND_OBJECTS, then its DESTROYED_MISSILE records
+        for (int r = 0; r < nR; r++) {
+            int rid = h->h_radar_id[(size_t)sc * o.R + r];
+            list_msg(t, ZRK_MSG_ALL_OBJECTS, rid, ZRK_CCP_ID, mask.data());
+            list_msg(t, ZRK_MSG_FOUND_OBJECTS, rid, ZRK_CCP_ID, mask.data() + (1 + r) * W);
+            for (int k = 0; k < det_prev && ri < nrec && rec[ri].tick == t && rec[ri].type == ZRK_MSG_DESTROYED_MISSILE; k++)
+                out.push_back(rec[ri++]);
+        }
+        // launchers and CCP, in emission order
+        while (ri < nrec && rec[ri].tick == t) out.push_back(rec[ri++]);
+        // Manager.add_message keeps each tick stably sorted by -relevance (Manager.py:56-58)
+        std::stable_sort(out.begin() + first, out.end(),
+                         [](const zrk_msg &a, const zrk_msg &b) { return a.relevance > b.relevance; });
+        det_prev = det_now;
+    }
+    if (n_out) *n_out = out.size();
+    if (n_ids_out) *n_ids_out = pool.size();
+    if (out.size() > cap || pool.size() > ids_cap) return ZRK_ERR_CAPACITY;
+    if (msgs && !out.empty()) memcpy(msgs, out.data(), out.size() * sizeof(zrk_msg));
+    if (ids && !pool.empty()) memcpy(ids, pool.data(), pool.size() * sizeof(int32_t));
+    return ZRK_OK;
+}
+
+extern "C" int zrk_read_state(zrk_handle *h, const zrk_state_view *v) {
+    if (!h || !v) return ZRK_ERR_ARG;
+    const Params &P = h->P;
+    const Layout &o = P.lo;
+    const int NS = o.NS, NSP = o.NSP, T = o.T, M = o.M, R = o.R, L = o.L, C = o.C;
+    const int CH = 2048;
+    std::vector<unsigned char> dyn, cst;
+    std::vector<double> traj;
+    for (int s0 = 0; s0 < o.B; s0 += CH) {
+        int s1 = std::min(o.B, s0 + CH), n = s1 - s0;
+        int rc = fetch_dyn(h, s0, s1, dyn);
+        if (rc) return rc;
+        cst.resize((size_t)n * o.cst_bytes);
+        traj.resize((size_t)n * 8 * NSP);
+        CK(cudaMemcpy(cst.data(), P.cst + (size_t)s0 * o.cst_bytes, cst.size(), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(traj.data(), P.traj + (size_t)s0 * 8 * NSP, traj.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int s = s0; s < s1; s++) {
+            const unsigned char *sm = dyn.data() + (size_t)(s - s0) * o.dyn_bytes;
+            const unsigned char *cs = cst.data() + (size_t)(s - s0) * o.cst_bytes;
+            const double *tj = traj.data() + (size_t)(s - s0) * 8 * NSP;
+            const int *hdr = (const int *)(sm + o.hdr), *sflags = (const int *)(sm + o.sflags);
+            const double *pos = (const double *)(sm + o.pos);
+            const int *chdr = (const int *)(cs + o.c_hdr);
+            const int nM = chdr[C_NM], nR = chdr[C_NR], nL = chdr[C_NL], nC = chdr[C_NC];
+            const int n_slots = hdr[H_NSLOTS];
+            auto stat = [&](int slot) { return slot >= 0 && slot < n_slots ? (sflags[slot] >> F_STATIC_SHIFT) : -1; };
+            // objects without a slot yet: missiles still on a launcher sit at the launcher position
+            for (int i = 0; i < NS; i++) {
+                size_t g = (size_t)s * NS + i;
+                if (v->slot_obj) v->slot_obj[g] = -1;
+                if (v->slot_alive) v->slot_alive[g] = 0;
+                if (v->has_prev) v->has_prev[g] = 0;
+                for (int k = 0; k < 3; k++) {
+                    if (v->pos) v->pos[3 * g + k] = 0.0;
+                    if (v->prev_pos) v->prev_pos[3 * g + k] = 0.0;
+                }
+            }
+            const int *c_m_launcher = (const int *)(cs + o.c_m_launcher);
+            const double *c_l_pos = (const double *)(cs + o.c_l_pos);
+            for (int m = 0; m < nM; m++)
+                for (int k = 0; k < 3; k++)
+                    if (v->pos) v->pos[3 * ((size_t)s * NS + T + m) + k] = c_l_pos[3 * c_m_launcher[m] + k];
+            for (int k = 0; k < n_slots; k++) {
+                int si = sflags[k] >> F_STATIC_SHIFT;
+                size_t gs = (size_t)s * NS + k, go = (size_t)s * NS + si;
+                // a slot is part of AirEnv.__objects once its missile was appended (not while pending)
+                bool listed = !(sflags[k] & F_PENDING);
+                if (v->slot_obj) v->slot_obj[gs] = listed ? si : -1;
+                if (v->slot_alive) v->slot_alive[gs] = (sflags[k] & F_ALIVE) ? 1 : 0;
+                if (v->has_prev) v->has_prev[go] = (sflags[k] & F_HASPREV) ? 1 : 0;
+                for (int c = 0; c < 3; c++) {
+                    if (v->pos) v->pos[3 * go + c] = pos[c * NSP + k];
+                    if (v->prev_pos) v->prev_pos[3 * go + c] = (sflags[k] & F_HASPREV) ? pos[(3 + c) * NSP + k] : 0.0;
+                }
+            }
+            const double *rad_cur = (const double *)(sm + o.rad_cur);
+            for (int r = 0; r < R; r++) {
+                if (v->radar_az) v->radar_az[(size_t)s * R + r] = r < nR ? rad_cur[2 * r] : 0.0;
+                if (v->radar_el) v->radar_el[(size_t)s * R + r] = r < nR ? rad_cur[2 * r + 1] : 0.0;
+            }
+            const int *m_status = (const int *)(sm + o.m_status), *m_target = (const int *)(sm + o.m_target),
+                      *m_slot = (const int *)(sm + o.m_slot);
+            const double *m_period = (const double *)(sm + o.m_period);
+            for (int m = 0; m < M; m++) {
+                size_t g = (size_t)s * M + m;
+                bool live = m < nM;
+                int k = live ? m_slot[m] : -1;
+                if (v->missile_status) v->missile_status[g] = live ? (uint8_t)m_status[m] : 0;
+                if (v->missile_period) v->missile_period[g] = live ? m_period[m] : 0.0;
+                if (v->missile_t0) v->missile_t0[g] = k >= 0 ? tj[3 * NSP + k] : 0.0;
+                if (v->missile_target) v->missile_target[g] = live && m_target[m] >= 0 ? stat(m_target[m]) : -1;
+                for (int c = 0; c < 3; c++)
+                    if (v->missile_vel) v->missile_vel[3 * g + c] = k >= 0 ? tj[(4 + c) * NSP + k] : 0.0;
+            }
+            const int *st_n = (const int *)(sm + o.st_n);
+            for (int l = 0; l < L; l++)
+                if (v->launcher_count) v->launcher_count[(size_t)s * L + l] = l < nL ? st_n[l] : 0;
+            const int n_te = hdr[H_NTE], n_me = hdr[H_NME];
+            if (v->ccp_n_targets) v->ccp_n_targets[s] = n_te;
+            if (v->ccp_n_missiles) v->ccp_n_missiles[s] = n_me;
+            const int *te_key = (const int *)(sm + o.te_key), *te_ref = (const int *)(sm + o.te_ref),
+                      *te_upd = (const int *)(sm + o.te_upd), *te_follow = (const int *)(sm + o.te_follow),
+                      *te_mid = (const int *)(sm + o.te_mid);
+            const int *me_key = (const int *)(sm + o.me_key), *me_ref = (const int *)(sm + o.me_ref),
+                      *me_upd = (const int *)(sm + o.me_upd), *me_tid = (const int *)(sm + o.me_tid);
+            for (int e = 0; e < NS; e++) {
+                size_t g = (size_t)s * NS + e;
+                bool lt = e < n_te, lm = e < n_me;
+                if (v->ccp_t_key) v->ccp_t_key[g] = lt ? te_key[e] : 0;
+                if (v->ccp_t_ref) v->ccp_t_ref[g] = lt ? stat(te_ref[e]) : -1;
+                if (v->ccp_t_upd) v->ccp_t_upd[g] = lt ? te_upd[e] : 0;
+                if (v->ccp_t_missile) v->ccp_t_missile[g] = lt ? te_mid[e] : ZRK_NONE;
+                if (v->ccp_t_following) v->ccp_t_following[g] = lt ? (uint8_t)te_follow[e] : 0;
+                if (v->ccp_m_key) v->ccp_m_key[g] = lm ? me_key[e] : 0;
+                if (v->ccp_m_ref) v->ccp_m_ref[g] = lm ? stat(me_ref[e]) : -1;
+                if (v->ccp_m_upd) v->ccp_m_upd[g] = lm ? me_upd[e] : 0;
+                if (v->ccp_m_target) v->ccp_m_target[g] = lm ? me_tid[e] : ZRK_NONE;
+            }
+            const int *capv = (const int *)(sm + o.cap), *lnc = (const int *)(sm + o.launched);
+            for (int c = 0; c < C; c++) {
+                if (v->ccp_capacity) v->ccp_capacity[(size_t)s * C + c] = c < nC ? capv[c] : 0;
+                if (v->ccp_launched) v->ccp_launched[(size_t)s * C + c] = c < nC ? lnc[c] : 0;
+            }
+        }
+    }
+    return ZRK_OK;
+}
+
+extern "C" int zrk_device_ptr(zrk_handle *h, const char *name, void **ptr, size_t *bytes) {
+    if (!h || !name || !ptr) return ZRK_ERR_ARG;
+    const Params &P = h->P;
+    const Layout &o = P.lo;
+    std::string n(name);
+    size_t sz = 0;
+    void *p = nullptr;
+    if (n == "dyn") { p = P.dyn; sz = (size_t)o.B * o.dyn_bytes; }
+    else if (n == "cst") { p = (void *)P.cst; sz = (size_t)o.B * o.cst_bytes; }
+    else if (n == "traj") { p = P.traj; sz = (size_t)o.B * 8 * o.NSP * sizeof(double); }
+    else if (n == "rec") { p = P.rec; sz = (size_t)o.B * P.log_cap * sizeof(zrk_msg); }
+    else if (n == "masks") { p = P.masks; sz = (size_t)P.mask_ticks * o.B * (1 + o.RP) * P.mask_words * sizeof(unsigned); }
+    else return ZRK_ERR_ARG;
+    *ptr = p;
+    if (bytes) *bytes = sz;
+    return ZRK_OK;
+}

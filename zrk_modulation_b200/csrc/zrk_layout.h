@@ -1,0 +1,140 @@
+// zrk_layout.h — device data layout shared by the host library and the tick kernel.
+//
+// Per scenario the device keeps three things:
+//   traj   [B][4][NSP] double2   per AirEnv slot: (p0x,p0y) (p0z,t0) (vx,vy) (vz,speed)
+//                                 = Trajectory + speed_mod (AirObject.py:15-36).  Read into
+//                                 registers by the slot's lane; written only at a launch.
+//   dyn    [B][dyn_bytes]        everything that changes every tick, as one blob whose image in
+//                                 shared memory is byte-identical (prologue/epilogue are plain
+//                                 coalesced 16-byte copies).
+//   cst    [B][cst_bytes]        read-only scenario parameters (radars, launchers, missiles, CCP).
+// Byte offsets of every array inside the blobs are computed once on the host (make_layout).
+#ifndef ZRK_LAYOUT_H
+#define ZRK_LAYOUT_H
+
+#include "../../include/zrk_b200.h"
+
+namespace zrk {
+
+// slot flag bits (dyn.sflags); static index in bits 8..
+enum { F_ALIVE = 1, F_PENDING = 2, F_HASPREV = 4, F_MISSILE = 8, F_TTYPE_SHIFT = 4, F_STATIC_SHIFT = 8 };
+// header words (ints) at dyn.hdr
+enum {
+    H_TICK = 0, H_NSLOTS, H_NTE, H_NME, H_CCP_INIT, H_FAULT, H_FAULT_TICK, H_NREC,
+    H_DETN0, H_DETN1, H_MBN0, H_MBN1, H_LN, H_FLAGS, H_TMP0, H_TMP1, H_WORDS = 16
+};
+enum { MB_COMMAND = 0, MB_SUCCESS = 1, MB_CANCEL = 2, MB_COUNTREQ = 3 };
+enum { ST_READY = 0, ST_ACTIVE = 1, ST_DETONATED = 2 };
+// cst header words
+enum { RAD_PAR_STRIDE = 10 };  // radar_par[8] + max_distance^2 bracket (lo, hi)
+enum { C_NT = 0, C_NR, C_NL, C_NM, C_NC, C_AIRENV_ID, C_CCP_ID, C_TICK_LIMIT, C_WORDS = 8 };
+
+struct Layout {
+    // padded dimensions
+    int B, T, M, NS, R, L, C;
+    int NSP, MP, RP, LP, CP, Q;
+    int team, teams_per_cta;
+    // dyn blob (byte offsets)
+    int hdr, counts, pos, speed, sid, sflags, srf;
+    int te_key, te_ref, te_upd, te_follow, te_mid;
+    int me_key, me_ref, me_upd, me_tid;
+    int rad_cur, st_n, st, cap, launched;
+    int m_status, m_target, m_slot, m_birth, m_period;
+    int det_mid, det_tid, det_flag, mb_type, mb_l, mb_a, ln_m;
+    int dyn_bytes;
+    // cst blob
+    int c_hdr, c_rad_id, c_rad_pos, c_rad_par, c_l_id, c_l_pos;
+    int c_m_id, c_m_launcher, c_m_v0, c_m_v0sq, c_m_radius;
+    int c_cl_id, c_cl_launcher, c_cl_pos;
+    int cst_bytes;
+    // scratch (shared memory only), offsets from the start of the team's region
+    int x_claim, x_detlist, x_wscr, x_need, x_ok;
+    int team_smem_bytes;
+};
+
+struct Params {
+    Layout lo;
+    int dt_ms;
+    double dt_s;        // to_seconds(dt)                      (AirObject.py:5-7)
+    double range_step;  // POSSIBLE_TARGET_RADIUS * to_seconds(dt) (CCP.py:186-187)
+    unsigned log_types;
+    int log_cap;
+    int mask_ticks, mask_words;  // words per mask row; a tick's row set is (1 + R) rows
+    int noise_period, noise_radars, noise_objects;
+    long long noise_stride;
+    double *traj;             // as double2
+    unsigned char *dyn;
+    const unsigned char *cst;
+    zrk_msg *rec;
+    unsigned *masks;
+    const double *noise;
+};
+
+static inline int zrk_align(int x, int a) { return (x + a - 1) / a * a; }
+
+// Smallest supported team (threads per scenario) covering ns slots; 0 if too large.
+static inline int zrk_team_for(int ns) {
+    for (int t = 32; t <= 1024; t *= 2)
+        if (ns <= t) return t;
+    return 0;
+}
+
+static inline Layout make_layout(int B, int T, int M, int R, int L, int C) {
+    Layout o;
+    o.B = B; o.T = T; o.M = M; o.NS = T + M; o.R = R; o.L = L; o.C = C;
+    o.team = zrk_team_for(o.NS);
+    o.teams_per_cta = o.team >= 128 ? 1 : 128 / (o.team ? o.team : 128);
+    o.NSP = zrk_align(o.NS > 0 ? o.NS : 1, 2);
+    o.MP = zrk_align(M > 0 ? M : 1, 2);
+    o.RP = R > 0 ? R : 1;
+    o.LP = zrk_align(L > 0 ? L : 1, 2);
+    o.CP = zrk_align(C > 0 ? C : 1, 2);
+    o.Q = zrk_align(2 * o.MP + o.CP, 2);
+    int p = 0;
+    auto take = [&p](int bytes) { int at = p; p += zrk_align(bytes, 8); return at; };
+    o.hdr = take(4 * H_WORDS);
+    o.counts = take(4 * ZRK_MSG_NTYPES);
+    o.pos = take(8 * 6 * o.NSP);
+    o.speed = take(8 * o.NSP);
+    o.sid = take(4 * o.NSP);
+    o.sflags = take(4 * o.NSP);
+    o.srf = take(4 * o.NSP);
+    o.te_key = take(4 * o.NSP); o.te_ref = take(4 * o.NSP); o.te_upd = take(4 * o.NSP);
+    o.te_follow = take(4 * o.NSP); o.te_mid = take(4 * o.NSP);
+    o.me_key = take(4 * o.MP); o.me_ref = take(4 * o.MP); o.me_upd = take(4 * o.MP); o.me_tid = take(4 * o.MP);
+    o.rad_cur = take(8 * 2 * o.RP);
+    o.st_n = take(4 * o.LP);
+    o.st = take(4 * o.LP * o.MP);
+    o.cap = take(4 * o.CP);
+    o.launched = take(4 * o.CP);
+    o.m_status = take(4 * o.MP); o.m_target = take(4 * o.MP); o.m_slot = take(4 * o.MP);
+    o.m_birth = take(4 * o.MP);
+    o.m_period = take(8 * o.MP);
+    o.det_mid = take(4 * 2 * o.MP); o.det_tid = take(4 * 2 * o.MP); o.det_flag = take(4 * 2 * o.MP);
+    o.mb_type = take(4 * 2 * o.Q); o.mb_l = take(4 * 2 * o.Q); o.mb_a = take(4 * 2 * o.Q);
+    o.ln_m = take(4 * o.MP);
+    o.dyn_bytes = zrk_align(p, 16);
+    p = 0;
+    o.c_hdr = take(4 * C_WORDS);
+    o.c_rad_id = take(4 * o.RP);
+    o.c_rad_pos = take(8 * 3 * o.RP);
+    o.c_rad_par = take(8 * RAD_PAR_STRIDE * o.RP);
+    o.c_l_id = take(4 * o.LP);
+    o.c_l_pos = take(8 * 3 * o.LP);
+    o.c_m_id = take(4 * o.MP); o.c_m_launcher = take(4 * o.MP);
+    o.c_m_v0 = take(8 * o.MP); o.c_m_v0sq = take(8 * o.MP); o.c_m_radius = take(8 * o.MP);
+    o.c_cl_id = take(4 * o.CP); o.c_cl_launcher = take(4 * o.CP);
+    o.c_cl_pos = take(8 * 3 * o.CP);
+    o.cst_bytes = zrk_align(p, 16);
+    p = o.dyn_bytes + o.cst_bytes;
+    o.x_claim = take(4 * (o.NSP + o.MP));
+    o.x_detlist = take(4 * o.NSP);
+    o.x_wscr = take(4 * 40);
+    o.x_need = take(4 * o.NSP);
+    o.x_ok = take(4 * o.NSP);
+    o.team_smem_bytes = zrk_align(p, 16);
+    return o;
+}
+
+}  // namespace zrk
+#endif

@@ -1,0 +1,135 @@
+"""Thin numpy wrapper over the C ABI (include/zrk_b200.h): one Engine = one zrk_handle."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _cabi
+from .scenario import Batch
+
+
+class ZrkError(RuntimeError):
+    def __init__(self, rc: int, msg: str):
+        super().__init__(f"zrk error {rc}: {msg}")
+        self.rc = rc
+
+
+class Engine:
+    """Device state of a batch of scenarios plus the tick loop.
+
+    `lib` defaults to the CUDA library (libzrk_b200.so); there is no CPU fallback."""
+
+    def __init__(self, batch: Batch, log_types: int = _cabi.LOG_EVENTS, log_capacity: int = 0,
+                 mask_ticks: int = 0, ticks_per_launch: int = 0, device: int = 0, exact_only: bool = False,
+                 lib=None):
+        self.lib = lib if lib is not None else _cabi.load()
+        self.batch = batch
+        self._h = C.c_void_p()
+        opt = _cabi.ZrkOptions()
+        opt.device = device
+        opt.log_types = log_types
+        opt.log_capacity = log_capacity
+        opt.mask_ticks = mask_ticks
+        opt.ticks_per_launch = ticks_per_launch
+        opt.reserved[0] = 1 if exact_only else 0
+        self.log_types = log_types
+        desc = batch.desc()
+        rc = self.lib.zrk_create(C.byref(desc), C.byref(opt), C.byref(self._h))
+        if rc != 0:
+            msg = self.lib.zrk_last_error(None)
+            self._h = C.c_void_p()
+            raise ZrkError(rc, msg.decode() if msg else "")
+
+    # -- lifecycle
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.zrk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self.lib.zrk_last_error(self._h)
+            raise ZrkError(rc, msg.decode() if msg else "")
+
+    # -- the tick
+    def step(self, n_ticks: int = 1):
+        self._ck(self.lib.zrk_step(self._h, int(n_ticks)))
+
+    def sync(self):
+        self._ck(self.lib.zrk_sync(self._h))
+
+    def time(self):
+        t, ms = C.c_int64(), C.c_int64()
+        self._ck(self.lib.zrk_get_time(self._h, C.byref(t), C.byref(ms)))
+        return t.value, ms.value
+
+    # -- reads
+    def status(self):
+        B = self.batch.n_scenarios
+        fc, ft, nr = (np.zeros(B, dtype=np.int32) for _ in range(3))
+        p = lambda a: a.ctypes.data_as(_cabi._pi32)
+        self._ck(self.lib.zrk_read_status(self._h, p(fc), p(ft), p(nr)))
+        return fc, ft, nr
+
+    def counts(self) -> np.ndarray:
+        B = self.batch.n_scenarios
+        c = np.zeros((B, _cabi.ZRK_MSG_NTYPES), dtype=np.int64)
+        self._ck(self.lib.zrk_read_counts(self._h, c.ctypes.data_as(C.POINTER(C.c_int64))))
+        return c
+
+    def log_capacity(self) -> int:
+        return int(self.lib.zrk_log_capacity(self._h))
+
+    def records(self, s0: int = 0, s1: Optional[int] = None):
+        """Explicit records of scenarios [s0, s1): (structured array [n, cap], counts [n])."""
+        s1 = self.batch.n_scenarios if s1 is None else s1
+        cap = self.log_capacity()
+        recs = np.zeros((s1 - s0, cap), dtype=_cabi.MSG_DTYPE)
+        n = np.zeros(s1 - s0, dtype=np.int32)
+        self._ck(self.lib.zrk_read_records(self._h, s0, s1, recs.ctypes.data_as(C.POINTER(_cabi.ZrkMsg)),
+                                           n.ctypes.data_as(_cabi._pi32)))
+        return recs, n
+
+    def messages(self, scenario: int, tick0: int = 0, tick1: Optional[int] = None):
+        """Full message list of one scenario (needs LOG_FULL): (msgs structured array, id pool)."""
+        if tick1 is None:
+            tick1 = self.time()[0] + 1
+        n, nid = C.c_size_t(), C.c_size_t()
+        rc = self.lib.zrk_read_messages(self._h, scenario, tick0, tick1, None, 0, C.byref(n), None, 0, C.byref(nid))
+        if rc not in (0, _cabi.ERR_CAPACITY) or (rc == _cabi.ERR_CAPACITY and n.value == 0 and nid.value == 0):
+            self._ck(rc)
+        msgs = np.zeros(max(1, n.value), dtype=_cabi.MSG_DTYPE)
+        ids = np.zeros(max(1, nid.value), dtype=np.int32)
+        self._ck(self.lib.zrk_read_messages(self._h, scenario, tick0, tick1,
+                                            msgs.ctypes.data_as(C.POINTER(_cabi.ZrkMsg)), msgs.shape[0], C.byref(n),
+                                            ids.ctypes.data_as(_cabi._pi32), ids.shape[0], C.byref(nid)))
+        return msgs[:n.value], ids[:nid.value]
+
+    def state(self):
+        arrays, view = _cabi.alloc_state(self.batch.dims())
+        self._ck(self.lib.zrk_read_state(self._h, C.byref(view)))
+        return arrays
+
+    def launch_stats(self):
+        n, ms = C.c_int64(), C.c_double()
+        self._ck(self.lib.zrk_launch_stats(self._h, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    def device_ptr(self, name: str):
+        p, sz = C.c_void_p(), C.c_size_t()
+        self._ck(self.lib.zrk_device_ptr(self._h, name.encode(), C.byref(p), C.byref(sz)))
+        return p.value, sz.value

@@ -28,6 +28,10 @@
 struct uint4 {
     unsigned x, y, z, w;
 };
+struct double2 {
+    double x, y;
+};
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
 struct dim3 {
     unsigned x, y, z;
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
@@ -144,5 +148,27 @@ inline int atomicOr(int *p, int v) {
     return o;
 }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __reduce_min_sync(unsigned, int v) {
+    zrk_emu::Warp &w = zrk_emu::my_warp();
+    w.vals[zrk_emu::my_lane()] = (uint64_t)(int64_t)v;
+    zrk_emu::barrier_wait(w.bar, 32);
+    int m = v;
+    for (int i = 0; i < 32; i++) {
+        int x = (int)(int64_t)w.vals[i];
+        if (x < m) m = x;
+    }
+    zrk_emu::barrier_wait(w.bar, 32);
+    return m;
+}
+inline unsigned __match_any_sync(unsigned, int v) {
+    zrk_emu::Warp &w = zrk_emu::my_warp();
+    w.vals[zrk_emu::my_lane()] = (uint64_t)(int64_t)v;
+    zrk_emu::barrier_wait(w.bar, 32);
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++)
+        if ((int)(int64_t)w.vals[i] == v) r |= 1u << i;
+    zrk_emu::barrier_wait(w.bar, 32);
+    return r;
+}
 
 #endif

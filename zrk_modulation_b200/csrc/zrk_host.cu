@@ -47,7 +47,8 @@ __global__ void zrk_init_kernel(const Params P, const DevDesc d, int *err) {
     const Layout &o = P.lo;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= o.B) return;
-    const int NSP = o.NSP, MP = o.MP;
+    const int NSP = o.team, MP = o.MP;
+    const HotOff &ho = o.hot;
     unsigned char *sm = P.dyn + (size_t)b * o.dyn_bytes;
     unsigned char *cs = const_cast<unsigned char *>(P.cst) + (size_t)b * o.cst_bytes;
     double *traj = P.traj + (size_t)b * 8 * NSP;
@@ -58,29 +59,33 @@ __global__ void zrk_init_kernel(const Params P, const DevDesc d, int *err) {
         atomicOr(err, 1);
         return;
     }
-    int *hdr = (int *)(sm + o.hdr);
+    int *hdr = (int *)(sm + ho.hdr);
     hdr[H_NSLOTS] = nT;
-    double *pos = (double *)(sm + o.pos), *speed = (double *)(sm + o.speed);
-    int *sid = (int *)(sm + o.sid), *sflags = (int *)(sm + o.sflags), *srf = (int *)(sm + o.srf);
+    double2 *pxy = (double2 *)(sm + ho.pxy), *pzs = (double2 *)(sm + ho.pzs);
+    int *sid = (int *)(sm + ho.sid), *sflags = (int *)(sm + ho.sflags), *srf = (int *)(sm + ho.srf),
+        *own = (int *)(sm + ho.own);
     for (int t = 0; t < nT; t++) {
         size_t g = (size_t)b * d.T + t;
         double vx = d.target_vel[3 * g], vy = d.target_vel[3 * g + 1], vz = d.target_vel[3 * g + 2];
         double sp = sqrt(dot3(vx, vy, vz, vx, vy, vz));  // np.linalg.norm (AirObject.py:36)
         for (int k = 0; k < 3; k++) {
-            pos[k * NSP + t] = d.target_pos[3 * g + k];
             traj[k * NSP + t] = d.target_pos[3 * g + k];
             traj[(4 + k) * NSP + t] = d.target_vel[3 * g + k];
         }
         traj[3 * NSP + t] = 0.0;
         traj[7 * NSP + t] = sp;
-        speed[t] = sp;
+        pxy[t] = make_double2(d.target_pos[3 * g], d.target_pos[3 * g + 1]);
+        pzs[t] = make_double2(d.target_pos[3 * g + 2], sp);
         sid[t] = d.target_id[g];
         int tt = d.target_type ? d.target_type[g] : ZRK_ANOTHER;
         sflags[t] = F_ALIVE | ((tt & 3) << F_TTYPE_SHIFT) | (t << F_STATIC_SHIFT);
     }
-    for (int k = 0; k < NSP; k++) srf[k] = -1;
-    int *te_mid = (int *)(sm + o.te_mid);
-    for (int k = 0; k < NSP; k++) te_mid[k] = ZRK_NONE;
+    int *te_mid = (int *)(sm + ho.te_mid);
+    for (int k = 0; k < NSP; k++) {
+        srf[k] = -1;
+        own[k] = -1;
+        te_mid[k] = ZRK_NONE;
+    }
     int *chdr = (int *)(cs + o.c_hdr);
     chdr[C_NT] = nT; chdr[C_NR] = nR; chdr[C_NL] = nL; chdr[C_NM] = nM; chdr[C_NC] = nC;
     chdr[C_AIRENV_ID] = d.airenv_id ? d.airenv_id[b] : 1;
@@ -164,7 +169,7 @@ __global__ void zrk_summary_kernel(const Params P, int *out) {
     if (i >= (long long)o.B * ZRK_SUMMARY_WORDS) return;
     const int b = (int)(i / ZRK_SUMMARY_WORDS), w = (int)(i % ZRK_SUMMARY_WORDS);
     const unsigned char *sm = P.dyn + (size_t)b * o.dyn_bytes;
-    out[i] = w < H_WORDS ? ((const int *)(sm + o.hdr))[w] : ((const int *)(sm + o.counts))[w - H_WORDS];
+    out[i] = w < H_WORDS ? ((const int *)(sm + o.hot.hdr))[w] : ((const int *)(sm + o.hot.counts))[w - H_WORDS];
 }
 
 // ------------------------------------------------------------------ handle
@@ -338,7 +343,7 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
         size_t n = d->noise_scenario_stride ? (size_t)d->noise_scenario_stride * (B - 1) + one : one;
         if ((rc = dev_upload(h, d->noise, n, &P.noise)) != ZRK_OK) return rc;
     }
-    if ((rc = dev_alloc(h, (size_t)B * 8 * lo.NSP, &P.traj, true)) != ZRK_OK) return rc;
+    if ((rc = dev_alloc(h, (size_t)B * 8 * lo.team, &P.traj, true)) != ZRK_OK) return rc;
     if ((rc = dev_alloc(h, (size_t)B * lo.dyn_bytes, &P.dyn, true)) != ZRK_OK) return rc;
     unsigned char *cst = nullptr;
     if ((rc = dev_alloc(h, (size_t)B * lo.cst_bytes, &cst, true)) != ZRK_OK) return rc;
@@ -549,8 +554,8 @@ extern "C" int zrk_read_messages(zrk_handle *h, int sc, int tick0, int tick1, zr
     std::vector<unsigned char> dyn;
     int rc = fetch_dyn(h, sc, sc + 1, dyn);
     if (rc) return rc;
-    const int *hdr = (const int *)(dyn.data() + o.hdr);
-    const int *sid = (const int *)(dyn.data() + o.sid);
+    const int *hdr = (const int *)(dyn.data() + o.hot.hdr);
+    const int *sid = (const int *)(dyn.data() + o.hot.sid);
     const int done = hdr[H_TICK] + ((hdr[H_FAULT] & 63) ? 1 : 0);  // the faulting tick's messages exist too
     if (hdr[H_FAULT] & ZRK_FAULT_LOG_OVERFLOW) {
         h->err = "record log overflow: raise zrk_options.log_capacity";
@@ -631,7 +636,8 @@ extern "C" int zrk_read_state(zrk_handle *h, const zrk_state_view *v) {
     if (!h || !v) return ZRK_ERR_ARG;
     const Params &P = h->P;
     const Layout &o = P.lo;
-    const int NS = o.NS, NSP = o.NSP, T = o.T, M = o.M, R = o.R, L = o.L, C = o.C;
+    const int NS = o.NS, NSP = o.team, T = o.T, M = o.M, R = o.R, L = o.L, C = o.C;
+    const HotOff &ho = o.hot;
     const int CH = 2048;
     std::vector<unsigned char> dyn, cst;
     std::vector<double> traj;
@@ -647,8 +653,9 @@ extern "C" int zrk_read_state(zrk_handle *h, const zrk_state_view *v) {
             const unsigned char *sm = dyn.data() + (size_t)(s - s0) * o.dyn_bytes;
             const unsigned char *cs = cst.data() + (size_t)(s - s0) * o.cst_bytes;
             const double *tj = traj.data() + (size_t)(s - s0) * 8 * NSP;
-            const int *hdr = (const int *)(sm + o.hdr), *sflags = (const int *)(sm + o.sflags);
-            const double *pos = (const double *)(sm + o.pos);
+            const int *hdr = (const int *)(sm + ho.hdr), *sflags = (const int *)(sm + ho.sflags);
+            const double *pxy = (const double *)(sm + ho.pxy), *pzs = (const double *)(sm + ho.pzs);
+            const double *qxy = (const double *)(sm + ho.qxy), *qzw = (const double *)(sm + ho.qzw);
             const int *chdr = (const int *)(cs + o.c_hdr);
             const int nM = chdr[C_NM], nR = chdr[C_NR], nL = chdr[C_NL], nC = chdr[C_NC];
             const int n_slots = hdr[H_NSLOTS];
@@ -677,9 +684,11 @@ extern "C" int zrk_read_state(zrk_handle *h, const zrk_state_view *v) {
                 if (v->slot_obj) v->slot_obj[gs] = listed ? si : -1;
                 if (v->slot_alive) v->slot_alive[gs] = (sflags[k] & F_ALIVE) ? 1 : 0;
                 if (v->has_prev) v->has_prev[go] = (sflags[k] & F_HASPREV) ? 1 : 0;
+                const double pk[3] = {pxy[2 * k], pxy[2 * k + 1], pzs[2 * k]};
+                const double qk[3] = {qxy[2 * k], qxy[2 * k + 1], qzw[2 * k]};
                 for (int c = 0; c < 3; c++) {
-                    if (v->pos) v->pos[3 * go + c] = pos[c * NSP + k];
-                    if (v->prev_pos) v->prev_pos[3 * go + c] = (sflags[k] & F_HASPREV) ? pos[(3 + c) * NSP + k] : 0.0;
+                    if (v->pos) v->pos[3 * go + c] = pk[c];
+                    if (v->prev_pos) v->prev_pos[3 * go + c] = (sflags[k] & F_HASPREV) ? qk[c] : 0.0;
                 }
             }
             const double *rad_cur = (const double *)(sm + o.rad_cur);
@@ -707,9 +716,9 @@ extern "C" int zrk_read_state(zrk_handle *h, const zrk_state_view *v) {
             const int n_te = hdr[H_NTE], n_me = hdr[H_NME];
             if (v->ccp_n_targets) v->ccp_n_targets[s] = n_te;
             if (v->ccp_n_missiles) v->ccp_n_missiles[s] = n_me;
-            const int *te_key = (const int *)(sm + o.te_key), *te_ref = (const int *)(sm + o.te_ref),
-                      *te_upd = (const int *)(sm + o.te_upd), *te_follow = (const int *)(sm + o.te_follow),
-                      *te_mid = (const int *)(sm + o.te_mid);
+            const int *te_key = (const int *)(sm + ho.te_key), *te_ref = (const int *)(sm + ho.te_ref),
+                      *te_upd = (const int *)(sm + ho.te_upd), *te_follow = (const int *)(sm + ho.te_follow),
+                      *te_mid = (const int *)(sm + ho.te_mid);
             const int *me_key = (const int *)(sm + o.me_key), *me_ref = (const int *)(sm + o.me_ref),
                       *me_upd = (const int *)(sm + o.me_upd), *me_tid = (const int *)(sm + o.me_tid);
             for (int e = 0; e < NS; e++) {
@@ -744,7 +753,7 @@ extern "C" int zrk_device_ptr(zrk_handle *h, const char *name, void **ptr, size_
     void *p = nullptr;
     if (n == "dyn") { p = P.dyn; sz = (size_t)o.B * o.dyn_bytes; }
     else if (n == "cst") { p = (void *)P.cst; sz = (size_t)o.B * o.cst_bytes; }
-    else if (n == "traj") { p = P.traj; sz = (size_t)o.B * 8 * o.NSP * sizeof(double); }
+    else if (n == "traj") { p = P.traj; sz = (size_t)o.B * 8 * o.team * sizeof(double); }
     else if (n == "rec") { p = P.rec; sz = (size_t)o.B * P.log_cap * sizeof(zrk_msg); }
     else if (n == "masks") { p = P.masks; sz = (size_t)P.mask_ticks * o.B * (1 + o.RP) * P.mask_words * sizeof(unsigned); }
     else return ZRK_ERR_ARG;

@@ -1,14 +1,16 @@
 // zrk_layout.h — device data layout shared by the host library and the tick kernel.
 //
 // Per scenario the device keeps three things:
-//   traj   [B][4][NSP] double2   per AirEnv slot: (p0x,p0y) (p0z,t0) (vx,vy) (vz,speed)
+//   traj   [B][8][TEAM] double    per AirEnv slot: p0x p0y p0z t0 vx vy vz speed
 //                                 = Trajectory + speed_mod (AirObject.py:15-36).  Read into
 //                                 registers by the slot's lane; written only at a launch.
 //   dyn    [B][dyn_bytes]        everything that changes every tick, as one blob whose image in
 //                                 shared memory is byte-identical (prologue/epilogue are plain
-//                                 coalesced 16-byte copies).
+//                                 coalesced 16-byte copies).  It starts with the "hot" part,
+//                                 whose offsets depend only on TEAM (compile-time constants in
+//                                 the kernel), followed by the small launcher/missile/radar
+//                                 arrays at run-time offsets.
 //   cst    [B][cst_bytes]        read-only scenario parameters (radars, launchers, missiles, CCP).
-// Byte offsets of every array inside the blobs are computed once on the host (make_layout).
 #ifndef ZRK_LAYOUT_H
 #define ZRK_LAYOUT_H
 
@@ -25,18 +27,53 @@ enum {
 };
 enum { MB_COMMAND = 0, MB_SUCCESS = 1, MB_CANCEL = 2, MB_COUNTREQ = 3 };
 enum { ST_READY = 0, ST_ACTIVE = 1, ST_DETONATED = 2 };
-// cst header words
 enum { RAD_PAR_STRIDE = 10 };  // radar_par[8] + max_distance^2 bracket (lo, hi)
+// cst header words
 enum { C_NT = 0, C_NR, C_NL, C_NM, C_NC, C_AIRENV_ID, C_CCP_ID, C_TICK_LIMIT, C_WORDS = 8 };
 
+#if defined(__CUDACC__)
+#define ZRK_HD __host__ __device__
+#else
+#define ZRK_HD
+#endif
+
+// Hot part of the dyn blob: byte offsets as a function of TEAM only.
+struct HotOff {
+    int hdr, counts;
+    int pxy, pzs;  // double2[TEAM]: (pos.x, pos.y), (pos.z, speed_mod)
+    int qxy, qzw;  // double2[TEAM]: (prev.x, prev.y), (prev.z, unused)
+    int sid, sflags, srf, own;                        // int[TEAM]
+    int te_key, te_ref, te_upd, te_follow, te_mid;    // int[TEAM]  CCP._target_dict
+    int end;
+};
+ZRK_HD constexpr HotOff hot_off(int team) {
+    HotOff h{};
+    int p = 0;
+    h.hdr = p; p += 4 * H_WORDS;
+    h.counts = p; p += 80;  // 18 counters, padded to 16 bytes
+    h.pxy = p; p += 16 * team;
+    h.pzs = p; p += 16 * team;
+    h.qxy = p; p += 16 * team;
+    h.qzw = p; p += 16 * team;
+    h.sid = p; p += 4 * team;
+    h.sflags = p; p += 4 * team;
+    h.srf = p; p += 4 * team;
+    h.own = p; p += 4 * team;
+    h.te_key = p; p += 4 * team;
+    h.te_ref = p; p += 4 * team;
+    h.te_upd = p; p += 4 * team;
+    h.te_follow = p; p += 4 * team;
+    h.te_mid = p; p += 4 * team;
+    h.end = p;
+    return h;
+}
+
 struct Layout {
-    // padded dimensions
     int B, T, M, NS, R, L, C;
-    int NSP, MP, RP, LP, CP, Q;
+    int MP, RP, LP, CP, Q;
     int team, teams_per_cta;
-    // dyn blob (byte offsets)
-    int hdr, counts, pos, speed, sid, sflags, srf;
-    int te_key, te_ref, te_upd, te_follow, te_mid;
+    HotOff hot;
+    // cold part of the dyn blob (byte offsets)
     int me_key, me_ref, me_upd, me_tid;
     int rad_cur, st_n, st, cap, launched;
     int m_status, m_target, m_slot, m_birth, m_period;
@@ -48,6 +85,7 @@ struct Layout {
     int c_cl_id, c_cl_launcher, c_cl_pos;
     int cst_bytes;
     // scratch (shared memory only), offsets from the start of the team's region
+    int x_lxy, x_lzd;  // double2[TEAM + MP]: per CCP entry, the position link_object measures to
     int x_claim, x_detlist, x_wscr, x_need, x_ok;
     int team_smem_bytes;
 };
@@ -62,7 +100,7 @@ struct Params {
     int mask_ticks, mask_words;  // words per mask row; a tick's row set is (1 + R) rows
     int noise_period, noise_radars, noise_objects;
     long long noise_stride;
-    double *traj;             // as double2
+    double *traj;
     unsigned char *dyn;
     const unsigned char *cst;
     zrk_msg *rec;
@@ -80,27 +118,19 @@ static inline int zrk_team_for(int ns) {
 }
 
 static inline Layout make_layout(int B, int T, int M, int R, int L, int C) {
-    Layout o;
+    Layout o{};
     o.B = B; o.T = T; o.M = M; o.NS = T + M; o.R = R; o.L = L; o.C = C;
     o.team = zrk_team_for(o.NS);
-    o.teams_per_cta = o.team >= 128 ? 1 : 128 / (o.team ? o.team : 128);
-    o.NSP = zrk_align(o.NS > 0 ? o.NS : 1, 2);
+    const int team = o.team ? o.team : 32;
+    o.teams_per_cta = team >= 128 ? 1 : 128 / team;
     o.MP = zrk_align(M > 0 ? M : 1, 2);
     o.RP = R > 0 ? R : 1;
     o.LP = zrk_align(L > 0 ? L : 1, 2);
     o.CP = zrk_align(C > 0 ? C : 1, 2);
     o.Q = zrk_align(2 * o.MP + o.CP, 2);
-    int p = 0;
+    o.hot = hot_off(team);
+    int p = o.hot.end;
     auto take = [&p](int bytes) { int at = p; p += zrk_align(bytes, 8); return at; };
-    o.hdr = take(4 * H_WORDS);
-    o.counts = take(4 * ZRK_MSG_NTYPES);
-    o.pos = take(8 * 6 * o.NSP);
-    o.speed = take(8 * o.NSP);
-    o.sid = take(4 * o.NSP);
-    o.sflags = take(4 * o.NSP);
-    o.srf = take(4 * o.NSP);
-    o.te_key = take(4 * o.NSP); o.te_ref = take(4 * o.NSP); o.te_upd = take(4 * o.NSP);
-    o.te_follow = take(4 * o.NSP); o.te_mid = take(4 * o.NSP);
     o.me_key = take(4 * o.MP); o.me_ref = take(4 * o.MP); o.me_upd = take(4 * o.MP); o.me_tid = take(4 * o.MP);
     o.rad_cur = take(8 * 2 * o.RP);
     o.st_n = take(4 * o.LP);
@@ -127,11 +157,13 @@ static inline Layout make_layout(int B, int T, int M, int R, int L, int C) {
     o.c_cl_pos = take(8 * 3 * o.CP);
     o.cst_bytes = zrk_align(p, 16);
     p = o.dyn_bytes + o.cst_bytes;
-    o.x_claim = take(4 * (o.NSP + o.MP));
-    o.x_detlist = take(4 * o.NSP);
+    o.x_lxy = take(16 * (team + o.MP));
+    o.x_lzd = take(16 * (team + o.MP));
+    o.x_claim = take(4 * (team + o.MP));
+    o.x_detlist = take(4 * team);
     o.x_wscr = take(4 * 40);
-    o.x_need = take(4 * o.NSP);
-    o.x_ok = take(4 * o.NSP);
+    o.x_need = take(4 * team);
+    o.x_ok = take(4 * team);
     o.team_smem_bytes = zrk_align(p, 16);
     return o;
 }

@@ -108,9 +108,9 @@ __device__ __forceinline__ bool radar_sees(double dx, double dy, double dz, cons
 
 template <int TEAM, int TPC>
 struct Team {
-    int lane;      // 0..TEAM-1 within the scenario's team
-    int tic;       // team index inside the CTA
-    int *wscr;     // >= 34 ints of shared scratch
+    int lane;   // 0..TEAM-1 within the scenario's team
+    int tic;    // team index inside the CTA
+    int *wscr;  // >= 34 ints of shared scratch (TEAM > 32 only)
 
     __device__ __forceinline__ void sync() const {
         if (TEAM == 32) {
@@ -121,9 +121,30 @@ struct Team {
             ZRK_NAMED_BARRIER(tic + 1, TEAM);
         }
     }
-    // exclusive prefix sum in lane order; total returned to every lane
+    // exclusive prefix count of a predicate in lane order; total returned to every lane
+    __device__ __forceinline__ int rank(bool p, int &total) const {
+        const unsigned bal = __ballot_sync(ZRK_FULL, p);
+        const int below = __popc(bal & ((1u << (lane & 31)) - 1u));
+        if (TEAM == 32) {
+            total = __popc(bal);
+            return below;
+        }
+        const int w = lane >> 5;
+        if ((lane & 31) == 0) wscr[w] = __popc(bal);
+        sync();
+        int base = 0, tot = 0;
+        for (int i = 0; i < TEAM / 32; i++) {
+            int x = wscr[i];
+            if (i < w) base += x;
+            tot += x;
+        }
+        sync();
+        total = tot;
+        return base + below;
+    }
+    // exclusive prefix sum of small non-negative ints
     __device__ __forceinline__ int scan(int v, int &total) const {
-        int l32 = lane & 31;
+        const int l32 = lane & 31;
         int inc = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -134,7 +155,7 @@ struct Team {
             total = __shfl_sync(ZRK_FULL, inc, 31);
             return inc - v;
         }
-        int w = lane >> 5;
+        const int w = lane >> 5;
         if (l32 == 31) wscr[w] = inc;
         sync();
         int base = 0, tot = 0;
@@ -148,13 +169,9 @@ struct Team {
         return base + inc - v;
     }
     __device__ __forceinline__ int min(int v) const {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            int n = __shfl_xor_sync(ZRK_FULL, v, d);
-            v = n < v ? n : v;
-        }
+        v = __reduce_min_sync(ZRK_FULL, v);
         if (TEAM == 32) return v;
-        int w = lane >> 5;
+        const int w = lane >> 5;
         if ((lane & 31) == 0) wscr[w] = v;
         sync();
         int m = ZRK_IMAX;
@@ -165,7 +182,11 @@ struct Team {
         sync();
         return m;
     }
-    __device__ __forceinline__ bool any(bool p) const { return min(p ? 0 : 1) == 0; }
+    __device__ __forceinline__ bool any(bool p) const {
+        const bool w = __ballot_sync(ZRK_FULL, p) != 0;
+        if (TEAM == 32) return w;
+        return min(w ? 0 : 1) == 0;
+    }
 };
 
 // ------------------------------------------------------------------ record log
@@ -226,185 +247,141 @@ __device__ ZRK_NOINLINE int missile_solve(const double *mp, const double *tp, co
     return -1;
 }
 
-// ------------------------------------------------------------------ CCP.link_object
+// ------------------------------------------------------------------ shared-memory views
 
-// Shared-memory views of one scenario.
-struct Scen {
-    int *hdr;
-    unsigned *counts;
-    double *pos;  // [6][NSP]: pos xyz, prev xyz
-    double *speed;
-    int *sid, *sflags, *srf;
-    int *te_key, *te_ref, *te_upd, *te_follow, *te_mid;
-    int *me_key, *me_ref, *me_upd, *me_tid;
-    double *rad_cur;
-    int *st_n, *st, *cap, *launched;
-    int *m_status, *m_target, *m_slot, *m_birth;
-    double *m_period;
-    int *det_mid, *det_tid, *det_flag, *mb_type, *mb_l, *mb_a, *ln_m;
-    const int *c_hdr, *c_rad_id, *c_l_id, *c_m_id, *c_m_launcher, *c_cl_id, *c_cl_launcher;
-    const double *c_rad_pos, *c_rad_par, *c_l_pos, *c_m_v0, *c_m_v0sq, *c_m_radius, *c_cl_pos;
-    int *x_claim, *x_detlist, *x_wscr, *x_need, *x_ok;
+// Hot arrays at compile-time offsets from the team's shared-memory base.
+template <int TEAM>
+struct Hot {
+    static constexpr HotOff O = hot_off(TEAM);
+    unsigned char *sm;
+    __device__ __forceinline__ int *hdr() const { return (int *)(sm + O.hdr); }
+    __device__ __forceinline__ unsigned *counts() const { return (unsigned *)(sm + O.counts); }
+    __device__ __forceinline__ double2 *pxy() const { return (double2 *)(sm + O.pxy); }
+    __device__ __forceinline__ double2 *pzs() const { return (double2 *)(sm + O.pzs); }
+    __device__ __forceinline__ double2 *qxy() const { return (double2 *)(sm + O.qxy); }
+    __device__ __forceinline__ double2 *qzw() const { return (double2 *)(sm + O.qzw); }
+    __device__ __forceinline__ int *sid() const { return (int *)(sm + O.sid); }
+    __device__ __forceinline__ int *sflags() const { return (int *)(sm + O.sflags); }
+    __device__ __forceinline__ int *srf() const { return (int *)(sm + O.srf); }
+    __device__ __forceinline__ int *own() const { return (int *)(sm + O.own); }
+    __device__ __forceinline__ int *te_key() const { return (int *)(sm + O.te_key); }
+    __device__ __forceinline__ int *te_ref() const { return (int *)(sm + O.te_ref); }
+    __device__ __forceinline__ int *te_upd() const { return (int *)(sm + O.te_upd); }
+    __device__ __forceinline__ int *te_follow() const { return (int *)(sm + O.te_follow); }
+    __device__ __forceinline__ int *te_mid() const { return (int *)(sm + O.te_mid); }
 };
 
-__device__ __forceinline__ void bind(Scen &s, unsigned char *sm, const Layout &o) {
-    unsigned char *c = sm + o.dyn_bytes;
-    s.hdr = (int *)(sm + o.hdr);
-    s.counts = (unsigned *)(sm + o.counts);
-    s.pos = (double *)(sm + o.pos);
-    s.speed = (double *)(sm + o.speed);
-    s.sid = (int *)(sm + o.sid);
-    s.sflags = (int *)(sm + o.sflags);
-    s.srf = (int *)(sm + o.srf);
-    s.te_key = (int *)(sm + o.te_key);
-    s.te_ref = (int *)(sm + o.te_ref);
-    s.te_upd = (int *)(sm + o.te_upd);
-    s.te_follow = (int *)(sm + o.te_follow);
-    s.te_mid = (int *)(sm + o.te_mid);
-    s.me_key = (int *)(sm + o.me_key);
-    s.me_ref = (int *)(sm + o.me_ref);
-    s.me_upd = (int *)(sm + o.me_upd);
-    s.me_tid = (int *)(sm + o.me_tid);
-    s.rad_cur = (double *)(sm + o.rad_cur);
-    s.st_n = (int *)(sm + o.st_n);
-    s.st = (int *)(sm + o.st);
-    s.cap = (int *)(sm + o.cap);
-    s.launched = (int *)(sm + o.launched);
-    s.m_status = (int *)(sm + o.m_status);
-    s.m_target = (int *)(sm + o.m_target);
-    s.m_slot = (int *)(sm + o.m_slot);
-    s.m_birth = (int *)(sm + o.m_birth);
-    s.m_period = (double *)(sm + o.m_period);
-    s.det_mid = (int *)(sm + o.det_mid);
-    s.det_tid = (int *)(sm + o.det_tid);
-    s.det_flag = (int *)(sm + o.det_flag);
-    s.mb_type = (int *)(sm + o.mb_type);
-    s.mb_l = (int *)(sm + o.mb_l);
-    s.mb_a = (int *)(sm + o.mb_a);
-    s.ln_m = (int *)(sm + o.ln_m);
-    s.c_hdr = (const int *)(c + o.c_hdr);
-    s.c_rad_id = (const int *)(c + o.c_rad_id);
-    s.c_rad_pos = (const double *)(c + o.c_rad_pos);
-    s.c_rad_par = (const double *)(c + o.c_rad_par);
-    s.c_l_id = (const int *)(c + o.c_l_id);
-    s.c_l_pos = (const double *)(c + o.c_l_pos);
-    s.c_m_id = (const int *)(c + o.c_m_id);
-    s.c_m_launcher = (const int *)(c + o.c_m_launcher);
-    s.c_m_v0 = (const double *)(c + o.c_m_v0);
-    s.c_m_v0sq = (const double *)(c + o.c_m_v0sq);
-    s.c_m_radius = (const double *)(c + o.c_m_radius);
-    s.c_cl_id = (const int *)(c + o.c_cl_id);
-    s.c_cl_launcher = (const int *)(c + o.c_cl_launcher);
-    s.c_cl_pos = (const double *)(c + o.c_cl_pos);
-    s.x_claim = (int *)(sm + o.x_claim);
-    s.x_detlist = (int *)(sm + o.x_detlist);
-    s.x_wscr = (int *)(sm + o.x_wscr);
-    s.x_need = (int *)(sm + o.x_need);
-    s.x_ok = (int *)(sm + o.x_ok);
-}
+// Cold arrays (run-time offsets), resolved on use.
+#define ZRK_COLD_I(name) ((int *)(sm + o.name))
+#define ZRK_COLD_D(name) ((double *)(sm + o.name))
+#define ZRK_CST_I(name) ((const int *)(sm + o.dyn_bytes + o.name))
+#define ZRK_CST_D(name) ((const double *)(sm + o.dyn_bytes + o.name))
 
-// calc_range (CCP.py:176-188) for one (detection, entry) pair, exact.
-__device__ __forceinline__ void calc_range(double speed, double cur_time, int upd, const Params &P, double &lo,
-                                           double &hi) {
-    double d_t = cur_time - to_seconds((long long)upd * P.dt_ms);
+// ------------------------------------------------------------------ CCP.link_object
+
+// calc_range (CCP.py:176-188): d_t = cur_time - upd_time has been computed per entry.
+__device__ __forceinline__ void calc_range(double speed, double d_t, const Params &P, double &lo, double &hi) {
     lo = speed * (d_t - P.range_step);
     hi = speed * (d_t + P.range_step);
     lo = lo > 0 ? lo : 0;  // max(0, x)
     hi = hi > 0 ? hi : 0;
 }
 
-// CombatControlPoint.link_object (CCP.py:171-219): exact scan, one detection per lane.
-// cls: 0 NEW_TARGET, 1 OLD_TARGET (cand indexes te_*), 2 OLD_ROCKET (cand indexes me_*).
-__device__ ZRK_NOINLINE void link_exact(const Scen &s, const Params &P, int NSP, int tick, double cur_time,
+#define ZRK_FAR 1e300 /* link position of an entry link_object skips (upd_time == now) */
+
+// CombatControlPoint.link_object (CCP.py:171-219) for one detection, exact: sqrt per pair.
+// Entries are addressed by a unified index: [0, n_te) = _target_dict, TEAM + [0, n_me) =
+// _missile_dict; lxy/lzd hold, per entry, the position the reference measures to
+// (prev_pos, or pos for a missile whose prev_pos is None) and d_t.
+template <int TEAM>
+__device__ ZRK_NOINLINE void link_exact(const double2 *lxy, const double2 *lzd, int n_te, int n_me, const Params &P,
                                         double px, double py, double pz, double speed, int &cls, int &cand) {
     double curr = INFINITY;
     cls = 0;
     cand = -1;
-    int n_te = s.hdr[H_NTE], n_me = s.hdr[H_NME];
-    for (int e = 0; e < n_te; e++) {
-        int upd = s.te_upd[e];
-        if (upd == tick) continue;
-        int ref = s.te_ref[e];
-        double ex = s.pos[3 * NSP + ref] - px, ey = s.pos[4 * NSP + ref] - py, ez = s.pos[5 * NSP + ref] - pz;
-        double diff = sqrt(dot3(ex, ey, ez, ex, ey, ez));
-        double lo, hi;
-        calc_range(speed, cur_time, upd, P, lo, hi);
-        if (diff < curr && lo <= diff && diff <= hi) {
-            curr = diff;
-            cls = 1;
-            cand = e;
-        }
-    }
-    for (int e = 0; e < n_me; e++) {
-        int upd = s.me_upd[e];
-        if (upd == tick) continue;
-        int ref = s.me_ref[e];
-        int o = (s.sflags[ref] & F_HASPREV) ? 3 : 0;  // prev_pos, or pos when prev_pos is None
-        double ex = s.pos[(o + 0) * NSP + ref] - px, ey = s.pos[(o + 1) * NSP + ref] - py,
-               ez = s.pos[(o + 2) * NSP + ref] - pz;
-        double diff = sqrt(dot3(ex, ey, ez, ex, ey, ez));
-        double lo, hi;
-        calc_range(speed, cur_time, upd, P, lo, hi);
-        if (diff < curr && lo <= diff && diff <= hi) {
-            curr = diff;
-            cls = 2;
-            cand = e;
+    for (int pass = 0; pass < 2; pass++) {
+        const int n = pass ? n_me : n_te, base = pass ? TEAM : 0;
+        for (int e = 0; e < n; e++) {
+            const double2 a = lxy[base + e], c = lzd[base + e];
+            if (a.x >= ZRK_FAR) continue;
+            double ex = a.x - px, ey = a.y - py, ez = c.x - pz;
+            double diff = sqrt(dot3(ex, ey, ez, ex, ey, ez));
+            double lo, hi;
+            calc_range(speed, c.y, P, lo, hi);
+            if (diff < curr && lo <= diff && diff <= hi) {
+                curr = diff;
+                cls = pass + 1;
+                cand = e;
+            }
         }
     }
 }
 
-// The same scan in the squared-distance domain.  sqrt is monotone, so "diff < curr" and the
-// range test can be decided from d2 whenever d2 is not within a few ulps of best_d2 / lo^2 /
-// hi^2; any such borderline (or NaN) sets `unsure` and the caller redoes this detection with
-// link_exact.  Range bounds are cached per distinct upd tick.
-__device__ __forceinline__ void link_fast(const Scen &s, const Params &P, int NSP, int tick, double cur_time,
-                                          double px, double py, double pz, double speed, int &cls, int &cand,
-                                          bool &unsure) {
+// State of the squared-domain scan of one detection.
+struct LinkAcc {
+    double best, best_lo;  // smallest accepted d2 and best * (1 - EPS)
+    int ue;                // unified index of the accepted entry, -1 = none
+    bool unsure;           // a comparison was too close to call: redo with link_exact
+};
+
+// Full evaluation of one candidate entry in the squared-distance domain.  sqrt is monotone, so
+// "diff < curr" and "lo <= diff <= hi" are decided from d2 unless d2 is within a few ulps of
+// best / lo^2 / hi^2 (or NaN), which sets `unsure`.  Exact ties (d2 == best) go to the entry
+// that comes first in the reference's scan order.
+__device__ __forceinline__ void link_eval(LinkAcc &A, int ue, double ax, double d2, double d_t, double speed,
+                                          const Params &P) {
     const double EPS = 4e-15;
-    double best = INFINITY, best_lo = INFINITY;  // best_lo = best * (1 - EPS)
-    cls = 0;
-    cand = -1;
-    unsure = false;
-    int c_upd = -0x40000000;
-    double lo2a = 0, lo2b = 0, hi2a = 0, hi2b = 0;  // lo^2*(1-EPS), lo^2*(1+EPS), hi^2*(1-EPS), hi^2*(1+EPS)
-    int n_te = s.hdr[H_NTE], n_me = s.hdr[H_NME];
+    if (ax >= ZRK_FAR) return;  // upd_time == now: skipped by the reference (CCP.py:196, 208)
+    double lo, hi;
+    calc_range(speed, d_t, P, lo, hi);
+    const double l2 = lo * lo, h2 = hi * hi;
+    if (d2 > h2 * (1.0 + EPS) || d2 < l2 * (1.0 - EPS)) return;  // certainly outside [lo, hi]
+    const bool in_sure = d2 >= l2 * (1.0 + EPS) && d2 <= h2 * (1.0 - EPS);
+    if (d2 > A.best) return;
+    if (d2 == A.best) {
+        if (A.ue >= 0 && ue > A.ue) return;  // the earlier entry keeps an exact tie
+        if (in_sure) {
+            A.ue = ue;
+            return;
+        }
+    } else if (in_sure && d2 < A.best_lo) {
+        A.best = d2;
+        A.best_lo = d2 * (1.0 - EPS);
+        A.ue = ue;
+        return;
+    }
+    A.unsure = true;  // includes NaN: every comparison above was false
+}
+
+template <int TEAM>
+__device__ __forceinline__ void link_fast(const double2 *lxy, const double2 *lzd, int n_te, int n_me, int seed,
+                                          const Params &P, double px, double py, double pz, double speed, int &cls,
+                                          int &cand, bool &unsure) {
+    LinkAcc A;
+    A.best = INFINITY;
+    A.best_lo = INFINITY;
+    A.ue = -1;
+    A.unsure = false;
+    // Seed with the entry that tracked this slot last tick: it is almost always the nearest, and
+    // with best = its d2 nearly every other pair fails the single compare below.
+    if (seed >= 0) {
+        const double2 a = lxy[seed], c = lzd[seed];
+        double ex = a.x - px, ey = a.y - py, ez = c.x - pz;
+        link_eval(A, seed, a.x, dot3(ex, ey, ez, ex, ey, ez), c.y, speed, P);
+    }
     for (int pass = 0; pass < 2; pass++) {
-        int n = pass ? n_me : n_te;
-        const int *a_upd = pass ? s.me_upd : s.te_upd;
-        const int *a_ref = pass ? s.me_ref : s.te_ref;
+        const int n = pass ? n_me : n_te, base = pass ? TEAM : 0;
+#pragma unroll 4
         for (int e = 0; e < n; e++) {
-            int upd = a_upd[e];
-            if (upd == tick) continue;
-            int ref = a_ref[e];
-            int o = (!pass || (s.sflags[ref] & F_HASPREV)) ? 3 : 0;
-            double ex = s.pos[(o + 0) * NSP + ref] - px, ey = s.pos[(o + 1) * NSP + ref] - py,
-                   ez = s.pos[(o + 2) * NSP + ref] - pz;
+            const double2 a = lxy[base + e], c = lzd[base + e];
+            double ex = a.x - px, ey = a.y - py, ez = c.x - pz;
             double d2 = dot3(ex, ey, ez, ex, ey, ez);
-            if (upd != c_upd) {
-                double lo, hi;
-                calc_range(speed, cur_time, upd, P, lo, hi);
-                double l2 = lo * lo, h2 = hi * hi;
-                lo2a = l2 * (1.0 - EPS);
-                lo2b = l2 * (1.0 + EPS);
-                hi2a = h2 * (1.0 - EPS);
-                hi2b = h2 * (1.0 + EPS);
-                c_upd = upd;
-            }
-            if (d2 > hi2b || d2 < lo2a) continue;     // certainly outside [lo, hi]
-            if (d2 > best) continue;                  // sqrt(d2) >= curr
-            if (d2 == best) continue;                 // equal diff is not strictly smaller
-            bool in_sure = d2 >= lo2b && d2 <= hi2a;
-            bool less_sure = d2 < best_lo;
-            if (in_sure && less_sure) {
-                best = d2;
-                best_lo = d2 * (1.0 - EPS);
-                cls = pass + 1;
-                cand = e;
-            } else {
-                unsure = true;  // includes NaN: every comparison above was false
-            }
+            if (!(d2 > A.best) && base + e != seed) link_eval(A, base + e, a.x, d2, c.y, speed, P);
         }
     }
+    unsure = A.unsure;
+    cls = A.ue < 0 ? 0 : (A.ue >= TEAM ? 2 : 1);
+    cand = A.ue < 0 ? -1 : (A.ue >= TEAM ? A.ue - TEAM : A.ue);
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -413,7 +390,7 @@ template <int TEAM, int TPC, bool FAST>
 __global__ void __launch_bounds__(TEAM *TPC) zrk_tick_kernel(const Params P, int n_ticks) {
     ZRK_SMEM_DECL;
     const Layout &o = P.lo;
-    const int NSP = o.NSP, MP = o.MP, Q = o.Q;
+    const int MP = o.MP, Q = o.Q;
     Team<TEAM, TPC> tm;
     tm.tic = threadIdx.x / TEAM;
     tm.lane = threadIdx.x % TEAM;
@@ -421,9 +398,10 @@ __global__ void __launch_bounds__(TEAM *TPC) zrk_tick_kernel(const Params P, int
     const int b = blockIdx.x * TPC + tm.tic;
     if (b >= o.B) return;  // whole team leaves together
     unsigned char *sm = zrk_smem + (size_t)tm.tic * o.team_smem_bytes;
-    Scen s;
-    bind(s, sm, o);
-    tm.wscr = s.x_wscr;
+    Hot<TEAM> H;
+    H.sm = sm;
+    tm.wscr = (int *)(sm + o.x_wscr);
+    double2 *lxy = (double2 *)(sm + o.x_lxy), *lzd = (double2 *)(sm + o.x_lzd);
 
     // ---- prologue: HBM -> shared memory / registers
     {
@@ -434,132 +412,127 @@ __global__ void __launch_bounds__(TEAM *TPC) zrk_tick_kernel(const Params P, int
         uint4 *sc = (uint4 *)(sm + o.dyn_bytes);
         for (int i = lane; i < o.cst_bytes / 16; i += TEAM) sc[i] = gc[i];
     }
-    double *gtraj = P.traj + (size_t)b * 8 * NSP;  // [8][NSP]: p0x p0y p0z t0 vx vy vz speed
-    double p0x = 0, p0y = 0, p0z = 0, t0 = 0, vx = 0, vy = 0, vz = 0;
-    if (lane < o.NS) {
-        p0x = gtraj[0 * NSP + lane];
-        p0y = gtraj[1 * NSP + lane];
-        p0z = gtraj[2 * NSP + lane];
-        t0 = gtraj[3 * NSP + lane];
-        vx = gtraj[4 * NSP + lane];
-        vy = gtraj[5 * NSP + lane];
-        vz = gtraj[6 * NSP + lane];
-    }
+    double *gtraj = P.traj + (size_t)b * 8 * TEAM;  // [8][TEAM]: p0x p0y p0z t0 vx vy vz speed
+    double p0x = gtraj[0 * TEAM + lane], p0y = gtraj[1 * TEAM + lane], p0z = gtraj[2 * TEAM + lane];
+    double t0 = gtraj[3 * TEAM + lane];
+    double vx = gtraj[4 * TEAM + lane], vy = gtraj[5 * TEAM + lane], vz = gtraj[6 * TEAM + lane];
     tm.sync();
 
-    const int nR = s.c_hdr[C_NR], nL = s.c_hdr[C_NL], nC = s.c_hdr[C_NC], T = o.T;
-    const int ccp_id = s.c_hdr[C_CCP_ID], airenv_id = s.c_hdr[C_AIRENV_ID];
-    const int tick_limit = s.c_hdr[C_TICK_LIMIT];
+    const int *chdr = ZRK_CST_I(c_hdr);
+    const int nR = chdr[C_NR], nL = chdr[C_NL], nC = chdr[C_NC], T = o.T;
+    const int ccp_id = chdr[C_CCP_ID];
+    const int tick_limit = chdr[C_TICK_LIMIT];
     const bool has_ccp = ccp_id != ZRK_NONE;
     zrk_msg *rec = P.rec + (size_t)b * P.log_cap;
     const double *noise = P.noise ? P.noise + (size_t)b * P.noise_stride : nullptr;
-    (void)airenv_id;
+    int *const hdr = H.hdr();
 
     for (int it = 0; it < n_ticks; it++) {
-        const int tick = s.hdr[H_TICK];
-        if (s.hdr[H_FAULT] & 63) break;             // the reference run aborted here
+        const int tick = hdr[H_TICK];
+        if (hdr[H_FAULT] & 63) break;  // the reference run aborted here
         if (tick_limit >= 0 && tick >= tick_limit) break;
         const int par = tick & 1, prv = par ^ 1;
         const double now_s = to_seconds((long long)tick * P.dt_ms);
-        const int n_slots = s.hdr[H_NSLOTS];
-        const int det_prev = s.hdr[H_DETN0 + prv];
-        tm.sync();  // everyone has read the header before lane 0 resets the per-tick lists
+        const int n_slots = hdr[H_NSLOTS];
+        const int det_prev = hdr[H_DETN0 + prv];
+        const int mb_prev = hdr[H_MBN0 + prv];
+        int nrec = hdr[H_NREC];  // records written so far; kept uniform across the team
+        tm.sync();               // everyone has read the header before lane 0 resets the per-tick lists
         if (lane == 0) {
-            s.hdr[H_MBN0 + par] = 0;
-            s.hdr[H_DETN0 + par] = 0;
-            s.hdr[H_LN] = 0;
+            hdr[H_MBN0 + par] = 0;
+            hdr[H_DETN0 + par] = 0;
+            hdr[H_LN] = 0;
         }
 
         // ============ AirEnv.step (AirEnv.py:26-53)
         int fl = 0, my_id = 0;
         double px = 0, py = 0, pz = 0;
         if (lane < n_slots) {
-            fl = s.sflags[lane];
-            my_id = s.sid[lane];
-            if (fl & F_ALIVE) {  // :33-40 removal by id
+            fl = H.sflags()[lane];
+            my_id = H.sid()[lane];
+            if ((fl & F_ALIVE) && det_prev) {  // :33-40 removal by id
+                const int *dm = ZRK_COLD_I(det_mid) + prv * MP, *dt = ZRK_COLD_I(det_tid) + prv * MP;
                 for (int i = 0; i < det_prev; i++) {
-                    int tid = s.det_tid[prv * MP + i];
-                    if (my_id == s.det_mid[prv * MP + i] || (tid != ZRK_NONE && my_id == tid)) fl &= ~F_ALIVE;
+                    int tid = dt[i];
+                    if (my_id == dm[i] || (tid != ZRK_NONE && my_id == tid)) fl &= ~F_ALIVE;
                 }
             }
             if (fl & F_PENDING) {  // :42-43 NEW_MISSILE of the previous tick
                 int m = (fl >> F_STATIC_SHIFT) - T;
-                if (s.m_birth[m] == tick) {
+                if (ZRK_COLD_I(m_birth)[m] == tick) {
                     fl = (fl & ~F_PENDING) | F_ALIVE;
-                    p0x = ZRK_LDCG(&gtraj[0 * NSP + lane]);
-                    p0y = ZRK_LDCG(&gtraj[1 * NSP + lane]);
-                    p0z = ZRK_LDCG(&gtraj[2 * NSP + lane]);
-                    t0 = ZRK_LDCG(&gtraj[3 * NSP + lane]);
-                    vx = ZRK_LDCG(&gtraj[4 * NSP + lane]);
-                    vy = ZRK_LDCG(&gtraj[5 * NSP + lane]);
-                    vz = ZRK_LDCG(&gtraj[6 * NSP + lane]);
+                    p0x = ZRK_LDCG(&gtraj[0 * TEAM + lane]);
+                    p0y = ZRK_LDCG(&gtraj[1 * TEAM + lane]);
+                    p0z = ZRK_LDCG(&gtraj[2 * TEAM + lane]);
+                    t0 = ZRK_LDCG(&gtraj[3 * TEAM + lane]);
+                    vx = ZRK_LDCG(&gtraj[4 * TEAM + lane]);
+                    vy = ZRK_LDCG(&gtraj[5 * TEAM + lane]);
+                    vz = ZRK_LDCG(&gtraj[6 * TEAM + lane]);
                 }
             }
             if (fl & F_ALIVE) {  // AirObject.step (AirObject.py:39-42)
+                const double2 oxy = H.pxy()[lane], ozs = H.pzs()[lane];
                 if (t0 != now_s) {
-                    s.pos[3 * NSP + lane] = s.pos[0 * NSP + lane];
-                    s.pos[4 * NSP + lane] = s.pos[1 * NSP + lane];
-                    s.pos[5 * NSP + lane] = s.pos[2 * NSP + lane];
+                    H.qxy()[lane] = oxy;
+                    H.qzw()[lane] = make_double2(ozs.x, 0.0);
                     fl |= F_HASPREV;
                 } else {
                     fl &= ~F_HASPREV;
                 }
-                double dtm = now_s - t0;
+                const double dtm = now_s - t0;
                 px = p0x + vx * dtm;
                 py = p0y + vy * dtm;
                 pz = p0z + vz * dtm;
-                s.pos[0 * NSP + lane] = px;
-                s.pos[1 * NSP + lane] = py;
-                s.pos[2 * NSP + lane] = pz;
+                H.pxy()[lane] = make_double2(px, py);
+                H.pzs()[lane] = make_double2(pz, ozs.y);
             }
-            s.sflags[lane] = fl;
+            H.sflags()[lane] = fl;
         }
         const bool alive = (fl & F_ALIVE) != 0;
         tm.sync();
 
         // Missile.step, status 'active' (Missile.py:162-193), in slot order
-        int nrec_a;  // records written so far this tick (uniform across the team)
         {
-            int det = 0, det_tid = ZRK_NONE;
             const bool msl = alive && (fl & F_MISSILE);
-            if (msl) {
-                int m = (fl >> F_STATIC_SHIFT) - T;
-                int tg = s.m_target[m];
-                double ex = s.pos[0 * NSP + tg] - px, ey = s.pos[1 * NSP + tg] - py, ez = s.pos[2 * NSP + tg] - pz;
-                double dist = sqrt(dot3(ex, ey, ez, ex, ey, ez));
-                if (dist <= s.c_m_radius[m]) {
-                    det = 1;
-                    det_tid = s.sid[tg];
-                } else {
-                    double per = s.m_period[m] - P.dt_s;
-                    s.m_period[m] = per;
-                    if (per <= 0) det = 2;
+            if (tm.any(msl)) {
+                int det = 0, det_tid = ZRK_NONE;
+                if (msl) {
+                    const int m = (fl >> F_STATIC_SHIFT) - T;
+                    const int tg = ZRK_COLD_I(m_target)[m];
+                    const double2 txy = H.pxy()[tg], tzs = H.pzs()[tg];
+                    double ex = txy.x - px, ey = txy.y - py, ez = tzs.x - pz;
+                    double dist = sqrt(dot3(ex, ey, ez, ex, ey, ez));
+                    if (dist <= ZRK_CST_D(c_m_radius)[m]) {
+                        det = 1;
+                        det_tid = H.sid()[tg];
+                    } else {
+                        double per = ZRK_COLD_D(m_period)[m] - P.dt_s;
+                        ZRK_COLD_D(m_period)[m] = per;
+                        if (per <= 0) det = 2;
+                    }
+                    if (det) ZRK_COLD_I(m_status)[m] = ST_DETONATED;
                 }
-                if (det) s.m_status[m] = ST_DETONATED;
+                const bool lp = logged(P, ZRK_MSG_MISSILE_POS), ld = logged(P, ZRK_MSG_MISSILE_DETONATE);
+                int n_msl, n_det;
+                const int r_msl = tm.rank(msl, n_msl);
+                const int r_det = tm.rank(det != 0, n_det);
+                int ri = nrec + (lp ? r_msl : 0) + (ld ? r_det : 0);
+                if (msl && lp) put_rec(P, rec, ri++, tick, ZRK_MSG_MISSILE_POS, 0, my_id, ZRK_NONE, my_id, ZRK_NONE, 0, 0, 0);
+                if (det) {
+                    if (ld)
+                        put_rec(P, rec, ri, tick, ZRK_MSG_MISSILE_DETONATE, det == 2, my_id, ZRK_NONE, my_id, det_tid, 0, 0, 0);
+                    ZRK_COLD_I(det_mid)[par * MP + r_det] = my_id;
+                    ZRK_COLD_I(det_tid)[par * MP + r_det] = det_tid;
+                    ZRK_COLD_I(det_flag)[par * MP + r_det] = det == 2;
+                }
+                nrec += (lp ? n_msl : 0) + (ld ? n_det : 0);
+                if (lane == 0) {
+                    hdr[H_DETN0 + par] = n_det;
+                    H.counts()[ZRK_MSG_MISSILE_POS] += (unsigned)n_msl;
+                    H.counts()[ZRK_MSG_MISSILE_DETONATE] += (unsigned)n_det;
+                }
             }
-            const bool lp = logged(P, ZRK_MSG_MISSILE_POS), ld = logged(P, ZRK_MSG_MISSILE_DETONATE);
-            const int nrec = (msl && lp ? 1 : 0) + (det && ld ? 1 : 0);
-            int ptot, n_msl;
-            const int pex = tm.scan(nrec | ((det ? 1 : 0) << 16), ptot);
-            (void)tm.scan(msl ? 1 : 0, n_msl);
-            const int rbase = s.hdr[H_NREC];
-            int ri = rbase + (pex & 0xffff);
-            const int di = pex >> 16;
-            if (msl && lp) put_rec(P, rec, ri++, tick, ZRK_MSG_MISSILE_POS, 0, my_id, ZRK_NONE, my_id, ZRK_NONE, 0, 0, 0);
-            if (det) {
-                if (ld)
-                    put_rec(P, rec, ri, tick, ZRK_MSG_MISSILE_DETONATE, det == 2, my_id, ZRK_NONE, my_id, det_tid, 0, 0, 0);
-                s.det_mid[par * MP + di] = my_id;
-                s.det_tid[par * MP + di] = det_tid;
-                s.det_flag[par * MP + di] = det == 2;
-            }
-            nrec_a = rbase + (ptot & 0xffff);
-            if (lane == 0) {
-                s.hdr[H_DETN0 + par] = ptot >> 16;
-                s.counts[ZRK_MSG_MISSILE_POS] += (unsigned)n_msl;
-                s.counts[ZRK_MSG_MISSILE_DETONATE] += (unsigned)(ptot >> 16);
-                s.counts[ZRK_MSG_ACTIVE_OBJECTS] += 1;
-            }
+            if (lane == 0) H.counts()[ZRK_MSG_ACTIVE_OBJECTS] += 1;
         }
         unsigned *mrow = nullptr;
         if (P.masks) {
@@ -570,54 +543,63 @@ __global__ void __launch_bounds__(TEAM *TPC) zrk_tick_kernel(const Params P, int
 
         // ============ SectorRadar.step for every radar (Radar.py:144-205)
         int rf = -1;
-        for (int r = 0; r < nR; r++) {
-            const double *par_r = s.c_rad_par + RAD_PAR_STRIDE * r;
-            bool vis = false;
-            if (alive) {
-                double caz = s.rad_cur[2 * r], cel = s.rad_cur[2 * r + 1];
-                double dx = px - s.c_rad_pos[3 * r], dy = py - s.c_rad_pos[3 * r + 1], dz = pz - s.c_rad_pos[3 * r + 2];
-                vis = radar_sees<FAST>(dx, dy, dz, par_r, caz, caz + par_r[3], cel, cel + par_r[4]);
-                if (vis) {  // smooth_objects (Radar.py:138-142)
-                    if (noise) {
-                        const double *nz = noise + (((size_t)(tick % P.noise_period) * P.noise_radars + r) * P.noise_objects +
-                                                    (fl >> F_STATIC_SHIFT)) * 3;
-                        px += nz[0];
-                        py += nz[1];
-                        pz += nz[2];
+        {
+            const double *rad_cur = ZRK_COLD_D(rad_cur), *c_rad_pos = ZRK_CST_D(c_rad_pos), *c_rad_par = ZRK_CST_D(c_rad_par);
+            for (int r = 0; r < nR; r++) {
+                const double *par_r = c_rad_par + RAD_PAR_STRIDE * r;
+                bool vis = false;
+                if (alive) {
+                    double caz = rad_cur[2 * r], cel = rad_cur[2 * r + 1];
+                    double dx = px - c_rad_pos[3 * r], dy = py - c_rad_pos[3 * r + 1], dz = pz - c_rad_pos[3 * r + 2];
+                    vis = radar_sees<FAST>(dx, dy, dz, par_r, caz, caz + par_r[3], cel, cel + par_r[4]);
+                    if (vis) {  // smooth_objects (Radar.py:138-142)
+                        if (noise) {
+                            const double *nz = noise + (((size_t)(tick % P.noise_period) * P.noise_radars + r) * P.noise_objects +
+                                                        (fl >> F_STATIC_SHIFT)) * 3;
+                            px += nz[0];
+                            py += nz[1];
+                            pz += nz[2];
+                        }
+                        if (rf < 0) rf = r;
                     }
-                    if (rf < 0) rf = r;
                 }
+                if (mrow) {
+                    unsigned bal = __ballot_sync(ZRK_FULL, vis);
+                    if ((lane & 31) == 0 && (lane >> 5) < P.mask_words) mrow[(1 + r) * P.mask_words + (lane >> 5)] = bal;
+                }
+                // :193-203 one DESTROYED_MISSILE per MISSILE_DETONATE of the previous tick
+                if (det_prev && logged(P, ZRK_MSG_DESTROYED_MISSILE) && lane < det_prev)
+                    put_rec(P, rec, nrec + r * det_prev + lane, tick, ZRK_MSG_DESTROYED_MISSILE,
+                            ZRK_COLD_I(det_flag)[prv * MP + lane], ZRK_CST_I(c_rad_id)[r], ZRK_CCP_ID,
+                            ZRK_COLD_I(det_mid)[prv * MP + lane], ZRK_NONE, 0, 0, 0);
             }
-            if (mrow) {
-                unsigned bal = __ballot_sync(ZRK_FULL, vis);
-                if ((lane & 31) == 0 && (lane >> 5) < P.mask_words) mrow[(1 + r) * P.mask_words + (lane >> 5)] = bal;
-            }
-            // :193-203 one DESTROYED_MISSILE per MISSILE_DETONATE of the previous tick
-            if (det_prev && logged(P, ZRK_MSG_DESTROYED_MISSILE) && lane < det_prev)
-                put_rec(P, rec, nrec_a + r * det_prev + lane, tick, ZRK_MSG_DESTROYED_MISSILE,
-                        s.det_flag[prv * MP + lane], s.c_rad_id[r], ZRK_CCP_ID, s.det_mid[prv * MP + lane], ZRK_NONE,
-                        0, 0, 0);
+            if (nR && logged(P, ZRK_MSG_DESTROYED_MISSILE)) nrec += nR * det_prev;
         }
-        if (lane < NSP) s.srf[lane] = rf;
-        if (alive) {
-            s.pos[0 * NSP + lane] = px;
-            s.pos[1 * NSP + lane] = py;
-            s.pos[2 * NSP + lane] = pz;
+        H.srf()[lane] = rf;
+        if (alive && rf >= 0) {
+            H.pxy()[lane] = make_double2(px, py);
+            H.pzs()[lane].x = pz;
+        }
+        // anything for lane 0 to do alone this tick?  (uniform)
+        const bool serial = mb_prev != 0 || (has_ccp && !hdr[H_CCP_INIT]);
+        if (lane == 0) {
+            hdr[H_NREC] = nrec;
+            if (nR) {
+                H.counts()[ZRK_MSG_ALL_OBJECTS] += nR;
+                H.counts()[ZRK_MSG_FOUND_OBJECTS] += nR;
+                H.counts()[ZRK_MSG_DESTROYED_MISSILE] += nR * det_prev;
+            }
         }
         tm.sync();
 
-        // ============ lane 0: radar bookkeeping, MissileLauncher.step, CCP bookkeeping
+        // ============ lane 0: sector sweep, MissileLauncher.step, CCP bookkeeping
         if (lane == 0) {
-            s.hdr[H_NREC] = nrec_a;
-            if (nR) {
-                if (logged(P, ZRK_MSG_DESTROYED_MISSILE)) s.hdr[H_NREC] += nR * det_prev;
-                s.counts[ZRK_MSG_ALL_OBJECTS] += nR;
-                s.counts[ZRK_MSG_FOUND_OBJECTS] += nR;
-                s.counts[ZRK_MSG_DESTROYED_MISSILE] += nR * det_prev;
-            }
+            double *rad_cur = ZRK_COLD_D(rad_cur);
+            const double *c_rad_par = ZRK_CST_D(c_rad_par);
             for (int r = 0; r < nR; r++) {  // move_to_next_sector_circular (Radar.py:96-117)
-                const double *q = s.c_rad_par + RAD_PAR_STRIDE * r;
-                double caz = s.rad_cur[2 * r], cel = s.rad_cur[2 * r + 1];
+                const double *q = c_rad_par + RAD_PAR_STRIDE * r;
+                if (q[5] == 0.0 && q[6] == 0.0 && q[0] == q[1] && q[0] + q[3] < 360) continue;  // a sector that never moves
+                double caz = rad_cur[2 * r], cel = rad_cur[2 * r + 1];
                 int mode = (int)q[7];
                 if (mode == ZRK_SCAN_HORIZONTAL) {
                     if (caz + q[3] < 360)
@@ -634,164 +616,195 @@ __global__ void __launch_bounds__(TEAM *TPC) zrk_tick_kernel(const Params P, int
                     cel = pymod(cel + q[6], 90.0);
                     if (cel < q[6]) caz = pymod(caz + q[5], 360.0);
                 }
-                s.rad_cur[2 * r] = caz;
-                s.rad_cur[2 * r + 1] = cel;
+                rad_cur[2 * r] = caz;
+                rad_cur[2 * r + 1] = cel;
             }
-            // MissileLauncher.step (MissileLauncher.py:82-138)
-            const int n_prev = s.hdr[H_MBN0 + prv];
-            if (n_prev) {
-                int nrec = s.hdr[H_NREC];
-                for (int l = 0; l < nL; l++) {
-                    const int l_id = s.c_l_id[l];
-                    for (int i = 0; i < n_prev; i++) {
-                        if (s.mb_l[prv * Q + i] != l) continue;
-                        const int ty = s.mb_type[prv * Q + i], arg = s.mb_a[prv * Q + i];
+        }
+        if (serial) {
+            if (lane == 0) {
+                int *mb_type = ZRK_COLD_I(mb_type), *mb_l = ZRK_COLD_I(mb_l), *mb_a = ZRK_COLD_I(mb_a);
+                int *st_n = ZRK_COLD_I(st_n), *st = ZRK_COLD_I(st);
+                const int *c_m_id = ZRK_CST_I(c_m_id), *c_l_id = ZRK_CST_I(c_l_id);
+                const double *c_l_pos = ZRK_CST_D(c_l_pos);
+                int *m_target = ZRK_COLD_I(m_target);
+                unsigned *counts = H.counts();
+                int nr = nrec;
+                // MissileLauncher.step (MissileLauncher.py:82-138)
+                for (int l = 0; l < nL && mb_prev; l++) {
+                    const int l_id = c_l_id[l];
+                    for (int i = 0; i < mb_prev; i++) {
+                        if (mb_l[prv * Q + i] != l) continue;
+                        const int ty = mb_type[prv * Q + i], arg = mb_a[prv * Q + i];
                         if (ty == MB_COMMAND) {  // launch_missile (:58-80)
-                            if (s.st_n[l] == 0) continue;
-                            const int m = s.st[l * MP + (--s.st_n[l])];
-                            const int m_id = s.c_m_id[m], tg = arg;
-                            s.counts[ZRK_MSG_LAUNCH_MISSILE]++;
+                            if (st_n[l] == 0) continue;
+                            const int m = st[l * MP + (--st_n[l])];
+                            const int m_id = c_m_id[m], tg = arg;
+                            counts[ZRK_MSG_LAUNCH_MISSILE]++;
                             if (logged(P, ZRK_MSG_LAUNCH_MISSILE))
-                                put_rec(P, rec, nrec++, tick, ZRK_MSG_LAUNCH_MISSILE, 0, l_id, m_id, s.sid[tg], ZRK_NONE, 0, 0, 0);
+                                put_rec(P, rec, nr++, tick, ZRK_MSG_LAUNCH_MISSILE, 0, l_id, m_id, H.sid()[tg], ZRK_NONE, 0, 0, 0);
                             // Missile._launch (Missile.py:104-133)
-                            double tp[3] = {s.pos[0 * NSP + tg], s.pos[1 * NSP + tg], s.pos[2 * NSP + tg]};
+                            double tp[3] = {H.pxy()[tg].x, H.pxy()[tg].y, H.pzs()[tg].x};
                             double vt[3];
-                            if (s.sflags[tg] & F_MISSILE) {
+                            if (H.sflags()[tg] & F_MISSILE) {
                                 vt[0] = vt[1] = vt[2] = NAN;  // Missile.velocity is 0/0 (AirObject.py:35)
                             } else {
-                                double wx = ZRK_LDCG(&gtraj[4 * NSP + tg]), wy = ZRK_LDCG(&gtraj[5 * NSP + tg]),
-                                       wz = ZRK_LDCG(&gtraj[6 * NSP + tg]);
-                                double sp = s.speed[tg];
+                                double wx = ZRK_LDCG(&gtraj[4 * TEAM + tg]), wy = ZRK_LDCG(&gtraj[5 * TEAM + tg]),
+                                       wz = ZRK_LDCG(&gtraj[6 * TEAM + tg]);
+                                double sp = H.pzs()[tg].y;
                                 vt[0] = wx / sp * sp;  // target.velocity * target.speed_mod (Missile.py:59)
                                 vt[1] = wy / sp * sp;
                                 vt[2] = wz / sp * sp;
                             }
                             double V[3];
-                            int why = missile_solve(&s.c_l_pos[3 * l], tp, vt, s.c_m_v0[m], s.c_m_v0sq[m], s.m_period[m], V);
-                            const int q = s.hdr[H_MBN0 + par]++;
-                            s.mb_l[par * Q + q] = l;
-                            s.mb_a[par * Q + q] = m;
+                            const double v0 = ZRK_CST_D(c_m_v0)[m];
+                            int why = missile_solve(&c_l_pos[3 * l], tp, vt, v0, ZRK_CST_D(c_m_v0sq)[m], ZRK_COLD_D(m_period)[m], V);
+                            const int q = hdr[H_MBN0 + par]++;
+                            mb_l[par * Q + q] = l;
+                            mb_a[par * Q + q] = m;
                             if (why < 0) {
-                                const int k = s.hdr[H_NSLOTS]++;
-                                gtraj[0 * NSP + k] = s.c_l_pos[3 * l];
-                                gtraj[1 * NSP + k] = s.c_l_pos[3 * l + 1];
-                                gtraj[2 * NSP + k] = s.c_l_pos[3 * l + 2];
-                                gtraj[3 * NSP + k] = now_s;
-                                gtraj[4 * NSP + k] = V[0];
-                                gtraj[5 * NSP + k] = V[1];
-                                gtraj[6 * NSP + k] = V[2];
-                                gtraj[7 * NSP + k] = s.c_m_v0[m];
-                                s.pos[0 * NSP + k] = s.c_l_pos[3 * l];
-                                s.pos[1 * NSP + k] = s.c_l_pos[3 * l + 1];
-                                s.pos[2 * NSP + k] = s.c_l_pos[3 * l + 2];
-                                s.speed[k] = s.c_m_v0[m];
-                                s.sid[k] = m_id;
-                                s.sflags[k] = F_PENDING | F_MISSILE | ((T + m) << F_STATIC_SHIFT);
-                                s.m_status[m] = ST_ACTIVE;
-                                s.m_target[m] = tg;
-                                s.m_slot[m] = k;
-                                s.m_birth[m] = tick + 2;
-                                s.mb_type[par * Q + q] = MB_SUCCESS;
-                                s.counts[ZRK_MSG_LAUNCH_SUCCESSFUL]++;
+                                const int k = hdr[H_NSLOTS]++;
+                                gtraj[0 * TEAM + k] = c_l_pos[3 * l];
+                                gtraj[1 * TEAM + k] = c_l_pos[3 * l + 1];
+                                gtraj[2 * TEAM + k] = c_l_pos[3 * l + 2];
+                                gtraj[3 * TEAM + k] = now_s;
+                                gtraj[4 * TEAM + k] = V[0];
+                                gtraj[5 * TEAM + k] = V[1];
+                                gtraj[6 * TEAM + k] = V[2];
+                                gtraj[7 * TEAM + k] = v0;
+                                H.pxy()[k] = make_double2(c_l_pos[3 * l], c_l_pos[3 * l + 1]);
+                                H.pzs()[k] = make_double2(c_l_pos[3 * l + 2], v0);
+                                H.sid()[k] = m_id;
+                                H.sflags()[k] = F_PENDING | F_MISSILE | ((T + m) << F_STATIC_SHIFT);
+                                H.srf()[k] = -1;
+                                H.own()[k] = -1;
+                                ZRK_COLD_I(m_status)[m] = ST_ACTIVE;
+                                m_target[m] = tg;
+                                ZRK_COLD_I(m_slot)[m] = k;
+                                ZRK_COLD_I(m_birth)[m] = tick + 2;
+                                mb_type[par * Q + q] = MB_SUCCESS;
+                                counts[ZRK_MSG_LAUNCH_SUCCESSFUL]++;
                                 if (logged(P, ZRK_MSG_LAUNCH_SUCCESSFUL))
-                                    put_rec(P, rec, nrec++, tick, ZRK_MSG_LAUNCH_SUCCESSFUL, 0, m_id, l_id, m_id, s.sid[tg], V[0], V[1], V[2]);
+                                    put_rec(P, rec, nr++, tick, ZRK_MSG_LAUNCH_SUCCESSFUL, 0, m_id, l_id, m_id, H.sid()[tg], V[0], V[1], V[2]);
                             } else {
-                                s.mb_type[par * Q + q] = MB_CANCEL;
-                                s.counts[ZRK_MSG_LAUNCH_CANCELLED]++;
+                                mb_type[par * Q + q] = MB_CANCEL;
+                                counts[ZRK_MSG_LAUNCH_CANCELLED]++;
                                 if (logged(P, ZRK_MSG_LAUNCH_CANCELLED))
-                                    put_rec(P, rec, nrec++, tick, ZRK_MSG_LAUNCH_CANCELLED, 0, m_id, l_id, m_id, why, 0, 0, 0);
+                                    put_rec(P, rec, nr++, tick, ZRK_MSG_LAUNCH_CANCELLED, 0, m_id, l_id, m_id, why, 0, 0, 0);
                             }
                         } else if (ty == MB_SUCCESS) {  // :103-124
-                            const int m = arg, m_id = s.c_m_id[m], tid = s.sid[s.m_target[m]];
-                            s.counts[ZRK_MSG_LAUNCHED_MISSILE]++;
-                            s.counts[ZRK_MSG_NEW_MISSILE]++;
+                            const int m = arg, m_id = c_m_id[m], tid = H.sid()[m_target[m]];
+                            counts[ZRK_MSG_LAUNCHED_MISSILE]++;
+                            counts[ZRK_MSG_NEW_MISSILE]++;
                             if (logged(P, ZRK_MSG_LAUNCHED_MISSILE))
-                                put_rec(P, rec, nrec++, tick, ZRK_MSG_LAUNCHED_MISSILE, 0, l_id, ZRK_CCP_ID, m_id, tid, 0, 0, 0);
+                                put_rec(P, rec, nr++, tick, ZRK_MSG_LAUNCHED_MISSILE, 0, l_id, ZRK_CCP_ID, m_id, tid, 0, 0, 0);
                             if (logged(P, ZRK_MSG_NEW_MISSILE))
-                                put_rec(P, rec, nrec++, tick, ZRK_MSG_NEW_MISSILE, 0, l_id, ZRK_NONE, m_id, ZRK_NONE, 0, 0, 0);
-                            s.ln_m[s.hdr[H_LN]++] = m;
+                                put_rec(P, rec, nr++, tick, ZRK_MSG_NEW_MISSILE, 0, l_id, ZRK_NONE, m_id, ZRK_NONE, 0, 0, 0);
+                            ZRK_COLD_I(ln_m)[hdr[H_LN]++] = m;
                         } else if (ty == MB_CANCEL) {  // :125-128
-                            s.st[l * MP + (s.st_n[l]++)] = arg;
+                            st[l * MP + (st_n[l]++)] = arg;
                         } else {  // MissileCountRequestMessage (:129-138)
-                            s.counts[ZRK_MSG_MISSILE_COUNT_RESPONSE]++;
+                            counts[ZRK_MSG_MISSILE_COUNT_RESPONSE]++;
                             if (logged(P, ZRK_MSG_MISSILE_COUNT_RESPONSE))
-                                put_rec(P, rec, nrec++, tick, ZRK_MSG_MISSILE_COUNT_RESPONSE, 0, l_id, ccp_id, ZRK_NONE, s.st_n[l], 0, 0, 0);
+                                put_rec(P, rec, nr++, tick, ZRK_MSG_MISSILE_COUNT_RESPONSE, 0, l_id, ccp_id, ZRK_NONE, st_n[l], 0, 0, 0);
                             // CCP.get_current_missile_launcher_capacity (CCP.py:139-147), same tick
                             for (int c = 0; c < nC; c++)
-                                if (s.c_cl_launcher[c] == l) s.cap[c] = s.st_n[l];
+                                if (ZRK_CST_I(c_cl_launcher)[c] == l) ZRK_COLD_I(cap)[c] = st_n[l];
                         }
                     }
                 }
-                s.hdr[H_NREC] = nrec;
-            }
-            if (has_ccp) {
-                int nrec = s.hdr[H_NREC];
-                if (!s.hdr[H_CCP_INIT]) {  // send_request_msg_to_ml_capacity (CCP.py:122-137)
-                    for (int c = 0; c < nC; c++) {
-                        s.cap[c] = 0;
-                        s.launched[c] = 0;
-                        s.counts[ZRK_MSG_MISSILE_COUNT_REQUEST]++;
-                        if (logged(P, ZRK_MSG_MISSILE_COUNT_REQUEST))
-                            put_rec(P, rec, nrec++, tick, ZRK_MSG_MISSILE_COUNT_REQUEST, 0, ccp_id, s.c_cl_id[c], ZRK_NONE, ZRK_NONE, 0, 0, 0);
-                        const int q = s.hdr[H_MBN0 + par]++;
-                        s.mb_type[par * Q + q] = MB_COUNTREQ;
-                        s.mb_l[par * Q + q] = s.c_cl_launcher[c];
-                        s.mb_a[par * Q + q] = 0;
+                if (has_ccp) {
+                    if (!hdr[H_CCP_INIT]) {  // send_request_msg_to_ml_capacity (CCP.py:122-137)
+                        for (int c = 0; c < nC; c++) {
+                            ZRK_COLD_I(cap)[c] = 0;
+                            ZRK_COLD_I(launched)[c] = 0;
+                            counts[ZRK_MSG_MISSILE_COUNT_REQUEST]++;
+                            if (logged(P, ZRK_MSG_MISSILE_COUNT_REQUEST))
+                                put_rec(P, rec, nr++, tick, ZRK_MSG_MISSILE_COUNT_REQUEST, 0, ccp_id, ZRK_CST_I(c_cl_id)[c], ZRK_NONE, ZRK_NONE, 0, 0, 0);
+                            const int q = hdr[H_MBN0 + par]++;
+                            mb_type[par * Q + q] = MB_COUNTREQ;
+                            mb_l[par * Q + q] = ZRK_CST_I(c_cl_launcher)[c];
+                            mb_a[par * Q + q] = 0;
+                        }
+                        hdr[H_CCP_INIT] = 1;
                     }
-                    s.hdr[H_CCP_INIT] = 1;
-                }
-                s.hdr[H_NREC] = nrec;
-                // check_if_missiles_launched + add_missile (CCP.py:161-169, :102-109)
-                const int n_ln = s.hdr[H_LN];
-                for (int i = 0; i < n_ln; i++) {
-                    const int m = s.ln_m[i], m_id = s.c_m_id[m], tid = s.sid[s.m_target[m]];
-                    int e, n_me = s.hdr[H_NME];
-                    for (e = 0; e < n_me; e++)
-                        if (s.me_key[e] == m_id) break;
-                    if (e == n_me) s.hdr[H_NME] = n_me + 1;
-                    s.me_key[e] = m_id;
-                    s.me_ref[e] = s.m_slot[m];
-                    s.me_upd[e] = tick;
-                    s.me_tid[e] = tid;
-                    int t, n_te = s.hdr[H_NTE];
-                    for (t = 0; t < n_te; t++)
-                        if (s.te_key[t] == tid) break;
-                    if (t == n_te) {
-                        s.hdr[H_FAULT] |= ZRK_FAULT_KEY_ERROR_CCP107;
-                        s.hdr[H_FAULT_TICK] = tick;
-                        break;
+                    // check_if_missiles_launched + add_missile (CCP.py:161-169, :102-109)
+                    const int n_ln = hdr[H_LN];
+                    int *me_key = ZRK_COLD_I(me_key);
+                    for (int i = 0; i < n_ln; i++) {
+                        const int m = ZRK_COLD_I(ln_m)[i], m_id = c_m_id[m], tid = H.sid()[m_target[m]];
+                        int e, n_me = hdr[H_NME];
+                        for (e = 0; e < n_me; e++)
+                            if (me_key[e] == m_id) break;
+                        if (e == n_me) hdr[H_NME] = n_me + 1;
+                        me_key[e] = m_id;
+                        ZRK_COLD_I(me_ref)[e] = ZRK_COLD_I(m_slot)[m];
+                        ZRK_COLD_I(me_upd)[e] = tick;
+                        ZRK_COLD_I(me_tid)[e] = tid;
+                        H.own()[ZRK_COLD_I(m_slot)[m]] = TEAM + e;
+                        int t, n_te = hdr[H_NTE];
+                        for (t = 0; t < n_te; t++)
+                            if (H.te_key()[t] == tid) break;
+                        if (t == n_te) {
+                            hdr[H_FAULT] |= ZRK_FAULT_KEY_ERROR_CCP107;
+                            hdr[H_FAULT_TICK] = tick;
+                            break;
+                        }
+                        H.te_mid()[t] = m_id;
                     }
-                    s.te_mid[t] = m_id;
                 }
+                hdr[H_NREC] = nr;
             }
+            tm.sync();
+            nrec = hdr[H_NREC];
         }
-        tm.sync();
 
         // ============ CombatControlPoint.step, detections (CCP.py:406-429)
-        if (has_ccp && !(s.hdr[H_FAULT] & 63)) {
+        if (has_ccp && !(hdr[H_FAULT] & 63)) {
+            int n_te = hdr[H_NTE];
+            const int n_me = hdr[H_NME];
+            // what link_object measures to, per entry: prev_pos of the tracked object (or pos
+            // for a missile whose prev_pos is None) and d_t = now - upd_time
+            if (lane < n_te) {
+                const int ref = H.te_ref()[lane], upd = H.te_upd()[lane];
+                const double2 a = H.qxy()[ref], c = H.qzw()[ref];
+                lxy[lane] = make_double2(upd == tick ? ZRK_FAR : a.x, a.y);
+                lzd[lane] = make_double2(c.x, now_s - to_seconds((long long)upd * P.dt_ms));
+            }
+            if (lane < n_me) {
+                const int ref = ZRK_COLD_I(me_ref)[lane], upd = ZRK_COLD_I(me_upd)[lane];
+                const bool hp = (H.sflags()[ref] & F_HASPREV) != 0;
+                const double2 a = hp ? H.qxy()[ref] : H.pxy()[ref];
+                const double cz = hp ? H.qzw()[ref].x : H.pzs()[ref].x;
+                lxy[TEAM + lane] = make_double2(upd == tick ? ZRK_FAR : a.x, a.y);
+                lzd[TEAM + lane] = make_double2(cz, now_s - to_seconds((long long)upd * P.dt_ms));
+            }
             // processing order: FOUND_OBJECTS messages in radar order, objects in list order,
             // each id once -> (first radar that saw it, slot)
             int n_det = 0, myrank = -1;
             for (int r = 0; r < nR; r++) {
                 int tot;
-                int ex = tm.scan(rf == r ? 1 : 0, tot);
+                const int ex = tm.rank(rf == r, tot);
                 if (rf == r) myrank = n_det + ex;
                 n_det += tot;
             }
-            if (myrank >= 0) s.x_detlist[myrank] = lane;
+            int *detlist = (int *)(sm + o.x_detlist);
+            if (myrank >= 0) detlist[myrank] = lane;
             tm.sync();
             const int i = lane;
-            int slot = 0, did = 0, radar_id = 0;
+            int slot = 0, did = 0, radar_id = 0, seed = -1;
             double dpx = 0, dpy = 0, dpz = 0, dspeed = 0;
             bool unresolved = i < n_det;
             if (unresolved) {
-                slot = s.x_detlist[i];
-                did = s.sid[slot];
-                radar_id = s.c_rad_id[s.srf[slot]];
-                dpx = s.pos[0 * NSP + slot];
-                dpy = s.pos[1 * NSP + slot];
-                dpz = s.pos[2 * NSP + slot];
-                dspeed = s.speed[slot];
+                slot = detlist[i];
+                did = H.sid()[slot];
+                radar_id = ZRK_CST_I(c_rad_id)[H.srf()[slot]];
+                const double2 a = H.pxy()[slot], c = H.pzs()[slot];
+                dpx = a.x;
+                dpy = a.y;
+                dpz = c.x;
+                dspeed = c.y;
+                seed = H.own()[slot];
+                if (seed >= 0 && (seed >= TEAM ? seed - TEAM >= n_me : seed >= n_te)) seed = -1;
             }
             int lo_rank = 0;
             for (;;) {
@@ -799,53 +812,64 @@ __global__ void __launch_bounds__(TEAM *TPC) zrk_tick_kernel(const Params P, int
                 if (unresolved) {
                     if (FAST) {
                         bool unsure;
-                        link_fast(s, P, NSP, tick, now_s, dpx, dpy, dpz, dspeed, cls, cand, unsure);
-                        if (unsure) link_exact(s, P, NSP, tick, now_s, dpx, dpy, dpz, dspeed, cls, cand);
+                        link_fast<TEAM>(lxy, lzd, n_te, n_me, seed, P, dpx, dpy, dpz, dspeed, cls, cand, unsure);
+                        if (unsure) link_exact<TEAM>(lxy, lzd, n_te, n_me, P, dpx, dpy, dpz, dspeed, cls, cand);
                     } else {
-                        link_exact(s, P, NSP, tick, now_s, dpx, dpy, dpz, dspeed, cls, cand);
+                        link_exact<TEAM>(lxy, lzd, n_te, n_me, P, dpx, dpy, dpz, dspeed, cls, cand);
                     }
                     if (cls == 1)
                         claim = cand;
                     else if (cls == 2)
-                        claim = NSP + cand;
+                        claim = TEAM + cand;
                     else {  // add_target overwrites an existing key in place (CCP.py:92)
-                        const int n_te = s.hdr[H_NTE];
+                        const int *te_key = H.te_key();
                         for (int e = 0; e < n_te; e++)
-                            if (s.te_key[e] == did) {
+                            if (te_key[e] == did) {
                                 claim = e;
                                 break;
                             }
                     }
                 }
                 // a detection is final once no earlier unresolved detection touches the same entry
-                for (int x = lane; x < NSP + MP; x += TEAM) s.x_claim[x] = ZRK_IMAX;
-                tm.sync();
-                if (unresolved && claim >= 0) atomicMin(&s.x_claim[claim], i);
-                tm.sync();
-                const bool conflict = unresolved && claim >= 0 && s.x_claim[claim] != i;
+                bool conflict;
+                if (TEAM == 32) {
+                    const unsigned same = __match_any_sync(ZRK_FULL, unresolved ? claim : -2 - lane);
+                    conflict = unresolved && claim >= 0 && (same & ((1u << lane) - 1u)) != 0;
+                } else {
+                    int *x_claim = (int *)(sm + o.x_claim);
+                    for (int x = lane; x < TEAM + MP; x += TEAM) x_claim[x] = ZRK_IMAX;
+                    tm.sync();
+                    if (unresolved && claim >= 0) atomicMin(&x_claim[claim], i);
+                    tm.sync();
+                    conflict = unresolved && claim >= 0 && x_claim[claim] != i;
+                }
                 const int istar = tm.min(conflict ? i : ZRK_IMAX);
                 const bool fin = unresolved && i < istar;
 
-                const int following = (fin && cls == 1) ? s.te_follow[cand] : 0;
-                const int old_mid = (fin && cls == 1) ? s.te_mid[cand] : ZRK_NONE;
+                const int following = (fin && cls == 1) ? H.te_follow()[cand] : 0;
+                const int old_mid = (fin && cls == 1) ? H.te_mid()[cand] : ZRK_NONE;
                 const bool need = fin && (cls == 0 || (cls == 1 && !following));
                 int ok = 0;
                 bool anycap = false;
-                for (int c = 0; c < nC; c++) anycap = anycap || (s.launched[c] < s.cap[c]);
+                for (int c = 0; c < nC; c++) anycap = anycap || (ZRK_COLD_I(launched)[c] < ZRK_COLD_I(cap)[c]);
                 if (anycap && tm.any(need)) {  // try_to_launch_missile (CCP.py:287-320), in order
-                    if (i < NSP) s.x_need[i] = need;
+                    int *x_need = (int *)(sm + o.x_need), *x_ok = (int *)(sm + o.x_ok);
+                    x_need[i] = need;
                     tm.sync();
                     if (lane == 0) {
                         const int hi_rank = istar < n_det ? istar : n_det;
+                        int *launched = ZRK_COLD_I(launched);
+                        const int *cap = ZRK_COLD_I(cap);
+                        const double *c_cl_pos = ZRK_CST_D(c_cl_pos);
                         for (int j = lo_rank; j < hi_rank; j++) {
-                            if (!s.x_need[j]) continue;
-                            const int sl = s.x_detlist[j];
-                            double ox = s.pos[0 * NSP + sl], oy = s.pos[1 * NSP + sl], oz = s.pos[2 * NSP + sl];
+                            if (!x_need[j]) continue;
+                            const int sl = detlist[j];
+                            double ox = H.pxy()[sl].x, oy = H.pxy()[sl].y, oz = H.pzs()[sl].x;
                             double min_dist = INFINITY;
                             int best = -1;
                             for (int c = 0; c < nC; c++) {
-                                if (s.launched[c] < s.cap[c]) {
-                                    double q0 = s.c_cl_pos[3 * c] - ox, q1 = s.c_cl_pos[3 * c + 1] - oy, q2 = s.c_cl_pos[3 * c + 2] - oz;
+                                if (launched[c] < cap[c]) {
+                                    double q0 = c_cl_pos[3 * c] - ox, q1 = c_cl_pos[3 * c + 1] - oy, q2 = c_cl_pos[3 * c + 2] - oz;
                                     double dist = sqrt((q0 * q0 + q1 * q1) + q2 * q2);
                                     if (dist < min_dist) {
                                         best = c;
@@ -853,18 +877,18 @@ __global__ void __launch_bounds__(TEAM *TPC) zrk_tick_kernel(const Params P, int
                                     }
                                 }
                             }
-                            s.x_ok[j] = best + 1;
+                            x_ok[j] = best + 1;
                             if (best >= 0) {
-                                s.launched[best]++;
-                                const int q = s.hdr[H_MBN0 + par]++;
-                                s.mb_type[par * Q + q] = MB_COMMAND;
-                                s.mb_l[par * Q + q] = s.c_cl_launcher[best];
-                                s.mb_a[par * Q + q] = sl;
+                                launched[best]++;
+                                const int q = hdr[H_MBN0 + par]++;
+                                ZRK_COLD_I(mb_type)[par * Q + q] = MB_COMMAND;
+                                ZRK_COLD_I(mb_l)[par * Q + q] = ZRK_CST_I(c_cl_launcher)[best];
+                                ZRK_COLD_I(mb_a)[par * Q + q] = sl;
                             }
                         }
                     }
                     tm.sync();
-                    if (need) ok = s.x_ok[i];
+                    if (need) ok = x_ok[i];
                 }
                 // one message per finalised detection at most
                 int mtype = -1;
@@ -876,96 +900,102 @@ __global__ void __launch_bounds__(TEAM *TPC) zrk_tick_kernel(const Params P, int
                 }
                 const bool wr = mtype >= 0 && logged(P, mtype);
                 const bool app = fin && cls == 0 && claim < 0;
-                int ptot, ctot;
-                const int pex = tm.scan((wr ? 1 : 0) | ((app ? 1 : 0) << 16), ptot);
-                (void)tm.scan((mtype == ZRK_MSG_CCP_UPDATE_TARGET ? 1 : 0) | ((mtype == ZRK_MSG_LAUNCH_COMMAND ? 1 : 0) << 16), ctot);
-                const int rbase = s.hdr[H_NREC], n_te0 = s.hdr[H_NTE];
+                int n_wr = 0, n_app, n_cmd, n_upd;
+                int r_wr = 0;
+                const int r_app = tm.rank(app, n_app);
+                (void)tm.rank(mtype == ZRK_MSG_LAUNCH_COMMAND, n_cmd);
+                (void)tm.rank(mtype == ZRK_MSG_CCP_UPDATE_TARGET, n_upd);
+                if (P.log_types & (ZRK_TYPE_BIT(ZRK_MSG_LAUNCH_COMMAND) | ZRK_TYPE_BIT(ZRK_MSG_CCP_UPDATE_TARGET)))
+                    r_wr = tm.rank(wr, n_wr);
                 if (wr) {
                     if (mtype == ZRK_MSG_LAUNCH_COMMAND)
-                        put_rec(P, rec, rbase + (pex & 0xffff), tick, mtype, 0, ccp_id, s.c_cl_id[ok - 1], did, radar_id, dpx, dpy, dpz);
+                        put_rec(P, rec, nrec + r_wr, tick, mtype, 0, ccp_id, ZRK_CST_I(c_cl_id)[ok - 1], did, radar_id, dpx, dpy, dpz);
                     else
-                        put_rec(P, rec, rbase + (pex & 0xffff), tick, mtype, 0, ccp_id, radar_id, did, old_mid, 0, 0, 0);
+                        put_rec(P, rec, nrec + r_wr, tick, mtype, 0, ccp_id, radar_id, did, old_mid, 0, 0, 0);
                 }
                 if (fin) {
                     if (cls == 1) {  // old_target (CCP.py:332-359)
-                        s.te_ref[cand] = slot;
-                        s.te_upd[cand] = tick;
-                        if (!following) s.te_follow[cand] = ok != 0;
+                        H.te_ref()[cand] = slot;
+                        H.te_upd()[cand] = tick;
+                        if (!following) H.te_follow()[cand] = ok != 0;
+                        H.own()[slot] = cand;
+                        lxy[cand].x = ZRK_FAR;
                     } else if (cls == 2) {  // old_rocket (CCP.py:361-366)
-                        s.me_ref[cand] = slot;
-                        s.me_upd[cand] = tick;
+                        ZRK_COLD_I(me_ref)[cand] = slot;
+                        ZRK_COLD_I(me_upd)[cand] = tick;
+                        H.own()[slot] = TEAM + cand;
+                        lxy[TEAM + cand].x = ZRK_FAR;
                     } else {  // new_target + add_target (CCP.py:322-330, :88-93)
-                        const int e = claim >= 0 ? claim : n_te0 + (pex >> 16);
-                        s.te_key[e] = did;
-                        s.te_ref[e] = slot;
-                        s.te_upd[e] = tick;
-                        s.te_follow[e] = ok != 0;
-                        s.te_mid[e] = ZRK_NONE;
+                        const int e = claim >= 0 ? claim : n_te + r_app;
+                        H.te_key()[e] = did;
+                        H.te_ref()[e] = slot;
+                        H.te_upd()[e] = tick;
+                        H.te_follow()[e] = ok != 0;
+                        H.te_mid()[e] = ZRK_NONE;
+                        H.own()[slot] = e;
+                        lxy[e].x = ZRK_FAR;
                     }
                     unresolved = false;
                 }
-                tm.sync();
+                nrec += n_wr;
+                n_te += n_app;
                 if (lane == 0) {
-                    s.hdr[H_NREC] = rbase + (ptot & 0xffff);
-                    s.hdr[H_NTE] = n_te0 + (ptot >> 16);
-                    s.counts[ZRK_MSG_LAUNCH_COMMAND] += (unsigned)(ctot >> 16);
-                    s.counts[ZRK_MSG_CCP_UPDATE_TARGET] += (unsigned)(ctot & 0xffff);
+                    H.counts()[ZRK_MSG_LAUNCH_COMMAND] += (unsigned)n_cmd;
+                    H.counts()[ZRK_MSG_CCP_UPDATE_TARGET] += (unsigned)n_upd;
                 }
-                tm.sync();
                 if (istar == ZRK_IMAX) break;
                 lo_rank = istar;
+                tm.sync();  // entry updates of this round are visible to the next
             }
+            tm.sync();
 
             // ============ send_objects_to_GUI (CCP.py:237-284)
             {
-                const int n_me = s.hdr[H_NME], n_te = s.hdr[H_NTE];
                 const bool ldr = logged(P, ZRK_MSG_DRAW_OBJECTS);
                 int mref = -1, tref = -1;
                 bool dm = false, dt = false, bad = false;
                 if (lane < n_me) {
-                    mref = s.me_ref[lane];
-                    dm = s.srf[mref] >= 0;
+                    mref = ZRK_COLD_I(me_ref)[lane];
+                    dm = H.srf()[mref] >= 0;
                 }
                 if (lane < n_te) {
-                    tref = s.te_ref[lane];
-                    dt = s.srf[tref] >= 0;
-                    bad = dt && (s.sflags[tref] & F_MISSILE);  // .type on a Missile (CCP.py:259)
+                    tref = H.te_ref()[lane];
+                    dt = H.srf()[tref] >= 0;
+                    bad = dt && (H.sflags()[tref] & F_MISSILE);  // .type on a Missile (CCP.py:259)
                 }
-                const int efault = tm.min(bad ? lane : ZRK_IMAX);
+                const int efault = tm.any(bad) ? tm.min(bad ? lane : ZRK_IMAX) : ZRK_IMAX;
                 dt = dt && lane < efault;
                 const bool dother = efault == ZRK_IMAX && alive && rf < 0 && nR > 0;
                 int tot_m, tot_t, tot_o;
-                int ex_m = tm.scan(dm ? 1 : 0, tot_m);
-                int ex_t = tm.scan(dt ? 1 : 0, tot_t);
-                int ex_o = tm.scan(dother ? 1 : 0, tot_o);
-                const int rbase = s.hdr[H_NREC];
+                const int ex_m = tm.rank(dm, tot_m);
+                const int ex_t = tm.rank(dt, tot_t);
+                const int ex_o = tm.rank(dother, tot_o);
                 if (ldr) {
                     if (dm)
-                        put_rec(P, rec, rbase + ex_m, tick, ZRK_MSG_DRAW_OBJECTS, 1, ccp_id, ZRK_MANAGER_ID, s.sid[mref], ZRK_ZUR,
-                                s.pos[0 * NSP + mref], s.pos[1 * NSP + mref], s.pos[2 * NSP + mref]);
+                        put_rec(P, rec, nrec + ex_m, tick, ZRK_MSG_DRAW_OBJECTS, 1, ccp_id, ZRK_MANAGER_ID, H.sid()[mref], ZRK_ZUR,
+                                H.pxy()[mref].x, H.pxy()[mref].y, H.pzs()[mref].x);
                     if (dt)
-                        put_rec(P, rec, rbase + tot_m + ex_t, tick, ZRK_MSG_DRAW_OBJECTS, 1, ccp_id, ZRK_MANAGER_ID, s.sid[tref],
-                                (s.sflags[tref] >> F_TTYPE_SHIFT) & 3, s.pos[0 * NSP + tref], s.pos[1 * NSP + tref],
-                                s.pos[2 * NSP + tref]);
+                        put_rec(P, rec, nrec + tot_m + ex_t, tick, ZRK_MSG_DRAW_OBJECTS, 1, ccp_id, ZRK_MANAGER_ID, H.sid()[tref],
+                                (H.sflags()[tref] >> F_TTYPE_SHIFT) & 3, H.pxy()[tref].x, H.pxy()[tref].y, H.pzs()[tref].x);
                     if (dother)
-                        put_rec(P, rec, rbase + tot_m + tot_t + ex_o, tick, ZRK_MSG_DRAW_OBJECTS, 0, ccp_id, ZRK_MANAGER_ID, my_id,
+                        put_rec(P, rec, nrec + tot_m + tot_t + ex_o, tick, ZRK_MSG_DRAW_OBJECTS, 0, ccp_id, ZRK_MANAGER_ID, my_id,
                                 (fl & F_MISSILE) ? ZRK_ZUR : ((fl >> F_TTYPE_SHIFT) & 3), px, py, pz);
+                    nrec += tot_m + tot_t + tot_o;
                 }
-                tm.sync();
                 if (lane == 0) {
-                    if (ldr) s.hdr[H_NREC] = rbase + tot_m + tot_t + tot_o;
-                    s.counts[ZRK_MSG_DRAW_OBJECTS] += (unsigned)(tot_m + tot_t + tot_o);
+                    hdr[H_NTE] = n_te;
+                    H.counts()[ZRK_MSG_DRAW_OBJECTS] += (unsigned)(tot_m + tot_t + tot_o);
                     if (efault != ZRK_IMAX) {
-                        s.hdr[H_FAULT] |= ZRK_FAULT_ATTRIBUTE_ERROR_CCP259;
-                        s.hdr[H_FAULT_TICK] = tick;
+                        hdr[H_FAULT] |= ZRK_FAULT_ATTRIBUTE_ERROR_CCP259;
+                        hdr[H_FAULT_TICK] = tick;
                     }
                 }
             }
         }
-        tm.sync();
         if (lane == 0) {
-            if (s.hdr[H_NREC] > P.log_cap) s.hdr[H_FAULT] |= ZRK_FAULT_LOG_OVERFLOW;
-            if (!(s.hdr[H_FAULT] & 63)) s.hdr[H_TICK] = tick + 1;
+            hdr[H_NREC] = nrec;
+            if (nrec > P.log_cap) hdr[H_FAULT] |= ZRK_FAULT_LOG_OVERFLOW;
+            if (!(hdr[H_FAULT] & 63)) hdr[H_TICK] = tick + 1;
         }
         tm.sync();
     }

@@ -53,12 +53,14 @@ def make_batch(name, rank, pinned=False):
     from zrk_modulation_b200 import synthetic_batch
     B, T, R, L, mpl, ticks = WORKLOADS[name]
     b = synthetic_batch(B, T, n_radars=R, n_launchers=L, missiles_per_launcher=mpl, seed0=rank * B)
-    if pinned:
+    if pinned:  # page-locked host buffers: the H2D copies of zrk_create run at full PCIe rate
         import torch
-        for f in ("target_pos", "target_vel", "target_id", "target_type"):
-            t = torch.from_numpy(getattr(b, f)).pin_memory()
-            setattr(b, f, t.numpy())
-            b._keep.append(t)
+        b._pins = []
+        for f, v in list(vars(b).items()):
+            if isinstance(v, np.ndarray) and v.size and f != "durations":
+                t = torch.from_numpy(np.ascontiguousarray(v)).pin_memory()
+                setattr(b, f, t.numpy())
+                b._pins.append(t)
     return b, ticks
 
 
@@ -211,10 +213,13 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         t0 = time.perf_counter()
         eng = Engine(batch, device=dev, ticks_per_launch=args.ticks_per_launch)
+        ta = time.perf_counter()
         eng.step(ticks)
         c2 = eng.counts()  # per-scenario message counters + status: the step's result
         torch.cuda.synchronize()
         t1 = time.perf_counter()
+        if args.verbose and rank == 0:
+            print(f"e2e step {i}: create {1e3 * (ta - t0):.1f} ms, step+read {1e3 * (t1 - ta):.1f} ms", file=sys.stderr)
         barrier()
         eng.close()
         if i >= args.warmup:
@@ -278,6 +283,7 @@ def main():
     ap.add_argument("--ticks", type=int, default=0)
     ap.add_argument("--ticks-per-launch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

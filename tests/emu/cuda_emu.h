@@ -22,7 +22,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
 #define __align__(x) alignas(x)
 
 struct uint4 {
@@ -148,6 +148,7 @@ inline int atomicOr(int *p, int v) {
     return o;
 }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline float __fdividef(float a, float b) { return a / b; }
 inline int __reduce_min_sync(unsigned, int v) {
     zrk_emu::Warp &w = zrk_emu::my_warp();
     w.vals[zrk_emu::my_lane()] = (uint64_t)(int64_t)v;

@@ -13,7 +13,7 @@ struct ZrkEmuEvent {
 typedef ZrkEmuEvent *cudaEvent_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
-enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
 enum { cudaStreamNonBlocking = 1 };
 
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
@@ -38,6 +38,12 @@ inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b)
     *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
     return cudaSuccess;
 }
+typedef int cudaMemPool_t;
+enum { cudaMemPoolAttrReleaseThreshold = 4 };
+inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t *p, int) { *p = 0; return cudaSuccess; }
+inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, int, void *) { return cudaSuccess; }
+inline cudaError_t cudaMallocAsync(void **p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
+inline cudaError_t cudaFreeAsync(void *p, cudaStream_t) { return cudaFree(p); }
 template <typename F>
 inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 #endif

@@ -132,6 +132,8 @@ LIB_NAME = "libzrk_b200.so"
 
 
 def lib_path() -> str:
+    if os.environ.get("ZRK_B200_LIB"):  # development: A/B a differently tuned build of the same sources
+        return os.environ["ZRK_B200_LIB"]
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", LIB_NAME)
 
 

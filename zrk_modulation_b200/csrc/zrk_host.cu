@@ -104,6 +104,14 @@ __global__ void zrk_init_kernel(const Params P, const DevDesc d, int *err) {
         c_rad_par[RAD_PAR_STRIDE * r + 9] = md >= 0 ? md2 * (1.0 + 1e-14) : -1.0;
         rad_cur[2 * r] = d.radar_par[8 * g + 0];
         rad_cur[2 * r + 1] = d.radar_par[8 * g + 1];
+        // a start sector that the sweep maps onto itself stays there forever: skip the sweep
+        double caz = rad_cur[2 * r], cel = rad_cur[2 * r + 1];
+        radar_move(c_rad_par + RAD_PAR_STRIDE * r, caz, cel);
+        const bool fixed = caz == rad_cur[2 * r] && cel == rad_cur[2 * r + 1] &&
+                           !(caz == 0.0 && signbit(caz) != signbit(rad_cur[2 * r])) &&
+                           !(cel == 0.0 && signbit(cel) != signbit(rad_cur[2 * r + 1]));
+        c_rad_par[RAD_PAR_STRIDE * r + 10] = fixed ? 1.0 : 0.0;
+        c_rad_par[RAD_PAR_STRIDE * r + 11] = 0.0;
     }
     int *c_l_id = (int *)(cs + o.c_l_id);
     double *c_l_pos = (double *)(cs + o.c_l_pos);
@@ -194,6 +202,8 @@ struct zrk_handle {
     std::vector<int> h_radar_id, h_n_radars, h_airenv_id;
     int *d_summary = nullptr;
     std::vector<int> h_summary;
+    double *d_tsec = nullptr;
+    Params *d_self = nullptr;
 };
 
 static thread_local std::string g_create_err;
@@ -207,13 +217,29 @@ static thread_local std::string g_create_err;
         }                                                                                \
     } while (0)
 
+// Stream-ordered allocations from the device's default memory pool, which is told to keep
+// freed memory: creating and destroying handles in a loop then costs no cudaMalloc/cudaFree.
+static int pool_alloc(zrk_handle *h, void **p, size_t bytes) {
+    static thread_local int pool_ready_dev = -1;
+    if (pool_ready_dev != h->device) {
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, h->device));
+        unsigned long long keep = ~0ull;
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        pool_ready_dev = h->device;
+    }
+    CK(cudaMallocAsync(p, bytes ? bytes : 1, h->stream));
+    h->allocs.push_back(*p);
+    return ZRK_OK;
+}
+
 template <typename T>
 static int dev_upload(zrk_handle *h, const T *src, size_t n, const T **dst) {
     *dst = nullptr;
     if (!src || !n) return ZRK_OK;
     void *p = nullptr;
-    CK(cudaMalloc(&p, n * sizeof(T)));
-    h->allocs.push_back(p);
+    int rc = pool_alloc(h, &p, n * sizeof(T));
+    if (rc) return rc;
     CK(cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
     *dst = (const T *)p;
     return ZRK_OK;
@@ -221,8 +247,8 @@ static int dev_upload(zrk_handle *h, const T *src, size_t n, const T **dst) {
 template <typename T>
 static int dev_alloc(zrk_handle *h, size_t n, T **dst, bool zero) {
     void *p = nullptr;
-    CK(cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
-    h->allocs.push_back(p);
+    int rc = pool_alloc(h, &p, (n ? n : 1) * sizeof(T));
+    if (rc) return rc;
     if (zero) CK(cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), h->stream));
     *dst = (T *)p;
     return ZRK_OK;
@@ -259,9 +285,43 @@ extern "C" void zrk_destroy(zrk_handle *h) {
         cudaEventDestroy(pr.second);
     }
     for (auto e : h->free_events) cudaEventDestroy(e);
-    for (void *p : h->allocs) cudaFree(p);
+    for (void *p : h->allocs) cudaFreeAsync(p, h->stream);
+    cudaStreamSynchronize(h->stream);
     cudaStreamDestroy(h->stream);
     delete h;
+}
+
+// keep the device copy of Params (Params::self) current
+static int push_params(zrk_handle *h) {
+    if (!h->d_self) {
+        void *q = nullptr;
+        int rc = pool_alloc(h, &q, sizeof(Params));
+        if (rc) return rc;
+        h->d_self = (Params *)q;
+        h->P.self = h->d_self;
+    }
+    CK(cudaMemcpyAsync(h->d_self, &h->P, sizeof(Params), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return ZRK_OK;
+}
+
+// tsec[t] = to_seconds(t * dt): the same int / 1000 the reference evaluates (AirObject.py:5-7)
+static int ensure_tsec(zrk_handle *h, long long upto) {
+    if (upto <= h->P.tsec_n) return ZRK_OK;
+    long long n = h->P.tsec_n ? h->P.tsec_n : 1024;
+    while (n < upto) n *= 2;
+    if (n > (1 << 26)) return ZRK_OK;  // beyond the table the kernel divides
+    std::vector<double> t((size_t)n);
+    for (long long i = 0; i < n; i++) t[(size_t)i] = (double)(i * h->P.dt_ms) / 1000.0;
+    void *q = nullptr;
+    int rc = pool_alloc(h, &q, (size_t)n * sizeof(double));  // earlier, shorter tables stay alive until destroy
+    if (rc) return rc;
+    double *p = (double *)q;
+    CK(cudaMemcpyAsync(p, t.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->P.tsec = p;
+    h->P.tsec_n = (int)n;
+    return push_params(h);
 }
 
 static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options *opt) {
@@ -362,7 +422,7 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
     CK(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     // the uploaded description is no longer needed on the device
-    for (size_t i = 0; i < n_desc_allocs; i++) cudaFree(h->allocs[i]);
+    for (size_t i = 0; i < n_desc_allocs; i++) cudaFreeAsync(h->allocs[i], h->stream);
     h->allocs.erase(h->allocs.begin(), h->allocs.begin() + n_desc_allocs);
     if (herr & 1) {
         h->err = "per-scenario count exceeds the batch maximum, or missile_launcher out of range";
@@ -389,7 +449,8 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
     }
     tick_fn fn = pick_kernel(lo.team, h->fast);
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    return ZRK_OK;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    return ensure_tsec(h, 1024);
 }
 
 extern "C" int zrk_create(const zrk_batch_desc *desc, const zrk_options *opt, zrk_handle **out) {
@@ -437,6 +498,10 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
     tick_fn fn = pick_kernel(h->P.lo.team, h->fast);
     if (h->pending.size() > 4096) {
         int rc = resolve_events(h);
+        if (rc) return rc;
+    }
+    {
+        int rc = ensure_tsec(h, h->tick + n_ticks + 1);
         if (rc) return rc;
     }
     int left = n_ticks;

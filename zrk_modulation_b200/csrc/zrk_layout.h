@@ -23,11 +23,11 @@ enum { F_ALIVE = 1, F_PENDING = 2, F_HASPREV = 4, F_MISSILE = 8, F_TTYPE_SHIFT =
 // header words (ints) at dyn.hdr
 enum {
     H_TICK = 0, H_NSLOTS, H_NTE, H_NME, H_CCP_INIT, H_FAULT, H_FAULT_TICK, H_NREC,
-    H_DETN0, H_DETN1, H_MBN0, H_MBN1, H_LN, H_FLAGS, H_TMP0, H_TMP1, H_WORDS = 16
+    H_DETN0, H_DETN1, H_MBN0, H_MBN1, H_LN, H_FREECAP, H_TMP0, H_TMP1, H_WORDS = 16
 };
 enum { MB_COMMAND = 0, MB_SUCCESS = 1, MB_CANCEL = 2, MB_COUNTREQ = 3 };
 enum { ST_READY = 0, ST_ACTIVE = 1, ST_DETONATED = 2 };
-enum { RAD_PAR_STRIDE = 10 };  // radar_par[8] + max_distance^2 bracket (lo, hi)
+enum { RAD_PAR_STRIDE = 12 };  // radar_par[8] + max_distance^2 bracket (lo, hi) + [10] 1.0 if the sector never moves
 // cst header words
 enum { C_NT = 0, C_NR, C_NL, C_NM, C_NC, C_AIRENV_ID, C_CCP_ID, C_TICK_LIMIT, C_WORDS = 8 };
 
@@ -106,6 +106,9 @@ struct Params {
     zrk_msg *rec;
     unsigned *masks;
     const double *noise;
+    const double *tsec;  // tsec[t] = to_seconds(t * dt_ms) for t < tsec_n
+    int tsec_n;
+    const Params *self;  // this struct in device global memory (for out-of-line device functions)
 };
 
 static inline int zrk_align(int x, int a) { return (x + a - 1) / a * a; }

@@ -58,6 +58,10 @@ __device__ __forceinline__ double pymod(double a, double m) {
     return r;
 }
 __device__ __forceinline__ double to_seconds(long long ms) { return (double)ms / 1000.0; }
+// to_seconds(tick * dt) from the table the host fills with exactly that expression
+__device__ __forceinline__ double tick_seconds(const Params &P, int tick) {
+    return (tick >= 0 && tick < P.tsec_n) ? P.tsec[tick] : to_seconds((long long)tick * P.dt_ms);
+}
 
 #define ZRK_RAD2DEG 57.29577951308232 /* 180.0 / pi, as np.degrees multiplies */
 
@@ -76,32 +80,71 @@ __device__ ZRK_NOINLINE bool radar_sees_exact(double dx, double dy, double dz, d
 // 0/360 and 0/180 wrap points of the `%`) is at least ANG_MARGIN away from equality and the
 // squared range is outside the bracket around max_distance^2.  Everything else (and every
 // NaN) goes to radar_sees_exact.
+// atan2 in degrees, |error| < 1e-3 degrees (Abramowitz-Stegun 4.4.49 polynomial, fp32).
+__device__ __forceinline__ float atan2_deg_approx(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = __fdividef(mn, mx);  // 0/0 -> NaN -> every comparison false -> exact path
+    const float q = a * a;
+    float r = ((((0.0208351f * q - 0.085133f) * q + 0.180141f) * q - 0.3302995f) * q + 0.999866f) * a;
+    if (ay > ax) r = 1.57079637f - r;
+    if (x < 0.f) r = 3.14159274f - r;
+    if (y < 0.f) r = -r;
+    return r * 57.29577951f;
+}
+
 template <bool FAST>
 __device__ __forceinline__ bool radar_sees(double dx, double dy, double dz, const double *par, double az_lo,
                                            double az_hi, double el_lo, double el_hi) {
     if (FAST) {
-        const float ANG_MARGIN = 4e-3f;
-        double d2 = dot3(dx, dy, dz, dx, dy, dz);
+        const float M = 1e-2f;  // decision margin in degrees, 10x the approximation error
+        const double d2 = dot3(dx, dy, dz, dx, dy, dz);
         if (d2 > par[9]) return false;  // certainly farther than max_distance
-        bool range_sure = d2 <= par[8];
-        float fx = (float)dx, fy = (float)dy, fz = (float)dz;
-        float az = atan2f(fy, fx) * 57.29577951f;
-        if (az < 0.f) az += 360.f;
-        float rho = sqrtf(fx * fx + fy * fy);
-        float el = atan2f(fz, rho) * 57.29577951f;  // == asin(dz / distance), well conditioned
-        if (el < 0.f) el += 180.f;
-        float a0 = (float)az_lo, a1 = (float)az_hi, e0 = (float)el_lo, e1 = (float)el_hi;
-        bool wrap_far = az > ANG_MARGIN && az < 360.f - ANG_MARGIN && el > ANG_MARGIN && el < 180.f - ANG_MARGIN;
-        bool in_sure = az > a0 + ANG_MARGIN && az < a1 - ANG_MARGIN && el > e0 + ANG_MARGIN && el < e1 - ANG_MARGIN;
-        bool out_sure = az < a0 - ANG_MARGIN || az > a1 + ANG_MARGIN || el < e0 - ANG_MARGIN || el > e1 + ANG_MARGIN;
-        // thresholds themselves must be representable well enough in fp32: |x| <= 1e4 degrees
-        bool thr_ok = fabsf(a0) < 1e4f && fabsf(a1) < 1e4f && fabsf(e0) < 1e4f && fabsf(e1) < 1e4f;
-        if (wrap_far && thr_ok) {
-            if (out_sure) return false;
-            if (in_sure && range_sure) return true;
+        bool sure_in = d2 <= par[8], sure_out = false, ok = true;
+        const float fx = (float)dx, fy = (float)dy, fz = (float)dz;
+        // azimuth % 360 lies in [0, 360]: a sector covering all of it needs no angle at all
+        if (!(az_lo <= 0.0 && az_hi >= 360.0)) {
+            float az = atan2_deg_approx(fy, fx);
+            if (az < 0.f) az += 360.f;
+            const float a0 = (float)az_lo, a1 = (float)az_hi;
+            ok = ok && az > M && az < 360.f - M && fabsf(a0) < 1e4f && fabsf(a1) < 1e4f;  // away from the % wrap
+            sure_in = sure_in && az > a0 + M && az < a1 - M;
+            sure_out = sure_out || az < a0 - M || az > a1 + M;
+        }
+        if (!(el_lo <= 0.0 && el_hi >= 180.0)) {
+            float el = atan2_deg_approx(fz, sqrtf(fx * fx + fy * fy));  // == asin(dz / distance), well conditioned
+            if (el < 0.f) el += 180.f;
+            const float e0 = (float)el_lo, e1 = (float)el_hi;
+            ok = ok && el > M && el < 180.f - M && fabsf(e0) < 1e4f && fabsf(e1) < 1e4f;
+            sure_in = sure_in && el > e0 + M && el < e1 - M;
+            sure_out = sure_out || el < e0 - M || el > e1 + M;
+        }
+        if (ok) {
+            if (sure_out) return false;
+            if (sure_in) return true;
         }
     }
     return radar_sees_exact(dx, dy, dz, par[2], az_lo, az_hi, el_lo, el_hi);
+}
+
+// SectorRadar.move_to_next_sector_circular (Radar.py:96-117); q = radar_par of the radar.
+__device__ __forceinline__ void radar_move(const double *q, double &caz, double &cel) {
+    const int mode = (int)q[7];
+    if (mode == ZRK_SCAN_HORIZONTAL) {
+        if (caz + q[3] < 360)
+            caz = pymod(caz + q[5], 360.0);
+        else
+            caz = q[1];  // sic: elevation_start (Radar.py:105)
+        if (caz < q[5]) {
+            if (cel + q[6] < 90)
+                cel = pymod(cel + q[6], 90.0);
+            else
+                cel = q[1];
+        }
+    } else if (mode == ZRK_SCAN_VERTICAL) {
+        cel = pymod(cel + q[6], 90.0);
+        if (cel < q[6]) caz = pymod(caz + q[5], 360.0);
+    }
 }
 
 // ------------------------------------------------------------------ team primitives
@@ -280,9 +323,9 @@ struct Hot {
 // ------------------------------------------------------------------ CCP.link_object
 
 // calc_range (CCP.py:176-188): d_t = cur_time - upd_time has been computed per entry.
-__device__ __forceinline__ void calc_range(double speed, double d_t, const Params &P, double &lo, double &hi) {
-    lo = speed * (d_t - P.range_step);
-    hi = speed * (d_t + P.range_step);
+__device__ __forceinline__ void calc_range(double speed, double d_t, double range_step, double &lo, double &hi) {
+    lo = speed * (d_t - range_step);
+    hi = speed * (d_t + range_step);
     lo = lo > 0 ? lo : 0;  // max(0, x)
     hi = hi > 0 ? hi : 0;
 }
@@ -294,7 +337,7 @@ __device__ __forceinline__ void calc_range(double speed, double d_t, const Param
 // _missile_dict; lxy/lzd hold, per entry, the position the reference measures to
 // (prev_pos, or pos for a missile whose prev_pos is None) and d_t.
 template <int TEAM>
-__device__ ZRK_NOINLINE void link_exact(const double2 *lxy, const double2 *lzd, int n_te, int n_me, const Params &P,
+__device__ ZRK_NOINLINE void link_exact(const double2 *lxy, const double2 *lzd, int n_te, int n_me, double range_step,
                                         double px, double py, double pz, double speed, int &cls, int &cand) {
     double curr = INFINITY;
     cls = 0;
@@ -307,7 +350,7 @@ __device__ ZRK_NOINLINE void link_exact(const double2 *lxy, const double2 *lzd, 
             double ex = a.x - px, ey = a.y - py, ez = c.x - pz;
             double diff = sqrt(dot3(ex, ey, ez, ex, ey, ez));
             double lo, hi;
-            calc_range(speed, c.y, P, lo, hi);
+            calc_range(speed, c.y, range_step, lo, hi);
             if (diff < curr && lo <= diff && diff <= hi) {
                 curr = diff;
                 cls = pass + 1;
@@ -328,14 +371,14 @@ struct LinkAcc {
 // "diff < curr" and "lo <= diff <= hi" are decided from d2 unless d2 is within a few ulps of
 // best / lo^2 / hi^2 (or NaN), which sets `unsure`.  Exact ties (d2 == best) go to the entry
 // that comes first in the reference's scan order.
-__device__ __forceinline__ void link_eval(LinkAcc &A, int ue, double ax, double d2, double d_t, double speed,
-                                          const Params &P) {
+__device__ __forceinline__ void link_eval(LinkAcc &A, int ue, double d2, double d_t, double speed, double range_step) {
     const double EPS = 4e-15;
-    if (ax >= ZRK_FAR) return;  // upd_time == now: skipped by the reference (CCP.py:196, 208)
     double lo, hi;
-    calc_range(speed, d_t, P, lo, hi);
+    calc_range(speed, d_t, range_step, lo, hi);
     const double l2 = lo * lo, h2 = hi * hi;
-    if (d2 > h2 * (1.0 + EPS) || d2 < l2 * (1.0 - EPS)) return;  // certainly outside [lo, hi]
+    // certainly outside [lo, hi]; also drops the entries link_object skips (upd_time == now),
+    // whose link position ZRK_FAR makes d2 infinite
+    if (d2 > h2 * (1.0 + EPS) || d2 < l2 * (1.0 - EPS)) return;
     const bool in_sure = d2 >= l2 * (1.0 + EPS) && d2 <= h2 * (1.0 - EPS);
     if (d2 > A.best) return;
     if (d2 == A.best) {
@@ -353,9 +396,16 @@ __device__ __forceinline__ void link_eval(LinkAcc &A, int ue, double ax, double 
     A.unsure = true;  // includes NaN: every comparison above was false
 }
 
+__device__ __forceinline__ double link_d2(const double2 *lxy, const double2 *lzd, int ue, double px, double py,
+                                          double pz) {
+    const double2 a = lxy[ue];
+    const double ex = a.x - px, ey = a.y - py, ez = lzd[ue].x - pz;
+    return dot3(ex, ey, ez, ex, ey, ez);
+}
+
 template <int TEAM>
 __device__ __forceinline__ void link_fast(const double2 *lxy, const double2 *lzd, int n_te, int n_me, int seed,
-                                          const Params &P, double px, double py, double pz, double speed, int &cls,
+                                          double range_step, double px, double py, double pz, double speed, int &cls,
                                           int &cand, bool &unsure) {
     LinkAcc A;
     A.best = INFINITY;
@@ -364,19 +414,30 @@ __device__ __forceinline__ void link_fast(const double2 *lxy, const double2 *lzd
     A.unsure = false;
     // Seed with the entry that tracked this slot last tick: it is almost always the nearest, and
     // with best = its d2 nearly every other pair fails the single compare below.
-    if (seed >= 0) {
-        const double2 a = lxy[seed], c = lzd[seed];
-        double ex = a.x - px, ey = a.y - py, ez = c.x - pz;
-        link_eval(A, seed, a.x, dot3(ex, ey, ez, ex, ey, ez), c.y, speed, P);
-    }
+    if (seed >= 0) link_eval(A, seed, link_d2(lxy, lzd, seed, px, py, pz), lzd[seed].y, speed, range_step);
     for (int pass = 0; pass < 2; pass++) {
         const int n = pass ? n_me : n_te, base = pass ? TEAM : 0;
-#pragma unroll 4
-        for (int e = 0; e < n; e++) {
-            const double2 a = lxy[base + e], c = lzd[base + e];
-            double ex = a.x - px, ey = a.y - py, ez = c.x - pz;
-            double d2 = dot3(ex, ey, ez, ex, ey, ez);
-            if (!(d2 > A.best) && base + e != seed) link_eval(A, base + e, a.x, d2, c.y, speed, P);
+        int e = 0;
+        // four pairs at a time; the common case is that none of them can beat the best
+        for (; e + 4 <= n; e += 4) {
+            const int u = base + e;
+            const double d0 = link_d2(lxy, lzd, u, px, py, pz), d1 = link_d2(lxy, lzd, u + 1, px, py, pz);
+            const double d2 = link_d2(lxy, lzd, u + 2, px, py, pz), d3 = link_d2(lxy, lzd, u + 3, px, py, pz);
+            const bool h = (!(d0 > A.best) && u != seed) || (!(d1 > A.best) && u + 1 != seed) ||
+                           (!(d2 > A.best) && u + 2 != seed) || (!(d3 > A.best) && u + 3 != seed);
+            if (h) {
+#pragma unroll 1
+                for (int k = 0; k < 4; k++) {
+                    const double dk = link_d2(lxy, lzd, u + k, px, py, pz);
+                    if (!(dk > A.best) && u + k != seed) link_eval(A, u + k, dk, lzd[u + k].y, speed, range_step);
+                }
+            }
+        }
+#pragma unroll 1
+        for (; e < n; e++) {
+            const int u = base + e;
+            const double dk = link_d2(lxy, lzd, u, px, py, pz);
+            if (!(dk > A.best) && u != seed) link_eval(A, u, dk, lzd[u].y, speed, range_step);
         }
     }
     unsure = A.unsure;
@@ -384,10 +445,175 @@ __device__ __forceinline__ void link_fast(const double2 *lxy, const double2 *lzd
     cand = A.ue < 0 ? -1 : (A.ue >= TEAM ? A.ue - TEAM : A.ue);
 }
 
+// ------------------------------------------------------------------ lane 0 alone: launchers + CCP bookkeeping
+
+// MissileLauncher.step for every launcher (MissileLauncher.py:82-138) and the CCP's first-tick
+// capacity requests / LAUNCHED_MISSILE intake (CCP.py:122-169).  Rare, serial, kept out of line.
+template <int TEAM>
+__device__ ZRK_NOINLINE int serial_section(const Params *Pg, unsigned char *sm, double *gtraj, zrk_msg *rec, int tick,
+                                           double now_s, int mb_prev, int nrec) {
+    const Params &P = *Pg;  // the copy in global memory: a by-reference kernel parameter would be spilled
+    const Layout &o = P.lo;
+    const int MP = o.MP, Q = o.Q, T = o.T;
+    Hot<TEAM> H;
+    H.sm = sm;
+    int *const hdr = H.hdr();
+    const int *chdr = ZRK_CST_I(c_hdr);
+    const int nL = chdr[C_NL], nC = chdr[C_NC], ccp_id = chdr[C_CCP_ID];
+    const bool has_ccp = ccp_id != ZRK_NONE;
+    const int par = tick & 1, prv = par ^ 1;
+    int nr = nrec;
+    {
+        int *mb_type = ZRK_COLD_I(mb_type), *mb_l = ZRK_COLD_I(mb_l), *mb_a = ZRK_COLD_I(mb_a);
+        int *st_n = ZRK_COLD_I(st_n), *st = ZRK_COLD_I(st);
+        const int *c_m_id = ZRK_CST_I(c_m_id), *c_l_id = ZRK_CST_I(c_l_id);
+        const double *c_l_pos = ZRK_CST_D(c_l_pos);
+        int *m_target = ZRK_COLD_I(m_target);
+        unsigned *counts = H.counts();
+        // MissileLauncher.step (MissileLauncher.py:82-138)
+        for (int l = 0; l < nL && mb_prev; l++) {
+            const int l_id = c_l_id[l];
+            for (int i = 0; i < mb_prev; i++) {
+                if (mb_l[prv * Q + i] != l) continue;
+                const int ty = mb_type[prv * Q + i], arg = mb_a[prv * Q + i];
+                if (ty == MB_COMMAND) {  // launch_missile (:58-80)
+                    if (st_n[l] == 0) continue;
+                    const int m = st[l * MP + (--st_n[l])];
+                    const int m_id = c_m_id[m], tg = arg;
+                    counts[ZRK_MSG_LAUNCH_MISSILE]++;
+                    if (logged(P, ZRK_MSG_LAUNCH_MISSILE))
+                        put_rec(P, rec, nr++, tick, ZRK_MSG_LAUNCH_MISSILE, 0, l_id, m_id, H.sid()[tg], ZRK_NONE, 0, 0, 0);
+                    // Missile._launch (Missile.py:104-133)
+                    double tp[3] = {H.pxy()[tg].x, H.pxy()[tg].y, H.pzs()[tg].x};
+                    double vt[3];
+                    if (H.sflags()[tg] & F_MISSILE) {
+                        vt[0] = vt[1] = vt[2] = NAN;  // Missile.velocity is 0/0 (AirObject.py:35)
+                    } else {
+                        double wx = ZRK_LDCG(&gtraj[4 * TEAM + tg]), wy = ZRK_LDCG(&gtraj[5 * TEAM + tg]),
+                               wz = ZRK_LDCG(&gtraj[6 * TEAM + tg]);
+                        double sp = H.pzs()[tg].y;
+                        vt[0] = wx / sp * sp;  // target.velocity * target.speed_mod (Missile.py:59)
+                        vt[1] = wy / sp * sp;
+                        vt[2] = wz / sp * sp;
+                    }
+                    double V[3];
+                    const double v0 = ZRK_CST_D(c_m_v0)[m];
+                    int why = missile_solve(&c_l_pos[3 * l], tp, vt, v0, ZRK_CST_D(c_m_v0sq)[m], ZRK_COLD_D(m_period)[m], V);
+                    const int q = hdr[H_MBN0 + par]++;
+                    mb_l[par * Q + q] = l;
+                    mb_a[par * Q + q] = m;
+                    if (why < 0) {
+                        const int k = hdr[H_NSLOTS]++;
+                        gtraj[0 * TEAM + k] = c_l_pos[3 * l];
+                        gtraj[1 * TEAM + k] = c_l_pos[3 * l + 1];
+                        gtraj[2 * TEAM + k] = c_l_pos[3 * l + 2];
+                        gtraj[3 * TEAM + k] = now_s;
+                        gtraj[4 * TEAM + k] = V[0];
+                        gtraj[5 * TEAM + k] = V[1];
+                        gtraj[6 * TEAM + k] = V[2];
+                        gtraj[7 * TEAM + k] = v0;
+                        H.pxy()[k] = make_double2(c_l_pos[3 * l], c_l_pos[3 * l + 1]);
+                        H.pzs()[k] = make_double2(c_l_pos[3 * l + 2], v0);
+                        H.sid()[k] = m_id;
+                        H.sflags()[k] = F_PENDING | F_MISSILE | ((T + m) << F_STATIC_SHIFT);
+                        H.srf()[k] = -1;
+                        H.own()[k] = -1;
+                        ZRK_COLD_I(m_status)[m] = ST_ACTIVE;
+                        m_target[m] = tg;
+                        ZRK_COLD_I(m_slot)[m] = k;
+                        ZRK_COLD_I(m_birth)[m] = tick + 2;
+                        mb_type[par * Q + q] = MB_SUCCESS;
+                        counts[ZRK_MSG_LAUNCH_SUCCESSFUL]++;
+                        if (logged(P, ZRK_MSG_LAUNCH_SUCCESSFUL))
+                            put_rec(P, rec, nr++, tick, ZRK_MSG_LAUNCH_SUCCESSFUL, 0, m_id, l_id, m_id, H.sid()[tg], V[0], V[1], V[2]);
+                    } else {
+                        mb_type[par * Q + q] = MB_CANCEL;
+                        counts[ZRK_MSG_LAUNCH_CANCELLED]++;
+                        if (logged(P, ZRK_MSG_LAUNCH_CANCELLED))
+                            put_rec(P, rec, nr++, tick, ZRK_MSG_LAUNCH_CANCELLED, 0, m_id, l_id, m_id, why, 0, 0, 0);
+                    }
+                } else if (ty == MB_SUCCESS) {  // :103-124
+                    const int m = arg, m_id = c_m_id[m], tid = H.sid()[m_target[m]];
+                    counts[ZRK_MSG_LAUNCHED_MISSILE]++;
+                    counts[ZRK_MSG_NEW_MISSILE]++;
+                    if (logged(P, ZRK_MSG_LAUNCHED_MISSILE))
+                        put_rec(P, rec, nr++, tick, ZRK_MSG_LAUNCHED_MISSILE, 0, l_id, ZRK_CCP_ID, m_id, tid, 0, 0, 0);
+                    if (logged(P, ZRK_MSG_NEW_MISSILE))
+                        put_rec(P, rec, nr++, tick, ZRK_MSG_NEW_MISSILE, 0, l_id, ZRK_NONE, m_id, ZRK_NONE, 0, 0, 0);
+                    ZRK_COLD_I(ln_m)[hdr[H_LN]++] = m;
+                } else if (ty == MB_CANCEL) {  // :125-128
+                    st[l * MP + (st_n[l]++)] = arg;
+                } else {  // MissileCountRequestMessage (:129-138)
+                    counts[ZRK_MSG_MISSILE_COUNT_RESPONSE]++;
+                    if (logged(P, ZRK_MSG_MISSILE_COUNT_RESPONSE))
+                        put_rec(P, rec, nr++, tick, ZRK_MSG_MISSILE_COUNT_RESPONSE, 0, l_id, ccp_id, ZRK_NONE, st_n[l], 0, 0, 0);
+                    // CCP.get_current_missile_launcher_capacity (CCP.py:139-147), same tick
+                    for (int c = 0; c < nC; c++)
+                        if (ZRK_CST_I(c_cl_launcher)[c] == l) ZRK_COLD_I(cap)[c] = st_n[l];
+                    int fc = 0;
+                    for (int c = 0; c < nC; c++) {
+                        int d = ZRK_COLD_I(cap)[c] - ZRK_COLD_I(launched)[c];
+                        fc += d > 0 ? d : 0;
+                    }
+                    hdr[H_FREECAP] = fc;
+                }
+            }
+        }
+        if (has_ccp) {
+            if (!hdr[H_CCP_INIT]) {  // send_request_msg_to_ml_capacity (CCP.py:122-137)
+                for (int c = 0; c < nC; c++) {
+                    ZRK_COLD_I(cap)[c] = 0;
+                    ZRK_COLD_I(launched)[c] = 0;
+                    hdr[H_FREECAP] = 0;
+                    counts[ZRK_MSG_MISSILE_COUNT_REQUEST]++;
+                    if (logged(P, ZRK_MSG_MISSILE_COUNT_REQUEST))
+                        put_rec(P, rec, nr++, tick, ZRK_MSG_MISSILE_COUNT_REQUEST, 0, ccp_id, ZRK_CST_I(c_cl_id)[c], ZRK_NONE, ZRK_NONE, 0, 0, 0);
+                    const int q = hdr[H_MBN0 + par]++;
+                    mb_type[par * Q + q] = MB_COUNTREQ;
+                    mb_l[par * Q + q] = ZRK_CST_I(c_cl_launcher)[c];
+                    mb_a[par * Q + q] = 0;
+                }
+                hdr[H_CCP_INIT] = 1;
+            }
+            // check_if_missiles_launched + add_missile (CCP.py:161-169, :102-109)
+            const int n_ln = hdr[H_LN];
+            int *me_key = ZRK_COLD_I(me_key);
+            for (int i = 0; i < n_ln; i++) {
+                const int m = ZRK_COLD_I(ln_m)[i], m_id = c_m_id[m], tid = H.sid()[m_target[m]];
+                int e, n_me = hdr[H_NME];
+                for (e = 0; e < n_me; e++)
+                    if (me_key[e] == m_id) break;
+                if (e == n_me) hdr[H_NME] = n_me + 1;
+                me_key[e] = m_id;
+                ZRK_COLD_I(me_ref)[e] = ZRK_COLD_I(m_slot)[m];
+                ZRK_COLD_I(me_upd)[e] = tick;
+                ZRK_COLD_I(me_tid)[e] = tid;
+                H.own()[ZRK_COLD_I(m_slot)[m]] = TEAM + e;
+                int t, n_te = hdr[H_NTE];
+                for (t = 0; t < n_te; t++)
+                    if (H.te_key()[t] == tid) break;
+                if (t == n_te) {
+                    hdr[H_FAULT] |= ZRK_FAULT_KEY_ERROR_CCP107;
+                    hdr[H_FAULT_TICK] = tick;
+                    break;
+                }
+                H.te_mid()[t] = m_id;
+            }
+        }
+    }
+    return nr;
+}
+
 // ------------------------------------------------------------------ the kernel
 
+// resident CTAs per SM the register allocation is bounded for
+#ifndef ZRK_MINB_SMALL
+#define ZRK_MINB_SMALL 5
+#endif
+constexpr int min_blocks(int threads) { return threads <= 128 ? ZRK_MINB_SMALL : (threads == 256 ? 2 : 1); }
+
 template <int TEAM, int TPC, bool FAST>
-__global__ void __launch_bounds__(TEAM *TPC) zrk_tick_kernel(const Params P, int n_ticks) {
+__global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_kernel(const Params P, int n_ticks) {
     ZRK_SMEM_DECL;
     const Layout &o = P.lo;
     const int MP = o.MP, Q = o.Q;
@@ -432,7 +658,7 @@ __global__ void __launch_bounds__(TEAM *TPC) zrk_tick_kernel(const Params P, int
         if (hdr[H_FAULT] & 63) break;  // the reference run aborted here
         if (tick_limit >= 0 && tick >= tick_limit) break;
         const int par = tick & 1, prv = par ^ 1;
-        const double now_s = to_seconds((long long)tick * P.dt_ms);
+        const double now_s = tick_seconds(P, tick);
         const int n_slots = hdr[H_NSLOTS];
         const int det_prev = hdr[H_DETN0 + prv];
         const int mb_prev = hdr[H_MBN0 + prv];
@@ -598,161 +824,17 @@ __global__ void __launch_bounds__(TEAM *TPC) zrk_tick_kernel(const Params P, int
             const double *c_rad_par = ZRK_CST_D(c_rad_par);
             for (int r = 0; r < nR; r++) {  // move_to_next_sector_circular (Radar.py:96-117)
                 const double *q = c_rad_par + RAD_PAR_STRIDE * r;
-                if (q[5] == 0.0 && q[6] == 0.0 && q[0] == q[1] && q[0] + q[3] < 360) continue;  // a sector that never moves
+                if (q[10] != 0.0) continue;  // the start sector is a fixed point of the sweep
                 double caz = rad_cur[2 * r], cel = rad_cur[2 * r + 1];
-                int mode = (int)q[7];
-                if (mode == ZRK_SCAN_HORIZONTAL) {
-                    if (caz + q[3] < 360)
-                        caz = pymod(caz + q[5], 360.0);
-                    else
-                        caz = q[1];  // sic: elevation_start (Radar.py:105)
-                    if (caz < q[5]) {
-                        if (cel + q[6] < 90)
-                            cel = pymod(cel + q[6], 90.0);
-                        else
-                            cel = q[1];
-                    }
-                } else if (mode == ZRK_SCAN_VERTICAL) {
-                    cel = pymod(cel + q[6], 90.0);
-                    if (cel < q[6]) caz = pymod(caz + q[5], 360.0);
-                }
+                radar_move(q, caz, cel);
                 rad_cur[2 * r] = caz;
                 rad_cur[2 * r + 1] = cel;
             }
         }
         if (serial) {
             if (lane == 0) {
-                int *mb_type = ZRK_COLD_I(mb_type), *mb_l = ZRK_COLD_I(mb_l), *mb_a = ZRK_COLD_I(mb_a);
-                int *st_n = ZRK_COLD_I(st_n), *st = ZRK_COLD_I(st);
-                const int *c_m_id = ZRK_CST_I(c_m_id), *c_l_id = ZRK_CST_I(c_l_id);
-                const double *c_l_pos = ZRK_CST_D(c_l_pos);
-                int *m_target = ZRK_COLD_I(m_target);
-                unsigned *counts = H.counts();
-                int nr = nrec;
-                // MissileLauncher.step (MissileLauncher.py:82-138)
-                for (int l = 0; l < nL && mb_prev; l++) {
-                    const int l_id = c_l_id[l];
-                    for (int i = 0; i < mb_prev; i++) {
-                        if (mb_l[prv * Q + i] != l) continue;
-                        const int ty = mb_type[prv * Q + i], arg = mb_a[prv * Q + i];
-                        if (ty == MB_COMMAND) {  // launch_missile (:58-80)
-                            if (st_n[l] == 0) continue;
-                            const int m = st[l * MP + (--st_n[l])];
-                            const int m_id = c_m_id[m], tg = arg;
-                            counts[ZRK_MSG_LAUNCH_MISSILE]++;
-                            if (logged(P, ZRK_MSG_LAUNCH_MISSILE))
-                                put_rec(P, rec, nr++, tick, ZRK_MSG_LAUNCH_MISSILE, 0, l_id, m_id, H.sid()[tg], ZRK_NONE, 0, 0, 0);
-                            // Missile._launch (Missile.py:104-133)
-                            double tp[3] = {H.pxy()[tg].x, H.pxy()[tg].y, H.pzs()[tg].x};
-                            double vt[3];
-                            if (H.sflags()[tg] & F_MISSILE) {
-                                vt[0] = vt[1] = vt[2] = NAN;  // Missile.velocity is 0/0 (AirObject.py:35)
-                            } else {
-                                double wx = ZRK_LDCG(&gtraj[4 * TEAM + tg]), wy = ZRK_LDCG(&gtraj[5 * TEAM + tg]),
-                                       wz = ZRK_LDCG(&gtraj[6 * TEAM + tg]);
-                                double sp = H.pzs()[tg].y;
-                                vt[0] = wx / sp * sp;  // target.velocity * target.speed_mod (Missile.py:59)
-                                vt[1] = wy / sp * sp;
-                                vt[2] = wz / sp * sp;
-                            }
-                            double V[3];
-                            const double v0 = ZRK_CST_D(c_m_v0)[m];
-                            int why = missile_solve(&c_l_pos[3 * l], tp, vt, v0, ZRK_CST_D(c_m_v0sq)[m], ZRK_COLD_D(m_period)[m], V);
-                            const int q = hdr[H_MBN0 + par]++;
-                            mb_l[par * Q + q] = l;
-                            mb_a[par * Q + q] = m;
-                            if (why < 0) {
-                                const int k = hdr[H_NSLOTS]++;
-                                gtraj[0 * TEAM + k] = c_l_pos[3 * l];
-                                gtraj[1 * TEAM + k] = c_l_pos[3 * l + 1];
-                                gtraj[2 * TEAM + k] = c_l_pos[3 * l + 2];
-                                gtraj[3 * TEAM + k] = now_s;
-                                gtraj[4 * TEAM + k] = V[0];
-                                gtraj[5 * TEAM + k] = V[1];
-                                gtraj[6 * TEAM + k] = V[2];
-                                gtraj[7 * TEAM + k] = v0;
-                                H.pxy()[k] = make_double2(c_l_pos[3 * l], c_l_pos[3 * l + 1]);
-                                H.pzs()[k] = make_double2(c_l_pos[3 * l + 2], v0);
-                                H.sid()[k] = m_id;
-                                H.sflags()[k] = F_PENDING | F_MISSILE | ((T + m) << F_STATIC_SHIFT);
-                                H.srf()[k] = -1;
-                                H.own()[k] = -1;
-                                ZRK_COLD_I(m_status)[m] = ST_ACTIVE;
-                                m_target[m] = tg;
-                                ZRK_COLD_I(m_slot)[m] = k;
-                                ZRK_COLD_I(m_birth)[m] = tick + 2;
-                                mb_type[par * Q + q] = MB_SUCCESS;
-                                counts[ZRK_MSG_LAUNCH_SUCCESSFUL]++;
-                                if (logged(P, ZRK_MSG_LAUNCH_SUCCESSFUL))
-                                    put_rec(P, rec, nr++, tick, ZRK_MSG_LAUNCH_SUCCESSFUL, 0, m_id, l_id, m_id, H.sid()[tg], V[0], V[1], V[2]);
-                            } else {
-                                mb_type[par * Q + q] = MB_CANCEL;
-                                counts[ZRK_MSG_LAUNCH_CANCELLED]++;
-                                if (logged(P, ZRK_MSG_LAUNCH_CANCELLED))
-                                    put_rec(P, rec, nr++, tick, ZRK_MSG_LAUNCH_CANCELLED, 0, m_id, l_id, m_id, why, 0, 0, 0);
-                            }
-                        } else if (ty == MB_SUCCESS) {  // :103-124
-                            const int m = arg, m_id = c_m_id[m], tid = H.sid()[m_target[m]];
-                            counts[ZRK_MSG_LAUNCHED_MISSILE]++;
-                            counts[ZRK_MSG_NEW_MISSILE]++;
-                            if (logged(P, ZRK_MSG_LAUNCHED_MISSILE))
-                                put_rec(P, rec, nr++, tick, ZRK_MSG_LAUNCHED_MISSILE, 0, l_id, ZRK_CCP_ID, m_id, tid, 0, 0, 0);
-                            if (logged(P, ZRK_MSG_NEW_MISSILE))
-                                put_rec(P, rec, nr++, tick, ZRK_MSG_NEW_MISSILE, 0, l_id, ZRK_NONE, m_id, ZRK_NONE, 0, 0, 0);
-                            ZRK_COLD_I(ln_m)[hdr[H_LN]++] = m;
-                        } else if (ty == MB_CANCEL) {  // :125-128
-                            st[l * MP + (st_n[l]++)] = arg;
-                        } else {  // MissileCountRequestMessage (:129-138)
-                            counts[ZRK_MSG_MISSILE_COUNT_RESPONSE]++;
-                            if (logged(P, ZRK_MSG_MISSILE_COUNT_RESPONSE))
-                                put_rec(P, rec, nr++, tick, ZRK_MSG_MISSILE_COUNT_RESPONSE, 0, l_id, ccp_id, ZRK_NONE, st_n[l], 0, 0, 0);
-                            // CCP.get_current_missile_launcher_capacity (CCP.py:139-147), same tick
-                            for (int c = 0; c < nC; c++)
-                                if (ZRK_CST_I(c_cl_launcher)[c] == l) ZRK_COLD_I(cap)[c] = st_n[l];
-                        }
-                    }
-                }
-                if (has_ccp) {
-                    if (!hdr[H_CCP_INIT]) {  // send_request_msg_to_ml_capacity (CCP.py:122-137)
-                        for (int c = 0; c < nC; c++) {
-                            ZRK_COLD_I(cap)[c] = 0;
-                            ZRK_COLD_I(launched)[c] = 0;
-                            counts[ZRK_MSG_MISSILE_COUNT_REQUEST]++;
-                            if (logged(P, ZRK_MSG_MISSILE_COUNT_REQUEST))
-                                put_rec(P, rec, nr++, tick, ZRK_MSG_MISSILE_COUNT_REQUEST, 0, ccp_id, ZRK_CST_I(c_cl_id)[c], ZRK_NONE, ZRK_NONE, 0, 0, 0);
-                            const int q = hdr[H_MBN0 + par]++;
-                            mb_type[par * Q + q] = MB_COUNTREQ;
-                            mb_l[par * Q + q] = ZRK_CST_I(c_cl_launcher)[c];
-                            mb_a[par * Q + q] = 0;
-                        }
-                        hdr[H_CCP_INIT] = 1;
-                    }
-                    // check_if_missiles_launched + add_missile (CCP.py:161-169, :102-109)
-                    const int n_ln = hdr[H_LN];
-                    int *me_key = ZRK_COLD_I(me_key);
-                    for (int i = 0; i < n_ln; i++) {
-                        const int m = ZRK_COLD_I(ln_m)[i], m_id = c_m_id[m], tid = H.sid()[m_target[m]];
-                        int e, n_me = hdr[H_NME];
-                        for (e = 0; e < n_me; e++)
-                            if (me_key[e] == m_id) break;
-                        if (e == n_me) hdr[H_NME] = n_me + 1;
-                        me_key[e] = m_id;
-                        ZRK_COLD_I(me_ref)[e] = ZRK_COLD_I(m_slot)[m];
-                        ZRK_COLD_I(me_upd)[e] = tick;
-                        ZRK_COLD_I(me_tid)[e] = tid;
-                        H.own()[ZRK_COLD_I(m_slot)[m]] = TEAM + e;
-                        int t, n_te = hdr[H_NTE];
-                        for (t = 0; t < n_te; t++)
-                            if (H.te_key()[t] == tid) break;
-                        if (t == n_te) {
-                            hdr[H_FAULT] |= ZRK_FAULT_KEY_ERROR_CCP107;
-                            hdr[H_FAULT_TICK] = tick;
-                            break;
-                        }
-                        H.te_mid()[t] = m_id;
-                    }
-                }
-                hdr[H_NREC] = nr;
+                nrec = serial_section<TEAM>(P.self, sm, gtraj, rec, tick, now_s, mb_prev, nrec);
+                hdr[H_NREC] = nrec;
             }
             tm.sync();
             nrec = hdr[H_NREC];
@@ -768,7 +850,7 @@ __global__ void __launch_bounds__(TEAM *TPC) zrk_tick_kernel(const Params P, int
                 const int ref = H.te_ref()[lane], upd = H.te_upd()[lane];
                 const double2 a = H.qxy()[ref], c = H.qzw()[ref];
                 lxy[lane] = make_double2(upd == tick ? ZRK_FAR : a.x, a.y);
-                lzd[lane] = make_double2(c.x, now_s - to_seconds((long long)upd * P.dt_ms));
+                lzd[lane] = make_double2(c.x, now_s - tick_seconds(P, upd));
             }
             if (lane < n_me) {
                 const int ref = ZRK_COLD_I(me_ref)[lane], upd = ZRK_COLD_I(me_upd)[lane];
@@ -776,7 +858,7 @@ __global__ void __launch_bounds__(TEAM *TPC) zrk_tick_kernel(const Params P, int
                 const double2 a = hp ? H.qxy()[ref] : H.pxy()[ref];
                 const double cz = hp ? H.qzw()[ref].x : H.pzs()[ref].x;
                 lxy[TEAM + lane] = make_double2(upd == tick ? ZRK_FAR : a.x, a.y);
-                lzd[TEAM + lane] = make_double2(cz, now_s - to_seconds((long long)upd * P.dt_ms));
+                lzd[TEAM + lane] = make_double2(cz, now_s - tick_seconds(P, upd));
             }
             // processing order: FOUND_OBJECTS messages in radar order, objects in list order,
             // each id once -> (first radar that saw it, slot)
@@ -812,10 +894,10 @@ __global__ void __launch_bounds__(TEAM *TPC) zrk_tick_kernel(const Params P, int
                 if (unresolved) {
                     if (FAST) {
                         bool unsure;
-                        link_fast<TEAM>(lxy, lzd, n_te, n_me, seed, P, dpx, dpy, dpz, dspeed, cls, cand, unsure);
-                        if (unsure) link_exact<TEAM>(lxy, lzd, n_te, n_me, P, dpx, dpy, dpz, dspeed, cls, cand);
+                        link_fast<TEAM>(lxy, lzd, n_te, n_me, seed, P.range_step, dpx, dpy, dpz, dspeed, cls, cand, unsure);
+                        if (unsure) link_exact<TEAM>(lxy, lzd, n_te, n_me, P.range_step, dpx, dpy, dpz, dspeed, cls, cand);
                     } else {
-                        link_exact<TEAM>(lxy, lzd, n_te, n_me, P, dpx, dpy, dpz, dspeed, cls, cand);
+                        link_exact<TEAM>(lxy, lzd, n_te, n_me, P.range_step, dpx, dpy, dpz, dspeed, cls, cand);
                     }
                     if (cls == 1)
                         claim = cand;
@@ -850,9 +932,8 @@ __global__ void __launch_bounds__(TEAM *TPC) zrk_tick_kernel(const Params P, int
                 const int old_mid = (fin && cls == 1) ? H.te_mid()[cand] : ZRK_NONE;
                 const bool need = fin && (cls == 0 || (cls == 1 && !following));
                 int ok = 0;
-                bool anycap = false;
-                for (int c = 0; c < nC; c++) anycap = anycap || (ZRK_COLD_I(launched)[c] < ZRK_COLD_I(cap)[c]);
-                if (anycap && tm.any(need)) {  // try_to_launch_missile (CCP.py:287-320), in order
+                // hdr[H_FREECAP] = sum over launchers of max(0, capacity - launched), kept by lane 0
+                if (hdr[H_FREECAP] > 0 && tm.any(need)) {  // try_to_launch_missile (CCP.py:287-320), in order
                     int *x_need = (int *)(sm + o.x_need), *x_ok = (int *)(sm + o.x_ok);
                     x_need[i] = need;
                     tm.sync();
@@ -880,6 +961,7 @@ __global__ void __launch_bounds__(TEAM *TPC) zrk_tick_kernel(const Params P, int
                             x_ok[j] = best + 1;
                             if (best >= 0) {
                                 launched[best]++;
+                                hdr[H_FREECAP]--;
                                 const int q = hdr[H_MBN0 + par]++;
                                 ZRK_COLD_I(mb_type)[par * Q + q] = MB_COMMAND;
                                 ZRK_COLD_I(mb_l)[par * Q + q] = ZRK_CST_I(c_cl_launcher)[best];

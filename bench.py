@@ -104,6 +104,21 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def profiled_traffic(workload, ticks_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one tick-kernel launch, from the committed
+    `ncu --set full` summary of the same workload (profiles/*_summary.json), else None."""
+    import glob
+    best = None
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_summary.json"))):
+        try:
+            d = json.load(open(p))
+        except ValueError:
+            continue
+        if d.get("workload") == workload and abs(d.get("ticks_per_launch", 0) - ticks_per_launch) < 1e-9:
+            best = d.get("dram_bytes_per_launch")
+    return best
+
+
 def cpu_reference_throughput(name, n_scen_per_core, cores, ticks=None):
     """The reference tick on the host: oracle/zrk_oracle.c (the C restatement of the reference,
     pinned bit-exactly to it by tests/golden) on `cores` threads over a bounded sample of the
@@ -229,11 +244,9 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     assert np.array_equal(c2, counts), "end-to-end run disagrees with the device-resident run"
 
-    # ---- final statistics gather: the one collective of the path
-    stats = torch.from_numpy(np.concatenate([counts.sum(0), [(fc & 63 != 0).sum(), B]]).astype(np.int64)).cuda()
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-    stats = stats.cpu().numpy()
+    # ---- final statistics gather: the one collective of the path (NCCL all-reduce over NVLink)
+    from zrk_modulation_b200.distributed import describe_stats, gather_stats, local_stats
+    stats = gather_stats(local_stats(counts, fc), device=torch.device("cuda", dev))
 
     if rank == 0:
         value = units * world * args.steps / (total_ms * 1e-3)
@@ -253,14 +266,13 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "zrk_tick_kernel",
+                         "traffic": profiled_traffic(args.workload, ticks_per_launch), "peak_source": peak_src,
+                         "kernel": "zrk_tick_kernel",
                          "bytes_per_object_update": BYTES_PER_OBJECT_UPDATE,
                          "note": "algorithmic bytes of a one-tick-per-pass fp64 layout x object-updates per launch; "
                                  "a launch fuses ticks_per_launch ticks with state in shared memory, so real DRAM "
                                  "traffic is far lower (see profiles/)"},
-            "stats": {"messages_total": int(stats[:18].sum()), "missile_detonations": int(stats[_cabi.MSG_MISSILE_DETONATE]),
-                      "launches": int(stats[_cabi.MSG_LAUNCH_SUCCESSFUL]), "faulted_scenarios": int(stats[18]),
-                      "scenarios": int(stats[19])},
+            "stats": describe_stats(stats),
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

@@ -55,6 +55,68 @@ def ref():
     return _ref
 
 
+def canonicalise(messages, dt):
+    """{step time: [message objects]} -> (zrk_msg records, id pool, per-type counts).  Works on the
+    reference's message objects and on the mirror's (same attribute names)."""
+    NONE = _cabi.ZRK_NONE
+    nn = lambda v: NONE if v is None else int(v)
+    recs, ids = [], []
+    counts = np.zeros(_cabi.ZRK_MSG_NTYPES, dtype=np.int64)
+    for t in sorted(messages):
+        for m in messages[t]:
+            ty = _cabi.MSG_NAMES.index(m.type.name)
+            counts[ty] += 1
+            a = b = NONE
+            flag = 0
+            xyz = (0.0, 0.0, 0.0)
+            if ty == _cabi.MSG_MISSILE_POS:
+                a = m.missile_id
+            elif ty == _cabi.MSG_MISSILE_DETONATE:
+                a, b, flag = m.missile_id, nn(m.target_id), int(bool(m.self_detonation))
+            elif ty in (_cabi.MSG_ACTIVE_OBJECTS, _cabi.MSG_ALL_OBJECTS, _cabi.MSG_FOUND_OBJECTS):
+                lst = (m.active_objects if ty == _cabi.MSG_ACTIVE_OBJECTS else
+                       m.objects if ty == _cabi.MSG_ALL_OBJECTS else m.visible_objects)
+                a, b = len(ids), len(lst)
+                ids.extend(int(o.id) for o in lst)
+            elif ty == _cabi.MSG_DESTROYED_MISSILE:
+                assert isinstance(m.missile_id, tuple) and len(m.missile_id) == 1
+                a, flag = int(m.missile_id[0]), int(bool(m.self_detonation))
+            elif ty == _cabi.MSG_LAUNCH_MISSILE:
+                a = int(m.target.id)
+            elif ty == _cabi.MSG_LAUNCH_SUCCESSFUL:
+                a, b = int(m.missile.id), int(m.target_id)
+                xyz = tuple(float(x) for x in m.missile.trajectory.velocity)
+                assert m.launch_time == t / 1000
+            elif ty == _cabi.MSG_LAUNCH_CANCELLED:
+                a = int(m.missile.id)
+                b = [i for i, r in enumerate(CANCEL_REASONS) if m.reason.startswith(r)][0]
+            elif ty == _cabi.MSG_LAUNCHED_MISSILE:
+                a, b = int(m.missile.id), int(m.target_id)
+            elif ty == _cabi.MSG_NEW_MISSILE:
+                a = int(m.missile.id)
+            elif ty == _cabi.MSG_MISSILE_COUNT_RESPONSE:
+                b = int(m.count)
+            elif ty == _cabi.MSG_LAUNCH_COMMAND:
+                a, b = int(m.target.id), int(m.radar_id)
+                xyz = tuple(float(x) for x in m.target_position)
+            elif ty == _cabi.MSG_CCP_UPDATE_TARGET:
+                a, b = int(m.target.id), nn(m.missile_id)
+            elif ty == _cabi.MSG_DRAW_OBJECTS:
+                a = int(m.obj_id)
+                b = 3 if isinstance(m.target_type, str) else list(type(m.target_type)).index(m.target_type)
+                flag = int(bool(m.is_visible_by_radar))
+                xyz = tuple(float(x) for x in m.coordinates)
+            elif ty == _cabi.MSG_MISSILE_COUNT_REQUEST:
+                pass
+            else:
+                raise AssertionError(f"unexpected message type {m.type}")
+            assert m.send_time == t
+            recs.append((t // dt, ty, int(m.relevance), flag, 0, int(m.sender_id), nn(m.receiver_id),
+                         int(a), int(b), xyz))
+    msgs = np.array(recs, dtype=_cabi.MSG_DTYPE) if recs else np.zeros(0, dtype=_cabi.MSG_DTYPE)
+    return msgs, np.array(ids, dtype=np.int32), counts
+
+
 def run_reference(cfg: Dict[str, Any], noise: Optional[np.ndarray], n_ticks: Optional[int] = None):
     """Run one scenario through the reference.  Returns dict(msgs, ids, fault_code, fault_tick,
     fault_where, counts, state) in the oracle's output format."""
@@ -112,67 +174,11 @@ def run_reference(cfg: Dict[str, Any], noise: Optional[np.ndarray], n_ticks: Opt
     finally:
         SectorRadar.smooth_objects = orig
 
-    names = [t.name for t in MessageType]
-    assert names == _cabi.MSG_NAMES
-    tix = {t: i for i, t in enumerate(MessageType)}
-    NONE = _cabi.ZRK_NONE
-    nn = lambda v: NONE if v is None else int(v)
-    recs, ids = [], []
-    counts = np.zeros(_cabi.ZRK_MSG_NTYPES, dtype=np.int64)
-    for t in sorted(mgr.messages):
-        for m in mgr.messages[t]:
-            ty = tix[m.type]
-            counts[ty] += 1
-            a = b = NONE
-            flag = 0
-            xyz = (0.0, 0.0, 0.0)
-            if ty == _cabi.MSG_MISSILE_POS:
-                a = m.missile_id
-            elif ty == _cabi.MSG_MISSILE_DETONATE:
-                a, b, flag = m.missile_id, nn(m.target_id), int(bool(m.self_detonation))
-            elif ty in (_cabi.MSG_ACTIVE_OBJECTS, _cabi.MSG_ALL_OBJECTS, _cabi.MSG_FOUND_OBJECTS):
-                lst = (m.active_objects if ty == _cabi.MSG_ACTIVE_OBJECTS else
-                       m.objects if ty == _cabi.MSG_ALL_OBJECTS else m.visible_objects)
-                a, b = len(ids), len(lst)
-                ids.extend(int(o.id) for o in lst)
-            elif ty == _cabi.MSG_DESTROYED_MISSILE:
-                assert isinstance(m.missile_id, tuple) and len(m.missile_id) == 1
-                a, flag = int(m.missile_id[0]), int(bool(m.self_detonation))
-            elif ty == _cabi.MSG_LAUNCH_MISSILE:
-                a = int(m.target.id)
-            elif ty == _cabi.MSG_LAUNCH_SUCCESSFUL:
-                a, b = int(m.missile.id), int(m.target_id)
-                xyz = tuple(float(x) for x in m.missile.trajectory.velocity)
-                assert m.launch_time == t / 1000
-            elif ty == _cabi.MSG_LAUNCH_CANCELLED:
-                a = int(m.missile.id)
-                b = [i for i, r in enumerate(CANCEL_REASONS) if m.reason.startswith(r)][0]
-            elif ty == _cabi.MSG_LAUNCHED_MISSILE:
-                a, b = int(m.missile.id), int(m.target_id)
-            elif ty == _cabi.MSG_NEW_MISSILE:
-                a = int(m.missile.id)
-            elif ty == _cabi.MSG_MISSILE_COUNT_RESPONSE:
-                b = int(m.count)
-            elif ty == _cabi.MSG_LAUNCH_COMMAND:
-                a, b = int(m.target.id), int(m.radar_id)
-                xyz = tuple(float(x) for x in m.target_position)
-            elif ty == _cabi.MSG_CCP_UPDATE_TARGET:
-                a, b = int(m.target.id), nn(m.missile_id)
-            elif ty == _cabi.MSG_DRAW_OBJECTS:
-                a = int(m.obj_id)
-                b = 3 if isinstance(m.target_type, str) else list(type(m.target_type)).index(m.target_type)
-                flag = int(bool(m.is_visible_by_radar))
-                xyz = tuple(float(x) for x in m.coordinates)
-            elif ty == _cabi.MSG_MISSILE_COUNT_REQUEST:
-                pass
-            else:
-                raise AssertionError(f"unexpected message type {m.type}")
-            assert m.send_time == t
-            recs.append((t // dt, ty, int(m.relevance), flag, 0, int(m.sender_id), nn(m.receiver_id),
-                         int(a), int(b), xyz))
-    msgs = np.array(recs, dtype=_cabi.MSG_DTYPE) if recs else np.zeros(0, dtype=_cabi.MSG_DTYPE)
+    msgs, ids, counts = canonicalise(mgr.messages, dt)
 
     # final state in the zrk_state_view layout (batch of one)
+    NONE = _cabi.ZRK_NONE
+    nn = lambda v: NONE if v is None else int(v)
     B, NS, R, Mx, L, Cc = batch.dims()
     st, _ = _cabi.alloc_state((1, NS, R, Mx, L, Cc))
     env = mgr.modules[0]
@@ -245,6 +251,6 @@ def run_reference(cfg: Dict[str, Any], noise: Optional[np.ndarray], n_ticks: Opt
     else:
         st["ccp_t_ref"][:], st["ccp_m_ref"][:] = -1, -1
         st["ccp_t_missile"][:], st["ccp_m_target"][:] = NONE, NONE
-    return dict(msgs=msgs, ids=np.array(ids, dtype=np.int32), fault_code=fault_code,
+    return dict(msgs=msgs, ids=ids, fault_code=fault_code,
                 fault_tick=int(fault_tick), fault_where=fault_where, counts=counts, state=st,
                 state_known=known, batch=batch)

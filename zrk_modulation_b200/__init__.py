@@ -9,6 +9,12 @@ from ._cabi import (ZRK_NONE, LOG_EVENTS, LOG_BULK, LOG_MASKS, LOG_FULL, MSG_NAM
 from .scenario import (Batch, compile_batch, load_config, make_noise, synthetic_batch,  # noqa: F401
                        batch_to_config)
 
-__all__ = ["Batch", "compile_batch", "load_config", "make_noise", "synthetic_batch",
+from .messages import MessageType, TargetType  # noqa: F401,E402
+from .manager import (BaseModel, BatchedManager, BatchedTick, Timer, create_objects_from_config,  # noqa: F401,E402
+                      run_simulation_from_config)
+from .engine import Engine, ZrkError  # noqa: F401,E402
+
+__all__ = ["MessageType", "TargetType", "BaseModel", "BatchedManager", "BatchedTick", "Timer",
+           "create_objects_from_config", "run_simulation_from_config", "Engine", "ZrkError","Batch", "compile_batch", "load_config", "make_noise", "synthetic_batch",
            "batch_to_config", "ZRK_NONE", "LOG_EVENTS", "LOG_BULK", "LOG_MASKS", "LOG_FULL",
            "MSG_NAMES"]

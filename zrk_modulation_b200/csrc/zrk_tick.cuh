@@ -608,7 +608,7 @@ __device__ ZRK_NOINLINE int serial_section(const Params *Pg, unsigned char *sm, 
 
 // resident CTAs per SM the register allocation is bounded for
 #ifndef ZRK_MINB_SMALL
-#define ZRK_MINB_SMALL 5
+#define ZRK_MINB_SMALL 4
 #endif
 constexpr int min_blocks(int threads) { return threads <= 128 ? ZRK_MINB_SMALL : (threads == 256 ? 2 : 1); }
 

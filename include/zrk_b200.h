@@ -283,7 +283,7 @@ int zrk_read_messages(zrk_handle *h, int scenario, int tick0, int tick1, zrk_msg
                       size_t *n, int32_t *ids, size_t ids_cap, size_t *n_ids);
 int zrk_read_state(zrk_handle *h, const zrk_state_view *view);
 /* Device pointers for zero-copy consumers (torch): borrowed, valid until zrk_destroy. */
-int zrk_device_ptr(zrk_handle *h, const char *name, void **ptr, size_t *bytes);
+int zrk_device_ptr(zrk_handle *h, const char *name, void **ptr, size_t *bytes); /* "dyn", "cst", "rec", "masks" */
 /* Kernel launches issued by this handle and device time spent in them (CUDA events), ms. */
 int zrk_launch_stats(zrk_handle *h, int64_t *n_launches, double *kernel_ms);
 const char *zrk_last_error(zrk_handle *h); /* h may be NULL: error of the last failed zrk_create */

@@ -32,6 +32,10 @@ struct double2 {
     double x, y;
 };
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
+struct float4 {
+    float x, y, z, w;
+};
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 struct dim3 {
     unsigned x, y, z;
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}

@@ -18,7 +18,7 @@ sys.path.insert(0, os.path.join(HERE, "..", ".."))
 sys.path.insert(0, os.path.join(HERE, ".."))
 
 import refharness as RH  # noqa: E402
-from scenarios import random_config  # noqa: E402
+from scenarios import SPECIAL_KINDS, random_config, special_config  # noqa: E402
 from zrk_modulation_b200 import compile_batch, load_config, make_noise  # noqa: E402
 
 
@@ -50,5 +50,17 @@ def main():
             save(f"{fam}_{seed:02d}", cfg, noise)
 
 
+def special():
+    for kind in SPECIAL_KINDS:
+        cfg = special_config(kind)
+        b = compile_batch(cfg)
+        save(f"special_{kind}", cfg, make_noise(8, b.max_radars, b.n_slots, seed=5))
+        save(f"special_{kind}_nonoise", cfg, None)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "special":
+        special()
+    else:
+        main()
+        special()

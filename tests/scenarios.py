@@ -72,3 +72,42 @@ def random_config(seed: int, family: str = "mixed"):
         cfg["combat_control_point"] = {"id": 0, "missile_launcher_ids": ids,
                                        "radar_ids": [5 + r for r in range(n_radars)]}
     return cfg
+
+
+def special_config(kind: str):
+    """Hand-made scenarios for the corners of the association scan and the visibility filter."""
+    cfg = random_config(7, "mid")
+    cfg["simulation"] = {"time_step": 200, "duration": 200 * 60}
+    t = cfg["air_environment"]["targets"]
+    if kind == "twins":          # identical tracks: exact distance ties on every tick
+        t[1]["position"], t[1]["velocity"] = list(t[0]["position"]), list(t[0]["velocity"])
+        t[3]["position"], t[3]["velocity"] = list(t[2]["position"]), list(t[2]["velocity"])
+    elif kind == "near_twins":   # tracks a few ulps apart: near-ties, the exact path must decide
+        t[1]["position"] = [t[0]["position"][0] * (1 + 2e-16), t[0]["position"][1], t[0]["position"][2]]
+        t[1]["velocity"] = list(t[0]["velocity"])
+        t[3]["position"] = [t[2]["position"][0], t[2]["position"][1] + 1e-9, t[2]["position"][2]]
+        t[3]["velocity"] = list(t[2]["velocity"])
+    elif kind == "far_field":    # coordinates beyond the fp32-safe range of the scan pre-filter
+        for i, tt in enumerate(t):
+            tt["position"] = [2.0e5 + 3000.0 * i, -1.5e5 + 1000.0 * i, 9000.0]
+        for r in cfg["radars"]:
+            r["max_distance"] = 1.0e6
+            r.update(azimuth_start=0.0, azimuth_range=360.0, azimuth_speed=0.0, elevation_start=0.0,
+                     elevation_range=180.0, elevation_speed=0.0, scan_mode="horizontal")
+    elif kind == "on_axis":      # objects exactly on sector edges / coordinate axes of the radar
+        r = cfg["radars"][0]
+        r.update(position=[0.0, 0.0, 0.0], azimuth_start=0.0, azimuth_range=90.0, azimuth_speed=0.0,
+                 elevation_start=0.0, elevation_range=90.0, elevation_speed=0.0, max_distance=5000.0,
+                 scan_mode="horizontal")
+        t[0].update(position=[1000.0, 0.0, 0.0], velocity=[10.0, 0.0, 0.0])      # az = 0, el = 0
+        t[1].update(position=[0.0, 1000.0, 500.0], velocity=[0.0, 10.0, 0.0])    # az = 90
+        t[2].update(position=[3000.0, 4000.0, 0.0], velocity=[0.0, 0.0, 0.0])    # distance = max_distance, stationary
+        t[3].update(position=[0.0, 0.0, 1000.0], velocity=[0.0, 0.0, 5.0])       # straight overhead
+        if len(t) > 4:
+            t[4].update(position=[0.0, 0.0, 0.0], velocity=[1.0, 1.0, 1.0])      # starts at the radar: distance 0
+    else:
+        raise ValueError(kind)
+    return cfg
+
+
+SPECIAL_KINDS = ["twins", "near_twins", "far_field", "on_axis"]

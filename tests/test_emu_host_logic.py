@@ -8,7 +8,7 @@ import pytest
 import emu_lib
 import parity
 from enginecheck import check_batch_counts, check_batch_full
-from scenarios import random_config
+from scenarios import SPECIAL_KINDS, random_config, special_config
 from zrk_modulation_b200 import compile_batch, make_noise, synthetic_batch
 from zrk_modulation_b200.engine import Engine, ZrkError
 
@@ -32,6 +32,16 @@ def test_emulated_tick_random(lib, family, seed, tpl):
     b = compile_batch(cfg)
     b.set_noise(make_noise(8, b.max_radars, b.n_slots, seed=seed))
     check_batch_full(b, b.n_ticks(0), lib=lib, ticks_per_launch=tpl)
+
+
+@pytest.mark.parametrize("kind", SPECIAL_KINDS)
+@pytest.mark.parametrize("noise", [False, True])
+def test_emulated_tick_corner_cases(lib, kind, noise):
+    cfg = special_config(kind)
+    b = compile_batch(cfg)
+    if noise:
+        b.set_noise(make_noise(8, b.max_radars, b.n_slots, seed=5))
+    check_batch_full(b, b.n_ticks(0), lib=lib)
 
 
 def test_ragged_batch_and_chunked_steps(lib):

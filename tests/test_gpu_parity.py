@@ -9,7 +9,7 @@ import pytest
 import parity
 from enginecheck import check_batch_counts, check_batch_full
 from oracle import oracle as O
-from scenarios import random_config
+from scenarios import SPECIAL_KINDS, random_config, special_config
 from zrk_modulation_b200 import LOG_FULL, compile_batch, make_noise, synthetic_batch
 from zrk_modulation_b200.engine import Engine
 
@@ -40,6 +40,19 @@ def test_random_scenarios_full_log(family, tpl):
         b = compile_batch(cfg)
         b.set_noise(make_noise(8, b.max_radars, b.n_slots, seed=seed))
         check_batch_full(b, b.n_ticks(0), ticks_per_launch=tpl)
+
+
+@pytest.mark.parametrize("kind", SPECIAL_KINDS)
+@pytest.mark.parametrize("noise", [False, True])
+@pytest.mark.parametrize("exact_only", [False, True])
+def test_corner_cases(kind, noise, exact_only):
+    """Exact distance ties, near-ties a few ulps apart, coordinates beyond the fp32 pre-filter's
+    range, objects exactly on sector edges / at the radar."""
+    cfg = special_config(kind)
+    b = compile_batch(cfg)
+    if noise:
+        b.set_noise(make_noise(8, b.max_radars, b.n_slots, seed=5))
+    check_batch_full(b, b.n_ticks(0), exact_only=exact_only)
 
 
 def test_ragged_batch_chunked():

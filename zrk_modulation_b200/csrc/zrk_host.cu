@@ -51,7 +51,6 @@ __global__ void zrk_init_kernel(const Params P, const DevDesc d, int *err) {
     const HotOff &ho = o.hot;
     unsigned char *sm = P.dyn + (size_t)b * o.dyn_bytes;
     unsigned char *cs = const_cast<unsigned char *>(P.cst) + (size_t)b * o.cst_bytes;
-    double *traj = P.traj + (size_t)b * 8 * NSP;
     const int nT = d.n_targets ? d.n_targets[b] : d.T, nR = d.n_radars ? d.n_radars[b] : d.R;
     const int nL = d.n_launchers ? d.n_launchers[b] : d.L, nM = d.n_missiles ? d.n_missiles[b] : d.M;
     const int nC = d.n_ccp_launchers ? d.n_ccp_launchers[b] : d.C;
@@ -62,18 +61,18 @@ __global__ void zrk_init_kernel(const Params P, const DevDesc d, int *err) {
     int *hdr = (int *)(sm + ho.hdr);
     hdr[H_NSLOTS] = nT;
     double2 *pxy = (double2 *)(sm + ho.pxy), *pzs = (double2 *)(sm + ho.pzs);
+    double2 *txy = (double2 *)(sm + ho.txy), *tzt = (double2 *)(sm + ho.tzt), *vxy = (double2 *)(sm + ho.vxy),
+            *vzw = (double2 *)(sm + ho.vzw);
     int *sid = (int *)(sm + ho.sid), *sflags = (int *)(sm + ho.sflags), *srf = (int *)(sm + ho.srf),
         *own = (int *)(sm + ho.own);
     for (int t = 0; t < nT; t++) {
         size_t g = (size_t)b * d.T + t;
         double vx = d.target_vel[3 * g], vy = d.target_vel[3 * g + 1], vz = d.target_vel[3 * g + 2];
         double sp = sqrt(dot3(vx, vy, vz, vx, vy, vz));  // np.linalg.norm (AirObject.py:36)
-        for (int k = 0; k < 3; k++) {
-            traj[k * NSP + t] = d.target_pos[3 * g + k];
-            traj[(4 + k) * NSP + t] = d.target_vel[3 * g + k];
-        }
-        traj[3 * NSP + t] = 0.0;
-        traj[7 * NSP + t] = sp;
+        txy[t] = make_double2(d.target_pos[3 * g], d.target_pos[3 * g + 1]);  // Trajectory (main.py:134-138)
+        tzt[t] = make_double2(d.target_pos[3 * g + 2], 0.0);
+        vxy[t] = make_double2(vx, vy);
+        vzw[t] = make_double2(vz, 0.0);
         pxy[t] = make_double2(d.target_pos[3 * g], d.target_pos[3 * g + 1]);
         pzs[t] = make_double2(d.target_pos[3 * g + 2], sp);
         sid[t] = d.target_id[g];
@@ -403,7 +402,6 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
         size_t n = d->noise_scenario_stride ? (size_t)d->noise_scenario_stride * (B - 1) + one : one;
         if ((rc = dev_upload(h, d->noise, n, &P.noise)) != ZRK_OK) return rc;
     }
-    if ((rc = dev_alloc(h, (size_t)B * 8 * lo.team, &P.traj, true)) != ZRK_OK) return rc;
     if ((rc = dev_alloc(h, (size_t)B * lo.dyn_bytes, &P.dyn, true)) != ZRK_OK) return rc;
     unsigned char *cst = nullptr;
     if ((rc = dev_alloc(h, (size_t)B * lo.cst_bytes, &cst, true)) != ZRK_OK) return rc;
@@ -705,19 +703,16 @@ extern "C" int zrk_read_state(zrk_handle *h, const zrk_state_view *v) {
     const HotOff &ho = o.hot;
     const int CH = 2048;
     std::vector<unsigned char> dyn, cst;
-    std::vector<double> traj;
     for (int s0 = 0; s0 < o.B; s0 += CH) {
         int s1 = std::min(o.B, s0 + CH), n = s1 - s0;
         int rc = fetch_dyn(h, s0, s1, dyn);
         if (rc) return rc;
         cst.resize((size_t)n * o.cst_bytes);
-        traj.resize((size_t)n * 8 * NSP);
         CK(cudaMemcpy(cst.data(), P.cst + (size_t)s0 * o.cst_bytes, cst.size(), cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(traj.data(), P.traj + (size_t)s0 * 8 * NSP, traj.size() * sizeof(double), cudaMemcpyDeviceToHost));
         for (int s = s0; s < s1; s++) {
             const unsigned char *sm = dyn.data() + (size_t)(s - s0) * o.dyn_bytes;
             const unsigned char *cs = cst.data() + (size_t)(s - s0) * o.cst_bytes;
-            const double *tj = traj.data() + (size_t)(s - s0) * 8 * NSP;
+            const double *tzt = (const double *)(sm + ho.tzt), *vxy = (const double *)(sm + ho.vxy), *vzw = (const double *)(sm + ho.vzw);
             const int *hdr = (const int *)(sm + ho.hdr), *sflags = (const int *)(sm + ho.sflags);
             const double *pxy = (const double *)(sm + ho.pxy), *pzs = (const double *)(sm + ho.pzs);
             const double *qxy = (const double *)(sm + ho.qxy), *qzw = (const double *)(sm + ho.qzw);
@@ -770,10 +765,11 @@ extern "C" int zrk_read_state(zrk_handle *h, const zrk_state_view *v) {
                 int k = live ? m_slot[m] : -1;
                 if (v->missile_status) v->missile_status[g] = live ? (uint8_t)m_status[m] : 0;
                 if (v->missile_period) v->missile_period[g] = live ? m_period[m] : 0.0;
-                if (v->missile_t0) v->missile_t0[g] = k >= 0 ? tj[3 * NSP + k] : 0.0;
+                if (v->missile_t0) v->missile_t0[g] = k >= 0 ? tzt[2 * k + 1] : 0.0;
                 if (v->missile_target) v->missile_target[g] = live && m_target[m] >= 0 ? stat(m_target[m]) : -1;
+                const double vk[3] = {k >= 0 ? vxy[2 * k] : 0.0, k >= 0 ? vxy[2 * k + 1] : 0.0, k >= 0 ? vzw[2 * k] : 0.0};
                 for (int c = 0; c < 3; c++)
-                    if (v->missile_vel) v->missile_vel[3 * g + c] = k >= 0 ? tj[(4 + c) * NSP + k] : 0.0;
+                    if (v->missile_vel) v->missile_vel[3 * g + c] = vk[c];
             }
             const int *st_n = (const int *)(sm + o.st_n);
             for (int l = 0; l < L; l++)
@@ -818,7 +814,6 @@ extern "C" int zrk_device_ptr(zrk_handle *h, const char *name, void **ptr, size_
     void *p = nullptr;
     if (n == "dyn") { p = P.dyn; sz = (size_t)o.B * o.dyn_bytes; }
     else if (n == "cst") { p = (void *)P.cst; sz = (size_t)o.B * o.cst_bytes; }
-    else if (n == "traj") { p = P.traj; sz = (size_t)o.B * 8 * o.team * sizeof(double); }
     else if (n == "rec") { p = P.rec; sz = (size_t)o.B * P.log_cap * sizeof(zrk_msg); }
     else if (n == "masks") { p = P.masks; sz = (size_t)P.mask_ticks * o.B * (1 + o.RP) * P.mask_words * sizeof(unsigned); }
     else return ZRK_ERR_ARG;

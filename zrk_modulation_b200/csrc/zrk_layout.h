@@ -1,10 +1,8 @@
 // zrk_layout.h — device data layout shared by the host library and the tick kernel.
 //
-// Per scenario the device keeps three things:
-//   traj   [B][8][TEAM] double    per AirEnv slot: p0x p0y p0z t0 vx vy vz speed
-//                                 = Trajectory + speed_mod (AirObject.py:15-36).  Read into
-//                                 registers by the slot's lane; written only at a launch.
-//   dyn    [B][dyn_bytes]        everything that changes every tick, as one blob whose image in
+// Per scenario the device keeps two things:
+//   dyn    [B][dyn_bytes]        the scenario's state (Trajectory + speed_mod per AirEnv slot,
+//                                 AirObject.py:15-36; positions; CCP tracks; ...) as one blob whose image in
 //                                 shared memory is byte-identical (prologue/epilogue are plain
 //                                 coalesced 16-byte copies).  It starts with the "hot" part,
 //                                 whose offsets depend only on TEAM (compile-time constants in
@@ -42,6 +40,8 @@ struct HotOff {
     int hdr, counts;
     int pxy, pzs;  // double2[TEAM]: (pos.x, pos.y), (pos.z, speed_mod)
     int qxy, qzw;  // double2[TEAM]: (prev.x, prev.y), (prev.z, unused)
+    int txy, tzt;  // double2[TEAM]: trajectory (start_pos.x, start_pos.y), (start_pos.z, start_time)
+    int vxy, vzw;  // double2[TEAM]: trajectory velocity (x, y), (z, unused)
     int sid, sflags, srf, own;                        // int[TEAM]
     int te_key, te_ref, te_upd, te_follow, te_mid;    // int[TEAM]  CCP._target_dict
     int end;
@@ -55,6 +55,10 @@ ZRK_HD constexpr HotOff hot_off(int team) {
     h.pzs = p; p += 16 * team;
     h.qxy = p; p += 16 * team;
     h.qzw = p; p += 16 * team;
+    h.txy = p; p += 16 * team;
+    h.tzt = p; p += 16 * team;
+    h.vxy = p; p += 16 * team;
+    h.vzw = p; p += 16 * team;
     h.sid = p; p += 4 * team;
     h.sflags = p; p += 4 * team;
     h.srf = p; p += 4 * team;
@@ -86,6 +90,7 @@ struct Layout {
     int cst_bytes;
     // scratch (shared memory only), offsets from the start of the team's region
     int x_lxy, x_lzd;  // double2[TEAM + MP]: per CCP entry, the position link_object measures to
+    int x_lf;          // float4[TEAM + MP]: the same position rounded to fp32 (scan pre-filter)
     int x_claim, x_detlist, x_wscr, x_need, x_ok;
     int team_smem_bytes;
 };
@@ -100,7 +105,6 @@ struct Params {
     int mask_ticks, mask_words;  // words per mask row; a tick's row set is (1 + R) rows
     int noise_period, noise_radars, noise_objects;
     long long noise_stride;
-    double *traj;
     unsigned char *dyn;
     const unsigned char *cst;
     zrk_msg *rec;
@@ -162,6 +166,7 @@ static inline Layout make_layout(int B, int T, int M, int R, int L, int C) {
     p = o.dyn_bytes + o.cst_bytes;
     o.x_lxy = take(16 * (team + o.MP));
     o.x_lzd = take(16 * (team + o.MP));
+    o.x_lf = take(16 * (team + o.MP));
     o.x_claim = take(4 * (team + o.MP));
     o.x_detlist = take(4 * team);
     o.x_wscr = take(4 * 40);

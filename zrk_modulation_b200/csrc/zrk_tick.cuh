@@ -2,8 +2,8 @@
 //
 // One TEAM of threads per scenario, one lane per AirEnv slot (AirEnv.__objects position,
 // AirEnv.py:24).  A launch runs n_ticks passes of the loop body of Manager.run_simulation
-// (Manager.py:116-140) with the scenario's mutable state resident in shared memory and the
-// slot trajectories in registers; the state is read from / written back to HBM once per launch.
+// (Manager.py:116-140) with the scenario's state resident in shared memory; it is read from /
+// written back to HBM once per launch.
 //
 // Arithmetic is fp64 and written so that every result that reaches state or a decision is
 // the same IEEE operation sequence the reference (numpy) performs: no FMA contraction (the
@@ -303,6 +303,10 @@ struct Hot {
     __device__ __forceinline__ double2 *pzs() const { return (double2 *)(sm + O.pzs); }
     __device__ __forceinline__ double2 *qxy() const { return (double2 *)(sm + O.qxy); }
     __device__ __forceinline__ double2 *qzw() const { return (double2 *)(sm + O.qzw); }
+    __device__ __forceinline__ double2 *txy() const { return (double2 *)(sm + O.txy); }
+    __device__ __forceinline__ double2 *tzt() const { return (double2 *)(sm + O.tzt); }
+    __device__ __forceinline__ double2 *vxy() const { return (double2 *)(sm + O.vxy); }
+    __device__ __forceinline__ double2 *vzw() const { return (double2 *)(sm + O.vzw); }
     __device__ __forceinline__ int *sid() const { return (int *)(sm + O.sid); }
     __device__ __forceinline__ int *sflags() const { return (int *)(sm + O.sflags); }
     __device__ __forceinline__ int *srf() const { return (int *)(sm + O.srf); }
@@ -403,41 +407,70 @@ __device__ __forceinline__ double link_d2(const double2 *lxy, const double2 *lzd
     return dot3(ex, ey, ez, ex, ey, ez);
 }
 
+// fp32 pre-filter of the scan.  Link positions and the detection are rounded to fp32; for
+// |coordinate| <= 65536 m the fp32 distance differs from the fp64 one by < 0.05 m, so a pair whose
+// fp32 squared distance exceeds (sqrt(best) + 0.25 m)^2 cannot beat or tie the best.
+#define ZRK_F32_COORD_MAX 65536.0
+__device__ __forceinline__ float link_threshold(double best, bool f32ok) {
+    if (!f32ok || !(best < 1e30)) return INFINITY;
+    const double r = sqrt(best) + 0.25;
+    return (float)(r * r) * 1.000001f;
+}
+__device__ __forceinline__ float link_d2f(const float4 *lf, int ue, float fx, float fy, float fz) {
+    const float4 a = lf[ue];
+    const float ex = a.x - fx, ey = a.y - fy, ez = a.z - fz;
+    return fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+}
+
 template <int TEAM>
-__device__ __forceinline__ void link_fast(const double2 *lxy, const double2 *lzd, int n_te, int n_me, int seed,
-                                          double range_step, double px, double py, double pz, double speed, int &cls,
-                                          int &cand, bool &unsure) {
+__device__ __forceinline__ void link_fast(const float4 *lf, const double2 *lxy, const double2 *lzd, int n_te, int n_me,
+                                          int seed, double range_step, double px, double py, double pz, double speed,
+                                          int &cls, int &cand, bool &unsure) {
     LinkAcc A;
     A.best = INFINITY;
     A.best_lo = INFINITY;
     A.ue = -1;
     A.unsure = false;
     // Seed with the entry that tracked this slot last tick: it is almost always the nearest, and
-    // with best = its d2 nearly every other pair fails the single compare below.
+    // with best = its d2 nearly every other pair fails the single fp32 compare below.
     if (seed >= 0) link_eval(A, seed, link_d2(lxy, lzd, seed, px, py, pz), lzd[seed].y, speed, range_step);
+    const bool f32ok = fabs(px) <= ZRK_F32_COORD_MAX && fabs(py) <= ZRK_F32_COORD_MAX && fabs(pz) <= ZRK_F32_COORD_MAX;
+    const float fx = (float)px, fy = (float)py, fz = (float)pz;
+    float thr = link_threshold(A.best, f32ok);
     for (int pass = 0; pass < 2; pass++) {
         const int n = pass ? n_me : n_te, base = pass ? TEAM : 0;
         int e = 0;
         // four pairs at a time; the common case is that none of them can beat the best
         for (; e + 4 <= n; e += 4) {
             const int u = base + e;
-            const double d0 = link_d2(lxy, lzd, u, px, py, pz), d1 = link_d2(lxy, lzd, u + 1, px, py, pz);
-            const double d2 = link_d2(lxy, lzd, u + 2, px, py, pz), d3 = link_d2(lxy, lzd, u + 3, px, py, pz);
-            const bool h = (!(d0 > A.best) && u != seed) || (!(d1 > A.best) && u + 1 != seed) ||
-                           (!(d2 > A.best) && u + 2 != seed) || (!(d3 > A.best) && u + 3 != seed);
+            const float d0 = link_d2f(lf, u, fx, fy, fz), d1 = link_d2f(lf, u + 1, fx, fy, fz);
+            const float d2 = link_d2f(lf, u + 2, fx, fy, fz), d3 = link_d2f(lf, u + 3, fx, fy, fz);
+            // bitwise, not short-circuit: all four chains are issued before the one branch
+            const bool h = (!(d0 > thr) & (u != seed)) | (!(d1 > thr) & (u + 1 != seed)) |
+                           (!(d2 > thr) & (u + 2 != seed)) | (!(d3 > thr) & (u + 3 != seed));
             if (h) {
 #pragma unroll 1
                 for (int k = 0; k < 4; k++) {
-                    const double dk = link_d2(lxy, lzd, u + k, px, py, pz);
-                    if (!(dk > A.best) && u + k != seed) link_eval(A, u + k, dk, lzd[u + k].y, speed, range_step);
+                    if (!(link_d2f(lf, u + k, fx, fy, fz) > thr) && u + k != seed) {
+                        const double dk = link_d2(lxy, lzd, u + k, px, py, pz);
+                        if (!(dk > A.best)) {
+                            link_eval(A, u + k, dk, lzd[u + k].y, speed, range_step);
+                            thr = link_threshold(A.best, f32ok);
+                        }
+                    }
                 }
             }
         }
 #pragma unroll 1
         for (; e < n; e++) {
             const int u = base + e;
-            const double dk = link_d2(lxy, lzd, u, px, py, pz);
-            if (!(dk > A.best) && u != seed) link_eval(A, u, dk, lzd[u].y, speed, range_step);
+            if (!(link_d2f(lf, u, fx, fy, fz) > thr) && u != seed) {
+                const double dk = link_d2(lxy, lzd, u, px, py, pz);
+                if (!(dk > A.best)) {
+                    link_eval(A, u, dk, lzd[u].y, speed, range_step);
+                    thr = link_threshold(A.best, f32ok);
+                }
+            }
         }
     }
     unsure = A.unsure;
@@ -445,12 +478,19 @@ __device__ __forceinline__ void link_fast(const double2 *lxy, const double2 *lzd
     cand = A.ue < 0 ? -1 : (A.ue >= TEAM ? A.ue - TEAM : A.ue);
 }
 
+// fp32 image of one link position: NaN (always a candidate) outside the fp32-safe range
+__device__ __forceinline__ float4 link_f32(double x, double y, double z) {
+    const bool ok = (x >= ZRK_FAR || fabs(x) <= ZRK_F32_COORD_MAX) && fabs(y) <= ZRK_F32_COORD_MAX &&
+                    fabs(z) <= ZRK_F32_COORD_MAX;
+    return ok ? make_float4(x >= ZRK_FAR ? 1e30f : (float)x, (float)y, (float)z, 0.f) : make_float4(NAN, NAN, NAN, 0.f);
+}
+
 // ------------------------------------------------------------------ lane 0 alone: launchers + CCP bookkeeping
 
 // MissileLauncher.step for every launcher (MissileLauncher.py:82-138) and the CCP's first-tick
 // capacity requests / LAUNCHED_MISSILE intake (CCP.py:122-169).  Rare, serial, kept out of line.
 template <int TEAM>
-__device__ ZRK_NOINLINE int serial_section(const Params *Pg, unsigned char *sm, double *gtraj, zrk_msg *rec, int tick,
+__device__ ZRK_NOINLINE int serial_section(const Params *Pg, unsigned char *sm, zrk_msg *rec, int tick,
                                            double now_s, int mb_prev, int nrec) {
     const Params &P = *Pg;  // the copy in global memory: a by-reference kernel parameter would be spilled
     const Layout &o = P.lo;
@@ -489,8 +529,7 @@ __device__ ZRK_NOINLINE int serial_section(const Params *Pg, unsigned char *sm, 
                     if (H.sflags()[tg] & F_MISSILE) {
                         vt[0] = vt[1] = vt[2] = NAN;  // Missile.velocity is 0/0 (AirObject.py:35)
                     } else {
-                        double wx = ZRK_LDCG(&gtraj[4 * TEAM + tg]), wy = ZRK_LDCG(&gtraj[5 * TEAM + tg]),
-                               wz = ZRK_LDCG(&gtraj[6 * TEAM + tg]);
+                        double wx = H.vxy()[tg].x, wy = H.vxy()[tg].y, wz = H.vzw()[tg].x;
                         double sp = H.pzs()[tg].y;
                         vt[0] = wx / sp * sp;  // target.velocity * target.speed_mod (Missile.py:59)
                         vt[1] = wy / sp * sp;
@@ -504,14 +543,10 @@ __device__ ZRK_NOINLINE int serial_section(const Params *Pg, unsigned char *sm, 
                     mb_a[par * Q + q] = m;
                     if (why < 0) {
                         const int k = hdr[H_NSLOTS]++;
-                        gtraj[0 * TEAM + k] = c_l_pos[3 * l];
-                        gtraj[1 * TEAM + k] = c_l_pos[3 * l + 1];
-                        gtraj[2 * TEAM + k] = c_l_pos[3 * l + 2];
-                        gtraj[3 * TEAM + k] = now_s;
-                        gtraj[4 * TEAM + k] = V[0];
-                        gtraj[5 * TEAM + k] = V[1];
-                        gtraj[6 * TEAM + k] = V[2];
-                        gtraj[7 * TEAM + k] = v0;
+                        H.txy()[k] = make_double2(c_l_pos[3 * l], c_l_pos[3 * l + 1]);  // new Trajectory (Missile.py:110-114)
+                        H.tzt()[k] = make_double2(c_l_pos[3 * l + 2], now_s);
+                        H.vxy()[k] = make_double2(V[0], V[1]);
+                        H.vzw()[k] = make_double2(V[2], 0.0);
                         H.pxy()[k] = make_double2(c_l_pos[3 * l], c_l_pos[3 * l + 1]);
                         H.pzs()[k] = make_double2(c_l_pos[3 * l + 2], v0);
                         H.sid()[k] = m_id;
@@ -628,6 +663,7 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
     H.sm = sm;
     tm.wscr = (int *)(sm + o.x_wscr);
     double2 *lxy = (double2 *)(sm + o.x_lxy), *lzd = (double2 *)(sm + o.x_lzd);
+    float4 *lf = (float4 *)(sm + o.x_lf);
 
     // ---- prologue: HBM -> shared memory / registers
     {
@@ -638,10 +674,6 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
         uint4 *sc = (uint4 *)(sm + o.dyn_bytes);
         for (int i = lane; i < o.cst_bytes / 16; i += TEAM) sc[i] = gc[i];
     }
-    double *gtraj = P.traj + (size_t)b * 8 * TEAM;  // [8][TEAM]: p0x p0y p0z t0 vx vy vz speed
-    double p0x = gtraj[0 * TEAM + lane], p0y = gtraj[1 * TEAM + lane], p0z = gtraj[2 * TEAM + lane];
-    double t0 = gtraj[3 * TEAM + lane];
-    double vx = gtraj[4 * TEAM + lane], vy = gtraj[5 * TEAM + lane], vz = gtraj[6 * TEAM + lane];
     tm.sync();
 
     const int *chdr = ZRK_CST_I(c_hdr);
@@ -687,17 +719,11 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
                 int m = (fl >> F_STATIC_SHIFT) - T;
                 if (ZRK_COLD_I(m_birth)[m] == tick) {
                     fl = (fl & ~F_PENDING) | F_ALIVE;
-                    p0x = ZRK_LDCG(&gtraj[0 * TEAM + lane]);
-                    p0y = ZRK_LDCG(&gtraj[1 * TEAM + lane]);
-                    p0z = ZRK_LDCG(&gtraj[2 * TEAM + lane]);
-                    t0 = ZRK_LDCG(&gtraj[3 * TEAM + lane]);
-                    vx = ZRK_LDCG(&gtraj[4 * TEAM + lane]);
-                    vy = ZRK_LDCG(&gtraj[5 * TEAM + lane]);
-                    vz = ZRK_LDCG(&gtraj[6 * TEAM + lane]);
                 }
             }
             if (fl & F_ALIVE) {  // AirObject.step (AirObject.py:39-42)
-                const double2 oxy = H.pxy()[lane], ozs = H.pzs()[lane];
+                const double2 oxy = H.pxy()[lane], ozs = H.pzs()[lane], szt = H.tzt()[lane];
+                const double t0 = szt.y;
                 if (t0 != now_s) {
                     H.qxy()[lane] = oxy;
                     H.qzw()[lane] = make_double2(ozs.x, 0.0);
@@ -706,9 +732,10 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
                     fl &= ~F_HASPREV;
                 }
                 const double dtm = now_s - t0;
-                px = p0x + vx * dtm;
-                py = p0y + vy * dtm;
-                pz = p0z + vz * dtm;
+                const double2 sxy = H.txy()[lane], wxy = H.vxy()[lane];
+                px = sxy.x + wxy.x * dtm;  // Trajectory.get_pos (AirObject.py:23-25)
+                py = sxy.y + wxy.y * dtm;
+                pz = szt.x + H.vzw()[lane].x * dtm;
                 H.pxy()[lane] = make_double2(px, py);
                 H.pzs()[lane] = make_double2(pz, ozs.y);
             }
@@ -833,7 +860,7 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
         }
         if (serial) {
             if (lane == 0) {
-                nrec = serial_section<TEAM>(P.self, sm, gtraj, rec, tick, now_s, mb_prev, nrec);
+                nrec = serial_section<TEAM>(P.self, sm, rec, tick, now_s, mb_prev, nrec);
                 hdr[H_NREC] = nrec;
             }
             tm.sync();
@@ -849,16 +876,20 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
             if (lane < n_te) {
                 const int ref = H.te_ref()[lane], upd = H.te_upd()[lane];
                 const double2 a = H.qxy()[ref], c = H.qzw()[ref];
-                lxy[lane] = make_double2(upd == tick ? ZRK_FAR : a.x, a.y);
+                const double ax = upd == tick ? ZRK_FAR : a.x;
+                lxy[lane] = make_double2(ax, a.y);
                 lzd[lane] = make_double2(c.x, now_s - tick_seconds(P, upd));
+                if (FAST) lf[lane] = link_f32(ax, a.y, c.x);
             }
             if (lane < n_me) {
                 const int ref = ZRK_COLD_I(me_ref)[lane], upd = ZRK_COLD_I(me_upd)[lane];
                 const bool hp = (H.sflags()[ref] & F_HASPREV) != 0;
                 const double2 a = hp ? H.qxy()[ref] : H.pxy()[ref];
                 const double cz = hp ? H.qzw()[ref].x : H.pzs()[ref].x;
-                lxy[TEAM + lane] = make_double2(upd == tick ? ZRK_FAR : a.x, a.y);
+                const double ax = upd == tick ? ZRK_FAR : a.x;
+                lxy[TEAM + lane] = make_double2(ax, a.y);
                 lzd[TEAM + lane] = make_double2(cz, now_s - tick_seconds(P, upd));
+                if (FAST) lf[TEAM + lane] = link_f32(ax, a.y, cz);
             }
             // processing order: FOUND_OBJECTS messages in radar order, objects in list order,
             // each id once -> (first radar that saw it, slot)
@@ -894,7 +925,7 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
                 if (unresolved) {
                     if (FAST) {
                         bool unsure;
-                        link_fast<TEAM>(lxy, lzd, n_te, n_me, seed, P.range_step, dpx, dpy, dpz, dspeed, cls, cand, unsure);
+                        link_fast<TEAM>(lf, lxy, lzd, n_te, n_me, seed, P.range_step, dpx, dpy, dpz, dspeed, cls, cand, unsure);
                         if (unsure) link_exact<TEAM>(lxy, lzd, n_te, n_me, P.range_step, dpx, dpy, dpz, dspeed, cls, cand);
                     } else {
                         link_exact<TEAM>(lxy, lzd, n_te, n_me, P.range_step, dpx, dpy, dpz, dspeed, cls, cand);
@@ -1002,11 +1033,13 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
                         if (!following) H.te_follow()[cand] = ok != 0;
                         H.own()[slot] = cand;
                         lxy[cand].x = ZRK_FAR;
+                        if (FAST) lf[cand].x = 1e30f;
                     } else if (cls == 2) {  // old_rocket (CCP.py:361-366)
                         ZRK_COLD_I(me_ref)[cand] = slot;
                         ZRK_COLD_I(me_upd)[cand] = tick;
                         H.own()[slot] = TEAM + cand;
                         lxy[TEAM + cand].x = ZRK_FAR;
+                        if (FAST) lf[TEAM + cand].x = 1e30f;
                     } else {  // new_target + add_target (CCP.py:322-330, :88-93)
                         const int e = claim >= 0 ? claim : n_te + r_app;
                         H.te_key()[e] = did;
@@ -1016,6 +1049,7 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
                         H.te_mid()[e] = ZRK_NONE;
                         H.own()[slot] = e;
                         lxy[e].x = ZRK_FAR;
+                        if (FAST) lf[e] = make_float4(1e30f, 0.f, 0.f, 0.f);
                     }
                     unresolved = false;
                 }

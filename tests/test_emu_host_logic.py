@@ -67,6 +67,11 @@ def test_team_of_64_and_128(lib):
     check_batch_full(b, 12, lib=lib)
 
 
+def test_team_of_1024_fits_shared_memory(lib):
+    b = synthetic_batch(1, 600, n_radars=1, noise_period=4)
+    check_batch_full(b, 3, lib=lib)
+
+
 def test_events_mode_counts(lib):
     b = synthetic_batch(8, 24, n_radars=1, n_launchers=2, missiles_per_launcher=4, noise_period=8)
     check_batch_counts(b, 40, lib=lib, n_threads=2, sample=4)

@@ -62,7 +62,7 @@ __global__ void zrk_init_kernel(const Params P, const DevDesc d, int *err) {
     hdr[H_NSLOTS] = nT;
     double2 *pxy = (double2 *)(sm + ho.pxy), *pzs = (double2 *)(sm + ho.pzs);
     double2 *txy = (double2 *)(sm + ho.txy), *tzt = (double2 *)(sm + ho.tzt), *vxy = (double2 *)(sm + ho.vxy),
-            *vzw = (double2 *)(sm + ho.vzw);
+            *qzw = (double2 *)(sm + ho.qzw);
     int *sid = (int *)(sm + ho.sid), *sflags = (int *)(sm + ho.sflags), *srf = (int *)(sm + ho.srf),
         *own = (int *)(sm + ho.own);
     for (int t = 0; t < nT; t++) {
@@ -72,7 +72,7 @@ __global__ void zrk_init_kernel(const Params P, const DevDesc d, int *err) {
         txy[t] = make_double2(d.target_pos[3 * g], d.target_pos[3 * g + 1]);  // Trajectory (main.py:134-138)
         tzt[t] = make_double2(d.target_pos[3 * g + 2], 0.0);
         vxy[t] = make_double2(vx, vy);
-        vzw[t] = make_double2(vz, 0.0);
+        qzw[t] = make_double2(0.0, vz);
         pxy[t] = make_double2(d.target_pos[3 * g], d.target_pos[3 * g + 1]);
         pzs[t] = make_double2(d.target_pos[3 * g + 2], sp);
         sid[t] = d.target_id[g];
@@ -712,7 +712,7 @@ extern "C" int zrk_read_state(zrk_handle *h, const zrk_state_view *v) {
         for (int s = s0; s < s1; s++) {
             const unsigned char *sm = dyn.data() + (size_t)(s - s0) * o.dyn_bytes;
             const unsigned char *cs = cst.data() + (size_t)(s - s0) * o.cst_bytes;
-            const double *tzt = (const double *)(sm + ho.tzt), *vxy = (const double *)(sm + ho.vxy), *vzw = (const double *)(sm + ho.vzw);
+            const double *tzt = (const double *)(sm + ho.tzt), *vxy = (const double *)(sm + ho.vxy);
             const int *hdr = (const int *)(sm + ho.hdr), *sflags = (const int *)(sm + ho.sflags);
             const double *pxy = (const double *)(sm + ho.pxy), *pzs = (const double *)(sm + ho.pzs);
             const double *qxy = (const double *)(sm + ho.qxy), *qzw = (const double *)(sm + ho.qzw);
@@ -767,7 +767,7 @@ extern "C" int zrk_read_state(zrk_handle *h, const zrk_state_view *v) {
                 if (v->missile_period) v->missile_period[g] = live ? m_period[m] : 0.0;
                 if (v->missile_t0) v->missile_t0[g] = k >= 0 ? tzt[2 * k + 1] : 0.0;
                 if (v->missile_target) v->missile_target[g] = live && m_target[m] >= 0 ? stat(m_target[m]) : -1;
-                const double vk[3] = {k >= 0 ? vxy[2 * k] : 0.0, k >= 0 ? vxy[2 * k + 1] : 0.0, k >= 0 ? vzw[2 * k] : 0.0};
+                const double vk[3] = {k >= 0 ? vxy[2 * k] : 0.0, k >= 0 ? vxy[2 * k + 1] : 0.0, k >= 0 ? qzw[2 * k + 1] : 0.0};
                 for (int c = 0; c < 3; c++)
                     if (v->missile_vel) v->missile_vel[3 * g + c] = vk[c];
             }

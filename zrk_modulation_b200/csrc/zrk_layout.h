@@ -39,9 +39,9 @@ enum { C_NT = 0, C_NR, C_NL, C_NM, C_NC, C_AIRENV_ID, C_CCP_ID, C_TICK_LIMIT, C_
 struct HotOff {
     int hdr, counts;
     int pxy, pzs;  // double2[TEAM]: (pos.x, pos.y), (pos.z, speed_mod)
-    int qxy, qzw;  // double2[TEAM]: (prev.x, prev.y), (prev.z, unused)
+    int qxy, qzw;  // double2[TEAM]: (prev.x, prev.y), (prev.z, trajectory velocity.z)
     int txy, tzt;  // double2[TEAM]: trajectory (start_pos.x, start_pos.y), (start_pos.z, start_time)
-    int vxy, vzw;  // double2[TEAM]: trajectory velocity (x, y), (z, unused)
+    int vxy;       // double2[TEAM]: trajectory velocity (x, y)
     int sid, sflags, srf, own;                        // int[TEAM]
     int te_key, te_ref, te_upd, te_follow, te_mid;    // int[TEAM]  CCP._target_dict
     int end;
@@ -58,7 +58,6 @@ ZRK_HD constexpr HotOff hot_off(int team) {
     h.txy = p; p += 16 * team;
     h.tzt = p; p += 16 * team;
     h.vxy = p; p += 16 * team;
-    h.vzw = p; p += 16 * team;
     h.sid = p; p += 4 * team;
     h.sflags = p; p += 4 * team;
     h.srf = p; p += 4 * team;
@@ -91,7 +90,7 @@ struct Layout {
     // scratch (shared memory only), offsets from the start of the team's region
     int x_lxy, x_lzd;  // double2[TEAM + MP]: per CCP entry, the position link_object measures to
     int x_lf;          // float4[TEAM + MP]: the same position rounded to fp32 (scan pre-filter)
-    int x_claim, x_detlist, x_wscr, x_need, x_ok;
+    int x_claim, x_detlist, x_wscr, x_need;  // x_need doubles as the launch result (x_ok)
     int team_smem_bytes;
 };
 
@@ -171,7 +170,6 @@ static inline Layout make_layout(int B, int T, int M, int R, int L, int C) {
     o.x_detlist = take(4 * team);
     o.x_wscr = take(4 * 40);
     o.x_need = take(4 * team);
-    o.x_ok = take(4 * team);
     o.team_smem_bytes = zrk_align(p, 16);
     return o;
 }

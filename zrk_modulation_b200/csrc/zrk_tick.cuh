@@ -306,7 +306,6 @@ struct Hot {
     __device__ __forceinline__ double2 *txy() const { return (double2 *)(sm + O.txy); }
     __device__ __forceinline__ double2 *tzt() const { return (double2 *)(sm + O.tzt); }
     __device__ __forceinline__ double2 *vxy() const { return (double2 *)(sm + O.vxy); }
-    __device__ __forceinline__ double2 *vzw() const { return (double2 *)(sm + O.vzw); }
     __device__ __forceinline__ int *sid() const { return (int *)(sm + O.sid); }
     __device__ __forceinline__ int *sflags() const { return (int *)(sm + O.sflags); }
     __device__ __forceinline__ int *srf() const { return (int *)(sm + O.srf); }
@@ -529,7 +528,7 @@ __device__ ZRK_NOINLINE int serial_section(const Params *Pg, unsigned char *sm, 
                     if (H.sflags()[tg] & F_MISSILE) {
                         vt[0] = vt[1] = vt[2] = NAN;  // Missile.velocity is 0/0 (AirObject.py:35)
                     } else {
-                        double wx = H.vxy()[tg].x, wy = H.vxy()[tg].y, wz = H.vzw()[tg].x;
+                        double wx = H.vxy()[tg].x, wy = H.vxy()[tg].y, wz = H.qzw()[tg].y;
                         double sp = H.pzs()[tg].y;
                         vt[0] = wx / sp * sp;  // target.velocity * target.speed_mod (Missile.py:59)
                         vt[1] = wy / sp * sp;
@@ -546,7 +545,7 @@ __device__ ZRK_NOINLINE int serial_section(const Params *Pg, unsigned char *sm, 
                         H.txy()[k] = make_double2(c_l_pos[3 * l], c_l_pos[3 * l + 1]);  // new Trajectory (Missile.py:110-114)
                         H.tzt()[k] = make_double2(c_l_pos[3 * l + 2], now_s);
                         H.vxy()[k] = make_double2(V[0], V[1]);
-                        H.vzw()[k] = make_double2(V[2], 0.0);
+                        H.qzw()[k] = make_double2(0.0, V[2]);
                         H.pxy()[k] = make_double2(c_l_pos[3 * l], c_l_pos[3 * l + 1]);
                         H.pzs()[k] = make_double2(c_l_pos[3 * l + 2], v0);
                         H.sid()[k] = m_id;
@@ -726,7 +725,7 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
                 const double t0 = szt.y;
                 if (t0 != now_s) {
                     H.qxy()[lane] = oxy;
-                    H.qzw()[lane] = make_double2(ozs.x, 0.0);
+                    H.qzw()[lane].x = ozs.x;
                     fl |= F_HASPREV;
                 } else {
                     fl &= ~F_HASPREV;
@@ -735,7 +734,7 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
                 const double2 sxy = H.txy()[lane], wxy = H.vxy()[lane];
                 px = sxy.x + wxy.x * dtm;  // Trajectory.get_pos (AirObject.py:23-25)
                 py = sxy.y + wxy.y * dtm;
-                pz = szt.x + H.vzw()[lane].x * dtm;
+                pz = szt.x + H.qzw()[lane].y * dtm;
                 H.pxy()[lane] = make_double2(px, py);
                 H.pzs()[lane] = make_double2(pz, ozs.y);
             }
@@ -965,7 +964,7 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
                 int ok = 0;
                 // hdr[H_FREECAP] = sum over launchers of max(0, capacity - launched), kept by lane 0
                 if (hdr[H_FREECAP] > 0 && tm.any(need)) {  // try_to_launch_missile (CCP.py:287-320), in order
-                    int *x_need = (int *)(sm + o.x_need), *x_ok = (int *)(sm + o.x_ok);
+                    int *x_need = (int *)(sm + o.x_need);
                     x_need[i] = need;
                     tm.sync();
                     if (lane == 0) {
@@ -989,7 +988,7 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
                                     }
                                 }
                             }
-                            x_ok[j] = best + 1;
+                            x_need[j] = best + 1;  // overwritten with the result: 0 = no launcher, c + 1
                             if (best >= 0) {
                                 launched[best]++;
                                 hdr[H_FREECAP]--;
@@ -1001,7 +1000,7 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
                         }
                     }
                     tm.sync();
-                    if (need) ok = x_ok[i];
+                    if (need) ok = x_need[i];
                 }
                 // one message per finalised detection at most
                 int mtype = -1;

@@ -14,7 +14,7 @@ MARKS = [("helpers (dot3, pymod, tsec)", None), ("radar_sees", "SectorRadar.find
          ("radar_move", "SectorRadar.move_to_next_sector_circular"), ("team primitives", "team primitives"),
          ("put_rec", "record log"), ("missile_solve", "Missile._calculate_trajectory_params"),
          ("views", "shared-memory views"), ("calc_range/link_exact", "CCP.link_object"),
-         ("link_eval", "State of the squared-domain scan"), ("link_fast (scan)", "void link_fast("),
+         ("link_eval", "State of the squared-domain scan"), ("link_d2 (fp64 pair distance)", "double link_d2("), ("link scan (fp32 filter + loop)", "fp32 pre-filter of the scan"),
          ("serial_section", "lane 0 alone: launchers"), ("kernel prologue", "the kernel"),
          ("tick head", "for (int it = 0; it < n_ticks; it++)"), ("AirEnv.step", "AirEnv.step (AirEnv.py:26-53)"),
          ("Missile.step", "Missile.step, status 'active'"), ("radar loop", "SectorRadar.step for every radar"),

@@ -28,6 +28,12 @@
 struct uint4 {
     unsigned x, y, z, w;
 };
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+inline long long __double_as_longlong(double d) {
+    long long r;
+    memcpy(&r, &d, 8);
+    return r;
+}
 struct double2 {
     double x, y;
 };

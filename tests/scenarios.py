@@ -105,9 +105,21 @@ def special_config(kind: str):
         t[3].update(position=[0.0, 0.0, 1000.0], velocity=[0.0, 0.0, 5.0])       # straight overhead
         if len(t) > 4:
             t[4].update(position=[0.0, 0.0, 0.0], velocity=[1.0, 1.0, 1.0])      # starts at the radar: distance 0
+    elif kind == "late_launch":  # targets enter radar range after > 100 ticks: launches with a large clock value
+        cfg["simulation"] = {"time_step": 200, "duration": 200 * 260}
+        cfg["radars"] = [{"id": 5, "position": [0.0, 0.0, 0.0], "azimuth_start": 0.0, "elevation_start": 0.0,
+                          "max_distance": 9000.0, "azimuth_range": 360.0, "elevation_range": 90.0,
+                          "azimuth_speed": 0.0, "elevation_speed": 0.0, "scan_mode": "horizontal"}]
+        cfg["missile_launchers"] = [{"id": 100, "position": [300.0, 200.0, 0.0], "missiles": [
+            {"id": 5000 + i, "velocity": 900, "explosion_radius": 120, "life_time": 40} for i in range(3)]}]
+        cfg["combat_control_point"] = {"id": 0, "missile_launcher_ids": [100], "radar_ids": [5]}
+        del t[3:]
+        t[0].update(position=[16000.0, 1000.0, 2000.0], velocity=[-250.0, 0.0, 0.0])   # in range after ~28 s
+        t[1].update(position=[-2000.0, 19000.0, 3000.0], velocity=[10.0, -260.0, 0.0])  # ~38 s
+        t[2].update(position=[9000.0, 12000.0, 1500.0], velocity=[-150.0, -200.0, 0.0])  # ~25 s
     else:
         raise ValueError(kind)
     return cfg
 
 
-SPECIAL_KINDS = ["twins", "near_twins", "far_field", "on_axis"]
+SPECIAL_KINDS = ["twins", "near_twins", "far_field", "on_axis", "late_launch"]

@@ -44,6 +44,7 @@ struct HotOff {
     int vxy;       // double2[TEAM]: trajectory velocity (x, y)
     int sid, sflags, srf, own;                        // int[TEAM]
     int te_key, te_ref, te_upd, te_follow, te_mid;    // int[TEAM]  CCP._target_dict
+    int te_upds;                                      // double[TEAM] TargetCCP.upd_time (seconds)
     int end;
 };
 ZRK_HD constexpr HotOff hot_off(int team) {
@@ -67,6 +68,7 @@ ZRK_HD constexpr HotOff hot_off(int team) {
     h.te_upd = p; p += 4 * team;
     h.te_follow = p; p += 4 * team;
     h.te_mid = p; p += 4 * team;
+    h.te_upds = p; p += 8 * team;
     h.end = p;
     return h;
 }
@@ -77,7 +79,7 @@ struct Layout {
     int team, teams_per_cta;
     HotOff hot;
     // cold part of the dyn blob (byte offsets)
-    int me_key, me_ref, me_upd, me_tid;
+    int me_key, me_ref, me_upd, me_tid, me_upds;
     int rad_cur, st_n, st, cap, launched;
     int m_status, m_target, m_slot, m_birth, m_period;
     int det_mid, det_tid, det_flag, mb_type, mb_l, mb_a, ln_m;
@@ -138,6 +140,7 @@ static inline Layout make_layout(int B, int T, int M, int R, int L, int C) {
     int p = o.hot.end;
     auto take = [&p](int bytes) { int at = p; p += zrk_align(bytes, 8); return at; };
     o.me_key = take(4 * o.MP); o.me_ref = take(4 * o.MP); o.me_upd = take(4 * o.MP); o.me_tid = take(4 * o.MP);
+    o.me_upds = take(8 * o.MP);
     o.rad_cur = take(8 * 2 * o.RP);
     o.st_n = take(4 * o.LP);
     o.st = take(4 * o.LP * o.MP);

@@ -236,20 +236,14 @@ struct Team {
 
 __device__ __forceinline__ void put_rec(const Params &P, zrk_msg *base, int idx, int tick, int type, int flag,
                                         int sender, int receiver, int a, int b, double x, double y, double z) {
-    if (idx < P.log_cap) {
-        zrk_msg *r = base + idx;
-        r->tick = tick;
-        r->type = (unsigned char)type;
-        r->relevance = (unsigned char)(type == ZRK_MSG_MISSILE_COUNT_REQUEST ? 3 : 1);
-        r->flag = (unsigned char)flag;
-        r->pad = 0;
-        r->sender = sender;
-        r->receiver = receiver;
-        r->a = a;
-        r->b = b;
-        r->xyz[0] = x;
-        r->xyz[1] = y;
-        r->xyz[2] = z;
+    if (idx < P.log_cap) {  // one 48-byte record = three 16-byte stores
+        uint4 *r = (uint4 *)(base + idx);
+        const unsigned w1 = (unsigned)type | ((type == ZRK_MSG_MISSILE_COUNT_REQUEST ? 3u : 1u) << 8) | ((unsigned)(flag & 0xff) << 16);
+        const unsigned long long xb = (unsigned long long)__double_as_longlong(x), yb = (unsigned long long)__double_as_longlong(y),
+                                 zb = (unsigned long long)__double_as_longlong(z);
+        r[0] = make_uint4((unsigned)tick, w1, (unsigned)sender, (unsigned)receiver);
+        r[1] = make_uint4((unsigned)a, (unsigned)b, (unsigned)xb, (unsigned)(xb >> 32));
+        r[2] = make_uint4((unsigned)yb, (unsigned)(yb >> 32), (unsigned)zb, (unsigned)(zb >> 32));
     }
 }
 __device__ __forceinline__ bool logged(const Params &P, int type) { return (P.log_types >> type) & 1u; }
@@ -315,6 +309,7 @@ struct Hot {
     __device__ __forceinline__ int *te_upd() const { return (int *)(sm + O.te_upd); }
     __device__ __forceinline__ int *te_follow() const { return (int *)(sm + O.te_follow); }
     __device__ __forceinline__ int *te_mid() const { return (int *)(sm + O.te_mid); }
+    __device__ __forceinline__ double *te_upds() const { return (double *)(sm + O.te_upds); }
 };
 
 // Cold arrays (run-time offsets), resolved on use.
@@ -621,6 +616,7 @@ __device__ ZRK_NOINLINE int serial_section(const Params *Pg, unsigned char *sm, 
                 me_key[e] = m_id;
                 ZRK_COLD_I(me_ref)[e] = ZRK_COLD_I(m_slot)[m];
                 ZRK_COLD_I(me_upd)[e] = tick;
+                ZRK_COLD_D(me_upds)[e] = now_s;
                 ZRK_COLD_I(me_tid)[e] = tid;
                 H.own()[ZRK_COLD_I(m_slot)[m]] = TEAM + e;
                 int t, n_te = hdr[H_NTE];
@@ -684,12 +680,14 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
     const double *noise = P.noise ? P.noise + (size_t)b * P.noise_stride : nullptr;
     int *const hdr = H.hdr();
 
+    double now_next = tick_seconds(P, hdr[H_TICK]);
     for (int it = 0; it < n_ticks; it++) {
         const int tick = hdr[H_TICK];
         if (hdr[H_FAULT] & 63) break;  // the reference run aborted here
         if (tick_limit >= 0 && tick >= tick_limit) break;
         const int par = tick & 1, prv = par ^ 1;
-        const double now_s = tick_seconds(P, tick);
+        const double now_s = now_next;          // to_seconds(time.get_time())
+        now_next = tick_seconds(P, tick + 1);  // loaded a tick ahead: its latency is never waited for
         const int n_slots = hdr[H_NSLOTS];
         const int det_prev = hdr[H_DETN0 + prv];
         const int mb_prev = hdr[H_MBN0 + prv];
@@ -704,9 +702,17 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
         // ============ AirEnv.step (AirEnv.py:26-53)
         int fl = 0, my_id = 0;
         double px = 0, py = 0, pz = 0;
+        double nz0 = 0, nz1 = 0, nz2 = 0;  // radar 0's noise for this slot, fetched early
         if (lane < n_slots) {
             fl = H.sflags()[lane];
             my_id = H.sid()[lane];
+            if (noise && nR) {
+                const double *nz = noise + (((size_t)(tick % P.noise_period) * P.noise_radars) * P.noise_objects +
+                                            (fl >> F_STATIC_SHIFT)) * 3;
+                nz0 = nz[0];
+                nz1 = nz[1];
+                nz2 = nz[2];
+            }
             if ((fl & F_ALIVE) && det_prev) {  // :33-40 removal by id
                 const int *dm = ZRK_COLD_I(det_mid) + prv * MP, *dt = ZRK_COLD_I(det_tid) + prv * MP;
                 for (int i = 0; i < det_prev; i++) {
@@ -806,11 +812,16 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
                     vis = radar_sees<FAST>(dx, dy, dz, par_r, caz, caz + par_r[3], cel, cel + par_r[4]);
                     if (vis) {  // smooth_objects (Radar.py:138-142)
                         if (noise) {
-                            const double *nz = noise + (((size_t)(tick % P.noise_period) * P.noise_radars + r) * P.noise_objects +
-                                                        (fl >> F_STATIC_SHIFT)) * 3;
-                            px += nz[0];
-                            py += nz[1];
-                            pz += nz[2];
+                            if (r) {
+                                const double *nz = noise + (((size_t)(tick % P.noise_period) * P.noise_radars + r) * P.noise_objects +
+                                                            (fl >> F_STATIC_SHIFT)) * 3;
+                                nz0 = nz[0];
+                                nz1 = nz[1];
+                                nz2 = nz[2];
+                            }
+                            px += nz0;
+                            py += nz1;
+                            pz += nz2;
                         }
                         if (rf < 0) rf = r;
                     }
@@ -877,7 +888,7 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
                 const double2 a = H.qxy()[ref], c = H.qzw()[ref];
                 const double ax = upd == tick ? ZRK_FAR : a.x;
                 lxy[lane] = make_double2(ax, a.y);
-                lzd[lane] = make_double2(c.x, now_s - tick_seconds(P, upd));
+                lzd[lane] = make_double2(c.x, now_s - H.te_upds()[lane]);
                 if (FAST) lf[lane] = link_f32(ax, a.y, c.x);
             }
             if (lane < n_me) {
@@ -887,7 +898,7 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
                 const double cz = hp ? H.qzw()[ref].x : H.pzs()[ref].x;
                 const double ax = upd == tick ? ZRK_FAR : a.x;
                 lxy[TEAM + lane] = make_double2(ax, a.y);
-                lzd[TEAM + lane] = make_double2(cz, now_s - tick_seconds(P, upd));
+                lzd[TEAM + lane] = make_double2(cz, now_s - ZRK_COLD_D(me_upds)[lane]);
                 if (FAST) lf[TEAM + lane] = link_f32(ax, a.y, cz);
             }
             // processing order: FOUND_OBJECTS messages in radar order, objects in list order,
@@ -1029,6 +1040,7 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
                     if (cls == 1) {  // old_target (CCP.py:332-359)
                         H.te_ref()[cand] = slot;
                         H.te_upd()[cand] = tick;
+                        H.te_upds()[cand] = now_s;
                         if (!following) H.te_follow()[cand] = ok != 0;
                         H.own()[slot] = cand;
                         lxy[cand].x = ZRK_FAR;
@@ -1036,6 +1048,7 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
                     } else if (cls == 2) {  // old_rocket (CCP.py:361-366)
                         ZRK_COLD_I(me_ref)[cand] = slot;
                         ZRK_COLD_I(me_upd)[cand] = tick;
+                        ZRK_COLD_D(me_upds)[cand] = now_s;
                         H.own()[slot] = TEAM + cand;
                         lxy[TEAM + cand].x = ZRK_FAR;
                         if (FAST) lf[TEAM + cand].x = 1e30f;
@@ -1044,6 +1057,7 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
                         H.te_key()[e] = did;
                         H.te_ref()[e] = slot;
                         H.te_upd()[e] = tick;
+                        H.te_upds()[e] = now_s;
                         H.te_follow()[e] = ok != 0;
                         H.te_mid()[e] = ZRK_NONE;
                         H.own()[slot] = e;

@@ -284,6 +284,13 @@ int zrk_read_messages(zrk_handle *h, int scenario, int tick0, int tick1, zrk_msg
 int zrk_read_state(zrk_handle *h, const zrk_state_view *view);
 /* Device pointers for zero-copy consumers (torch): borrowed, valid until zrk_destroy. */
 int zrk_device_ptr(zrk_handle *h, const char *name, void **ptr, size_t *bytes); /* "dyn", "cst", "rec", "masks" */
+/* Checkpoint / resume (absent in the reference): the complete device state of the
+ * batch (scenario state, record log, mask history, clock) as one opaque host blob.
+ * zrk_state_bytes gives the size; zrk_load_state needs a handle created from the same
+ * zrk_batch_desc and zrk_options. */
+int zrk_state_bytes(zrk_handle *h, size_t *bytes);
+int zrk_save_state(zrk_handle *h, void *buf, size_t cap);
+int zrk_load_state(zrk_handle *h, const void *buf, size_t bytes);
 /* Kernel launches issued by this handle and device time spent in them (CUDA events), ms. */
 int zrk_launch_stats(zrk_handle *h, int64_t *n_launches, double *kernel_ms);
 const char *zrk_last_error(zrk_handle *h); /* h may be NULL: error of the last failed zrk_create */

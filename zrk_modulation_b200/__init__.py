@@ -7,7 +7,7 @@ reference's BaseModel / Manager / message interface.  There is no CPU fallback.
 """
 from ._cabi import (ZRK_NONE, LOG_EVENTS, LOG_BULK, LOG_MASKS, LOG_FULL, MSG_NAMES)  # noqa: F401
 from .scenario import (Batch, compile_batch, load_config, make_noise, synthetic_batch,  # noqa: F401
-                       batch_to_config)
+                       batch_to_config, perturbed_batch)
 
 from .messages import MessageType, TargetType  # noqa: F401,E402
 from .manager import (BaseModel, BatchedManager, BatchedTick, Timer, create_objects_from_config,  # noqa: F401,E402
@@ -16,5 +16,5 @@ from .engine import Engine, ZrkError  # noqa: F401,E402
 
 __all__ = ["MessageType", "TargetType", "BaseModel", "BatchedManager", "BatchedTick", "Timer",
            "create_objects_from_config", "run_simulation_from_config", "Engine", "ZrkError","Batch", "compile_batch", "load_config", "make_noise", "synthetic_batch",
-           "batch_to_config", "ZRK_NONE", "LOG_EVENTS", "LOG_BULK", "LOG_MASKS", "LOG_FULL",
+           "batch_to_config", "perturbed_batch", "ZRK_NONE", "LOG_EVENTS", "LOG_BULK", "LOG_MASKS", "LOG_FULL",
            "MSG_NAMES"]

@@ -168,6 +168,9 @@ def declare(lib):
     lib.zrk_read_messages.argtypes = [H, C.c_int, C.c_int, C.c_int, C.POINTER(ZrkMsg), C.c_size_t,
                                       C.POINTER(C.c_size_t), _pi32, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.zrk_read_state.argtypes = [H, C.POINTER(ZrkStateView)]
+    lib.zrk_state_bytes.argtypes = [H, C.POINTER(C.c_size_t)]
+    lib.zrk_save_state.argtypes = [H, C.c_void_p, C.c_size_t]
+    lib.zrk_load_state.argtypes = [H, C.c_void_p, C.c_size_t]
     lib.zrk_device_ptr.argtypes = [H, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     lib.zrk_launch_stats.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     lib.zrk_last_error.argtypes = [H]
@@ -177,7 +180,8 @@ def declare(lib):
     lib.zrk_abi_version.argtypes = []
     for f in ("zrk_create", "zrk_step", "zrk_sync", "zrk_get_time", "zrk_read_status",
               "zrk_read_counts", "zrk_read_records", "zrk_log_capacity", "zrk_read_messages",
-              "zrk_read_state", "zrk_device_ptr", "zrk_launch_stats", "zrk_abi_version"):
+              "zrk_read_state", "zrk_device_ptr", "zrk_launch_stats", "zrk_abi_version", "zrk_state_bytes",
+              "zrk_save_state", "zrk_load_state"):
         getattr(lib, f).restype = C.c_int
     return lib
 
@@ -185,4 +189,4 @@ def declare(lib):
 EXPORTED_SYMBOLS = ["zrk_create", "zrk_step", "zrk_sync", "zrk_get_time", "zrk_read_status",
                     "zrk_read_counts", "zrk_read_records", "zrk_log_capacity", "zrk_read_messages",
                     "zrk_read_state", "zrk_device_ptr", "zrk_launch_stats", "zrk_last_error",
-                    "zrk_destroy", "zrk_abi_version"]
+                    "zrk_destroy", "zrk_abi_version", "zrk_state_bytes", "zrk_save_state", "zrk_load_state"]

@@ -805,6 +805,79 @@ extern "C" int zrk_read_state(zrk_handle *h, const zrk_state_view *v) {
     return ZRK_OK;
 }
 
+// ------------------------------------------------------------------ checkpoint / resume
+
+struct SaveHeader {
+    unsigned long long magic;
+    long long tick;
+    unsigned long long dyn_bytes, rec_bytes, mask_bytes;
+    int B, team, log_cap, mask_ticks;
+};
+static const unsigned long long ZRK_SAVE_MAGIC = 0x5a524b5f53415645ull;  // "ZRK_SAVE"
+
+static void save_sizes(const zrk_handle *h, SaveHeader &sh) {
+    const Params &P = h->P;
+    const Layout &o = P.lo;
+    sh.magic = ZRK_SAVE_MAGIC;
+    sh.tick = h->tick;
+    sh.dyn_bytes = (unsigned long long)o.B * o.dyn_bytes;
+    sh.rec_bytes = (unsigned long long)o.B * P.log_cap * sizeof(zrk_msg);
+    sh.mask_bytes = P.masks ? (unsigned long long)P.mask_ticks * o.B * (1 + o.RP) * P.mask_words * sizeof(unsigned) : 0;
+    sh.B = o.B;
+    sh.team = o.team;
+    sh.log_cap = P.log_cap;
+    sh.mask_ticks = P.mask_ticks;
+}
+
+extern "C" int zrk_state_bytes(zrk_handle *h, size_t *bytes) {
+    if (!h || !bytes) return ZRK_ERR_ARG;
+    SaveHeader sh;
+    save_sizes(h, sh);
+    *bytes = sizeof(SaveHeader) + sh.dyn_bytes + sh.rec_bytes + sh.mask_bytes;
+    return ZRK_OK;
+}
+
+extern "C" int zrk_save_state(zrk_handle *h, void *buf, size_t cap) {
+    if (!h || !buf) return ZRK_ERR_ARG;
+    SaveHeader sh;
+    save_sizes(h, sh);
+    if (cap < sizeof(SaveHeader) + sh.dyn_bytes + sh.rec_bytes + sh.mask_bytes) return ZRK_ERR_CAPACITY;
+    int rc = zrk_sync(h);
+    if (rc) return rc;
+    unsigned char *p = (unsigned char *)buf;
+    memcpy(p, &sh, sizeof sh);
+    p += sizeof sh;
+    CK(cudaMemcpy(p, h->P.dyn, sh.dyn_bytes, cudaMemcpyDeviceToHost));
+    p += sh.dyn_bytes;
+    CK(cudaMemcpy(p, h->P.rec, sh.rec_bytes, cudaMemcpyDeviceToHost));
+    p += sh.rec_bytes;
+    if (sh.mask_bytes) CK(cudaMemcpy(p, h->P.masks, sh.mask_bytes, cudaMemcpyDeviceToHost));
+    return ZRK_OK;
+}
+
+extern "C" int zrk_load_state(zrk_handle *h, const void *buf, size_t bytes) {
+    if (!h || !buf || bytes < sizeof(SaveHeader)) return ZRK_ERR_ARG;
+    SaveHeader sh, mine;
+    memcpy(&sh, buf, sizeof sh);
+    save_sizes(h, mine);
+    if (sh.magic != ZRK_SAVE_MAGIC || sh.B != mine.B || sh.team != mine.team || sh.log_cap != mine.log_cap ||
+        sh.mask_ticks != mine.mask_ticks || sh.dyn_bytes != mine.dyn_bytes || sh.rec_bytes != mine.rec_bytes ||
+        sh.mask_bytes != mine.mask_bytes || bytes < sizeof(SaveHeader) + sh.dyn_bytes + sh.rec_bytes + sh.mask_bytes) {
+        h->err = "checkpoint does not match this handle (different batch shape or options)";
+        return ZRK_ERR_ARG;
+    }
+    int rc = zrk_sync(h);
+    if (rc) return rc;
+    const unsigned char *p = (const unsigned char *)buf + sizeof sh;
+    CK(cudaMemcpy(h->P.dyn, p, sh.dyn_bytes, cudaMemcpyHostToDevice));
+    p += sh.dyn_bytes;
+    CK(cudaMemcpy(h->P.rec, p, sh.rec_bytes, cudaMemcpyHostToDevice));
+    p += sh.rec_bytes;
+    if (sh.mask_bytes) CK(cudaMemcpy(h->P.masks, p, sh.mask_bytes, cudaMemcpyHostToDevice));
+    h->tick = sh.tick;
+    return ensure_tsec(h, h->tick + 2);
+}
+
 extern "C" int zrk_device_ptr(zrk_handle *h, const char *name, void **ptr, size_t *bytes) {
     if (!h || !name || !ptr) return ZRK_ERR_ARG;
     const Params &P = h->P;

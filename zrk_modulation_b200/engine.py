@@ -124,6 +124,39 @@ class Engine:
         self._ck(self.lib.zrk_read_state(self._h, C.byref(view)))
         return arrays
 
+    # -- checkpoint / resume
+    def save_state(self) -> np.ndarray:
+        """The complete device state as an opaque uint8 array (zrk_save_state)."""
+        n = C.c_size_t()
+        self._ck(self.lib.zrk_state_bytes(self._h, C.byref(n)))
+        buf = np.empty(n.value, dtype=np.uint8)
+        self._ck(self.lib.zrk_save_state(self._h, buf.ctypes.data_as(C.c_void_p), n.value))
+        return buf
+
+    def load_state(self, buf: np.ndarray) -> None:
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        self._ck(self.lib.zrk_load_state(self._h, buf.ctypes.data_as(C.c_void_p), buf.nbytes))
+
+    def outcomes(self, s0: int = 0, s1: Optional[int] = None) -> dict:
+        """Per-scenario outcome table from the event log and counters (the structured replacement
+        of the reference's text log, main.py:21-28): launches, cancelled launches, targets
+        destroyed, self-detonations, first launch / last detonation tick, fault."""
+        A = _cabi
+        s1 = self.batch.n_scenarios if s1 is None else s1
+        recs, n = self.records(s0, s1)
+        live = np.arange(recs.shape[1])[None, :] < n[:, None]
+        ty, tick, flag = recs["type"], recs["tick"].astype(np.int64), recs["flag"]
+        det = live & (ty == A.MSG_MISSILE_DETONATE)
+        ok = live & (ty == A.MSG_LAUNCH_SUCCESSFUL)
+        big = np.iinfo(np.int64).max
+        first_launch = np.where(ok, tick, big).min(axis=1)
+        last_det = np.where(det, tick, -1).max(axis=1)
+        fc, ft, _ = self.status()
+        return {"launches": ok.sum(axis=1), "cancelled": (live & (ty == A.MSG_LAUNCH_CANCELLED)).sum(axis=1),
+                "targets_destroyed": (det & (flag == 0)).sum(axis=1), "self_detonations": (det & (flag != 0)).sum(axis=1),
+                "first_launch_tick": np.where(first_launch == big, -1, first_launch), "last_detonation_tick": last_det,
+                "fault_code": fc[s0:s1] & 63, "fault_tick": ft[s0:s1], "messages": self.counts()[s0:s1].sum(axis=1)}
+
     def launch_stats(self):
         n, ms = C.c_int64(), C.c_double()
         self._ck(self.lib.zrk_launch_stats(self._h, C.byref(n), C.byref(ms)))

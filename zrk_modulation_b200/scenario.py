@@ -321,6 +321,22 @@ def synthetic_batch(n_scenarios: int, n_targets: int, n_radars: int = 1, n_launc
     return b
 
 
+def perturbed_batch(config: Union[Dict[str, Any], str], n_scenarios: int, pos_sigma: float = 100.0,
+                    vel_sigma: float = 5.0, seed: int = 0, noise: Optional[np.ndarray] = None) -> Batch:
+    """Monte-Carlo family around one scenario: `n_scenarios` copies of `config` whose target
+    start positions / velocities are perturbed by N(0, pos_sigma^2) / N(0, vel_sigma^2);
+    scenario 0 is the unperturbed original."""
+    base = compile_batch(config, noise=noise)
+    rep = lambda a: np.repeat(a, n_scenarios, axis=0)
+    b = Batch(**{f: (rep(v) if isinstance(v, np.ndarray) and f != "noise" else v)
+                 for f, v in vars(base).items() if f not in ("_keep",)})
+    rng = np.random.default_rng(seed)
+    T = int(base.n_targets[0])
+    b.target_pos[1:, :T] += rng.normal(0.0, pos_sigma, size=(n_scenarios - 1, T, 3))
+    b.target_vel[1:, :T] += rng.normal(0.0, vel_sigma, size=(n_scenarios - 1, T, 3))
+    return b
+
+
 def batch_to_config(b: Batch, s: int) -> Dict[str, Any]:
     """Inverse of compile_batch for one scenario: a dict in the reference's YAML schema."""
     T = int(b.n_targets[s])

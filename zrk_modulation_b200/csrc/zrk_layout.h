@@ -73,6 +73,11 @@ ZRK_HD constexpr HotOff hot_off(int team) {
     return h;
 }
 
+// threads per CTA for teams smaller than a CTA (TEAM = 32, 64)
+#ifndef ZRK_CTA_THREADS
+#define ZRK_CTA_THREADS 128
+#endif
+
 struct Layout {
     int B, T, M, NS, R, L, C;
     int MP, RP, LP, CP, Q;
@@ -130,7 +135,7 @@ static inline Layout make_layout(int B, int T, int M, int R, int L, int C) {
     o.B = B; o.T = T; o.M = M; o.NS = T + M; o.R = R; o.L = L; o.C = C;
     o.team = zrk_team_for(o.NS);
     const int team = o.team ? o.team : 32;
-    o.teams_per_cta = team >= 128 ? 1 : 128 / team;
+    o.teams_per_cta = team >= ZRK_CTA_THREADS ? 1 : ZRK_CTA_THREADS / team;
     o.MP = zrk_align(M > 0 ? M : 1, 2);
     o.RP = R > 0 ? R : 1;
     o.LP = zrk_align(L > 0 ? L : 1, 2);

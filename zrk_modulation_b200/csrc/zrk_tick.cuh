@@ -640,7 +640,7 @@ __device__ ZRK_NOINLINE int serial_section(const Params *Pg, unsigned char *sm, 
 #ifndef ZRK_MINB_SMALL
 #define ZRK_MINB_SMALL 4
 #endif
-constexpr int min_blocks(int threads) { return threads <= 128 ? ZRK_MINB_SMALL : (threads == 256 ? 2 : 1); }
+constexpr int min_blocks(int threads) { return threads <= ZRK_CTA_THREADS ? ZRK_MINB_SMALL : (threads <= 128 ? 4 : (threads == 256 ? 2 : 1)); }
 
 template <int TEAM, int TPC, bool FAST>
 __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_kernel(const Params P, int n_ticks) {

@@ -25,12 +25,21 @@
 #define ZRK_NAMED_BARRIER(id, n) zrk_emu::named_barrier((id), (n))
 #define ZRK_SMEM_DECL unsigned char *zrk_smem = zrk_emu::dyn_smem()
 #define ZRK_LDCG(p) (*(p))
+#define ZRK_LD_EARLY(p) (*(p))
 #define ZRK_NOINLINE __attribute__((noinline))
 #else
 #include <cuda_runtime.h>
 #define ZRK_NAMED_BARRIER(id, n) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory")
 #define ZRK_SMEM_DECL extern __shared__ __align__(16) unsigned char zrk_smem[]
 #define ZRK_LDCG(p) __ldcg(p)
+// a read-only global load the compiler must issue where it is written (not sunk to its first use),
+// so that its latency overlaps the work in between
+__device__ __forceinline__ double zrk_ld_early(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+#define ZRK_LD_EARLY(p) zrk_ld_early(p)
 #define ZRK_NOINLINE __noinline__
 #endif
 
@@ -60,7 +69,7 @@ __device__ __forceinline__ double pymod(double a, double m) {
 __device__ __forceinline__ double to_seconds(long long ms) { return (double)ms / 1000.0; }
 // to_seconds(tick * dt) from the table the host fills with exactly that expression
 __device__ __forceinline__ double tick_seconds(const Params &P, int tick) {
-    return (tick >= 0 && tick < P.tsec_n) ? P.tsec[tick] : to_seconds((long long)tick * P.dt_ms);
+    return (tick >= 0 && tick < P.tsec_n) ? ZRK_LD_EARLY(&P.tsec[tick]) : to_seconds((long long)tick * P.dt_ms);
 }
 
 #define ZRK_RAD2DEG 57.29577951308232 /* 180.0 / pi, as np.degrees multiplies */
@@ -709,9 +718,9 @@ __global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_ker
             if (noise && nR) {
                 const double *nz = noise + (((size_t)(tick % P.noise_period) * P.noise_radars) * P.noise_objects +
                                             (fl >> F_STATIC_SHIFT)) * 3;
-                nz0 = nz[0];
-                nz1 = nz[1];
-                nz2 = nz[2];
+                nz0 = ZRK_LD_EARLY(nz);
+                nz1 = ZRK_LD_EARLY(nz + 1);
+                nz2 = ZRK_LD_EARLY(nz + 2);
             }
             if ((fl & F_ALIVE) && det_prev) {  // :33-40 removal by id
                 const int *dm = ZRK_COLD_I(det_mid) + prv * MP, *dt = ZRK_COLD_I(det_tid) + prv * MP;

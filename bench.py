@@ -195,7 +195,7 @@ def run_ours(args, rank, world, local_rank):
         eng = Engine(batch, device=dev, ticks_per_launch=args.ticks_per_launch)
         eng.sync()
         flush.fill_(i & 0xff)  # evict the freshly written state from L2
-        if i == args.warmup and rank == 0:
+        if i == 0 and rank == 0:  # same load during warm-up and timed steps: sample across both
             sampler = ClockSampler(dev)
         barrier()
         n0, ms0 = eng.launch_stats()
@@ -276,7 +276,7 @@ def run_ours(args, rank, world, local_rank):
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            v, n, tk, dt = cpu_reference_throughput(args.workload, 512, cores, min(ticks, 250))
+            v, n, tk, dt = cpu_reference_throughput(args.workload, 1024, cores, min(ticks, 250))
             line["cpu_baseline"] = {"value": v, "unit": "object-updates/s", "cores": cores, "kind": "port",
                                     "sample": f"{n} scenarios x {NS} slots x {tk} ticks in {dt:.2f}s, "
                                               f"oracle/zrk_oracle.c on {cores} host threads"}

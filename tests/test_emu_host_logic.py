@@ -53,6 +53,24 @@ def test_ragged_batch_and_chunked_steps(lib):
     check_batch_full(b, 40, lib=lib, step_chunks=[1, 2, 30, 7])
 
 
+def test_ragged_durations_stop_each_scenario_at_its_end(lib):
+    cfgs = [random_config(420 + i, "mixed") for i in range(4)]
+    for i, c in enumerate(cfgs):
+        c["simulation"] = {"time_step": 200, "duration": 200 * (10 + 7 * i)}
+    b = compile_batch(cfgs)
+    assert list(b.tick_limit) == [10, 17, 24, 31]
+    b.set_noise(make_noise(8, b.max_radars, b.n_slots, seed=2))
+    check_batch_full(b, 31, lib=lib)
+    from zrk_modulation_b200 import BatchedManager, MessageType
+    mgr = BatchedManager(b, log="full", lib=lib)
+    mgr.run_simulation(31 * 200)
+    for i, limit in enumerate([10, 17, 24, 31]):
+        v = mgr.scenario(i)
+        want = limit if not v.fault else v.fault[1] + 1
+        assert len(v.messages) == want and v.message_counts()[MessageType.ACTIVE_OBJECTS] == want
+    mgr.close()
+
+
 def test_exact_only_kernel_agrees(lib):
     cfg = random_config(410, "dense")
     b = compile_batch(cfg)

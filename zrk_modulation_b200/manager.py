@@ -265,6 +265,8 @@ class BatchedManager(ScenarioView):
         done = self.time.get_time() // self.batch.dt_ms
         if int(fc[s]) & 63:  # the reference aborted in tick ft: its messages exist, nothing later
             return int(ft[s]) + 1
+        if self.batch.tick_limit is not None:  # this scenario's own `while time < end_time`
+            done = min(done, int(self.batch.tick_limit[s]))
         return int(done)
 
     def _object_views(self, s: int) -> Dict[int, AirObjectView]:

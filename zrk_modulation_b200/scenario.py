@@ -255,6 +255,8 @@ def compile_batch(configs: Union[Dict[str, Any], str, Sequence[Union[Dict[str, A
             b.missile_radius[s, i], b.missile_life[s, i] = m["radius"], m["life"]
         for i, c in enumerate(f["ccp_launchers"]):
             b.ccp_launcher_id[s, i], b.ccp_launcher_pos[s, i] = c["id"], c["pos"]
+    if len({int(d) for d in b.durations}) > 1:  # ragged durations: every scenario stops at its own end_time
+        b.tick_limit = np.array([b.n_ticks(s) for s in range(B)], dtype=np.int32)
     b.set_noise(noise)
     return b
 

@@ -651,8 +651,13 @@ __device__ ZRK_NOINLINE int serial_section(const Params *Pg, unsigned char *sm, 
 #endif
 constexpr int min_blocks(int threads) { return threads <= ZRK_CTA_THREADS ? ZRK_MINB_SMALL : (threads <= 128 ? 4 : (threads == 256 ? 2 : 1)); }
 
+#ifdef ZRK_MAXNREG
+#define ZRK_KERNEL_ATTR __maxnreg__(ZRK_MAXNREG)
+#else
+#define ZRK_KERNEL_ATTR __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC))
+#endif
 template <int TEAM, int TPC, bool FAST>
-__global__ void __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC)) zrk_tick_kernel(const Params P, int n_ticks) {
+__global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
     ZRK_SMEM_DECL;
     const Layout &o = P.lo;
     const int MP = o.MP, Q = o.Q;

@@ -87,13 +87,33 @@ def test_synthetic_families_full_log(n_targets, radars, launchers, mpl, ticks, b
 
 
 def test_config2_shape_1000_objects():
-    """BASELINE config 2: one scenario, one radar, 1000 air objects.  All-visible for the ticks
-    the oracle finishes in seconds, then a 30-degree sweeping sector for longer."""
+    """BASELINE config 2: one scenario, one radar, 1000 air objects — SURVEY §8d's comparison plan:
+    50 ticks with everything visible, then 1000 ticks of a 30-degree sweeping sector, every
+    message against the oracle."""
     b = synthetic_batch(1, 1000, n_radars=1, seed0=7, noise_period=8)
-    check_batch_full(b, 6)
+    check_batch_full(b, 50)
     b = synthetic_batch(1, 1000, n_radars=1, seed0=8, noise_period=8)
     b.radar_par[0, 0] = [0.0, 0.0, 30000.0, 30.0, 90.0, 30.0, 0.0, 0.0]
-    check_batch_full(b, 40)
+    check_batch_full(b, 1000)
+
+
+def test_config2_full_length_self_consistency():
+    """Config 2 at its full 10 000 ticks (no oracle: size-independent properties): one launch per
+    256 ticks == one launch per tick-chunk of odd sizes; every tick emits ACTIVE/ALL/FOUND once."""
+    from zrk_modulation_b200 import _cabi as A
+    b = synthetic_batch(1, 1000, n_radars=1, seed0=9, noise_period=16)
+    b.radar_par[0, 0] = [0.0, 0.0, 30000.0, 30.0, 90.0, 30.0, 0.0, 0.0]
+    out = []
+    for tpl, chunks in ((0, [10000]), (37, [1234, 4321, 4445])):
+        with Engine(b, ticks_per_launch=tpl) as eng:
+            for c in chunks:
+                eng.step(c)
+            out.append((eng.counts(), eng.status(), eng.state()))
+    (c0, s0, st0), (c1, s1, st1) = out
+    assert np.array_equal(c0, c1) and all(np.array_equal(x, y) for x, y in zip(s0, s1))
+    assert parity.same_f64(st0["pos"], st1["pos"]) and np.array_equal(st0["ccp_t_upd"], st1["ccp_t_upd"])
+    done = 10000 if not (s0[0][0] & 63) else int(s0[1][0]) + 1
+    assert c0[0, A.MSG_ACTIVE_OBJECTS] == c0[0, A.MSG_ALL_OBJECTS] == c0[0, A.MSG_FOUND_OBJECTS] == done
 
 
 def test_events_mode_large_batch():

@@ -695,6 +695,9 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
     int *const hdr = H.hdr();
 
     double now_next = tick_seconds(P, hdr[H_TICK]);
+    // row of the noise table for this tick: (tick % period), advanced incrementally
+    int noise_w = noise ? hdr[H_TICK] % P.noise_period : 0;
+    const int noise_row = P.noise_radars * P.noise_objects * 3;  // doubles per tick row
     for (int it = 0; it < n_ticks; it++) {
         const int tick = hdr[H_TICK];
         if (hdr[H_FAULT] & 63) break;  // the reference run aborted here
@@ -721,8 +724,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
             fl = H.sflags()[lane];
             my_id = H.sid()[lane];
             if (noise && nR) {
-                const double *nz = noise + (((size_t)(tick % P.noise_period) * P.noise_radars) * P.noise_objects +
-                                            (fl >> F_STATIC_SHIFT)) * 3;
+                const double *nz = noise + (size_t)noise_w * noise_row + (fl >> F_STATIC_SHIFT) * 3;
                 nz0 = ZRK_LD_EARLY(nz);
                 nz1 = ZRK_LD_EARLY(nz + 1);
                 nz2 = ZRK_LD_EARLY(nz + 2);
@@ -827,8 +829,8 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
                     if (vis) {  // smooth_objects (Radar.py:138-142)
                         if (noise) {
                             if (r) {
-                                const double *nz = noise + (((size_t)(tick % P.noise_period) * P.noise_radars + r) * P.noise_objects +
-                                                            (fl >> F_STATIC_SHIFT)) * 3;
+                                const double *nz = noise + (size_t)noise_w * noise_row +
+                                                   ((size_t)r * P.noise_objects + (fl >> F_STATIC_SHIFT)) * 3;
                                 nz0 = nz[0];
                                 nz1 = nz[1];
                                 nz2 = nz[2];
@@ -970,8 +972,15 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
                 // a detection is final once no earlier unresolved detection touches the same entry
                 bool conflict;
                 if (TEAM == 32) {
-                    const unsigned same = __match_any_sync(ZRK_FULL, unresolved ? claim : -2 - lane);
-                    conflict = unresolved && claim >= 0 && (same & ((1u << lane) - 1u)) != 0;
+                    // lanes with my claim: claims are entry indices < 2 * TEAM = 64, compared bit by bit
+                    const bool has = unresolved && claim >= 0;
+                    unsigned same = __ballot_sync(ZRK_FULL, has);
+#pragma unroll
+                    for (int bit = 0; bit < 6; bit++) {
+                        const unsigned bb = __ballot_sync(ZRK_FULL, (claim >> bit) & 1);
+                        same &= ((claim >> bit) & 1) ? bb : ~bb;
+                    }
+                    conflict = has && (same & ((1u << lane) - 1u)) != 0;
                 } else {
                     int *x_claim = (int *)(sm + o.x_claim);
                     for (int x = lane; x < TEAM + MP; x += TEAM) x_claim[x] = ZRK_IMAX;
@@ -1140,6 +1149,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
             if (nrec > P.log_cap) hdr[H_FAULT] |= ZRK_FAULT_LOG_OVERFLOW;
             if (!(hdr[H_FAULT] & 63)) hdr[H_TICK] = tick + 1;
         }
+        if (++noise_w == P.noise_period) noise_w = 0;
         tm.sync();
     }
 

@@ -45,5 +45,7 @@ inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, int, void *) { return 
 inline cudaError_t cudaMallocAsync(void **p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
 inline cudaError_t cudaFreeAsync(void *p, cudaStream_t) { return cudaFree(p); }
 template <typename F>
+inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 1; return cudaSuccess; }
+template <typename F>
 inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 #endif

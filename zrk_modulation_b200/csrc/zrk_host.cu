@@ -447,7 +447,18 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
     }
     tick_fn fn = pick_kernel(lo.team, h->fast);
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    {
+        // shared-memory carve-out: what the resident CTAs need (registers bound their number), so
+        // that the rest of the 256 KB stays L1 for the noise table, the clock table and spills
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        int blocks = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, fn, h->block, h->smem_bytes));
+        const char *env = getenv("ZRK_CARVEOUT");
+        int pct = env ? atoi(env) : (int)((100.0 * blocks * (h->smem_bytes + 1024)) / (228.0 * 1024) + 4);
+        if (pct > 100) pct = 100;
+        if (pct < 8) pct = 8;
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
     return ensure_tsec(h, 1024);
 }
 

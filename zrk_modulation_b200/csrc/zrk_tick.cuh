@@ -931,6 +931,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
             tm.sync();
             const int i = lane;
             int slot = 0, did = 0, radar_id = 0, seed = -1;
+            bool seed_own = false;
             double dpx = 0, dpy = 0, dpz = 0, dspeed = 0;
             bool unresolved = i < n_det;
             if (unresolved) {
@@ -944,6 +945,8 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
                 dspeed = c.y;
                 seed = H.own()[slot];
                 if (seed >= 0 && (seed >= TEAM ? seed - TEAM >= n_me : seed >= n_te)) seed = -1;
+                // does the seed entry still refer to this very slot?  (then distinct slots have distinct seeds)
+                if (seed >= 0) seed_own = (seed >= TEAM ? ZRK_COLD_I(me_ref)[seed - TEAM] : H.te_ref()[seed]) == slot;
             }
             int lo_rank = 0;
             for (;;) {
@@ -967,6 +970,32 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
                                 claim = e;
                                 break;
                             }
+                    }
+                }
+                // Quiet tick (the common case): every detection re-acquired the track that followed its
+                // own slot, so all claims are distinct, nothing is appended, and with no launcher
+                // capacity left nothing can be launched: the whole round reduces to stamping the entries.
+                if (lo_rank == 0 && hdr[H_FREECAP] <= 0) {
+                    const bool quiet = !unresolved || (cls != 0 && claim == seed && seed_own);
+                    if (!tm.any(!quiet)) {
+                        const bool upd_msg = unresolved && cls == 1 && H.te_follow()[cand] != 0;
+                        int n_upd;
+                        const int r_upd = tm.rank(upd_msg, n_upd);
+                        if (unresolved) {
+                            if (cls == 1) {  // old_target, already followed or no missile to send (CCP.py:332-359)
+                                if (upd_msg && logged(P, ZRK_MSG_CCP_UPDATE_TARGET))
+                                    put_rec(P, rec, nrec + r_upd, tick, ZRK_MSG_CCP_UPDATE_TARGET, 0, ccp_id, radar_id, did,
+                                            H.te_mid()[cand], 0, 0, 0);
+                                H.te_upd()[cand] = tick;
+                                H.te_upds()[cand] = now_s;
+                            } else {  // old_rocket (CCP.py:361-366)
+                                ZRK_COLD_I(me_upd)[cand] = tick;
+                                ZRK_COLD_D(me_upds)[cand] = now_s;
+                            }
+                        }
+                        if (logged(P, ZRK_MSG_CCP_UPDATE_TARGET)) nrec += n_upd;
+                        if (lane == 0) H.counts()[ZRK_MSG_CCP_UPDATE_TARGET] += (unsigned)n_upd;
+                        break;
                     }
                 }
                 // a detection is final once no earlier unresolved detection touches the same entry

@@ -95,7 +95,8 @@ struct Layout {
     int c_cl_id, c_cl_launcher, c_cl_pos;
     int cst_bytes;
     // scratch (shared memory only), offsets from the start of the team's region
-    int x_lf;  // float4[TEAM + MP]: per CCP entry, the position link_object measures to, rounded to fp32
+    int x_lxy, x_lzd;  // double2[TEAM + MP]: per CCP entry, the position link_object measures to
+    int x_lf;          // float4[TEAM + MP]: the same position rounded to fp32 (scan pre-filter)
     int x_claim, x_detlist, x_wscr, x_need;  // x_need doubles as the launch result (x_ok)
     int team_smem_bytes;
 };
@@ -170,10 +171,12 @@ static inline Layout make_layout(int B, int T, int M, int R, int L, int C) {
     o.c_cl_pos = take(8 * 3 * o.CP);
     o.cst_bytes = zrk_align(p, 16);
     p = o.dyn_bytes + o.cst_bytes;
+    o.x_lxy = take(16 * (team + o.MP));
+    o.x_lzd = take(16 * (team + o.MP));
     o.x_lf = take(16 * (team + o.MP));
-    o.x_claim = take(team > 32 ? 4 * (team + o.MP) : 0);
+    o.x_claim = take(4 * (team + o.MP));
     o.x_detlist = take(4 * team);
-    o.x_wscr = take(team > 32 ? 4 * 40 : 0);
+    o.x_wscr = take(4 * 40);
     o.x_need = take(4 * team);
     o.team_smem_bytes = zrk_align(p, 16);
     return o;

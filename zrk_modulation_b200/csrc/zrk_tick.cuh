@@ -337,58 +337,27 @@ __device__ __forceinline__ void calc_range(double speed, double d_t, double rang
     hi = hi > 0 ? hi : 0;
 }
 
-
-// What link_object measures to, gathered on demand.  Entries are addressed by a unified index:
-// [0, n_te) = _target_dict, TEAM + [0, n_me) = _missile_dict.  For an entry the reference does not
-// skip (upd_time != now, CCP.py:196,208) get() yields prev_pos of the tracked object (pos for a
-// missile whose prev_pos is None, CCP.py:211-213) and d_t = now - upd_time.
-template <int TEAM>
-struct LinkSrc {
-    unsigned char *sm;
-    double now_s;
-    int tick, o_me_ref, o_me_upd, o_me_upds;
-    __device__ __forceinline__ bool get(int ue, double &x, double &y, double &z, double &d_t) const {
-        Hot<TEAM> H;
-        H.sm = sm;
-        if (ue < TEAM) {
-            if (H.te_upd()[ue] == tick) return false;
-            const int ref = H.te_ref()[ue];
-            const double2 a = H.qxy()[ref];
-            x = a.x;
-            y = a.y;
-            z = H.qzw()[ref].x;
-            d_t = now_s - H.te_upds()[ue];
-        } else {
-            const int e = ue - TEAM;
-            if (((const int *)(sm + o_me_upd))[e] == tick) return false;
-            const int ref = ((const int *)(sm + o_me_ref))[e];
-            const bool hp = (H.sflags()[ref] & F_HASPREV) != 0;
-            const double2 a = hp ? H.qxy()[ref] : H.pxy()[ref];
-            x = a.x;
-            y = a.y;
-            z = hp ? H.qzw()[ref].x : H.pzs()[ref].x;
-            d_t = now_s - ((const double *)(sm + o_me_upds))[e];
-        }
-        return true;
-    }
-};
+#define ZRK_FAR 1e300 /* link position of an entry link_object skips (upd_time == now) */
 
 // CombatControlPoint.link_object (CCP.py:171-219) for one detection, exact: sqrt per pair.
+// Entries are addressed by a unified index: [0, n_te) = _target_dict, TEAM + [0, n_me) =
+// _missile_dict; lxy/lzd hold, per entry, the position the reference measures to
+// (prev_pos, or pos for a missile whose prev_pos is None) and d_t.
 template <int TEAM>
-__device__ ZRK_NOINLINE void link_exact(const LinkSrc<TEAM> L, int n_te, int n_me, double range_step, double px,
-                                        double py, double pz, double speed, int &cls, int &cand) {
+__device__ ZRK_NOINLINE void link_exact(const double2 *lxy, const double2 *lzd, int n_te, int n_me, double range_step,
+                                        double px, double py, double pz, double speed, int &cls, int &cand) {
     double curr = INFINITY;
     cls = 0;
     cand = -1;
     for (int pass = 0; pass < 2; pass++) {
         const int n = pass ? n_me : n_te, base = pass ? TEAM : 0;
         for (int e = 0; e < n; e++) {
-            double x, y, z, d_t;
-            if (!L.get(base + e, x, y, z, d_t)) continue;
-            double ex = x - px, ey = y - py, ez = z - pz;
+            const double2 a = lxy[base + e], c = lzd[base + e];
+            if (a.x >= ZRK_FAR) continue;
+            double ex = a.x - px, ey = a.y - py, ez = c.x - pz;
             double diff = sqrt(dot3(ex, ey, ez, ex, ey, ez));
             double lo, hi;
-            calc_range(speed, d_t, range_step, lo, hi);
+            calc_range(speed, c.y, range_step, lo, hi);
             if (diff < curr && lo <= diff && diff <= hi) {
                 curr = diff;
                 cls = pass + 1;
@@ -414,7 +383,8 @@ __device__ __forceinline__ void link_eval(LinkAcc &A, int ue, double d2, double 
     double lo, hi;
     calc_range(speed, d_t, range_step, lo, hi);
     const double l2 = lo * lo, h2 = hi * hi;
-    // certainly outside [lo, hi]
+    // certainly outside [lo, hi]; also drops the entries link_object skips (upd_time == now),
+    // whose link position ZRK_FAR makes d2 infinite
     if (d2 > h2 * (1.0 + EPS) || d2 < l2 * (1.0 - EPS)) return;
     const bool in_sure = d2 >= l2 * (1.0 + EPS) && d2 <= h2 * (1.0 - EPS);
     if (d2 > A.best) return;
@@ -433,15 +403,11 @@ __device__ __forceinline__ void link_eval(LinkAcc &A, int ue, double d2, double 
     A.unsure = true;  // includes NaN: every comparison above was false
 }
 
-// fp64 evaluation of one candidate entry
-template <int TEAM>
-__device__ __forceinline__ void link_candidate(LinkAcc &A, const LinkSrc<TEAM> &L, int ue, double px, double py,
-                                               double pz, double speed, double range_step) {
-    double x, y, z, d_t;
-    if (!L.get(ue, x, y, z, d_t)) return;
-    const double ex = x - px, ey = y - py, ez = z - pz;
-    const double d2 = dot3(ex, ey, ez, ex, ey, ez);
-    if (!(d2 > A.best)) link_eval(A, ue, d2, d_t, speed, range_step);
+__device__ __forceinline__ double link_d2(const double2 *lxy, const double2 *lzd, int ue, double px, double py,
+                                          double pz) {
+    const double2 a = lxy[ue];
+    const double ex = a.x - px, ey = a.y - py, ez = lzd[ue].x - pz;
+    return dot3(ex, ey, ez, ex, ey, ez);
 }
 
 // fp32 pre-filter of the scan.  Link positions and the detection are rounded to fp32; for
@@ -460,7 +426,7 @@ __device__ __forceinline__ float link_d2f(const float4 *lf, int ue, float fx, fl
 }
 
 template <int TEAM>
-__device__ __forceinline__ void link_fast(const float4 *lf, const LinkSrc<TEAM> &L, int n_te, int n_me,
+__device__ __forceinline__ void link_fast(const float4 *lf, const double2 *lxy, const double2 *lzd, int n_te, int n_me,
                                           int seed, double range_step, double px, double py, double pz, double speed,
                                           int &cls, int &cand, bool &unsure) {
     LinkAcc A;
@@ -470,7 +436,7 @@ __device__ __forceinline__ void link_fast(const float4 *lf, const LinkSrc<TEAM> 
     A.unsure = false;
     // Seed with the entry that tracked this slot last tick: it is almost always the nearest, and
     // with best = its d2 nearly every other pair fails the single fp32 compare below.
-    if (seed >= 0) link_candidate<TEAM>(A, L, seed, px, py, pz, speed, range_step);
+    if (seed >= 0) link_eval(A, seed, link_d2(lxy, lzd, seed, px, py, pz), lzd[seed].y, speed, range_step);
     const bool f32ok = fabs(px) <= ZRK_F32_COORD_MAX && fabs(py) <= ZRK_F32_COORD_MAX && fabs(pz) <= ZRK_F32_COORD_MAX;
     const float fx = (float)px, fy = (float)py, fz = (float)pz;
     float thr = link_threshold(A.best, f32ok);
@@ -489,8 +455,11 @@ __device__ __forceinline__ void link_fast(const float4 *lf, const LinkSrc<TEAM> 
 #pragma unroll 1
                 for (int k = 0; k < 4; k++) {
                     if (!(link_d2f(lf, u + k, fx, fy, fz) > thr) && u + k != seed) {
-                        link_candidate<TEAM>(A, L, u + k, px, py, pz, speed, range_step);
-                        thr = link_threshold(A.best, f32ok);
+                        const double dk = link_d2(lxy, lzd, u + k, px, py, pz);
+                        if (!(dk > A.best)) {
+                            link_eval(A, u + k, dk, lzd[u + k].y, speed, range_step);
+                            thr = link_threshold(A.best, f32ok);
+                        }
                     }
                 }
             }
@@ -499,8 +468,11 @@ __device__ __forceinline__ void link_fast(const float4 *lf, const LinkSrc<TEAM> 
         for (; e < n; e++) {
             const int u = base + e;
             if (!(link_d2f(lf, u, fx, fy, fz) > thr) && u != seed) {
-                link_candidate<TEAM>(A, L, u, px, py, pz, speed, range_step);
-                thr = link_threshold(A.best, f32ok);
+                const double dk = link_d2(lxy, lzd, u, px, py, pz);
+                if (!(dk > A.best)) {
+                    link_eval(A, u, dk, lzd[u].y, speed, range_step);
+                    thr = link_threshold(A.best, f32ok);
+                }
             }
         }
     }
@@ -511,8 +483,9 @@ __device__ __forceinline__ void link_fast(const float4 *lf, const LinkSrc<TEAM> 
 
 // fp32 image of one link position: NaN (always a candidate) outside the fp32-safe range
 __device__ __forceinline__ float4 link_f32(double x, double y, double z) {
-    const bool ok = fabs(x) <= ZRK_F32_COORD_MAX && fabs(y) <= ZRK_F32_COORD_MAX && fabs(z) <= ZRK_F32_COORD_MAX;
-    return ok ? make_float4((float)x, (float)y, (float)z, 0.f) : make_float4(NAN, NAN, NAN, 0.f);
+    const bool ok = (x >= ZRK_FAR || fabs(x) <= ZRK_F32_COORD_MAX) && fabs(y) <= ZRK_F32_COORD_MAX &&
+                    fabs(z) <= ZRK_F32_COORD_MAX;
+    return ok ? make_float4(x >= ZRK_FAR ? 1e30f : (float)x, (float)y, (float)z, 0.f) : make_float4(NAN, NAN, NAN, 0.f);
 }
 
 // ------------------------------------------------------------------ lane 0 alone: launchers + CCP bookkeeping
@@ -698,6 +671,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
     Hot<TEAM> H;
     H.sm = sm;
     tm.wscr = (int *)(sm + o.x_wscr);
+    double2 *lxy = (double2 *)(sm + o.x_lxy), *lzd = (double2 *)(sm + o.x_lzd);
     float4 *lf = (float4 *)(sm + o.x_lf);
 
     // ---- prologue: HBM -> shared memory / registers
@@ -923,19 +897,25 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
         if (has_ccp && !(hdr[H_FAULT] & 63)) {
             int n_te = hdr[H_NTE];
             const int n_me = hdr[H_NME];
-            LinkSrc<TEAM> L;
-            L.sm = sm;
-            L.now_s = now_s;
-            L.tick = tick;
-            L.o_me_ref = o.me_ref;
-            L.o_me_upd = o.me_upd;
-            L.o_me_upds = o.me_upds;
-            // fp32 image of what link_object measures to, per entry (the scan's pre-filter)
-            if (FAST) {
-                double x, y, z, d_t;
-                if (lane < n_te) lf[lane] = L.get(lane, x, y, z, d_t) ? link_f32(x, y, z) : make_float4(1e30f, 0.f, 0.f, 0.f);
-                if (lane < n_me)
-                    lf[TEAM + lane] = L.get(TEAM + lane, x, y, z, d_t) ? link_f32(x, y, z) : make_float4(1e30f, 0.f, 0.f, 0.f);
+            // what link_object measures to, per entry: prev_pos of the tracked object (or pos
+            // for a missile whose prev_pos is None) and d_t = now - upd_time
+            if (lane < n_te) {
+                const int ref = H.te_ref()[lane], upd = H.te_upd()[lane];
+                const double2 a = H.qxy()[ref], c = H.qzw()[ref];
+                const double ax = upd == tick ? ZRK_FAR : a.x;
+                lxy[lane] = make_double2(ax, a.y);
+                lzd[lane] = make_double2(c.x, now_s - H.te_upds()[lane]);
+                if (FAST) lf[lane] = link_f32(ax, a.y, c.x);
+            }
+            if (lane < n_me) {
+                const int ref = ZRK_COLD_I(me_ref)[lane], upd = ZRK_COLD_I(me_upd)[lane];
+                const bool hp = (H.sflags()[ref] & F_HASPREV) != 0;
+                const double2 a = hp ? H.qxy()[ref] : H.pxy()[ref];
+                const double cz = hp ? H.qzw()[ref].x : H.pzs()[ref].x;
+                const double ax = upd == tick ? ZRK_FAR : a.x;
+                lxy[TEAM + lane] = make_double2(ax, a.y);
+                lzd[TEAM + lane] = make_double2(cz, now_s - ZRK_COLD_D(me_upds)[lane]);
+                if (FAST) lf[TEAM + lane] = link_f32(ax, a.y, cz);
             }
             // processing order: FOUND_OBJECTS messages in radar order, objects in list order,
             // each id once -> (first radar that saw it, slot)
@@ -974,10 +954,10 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
                 if (unresolved) {
                     if (FAST) {
                         bool unsure;
-                        link_fast<TEAM>(lf, L, n_te, n_me, seed, P.range_step, dpx, dpy, dpz, dspeed, cls, cand, unsure);
-                        if (unsure) link_exact<TEAM>(L, n_te, n_me, P.range_step, dpx, dpy, dpz, dspeed, cls, cand);
+                        link_fast<TEAM>(lf, lxy, lzd, n_te, n_me, seed, P.range_step, dpx, dpy, dpz, dspeed, cls, cand, unsure);
+                        if (unsure) link_exact<TEAM>(lxy, lzd, n_te, n_me, P.range_step, dpx, dpy, dpz, dspeed, cls, cand);
                     } else {
-                        link_exact<TEAM>(L, n_te, n_me, P.range_step, dpx, dpy, dpz, dspeed, cls, cand);
+                        link_exact<TEAM>(lxy, lzd, n_te, n_me, P.range_step, dpx, dpy, dpz, dspeed, cls, cand);
                     }
                     if (cls == 1)
                         claim = cand;
@@ -1115,12 +1095,14 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
                         H.te_upds()[cand] = now_s;
                         if (!following) H.te_follow()[cand] = ok != 0;
                         H.own()[slot] = cand;
+                        lxy[cand].x = ZRK_FAR;
                         if (FAST) lf[cand].x = 1e30f;
                     } else if (cls == 2) {  // old_rocket (CCP.py:361-366)
                         ZRK_COLD_I(me_ref)[cand] = slot;
                         ZRK_COLD_I(me_upd)[cand] = tick;
                         ZRK_COLD_D(me_upds)[cand] = now_s;
                         H.own()[slot] = TEAM + cand;
+                        lxy[TEAM + cand].x = ZRK_FAR;
                         if (FAST) lf[TEAM + cand].x = 1e30f;
                     } else {  // new_target + add_target (CCP.py:322-330, :88-93)
                         const int e = claim >= 0 ? claim : n_te + r_app;
@@ -1131,6 +1113,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
                         H.te_follow()[e] = ok != 0;
                         H.te_mid()[e] = ZRK_NONE;
                         H.own()[slot] = e;
+                        lxy[e].x = ZRK_FAR;
                         if (FAST) lf[e] = make_float4(1e30f, 0.f, 0.f, 0.f);
                     }
                     unresolved = false;

@@ -147,3 +147,32 @@ def test_events_only_manager_refuses_messages(request):
     with pytest.raises(RuntimeError):
         mgr.messages[0]
     mgr.close()
+
+
+@pytest.mark.reference
+def test_message_classes_match_the_reference_signatures():
+    """Every message class of modules/Messages.py exists in the mirror with the same constructor
+    parameters / defaults and the same __repr__ (build container only)."""
+    import inspect
+    import refharness as RH
+    if not RH.available():
+        pytest.skip("reference tree not present")
+    RH.ref()
+    from modules import Messages as R
+    names = [n for n in dir(R) if isinstance(getattr(R, n), type) and issubclass(getattr(R, n), R.BaseMessage)
+             and getattr(R, n) is not R.BaseMessage]
+    assert len(names) == 17
+
+    def shape(cls):
+        return [(p.name, p.default) for p in inspect.signature(cls.__init__).parameters.values()]
+
+    for n in names:
+        assert shape(getattr(R, n)) == shape(getattr(M, n)), n
+    assert [t.name for t in R.MessageType] == [t.name for t in M.MessageType]
+    assert [t.value for t in R.MessageType] == [t.value for t in M.MessageType]
+    for cls_name, kw in [("DestroyedMissileId", dict(sender_id=5, missile_id=10, time=200, receiver_id=0, self_detonation=True)),
+                         ("MissileCountResponseMessage", dict(sender_id=3, count=4, time=200, receiver_id=0)),
+                         ("MissileDetonateMessage", dict(sender_id=11, target_id=None, self_detonation=True)),
+                         ("MissileCountRequestMessage", dict(sender_id=0, time=0, receiver_id=3))]:
+        a, b = getattr(R, cls_name)(**kw), getattr(M, cls_name)(**kw)
+        assert repr(a) == repr(b) and vars(a).keys() == vars(b).keys()

@@ -10,6 +10,7 @@ the engine's state.
 """
 from __future__ import annotations
 
+import inspect
 from abc import ABCMeta
 from enum import Enum
 from typing import List, Optional
@@ -113,165 +114,129 @@ class BaseMessage(metaclass=ABCMeta):  # modules/BaseMessage.py:4-23
                 f"sender_id={self.sender_id}, receiver_id={self.receiver_id}, relevance={self.relevance}")
 
 
-class LaunchMissileMessage(BaseMessage):  # Messages.py:14
-    def __init__(self, sender_id: int, receiver_id: int = None, time: int = None, target=None):
-        super().__init__(type=MessageType.LAUNCH_MISSILE, send_time=time, sender_id=sender_id, receiver_id=receiver_id)
-        self.target = target
+_REQ = inspect.Parameter.empty
 
 
-class CPPLaunchMissileRequestMessage(BaseMessage):  # Messages.py:27
-    def __init__(self, sender_id: int, target, target_position: np.ndarray, radar_id: int, time: int = None,
-                 receiver_id: int = None, relevance: int = 1):
-        super().__init__(type=MessageType.LAUNCH_COMMAND, send_time=time, sender_id=sender_id,
-                         receiver_id=receiver_id, relevance=relevance)
-        self.target = target
-        self.target_position = target_position
-        self.radar_id = radar_id
+def _message_class(name, mtype, params, payload=(), tail=None, where=""):
+    """Build one message class of the reference's vocabulary from its description.
 
-    def __repr__(self) -> str:
-        return f"{super().__repr__()}, target={self.target}, target_position={self.target_position}, radar_id={self.radar_id}"
+    params:  constructor parameters in the reference's order, (name, default) with _REQ = required;
+             `sender_id`, `receiver_id`, `time` (-> send_time) and `relevance` feed BaseMessage.
+    payload: (attribute, function of the bound arguments) pairs set on the instance.
+    tail:    function of the instance giving what the reference's __repr__ appends."""
+    sig = inspect.Signature([inspect.Parameter("self", inspect.Parameter.POSITIONAL_OR_KEYWORD)] +
+                            [inspect.Parameter(n, inspect.Parameter.POSITIONAL_OR_KEYWORD, default=d) for n, d in params])
 
+    def __init__(self, *args, **kwargs):
+        v = sig.bind(self, *args, **kwargs)
+        v.apply_defaults()
+        v = v.arguments
+        BaseMessage.__init__(self, type=mtype, sender_id=v["sender_id"], receiver_id=v.get("receiver_id"),
+                             send_time=v.get("time"), relevance=v.get("relevance", 1))
+        for attr, fn in payload:
+            setattr(self, attr, fn(v))
 
-class LaunchedMissileMessage(BaseMessage):  # Messages.py:43
-    def __init__(self, sender_id: int, missile, target_id: int, time: int = None, receiver_id: int = None):
-        super().__init__(type=MessageType.LAUNCHED_MISSILE, send_time=time, sender_id=sender_id, receiver_id=receiver_id)
-        self.missile = missile
-        self.target_id = target_id
+    def __repr__(self):
+        return BaseMessage.__repr__(self) + (tail(self) if tail else "")
 
-    def __repr__(self) -> str:
-        return f"{super().__repr__()}, missile.id={self.missile.id if self.missile else None}, target_id={self.target_id}"
-
-
-class MissileCountRequestMessage(BaseMessage):  # Messages.py:58
-    def __init__(self, sender_id: int, time: int = None, receiver_id: int = None, relevance: int = 3):
-        super().__init__(type=MessageType.MISSILE_COUNT_REQUEST, send_time=time, sender_id=sender_id,
-                         receiver_id=receiver_id, relevance=relevance)
+    __init__.__signature__ = sig
+    return type(name, (BaseMessage,), {"__init__": __init__, "__repr__": __repr__, "__module__": __name__,
+                                       "__doc__": f"{mtype.name} message ({where})"})
 
 
-class MissileCountResponseMessage(BaseMessage):  # Messages.py:70
-    def __init__(self, sender_id: int, count: int, time: int = None, receiver_id: int = None):
-        super().__init__(type=MessageType.MISSILE_COUNT_RESPONSE, send_time=time, sender_id=sender_id, receiver_id=receiver_id)
-        self.count = count
-
-    def __repr__(self) -> str:
-        return f"{super().__repr__()}, count={self.count}"
+def _arg(name):
+    return lambda v: v[name]
 
 
-class AllObjectsMessage(BaseMessage):  # Messages.py:84
-    def __init__(self, sender_id: int, objects: List, time: int = None, receiver_id: int = None):
-        super().__init__(type=MessageType.ALL_OBJECTS, send_time=time, sender_id=sender_id, receiver_id=receiver_id)
-        self.objects = objects
+def _ids(objs):
+    return [o.id for o in objs] if objs else []
 
 
-class FoundObjectsMessage(BaseMessage):  # Messages.py:94
-    def __init__(self, sender_id: int, visible_objects: List, time: int = None, receiver_id: int = None):
-        super().__init__(type=MessageType.FOUND_OBJECTS, send_time=time, sender_id=sender_id, receiver_id=receiver_id)
-        self.visible_objects = visible_objects
-
-    def __repr__(self) -> str:
-        ids = [obj.id for obj in self.visible_objects] if self.visible_objects else []
-        return f"{super().__repr__()}, visible_objects.ids={ids}, visible_objects.count={len(ids)}"
-
-
-class CPPUpdateTargetRadarMessage(BaseMessage):  # Messages.py:109
-    def __init__(self, sender_id: int, target, missile_id: int, time: int = None, receiver_id: int = None):
-        super().__init__(type=MessageType.CCP_UPDATE_TARGET, send_time=time, sender_id=sender_id, receiver_id=receiver_id)
-        self.target = target
-        self.missile_id = missile_id
-
-    def __repr__(self) -> str:
-        return f"{super().__repr__()}, target.id={self.target.id if self.target else None}, missile_id={self.missile_id}"
-
-
-class ActiveObjectsMessage(BaseMessage):  # Messages.py:124
-    def __init__(self, sender_id: int, active_objects: List, time: int = None, receiver_id: int = None):
-        super().__init__(type=MessageType.ACTIVE_OBJECTS, send_time=time, sender_id=sender_id, receiver_id=receiver_id)
-        self.active_objects = active_objects
-
-    def __repr__(self) -> str:
-        ids = [obj.id for obj in self.active_objects] if self.active_objects else []
-        return f"{super().__repr__()}, active_objects.ids={ids}, active_objects.count={len(ids)}"
-
-
-class UpdateTargetPosition(BaseMessage):  # Messages.py:139 (never emitted: SURVEY 5.9#2)
-    def __init__(self, sender_id: int, upd_object, time: int = None, receiver_id: int = None):
-        super().__init__(type=MessageType.UPDATE_TARGET, send_time=time, sender_id=sender_id, receiver_id=receiver_id)
-        self.upd_object = upd_object
-
-
-class DestroyedMissileId(BaseMessage):  # Messages.py:153
-    def __init__(self, sender_id: int, missile_id: int, time: int = None, receiver_id: int = None,
-                 self_detonation: bool = False):
-        super().__init__(type=MessageType.DESTROYED_MISSILE, send_time=time, sender_id=sender_id, receiver_id=receiver_id)
-        self.missile_id = missile_id,  # the reference's trailing comma: a 1-tuple (Messages.py:160)
-        self.self_detonation = self_detonation
-
-    def __repr__(self) -> str:
-        return f"{super().__repr__()}, missile_id={self.missile_id}"
-
-
-class MissileDetonateMessage(BaseMessage):  # Messages.py:168
-    def __init__(self, sender_id: int, target_id: int = None, self_detonation: bool = False):
-        super().__init__(type=MessageType.MISSILE_DETONATE, sender_id=sender_id)
-        self.missile_id = sender_id
-        self.target_id = target_id
-        self.self_detonation = self_detonation
-
-    def __repr__(self) -> str:
-        return f"{super().__repr__()}, missile_id={self.missile_id}, target_id={self.target_id}"
-
-
-class MissilePosMessage(BaseMessage):  # Messages.py:184
-    def __init__(self, sender_id: int):
-        super().__init__(type=MessageType.MISSILE_POS, sender_id=sender_id)
-        self.missile_id = sender_id
-
-    def __repr__(self) -> str:
-        return f"{super().__repr__()}, missile_id={self.missile_id}"
-
-
-class MissileSuccessfulLaunchMessage(BaseMessage):  # Messages.py:198
-    def __init__(self, sender_id: int, launch_time: float, target, missile, receiver_id: int):
-        super().__init__(type=MessageType.LAUNCH_SUCCESSFUL, sender_id=sender_id, receiver_id=receiver_id)
-        self.missile = missile
-        self.launch_time = launch_time
-        self.target_id = target.id
-
-    def __repr__(self) -> str:
-        return f"{super().__repr__()}, missile_id={self.missile.id}, target_id={self.target_id}, launch_time={self.launch_time}"
-
-
-class MissileLaunchCancelledMessage(BaseMessage):  # Messages.py:214
-    def __init__(self, sender_id: int, reason: str, missile, receiver_id: int):
-        super().__init__(type=MessageType.LAUNCH_CANCELLED, sender_id=sender_id, receiver_id=receiver_id)
-        self.missile = missile
-        self.reason = reason
-
-    def __repr__(self) -> str:
-        return f"{super().__repr__()}, missile_id={self.missile.id}, reason=\"{self.reason}\""
-
-
-class CPPDrawerObjectsMessage(BaseMessage):  # Messages.py:229
-    def __init__(self, sender_id: int, obj_id: int, target_type, coordinates: np.ndarray, is_visible_by_radar: bool,
-                 time: int = None, receiver_id: int = None):
-        super().__init__(type=MessageType.DRAW_OBJECTS, send_time=time, sender_id=sender_id, receiver_id=receiver_id)
-        self.obj_id = obj_id
-        self.target_type = target_type
-        self.coordinates = coordinates
-        self.is_visible_by_radar = is_visible_by_radar
-
-    def __repr__(self) -> str:
-        return (f"{super().__repr__()}, obj_id={self.obj_id}, target_type={self.target_type}, "
-                f"coordinates={self.coordinates}, is_visible_by_radar={self.is_visible_by_radar}")
-
-
-class MissileToAirEnvMessage(BaseMessage):  # Messages.py:245
-    def __init__(self, sender_id: int, missile, time: int = None, receiver_id: int = None):
-        super().__init__(type=MessageType.NEW_MISSILE, send_time=time, sender_id=sender_id, receiver_id=receiver_id)
-        self.missile = missile
-
-    def __repr__(self) -> str:
-        return f"{super().__repr__()}, missile.id={self.missile.id if self.missile else None}"
+_T = MessageType
+LaunchMissileMessage = _message_class(
+    "LaunchMissileMessage", _T.LAUNCH_MISSILE, [("sender_id", _REQ), ("receiver_id", None), ("time", None), ("target", None)],
+    [("target", _arg("target"))], where="MissileLauncher -> Missile, Messages.py:14")
+CPPLaunchMissileRequestMessage = _message_class(
+    "CPPLaunchMissileRequestMessage", _T.LAUNCH_COMMAND,
+    [("sender_id", _REQ), ("target", _REQ), ("target_position", _REQ), ("radar_id", _REQ), ("time", None),
+     ("receiver_id", None), ("relevance", 1)],
+    [("target", _arg("target")), ("target_position", _arg("target_position")), ("radar_id", _arg("radar_id"))],
+    lambda m: f", target={m.target}, target_position={m.target_position}, radar_id={m.radar_id}",
+    where="CCP -> MissileLauncher, Messages.py:27")
+LaunchedMissileMessage = _message_class(
+    "LaunchedMissileMessage", _T.LAUNCHED_MISSILE,
+    [("sender_id", _REQ), ("missile", _REQ), ("target_id", _REQ), ("time", None), ("receiver_id", None)],
+    [("missile", _arg("missile")), ("target_id", _arg("target_id"))],
+    lambda m: f", missile.id={m.missile.id if m.missile else None}, target_id={m.target_id}",
+    where="MissileLauncher -> CCP, Messages.py:43")
+MissileCountRequestMessage = _message_class(
+    "MissileCountRequestMessage", _T.MISSILE_COUNT_REQUEST,
+    [("sender_id", _REQ), ("time", None), ("receiver_id", None), ("relevance", 3)],
+    where="CCP -> MissileLauncher, relevance 3, Messages.py:58")
+MissileCountResponseMessage = _message_class(
+    "MissileCountResponseMessage", _T.MISSILE_COUNT_RESPONSE,
+    [("sender_id", _REQ), ("count", _REQ), ("time", None), ("receiver_id", None)],
+    [("count", _arg("count"))], lambda m: f", count={m.count}", where="MissileLauncher -> CCP, Messages.py:70")
+AllObjectsMessage = _message_class(
+    "AllObjectsMessage", _T.ALL_OBJECTS, [("sender_id", _REQ), ("objects", _REQ), ("time", None), ("receiver_id", None)],
+    [("objects", _arg("objects"))], where="Radar -> CCP, Messages.py:84")
+FoundObjectsMessage = _message_class(
+    "FoundObjectsMessage", _T.FOUND_OBJECTS,
+    [("sender_id", _REQ), ("visible_objects", _REQ), ("time", None), ("receiver_id", None)],
+    [("visible_objects", _arg("visible_objects"))],
+    lambda m: f", visible_objects.ids={_ids(m.visible_objects)}, visible_objects.count={len(_ids(m.visible_objects))}",
+    where="Radar -> CCP, Messages.py:94")
+CPPUpdateTargetRadarMessage = _message_class(
+    "CPPUpdateTargetRadarMessage", _T.CCP_UPDATE_TARGET,
+    [("sender_id", _REQ), ("target", _REQ), ("missile_id", _REQ), ("time", None), ("receiver_id", None)],
+    [("target", _arg("target")), ("missile_id", _arg("missile_id"))],
+    lambda m: f", target.id={m.target.id if m.target else None}, missile_id={m.missile_id}",
+    where="CCP -> Radar, read by nobody, Messages.py:109")
+ActiveObjectsMessage = _message_class(
+    "ActiveObjectsMessage", _T.ACTIVE_OBJECTS,
+    [("sender_id", _REQ), ("active_objects", _REQ), ("time", None), ("receiver_id", None)],
+    [("active_objects", _arg("active_objects"))],
+    lambda m: f", active_objects.ids={_ids(m.active_objects)}, active_objects.count={len(_ids(m.active_objects))}",
+    where="AirEnv -> Radar, Messages.py:124")
+UpdateTargetPosition = _message_class(
+    "UpdateTargetPosition", _T.UPDATE_TARGET, [("sender_id", _REQ), ("upd_object", _REQ), ("time", None), ("receiver_id", None)],
+    [("upd_object", _arg("upd_object"))], where="Radar -> Missile, never emitted (SURVEY 5.9#2), Messages.py:139")
+DestroyedMissileId = _message_class(
+    "DestroyedMissileId", _T.DESTROYED_MISSILE,
+    [("sender_id", _REQ), ("missile_id", _REQ), ("time", None), ("receiver_id", None), ("self_detonation", False)],
+    # the reference's trailing comma makes this a 1-tuple (Messages.py:160)
+    [("missile_id", lambda v: (v["missile_id"],)), ("self_detonation", _arg("self_detonation"))],
+    lambda m: f", missile_id={m.missile_id}", where="Radar -> CCP, Messages.py:153")
+MissileDetonateMessage = _message_class(
+    "MissileDetonateMessage", _T.MISSILE_DETONATE, [("sender_id", _REQ), ("target_id", None), ("self_detonation", False)],
+    [("missile_id", _arg("sender_id")), ("target_id", _arg("target_id")), ("self_detonation", _arg("self_detonation"))],
+    lambda m: f", missile_id={m.missile_id}, target_id={m.target_id}", where="Missile -> AirEnv, Radar, Messages.py:168")
+MissilePosMessage = _message_class(
+    "MissilePosMessage", _T.MISSILE_POS, [("sender_id", _REQ)], [("missile_id", _arg("sender_id"))],
+    lambda m: f", missile_id={m.missile_id}", where="Missile -> AirEnv, Messages.py:184")
+MissileSuccessfulLaunchMessage = _message_class(
+    "MissileSuccessfulLaunchMessage", _T.LAUNCH_SUCCESSFUL,
+    [("sender_id", _REQ), ("launch_time", _REQ), ("target", _REQ), ("missile", _REQ), ("receiver_id", _REQ)],
+    [("missile", _arg("missile")), ("launch_time", _arg("launch_time")), ("target_id", lambda v: v["target"].id)],
+    lambda m: f", missile_id={m.missile.id}, target_id={m.target_id}, launch_time={m.launch_time}",
+    where="Missile -> MissileLauncher, Messages.py:198")
+MissileLaunchCancelledMessage = _message_class(
+    "MissileLaunchCancelledMessage", _T.LAUNCH_CANCELLED,
+    [("sender_id", _REQ), ("reason", _REQ), ("missile", _REQ), ("receiver_id", _REQ)],
+    [("missile", _arg("missile")), ("reason", _arg("reason"))],
+    lambda m: f", missile_id={m.missile.id}, reason=\"{m.reason}\"", where="Missile -> MissileLauncher, Messages.py:214")
+CPPDrawerObjectsMessage = _message_class(
+    "CPPDrawerObjectsMessage", _T.DRAW_OBJECTS,
+    [("sender_id", _REQ), ("obj_id", _REQ), ("target_type", _REQ), ("coordinates", _REQ), ("is_visible_by_radar", _REQ),
+     ("time", None), ("receiver_id", None)],
+    [("obj_id", _arg("obj_id")), ("target_type", _arg("target_type")), ("coordinates", _arg("coordinates")),
+     ("is_visible_by_radar", _arg("is_visible_by_radar"))],
+    lambda m: (f", obj_id={m.obj_id}, target_type={m.target_type}, coordinates={m.coordinates}, "
+               f"is_visible_by_radar={m.is_visible_by_radar}"), where="CCP -> GUI, Messages.py:229")
+MissileToAirEnvMessage = _message_class(
+    "MissileToAirEnvMessage", _T.NEW_MISSILE, [("sender_id", _REQ), ("missile", _REQ), ("time", None), ("receiver_id", None)],
+    [("missile", _arg("missile"))], lambda m: f", missile.id={m.missile.id if m.missile else None}",
+    where="MissileLauncher -> AirEnv, Messages.py:245")
 
 
 def _none(v: int) -> Optional[int]:

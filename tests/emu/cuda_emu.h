@@ -152,6 +152,11 @@ inline int atomicAdd(int *p, int v) {
     *p = o + v;
     return o;
 }
+inline int atomicExch(int *p, int v) {
+    int o = *p;
+    *p = v;
+    return o;
+}
 inline int atomicOr(int *p, int v) {
     int o = *p;
     *p = o | v;

@@ -98,6 +98,7 @@ struct Layout {
     int x_lxy, x_lzd;  // double2[TEAM + MP]: per CCP entry, the position link_object measures to
     int x_lf;          // float4[TEAM + MP]: the same position rounded to fp32 (scan pre-filter)
     int x_claim, x_detlist, x_wscr, x_need;  // x_need doubles as the launch result (x_ok)
+    int x_ghead, x_gnext;  // int[TEAM], int[TEAM + MP]: hash grid over the entries' link positions
     int team_smem_bytes;
 };
 
@@ -178,6 +179,8 @@ static inline Layout make_layout(int B, int T, int M, int R, int L, int C) {
     o.x_detlist = take(4 * team);
     o.x_wscr = take(4 * 40);
     o.x_need = take(4 * team);
+    o.x_ghead = take(4 * team);
+    o.x_gnext = take(4 * (team + o.MP));
     o.team_smem_bytes = zrk_align(p, 16);
     return o;
 }

@@ -425,8 +425,19 @@ __device__ __forceinline__ float link_d2f(const float4 *lf, int ue, float fx, fl
     return fmaf(ez, ez, fmaf(ey, ey, ex * ex));
 }
 
+// Hash grid over the entries' link positions (x, y of the fp32 image; cells of ZRK_CELL metres,
+// TEAM buckets, chained through gnext).  A detection whose acceptance radius sqrt(thr) is at most
+// one cell wide only has to look at the buckets of the <= 2 x 2 cells its radius touches: every
+// entry within that radius is in one of them (hash collisions only add harmless extra tests).
+#define ZRK_CELL 512.0f
+__device__ __forceinline__ int grid_cell(float v) { return (int)floorf(v * (1.0f / ZRK_CELL)); }
 template <int TEAM>
-__device__ __forceinline__ void link_fast(const float4 *lf, const double2 *lxy, const double2 *lzd, int n_te, int n_me,
+__device__ __forceinline__ int grid_bucket(int ix, int iy) {
+    return (int)(((unsigned)ix * 73856093u) ^ ((unsigned)iy * 19349663u)) & (TEAM - 1);
+}
+
+template <int TEAM>
+__device__ __forceinline__ void link_fast(const int *ghead, const int *gnext, bool grid_ok, const float4 *lf, const double2 *lxy, const double2 *lzd, int n_te, int n_me,
                                           int seed, double range_step, double px, double py, double pz, double speed,
                                           int &cls, int &cand, bool &unsure) {
     LinkAcc A;
@@ -440,38 +451,55 @@ __device__ __forceinline__ void link_fast(const float4 *lf, const double2 *lxy, 
     const bool f32ok = fabs(px) <= ZRK_F32_COORD_MAX && fabs(py) <= ZRK_F32_COORD_MAX && fabs(pz) <= ZRK_F32_COORD_MAX;
     const float fx = (float)px, fy = (float)py, fz = (float)pz;
     float thr = link_threshold(A.best, f32ok);
-    for (int pass = 0; pass < 2; pass++) {
-        const int n = pass ? n_me : n_te, base = pass ? TEAM : 0;
-        int e = 0;
-        // four pairs at a time; the common case is that none of them can beat the best
-        for (; e + 4 <= n; e += 4) {
-            const int u = base + e;
-            const float d0 = link_d2f(lf, u, fx, fy, fz), d1 = link_d2f(lf, u + 1, fx, fy, fz);
-            const float d2 = link_d2f(lf, u + 2, fx, fy, fz), d3 = link_d2f(lf, u + 3, fx, fy, fz);
-            // bitwise, not short-circuit: all four chains are issued before the one branch
-            const bool h = (!(d0 > thr) & (u != seed)) | (!(d1 > thr) & (u + 1 != seed)) |
-                           (!(d2 > thr) & (u + 2 != seed)) | (!(d3 > thr) & (u + 3 != seed));
-            if (h) {
-#pragma unroll 1
-                for (int k = 0; k < 4; k++) {
-                    if (!(link_d2f(lf, u + k, fx, fy, fz) > thr) && u + k != seed) {
-                        const double dk = link_d2(lxy, lzd, u + k, px, py, pz);
+    if (grid_ok && thr <= ZRK_CELL * ZRK_CELL) {
+        // the common case: a seeded detection only visits the few entries near it
+        const float r = sqrtf(thr);
+        const int ix0 = grid_cell(fx - r), ix1 = grid_cell(fx + r), iy0 = grid_cell(fy - r), iy1 = grid_cell(fy + r);
+        for (int ix = ix0; ix <= ix1; ix++)
+            for (int iy = iy0; iy <= iy1; iy++)
+                for (int u = ghead[grid_bucket<TEAM>(ix, iy)]; u >= 0; u = gnext[u]) {
+                    if (u != seed && !(link_d2f(lf, u, fx, fy, fz) > thr)) {
+                        const double dk = link_d2(lxy, lzd, u, px, py, pz);
                         if (!(dk > A.best)) {
-                            link_eval(A, u + k, dk, lzd[u + k].y, speed, range_step);
+                            link_eval(A, u, dk, lzd[u].y, speed, range_step);
                             thr = link_threshold(A.best, f32ok);
                         }
                     }
                 }
-            }
-        }
+    } else {
+        for (int pass = 0; pass < 2; pass++) {
+            const int n = pass ? n_me : n_te, base = pass ? TEAM : 0;
+            int e = 0;
+            // four pairs at a time; the common case is that none of them can beat the best
+            for (; e + 4 <= n; e += 4) {
+                const int u = base + e;
+                const float d0 = link_d2f(lf, u, fx, fy, fz), d1 = link_d2f(lf, u + 1, fx, fy, fz);
+                const float d2 = link_d2f(lf, u + 2, fx, fy, fz), d3 = link_d2f(lf, u + 3, fx, fy, fz);
+                // bitwise, not short-circuit: all four chains are issued before the one branch
+                const bool h = (!(d0 > thr) & (u != seed)) | (!(d1 > thr) & (u + 1 != seed)) |
+                               (!(d2 > thr) & (u + 2 != seed)) | (!(d3 > thr) & (u + 3 != seed));
+                if (h) {
 #pragma unroll 1
-        for (; e < n; e++) {
-            const int u = base + e;
-            if (!(link_d2f(lf, u, fx, fy, fz) > thr) && u != seed) {
-                const double dk = link_d2(lxy, lzd, u, px, py, pz);
-                if (!(dk > A.best)) {
-                    link_eval(A, u, dk, lzd[u].y, speed, range_step);
-                    thr = link_threshold(A.best, f32ok);
+                    for (int k = 0; k < 4; k++) {
+                        if (!(link_d2f(lf, u + k, fx, fy, fz) > thr) && u + k != seed) {
+                            const double dk = link_d2(lxy, lzd, u + k, px, py, pz);
+                            if (!(dk > A.best)) {
+                                link_eval(A, u + k, dk, lzd[u + k].y, speed, range_step);
+                                thr = link_threshold(A.best, f32ok);
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll 1
+            for (; e < n; e++) {
+                const int u = base + e;
+                if (!(link_d2f(lf, u, fx, fy, fz) > thr) && u != seed) {
+                    const double dk = link_d2(lxy, lzd, u, px, py, pz);
+                    if (!(dk > A.best)) {
+                        link_eval(A, u, dk, lzd[u].y, speed, range_step);
+                        thr = link_threshold(A.best, f32ok);
+                    }
                 }
             }
         }
@@ -673,6 +701,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
     tm.wscr = (int *)(sm + o.x_wscr);
     double2 *lxy = (double2 *)(sm + o.x_lxy), *lzd = (double2 *)(sm + o.x_lzd);
     float4 *lf = (float4 *)(sm + o.x_lf);
+    int *ghead = (int *)(sm + o.x_ghead), *gnext = (int *)(sm + o.x_gnext);
 
     // ---- prologue: HBM -> shared memory / registers
     {
@@ -899,13 +928,19 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
             const int n_me = hdr[H_NME];
             // what link_object measures to, per entry: prev_pos of the tracked object (or pos
             // for a missile whose prev_pos is None) and d_t = now - upd_time
+            bool bad_image = false;  // an entry outside the fp32-safe range: no grid this tick
+            if (FAST) ghead[lane] = -1;
             if (lane < n_te) {
                 const int ref = H.te_ref()[lane], upd = H.te_upd()[lane];
                 const double2 a = H.qxy()[ref], c = H.qzw()[ref];
                 const double ax = upd == tick ? ZRK_FAR : a.x;
                 lxy[lane] = make_double2(ax, a.y);
                 lzd[lane] = make_double2(c.x, now_s - H.te_upds()[lane]);
-                if (FAST) lf[lane] = link_f32(ax, a.y, c.x);
+                if (FAST) {
+                    const float4 f = link_f32(ax, a.y, c.x);
+                    lf[lane] = f;
+                    bad_image = !(f.x == f.x);
+                }
             }
             if (lane < n_me) {
                 const int ref = ZRK_COLD_I(me_ref)[lane], upd = ZRK_COLD_I(me_upd)[lane];
@@ -915,7 +950,26 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
                 const double ax = upd == tick ? ZRK_FAR : a.x;
                 lxy[TEAM + lane] = make_double2(ax, a.y);
                 lzd[TEAM + lane] = make_double2(cz, now_s - ZRK_COLD_D(me_upds)[lane]);
-                if (FAST) lf[TEAM + lane] = link_f32(ax, a.y, cz);
+                if (FAST) {
+                    const float4 f = link_f32(ax, a.y, cz);
+                    lf[TEAM + lane] = f;
+                    bad_image = bad_image || !(f.x == f.x);
+                }
+            }
+            bool grid_ok = false;
+            if (FAST) {
+                grid_ok = !tm.any(bad_image);
+                tm.sync();  // bucket heads are reset, fp32 images are written
+                if (grid_ok) {  // entries link_object skips (image x = 1e30) stay out of the grid
+                    if (lane < n_te && lf[lane].x < 1e29f) {
+                        const float4 f = lf[lane];
+                        gnext[lane] = atomicExch(&ghead[grid_bucket<TEAM>(grid_cell(f.x), grid_cell(f.y))], lane);
+                    }
+                    if (lane < n_me && lf[TEAM + lane].x < 1e29f) {
+                        const float4 f = lf[TEAM + lane];
+                        gnext[TEAM + lane] = atomicExch(&ghead[grid_bucket<TEAM>(grid_cell(f.x), grid_cell(f.y))], TEAM + lane);
+                    }
+                }
             }
             // processing order: FOUND_OBJECTS messages in radar order, objects in list order,
             // each id once -> (first radar that saw it, slot)
@@ -954,7 +1008,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
                 if (unresolved) {
                     if (FAST) {
                         bool unsure;
-                        link_fast<TEAM>(lf, lxy, lzd, n_te, n_me, seed, P.range_step, dpx, dpy, dpz, dspeed, cls, cand, unsure);
+                        link_fast<TEAM>(ghead, gnext, grid_ok, lf, lxy, lzd, n_te, n_me, seed, P.range_step, dpx, dpy, dpz, dspeed, cls, cand, unsure);
                         if (unsure) link_exact<TEAM>(lxy, lzd, n_te, n_me, P.range_step, dpx, dpy, dpz, dspeed, cls, cand);
                     } else {
                         link_exact<TEAM>(lxy, lzd, n_te, n_me, P.range_step, dpx, dpy, dpz, dspeed, cls, cand);

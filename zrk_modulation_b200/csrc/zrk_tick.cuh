@@ -928,8 +928,10 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
             const int n_me = hdr[H_NME];
             // what link_object measures to, per entry: prev_pos of the tracked object (or pos
             // for a missile whose prev_pos is None) and d_t = now - upd_time
+            // the hash grid pays off once a scan is long; warp-sized scenarios scan their few entries directly
+            const bool want_grid = FAST && TEAM > 32 && n_te + n_me >= 48;
             bool bad_image = false;  // an entry outside the fp32-safe range: no grid this tick
-            if (FAST) ghead[lane] = -1;
+            if (want_grid) ghead[lane] = -1;
             if (lane < n_te) {
                 const int ref = H.te_ref()[lane], upd = H.te_upd()[lane];
                 const double2 a = H.qxy()[ref], c = H.qzw()[ref];
@@ -957,7 +959,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
                 }
             }
             bool grid_ok = false;
-            if (FAST) {
+            if (want_grid) {
                 grid_ok = !tm.any(bad_image);
                 tm.sync();  // bucket heads are reset, fp32 images are written
                 if (grid_ok) {  // entries link_object skips (image x = 1e30) stay out of the grid

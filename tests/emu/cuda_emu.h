@@ -103,6 +103,15 @@ inline void __syncthreads() {
     zrk_emu::Block *b = zrk_emu::g_block;
     zrk_emu::barrier_wait(b->named[0], b->n_threads - b->n_done);
 }
+inline int __syncthreads_or(int pred) {
+    zrk_emu::Block *b = zrk_emu::g_block;
+    static int acc[2];
+    const int slot = b->named[0].gen & 1;  // the accumulator of the barrier generation being formed
+    if (b->named[0].count == 0) acc[slot] = 0;
+    acc[slot] |= pred ? 1 : 0;
+    __syncthreads();
+    return acc[slot];
+}
 inline void __syncwarp(unsigned = 0xffffffffu) { zrk_emu::barrier_wait(zrk_emu::my_warp().bar, 32); }
 
 template <typename T>

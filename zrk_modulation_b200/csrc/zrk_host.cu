@@ -262,7 +262,7 @@ static tick_fn pick_fast(bool fast) {
 static tick_fn pick_kernel(int team, bool fast) {
     switch (team) {
     case 32: return pick_fast<32, ZRK_CTA_THREADS / 32>(fast);
-    case 64: return pick_fast<64, (ZRK_CTA_THREADS >= 64 ? ZRK_CTA_THREADS / 64 : 1)>(fast);
+    case 64: return pick_fast<64, 1>(fast);
     case 128: return pick_fast<128, 1>(fast);
     case 256: return pick_fast<256, 1>(fast);
     case 512: return pick_fast<512, 1>(fast);

@@ -136,7 +136,7 @@ static inline Layout make_layout(int B, int T, int M, int R, int L, int C) {
     o.B = B; o.T = T; o.M = M; o.NS = T + M; o.R = R; o.L = L; o.C = C;
     o.team = zrk_team_for(o.NS);
     const int team = o.team ? o.team : 32;
-    o.teams_per_cta = team >= ZRK_CTA_THREADS ? 1 : ZRK_CTA_THREADS / team;
+    o.teams_per_cta = team > 32 ? 1 : ZRK_CTA_THREADS / 32;  // teams larger than a warp own their CTA
     o.MP = zrk_align(M > 0 ? M : 1, 2);
     o.RP = R > 0 ? R : 1;
     o.LP = zrk_align(L > 0 ? L : 1, 2);
@@ -177,7 +177,7 @@ static inline Layout make_layout(int B, int T, int M, int R, int L, int C) {
     o.x_lf = take(16 * (team + o.MP));
     o.x_claim = take(4 * (team + o.MP));
     o.x_detlist = take(4 * team);
-    o.x_wscr = take(4 * 40);
+    o.x_wscr = take(4 * 64);
     o.x_need = take(4 * team);
     o.x_ghead = take(4 * team);
     o.x_gnext = take(4 * (team + o.MP));

@@ -158,44 +158,60 @@ __device__ __forceinline__ void radar_move(const double *q, double &caz, double 
 
 // ------------------------------------------------------------------ team primitives
 
+// A TEAM of 32 is a warp (several per CTA, warp-synchronous); larger teams are exactly one CTA
+// and combine per-warp partial results through two alternating rows of shared scratch, so that a
+// collective costs ONE __syncthreads (the row written by call k+2 was last read before the
+// barrier of call k+1).
 template <int TEAM, int TPC>
 struct Team {
+    static_assert(TEAM == 32 || TPC == 1, "teams larger than a warp own their CTA");
+    static constexpr int WARPS = TEAM / 32;
     int lane;   // 0..TEAM-1 within the scenario's team
     int tic;    // team index inside the CTA
-    int *wscr;  // >= 34 ints of shared scratch (TEAM > 32 only)
+    int *wscr;  // 64 ints of shared scratch (TEAM > 32 only)
+    int flip;   // which scratch row the next collective uses (uniform across the team)
 
     __device__ __forceinline__ void sync() const {
         if (TEAM == 32) {
             __syncwarp();
-        } else if (TPC == 1) {
-            __syncthreads();
         } else {
-            ZRK_NAMED_BARRIER(tic + 1, TEAM);
+            __syncthreads();
         }
     }
+    __device__ __forceinline__ int *row() {
+        int *r = wscr + (flip ? 32 : 0);
+        flip ^= 1;
+        return r;
+    }
+    // per-warp values v (one per warp, held by every lane of that warp) -> exclusive prefix over
+    // warps for this thread's warp, and the total
+    __device__ __forceinline__ int across_warps(int v, int &total) {
+        const int l32 = lane & 31, w = lane >> 5;
+        int *r = row();
+        if (l32 == 0) r[w] = v;
+        __syncthreads();
+        const int x = l32 < WARPS ? r[l32] : 0;
+        int inc = x;
+#pragma unroll
+        for (int d = 1; d < WARPS; d <<= 1) {
+            const int n = __shfl_up_sync(ZRK_FULL, inc, d);
+            if (l32 >= d) inc += n;
+        }
+        total = __shfl_sync(ZRK_FULL, inc, WARPS - 1);
+        return __shfl_sync(ZRK_FULL, inc - x, w);
+    }
     // exclusive prefix count of a predicate in lane order; total returned to every lane
-    __device__ __forceinline__ int rank(bool p, int &total) const {
+    __device__ __forceinline__ int rank(bool p, int &total) {
         const unsigned bal = __ballot_sync(ZRK_FULL, p);
         const int below = __popc(bal & ((1u << (lane & 31)) - 1u));
         if (TEAM == 32) {
             total = __popc(bal);
             return below;
         }
-        const int w = lane >> 5;
-        if ((lane & 31) == 0) wscr[w] = __popc(bal);
-        sync();
-        int base = 0, tot = 0;
-        for (int i = 0; i < TEAM / 32; i++) {
-            int x = wscr[i];
-            if (i < w) base += x;
-            tot += x;
-        }
-        sync();
-        total = tot;
-        return base + below;
+        return across_warps(__popc(bal), total) + below;
     }
     // exclusive prefix sum of small non-negative ints
-    __device__ __forceinline__ int scan(int v, int &total) const {
+    __device__ __forceinline__ int scan(int v, int &total) {
         const int l32 = lane & 31;
         int inc = v;
 #pragma unroll
@@ -203,41 +219,25 @@ struct Team {
             int n = __shfl_up_sync(ZRK_FULL, inc, d);
             if (l32 >= d) inc += n;
         }
+        const int wsum = __shfl_sync(ZRK_FULL, inc, 31);
         if (TEAM == 32) {
-            total = __shfl_sync(ZRK_FULL, inc, 31);
+            total = wsum;
             return inc - v;
         }
-        const int w = lane >> 5;
-        if (l32 == 31) wscr[w] = inc;
-        sync();
-        int base = 0, tot = 0;
-        for (int i = 0; i < TEAM / 32; i++) {
-            int x = wscr[i];
-            if (i < w) base += x;
-            tot += x;
-        }
-        sync();
-        total = tot;
-        return base + inc - v;
+        return across_warps(wsum, total) + inc - v;
     }
-    __device__ __forceinline__ int min(int v) const {
+    __device__ __forceinline__ int min(int v) {
         v = __reduce_min_sync(ZRK_FULL, v);
         if (TEAM == 32) return v;
-        const int w = lane >> 5;
-        if ((lane & 31) == 0) wscr[w] = v;
-        sync();
-        int m = ZRK_IMAX;
-        for (int i = 0; i < TEAM / 32; i++) {
-            int x = wscr[i];
-            m = x < m ? x : m;
-        }
-        sync();
-        return m;
+        const int l32 = lane & 31;
+        int *r = row();
+        if (l32 == 0) r[lane >> 5] = v;
+        __syncthreads();
+        return __reduce_min_sync(ZRK_FULL, l32 < WARPS ? r[l32] : ZRK_IMAX);
     }
     __device__ __forceinline__ bool any(bool p) const {
-        const bool w = __ballot_sync(ZRK_FULL, p) != 0;
-        if (TEAM == 32) return w;
-        return min(w ? 0 : 1) == 0;
+        if (TEAM == 32) return __ballot_sync(ZRK_FULL, p) != 0;
+        return __syncthreads_or(p) != 0;
     }
 };
 
@@ -677,7 +677,7 @@ __device__ ZRK_NOINLINE int serial_section(const Params *Pg, unsigned char *sm, 
 #ifndef ZRK_MINB_SMALL
 #define ZRK_MINB_SMALL 4
 #endif
-constexpr int min_blocks(int threads) { return threads <= ZRK_CTA_THREADS ? ZRK_MINB_SMALL : (threads <= 128 ? 4 : (threads == 256 ? 2 : 1)); }
+constexpr int min_blocks(int threads) { return threads <= 64 ? 8 : (threads <= 128 ? ZRK_MINB_SMALL : (threads == 256 ? 2 : 1)); }
 
 #ifdef ZRK_MAXNREG
 #define ZRK_KERNEL_ATTR __maxnreg__(ZRK_MAXNREG)
@@ -699,6 +699,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
     Hot<TEAM> H;
     H.sm = sm;
     tm.wscr = (int *)(sm + o.x_wscr);
+    tm.flip = 0;
     double2 *lxy = (double2 *)(sm + o.x_lxy), *lzd = (double2 *)(sm + o.x_lzd);
     float4 *lf = (float4 *)(sm + o.x_lf);
     int *ghead = (int *)(sm + o.x_ghead), *gnext = (int *)(sm + o.x_gnext);

@@ -677,7 +677,10 @@ __device__ ZRK_NOINLINE int serial_section(const Params *Pg, unsigned char *sm, 
 #ifndef ZRK_MINB_SMALL
 #define ZRK_MINB_SMALL 4
 #endif
-constexpr int min_blocks(int threads) { return threads <= 64 ? 8 : (threads <= 128 ? ZRK_MINB_SMALL : (threads == 256 ? 2 : 1)); }
+#ifndef ZRK_MINB_256
+#define ZRK_MINB_256 2
+#endif
+constexpr int min_blocks(int threads) { return threads <= 64 ? 8 : (threads <= 128 ? ZRK_MINB_SMALL : (threads == 256 ? ZRK_MINB_256 : 1)); }
 
 #ifdef ZRK_MAXNREG
 #define ZRK_KERNEL_ATTR __maxnreg__(ZRK_MAXNREG)

@@ -124,6 +124,23 @@ def test_events_mode_large_batch():
     assert counts[:, A.MSG_LAUNCH_COMMAND].sum() > 0 and counts[:, A.MSG_MISSILE_DETONATE].sum() > 0
 
 
+def test_two_thousand_random_scenarios_in_one_ragged_batch():
+    """2 048 random scenarios of all four families (ragged counts, launches, cancels, sweeps, both
+    fault kinds) as ONE batch: per-scenario message counts, fault code / tick and sampled event
+    records against the oracle."""
+    fams = ["mixed", "dense", "mid", "tiny"]
+    cfgs = []
+    for i in range(2048):
+        c = random_config(10000 + i, fams[i % 4])
+        c["simulation"] = {"time_step": 200, "duration": 200 * 90}
+        cfgs.append(c)
+    b = compile_batch(cfgs)
+    b.set_noise(make_noise(16, b.max_radars, b.n_slots, seed=77))
+    counts = check_batch_counts(b, 90, n_threads=8, sample=48)
+    from zrk_modulation_b200 import _cabi as A
+    assert counts[:, A.MSG_LAUNCH_SUCCESSFUL].sum() > 500 and counts[:, A.MSG_LAUNCH_CANCELLED].sum() > 0
+
+
 def test_config3_counts():
     b = synthetic_batch(4096, 64, n_radars=1, seed0=9000)
     check_batch_counts(b, 40, n_threads=8, sample=8)

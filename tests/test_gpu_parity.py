@@ -124,14 +124,15 @@ def test_events_mode_large_batch():
     assert counts[:, A.MSG_LAUNCH_COMMAND].sum() > 0 and counts[:, A.MSG_MISSILE_DETONATE].sum() > 0
 
 
-def test_two_thousand_random_scenarios_in_one_ragged_batch():
-    """2 048 random scenarios of all four families (ragged counts, launches, cancels, sweeps, both
-    fault kinds) as ONE batch: per-scenario message counts, fault code / tick and sampled event
-    records against the oracle."""
+@pytest.mark.parametrize("n,seed0", [(2048, 10000), (16384, 50000)])
+def test_thousands_of_random_scenarios_in_one_ragged_batch(n, seed0):
+    """Thousands of random scenarios of all four families (ragged counts, launches, cancels,
+    sweeps, both fault kinds) as ONE batch: per-scenario message counts, fault code / tick and
+    sampled event records against the oracle."""
     fams = ["mixed", "dense", "mid", "tiny"]
     cfgs = []
-    for i in range(2048):
-        c = random_config(10000 + i, fams[i % 4])
+    for i in range(n):
+        c = random_config(seed0 + i, fams[i % 4])
         c["simulation"] = {"time_step": 200, "duration": 200 * 90}
         cfgs.append(c)
     b = compile_batch(cfgs)

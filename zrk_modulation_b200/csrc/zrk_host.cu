@@ -710,7 +710,7 @@ extern "C" int zrk_read_state(zrk_handle *h, const zrk_state_view *v) {
     if (!h || !v) return ZRK_ERR_ARG;
     const Params &P = h->P;
     const Layout &o = P.lo;
-    const int NS = o.NS, NSP = o.team, T = o.T, M = o.M, R = o.R, L = o.L, C = o.C;
+    const int NS = o.NS, T = o.T, M = o.M, R = o.R, L = o.L, C = o.C;
     const HotOff &ho = o.hot;
     const int CH = 2048;
     std::vector<unsigned char> dyn, cst;

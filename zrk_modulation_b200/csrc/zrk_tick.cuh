@@ -22,16 +22,12 @@
 
 #ifdef ZRK_EMU
 #include "cuda_emu.h"
-#define ZRK_NAMED_BARRIER(id, n) zrk_emu::named_barrier((id), (n))
 #define ZRK_SMEM_DECL unsigned char *zrk_smem = zrk_emu::dyn_smem()
-#define ZRK_LDCG(p) (*(p))
 #define ZRK_LD_EARLY(p) (*(p))
 #define ZRK_NOINLINE __attribute__((noinline))
 #else
 #include <cuda_runtime.h>
-#define ZRK_NAMED_BARRIER(id, n) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory")
 #define ZRK_SMEM_DECL extern __shared__ __align__(16) unsigned char zrk_smem[]
-#define ZRK_LDCG(p) __ldcg(p)
 // a read-only global load the compiler must issue where it is written (not sunk to its first use),
 // so that its latency overlaps the work in between
 __device__ __forceinline__ double zrk_ld_early(const double *p) {
@@ -209,22 +205,6 @@ struct Team {
             return below;
         }
         return across_warps(__popc(bal), total) + below;
-    }
-    // exclusive prefix sum of small non-negative ints
-    __device__ __forceinline__ int scan(int v, int &total) {
-        const int l32 = lane & 31;
-        int inc = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int n = __shfl_up_sync(ZRK_FULL, inc, d);
-            if (l32 >= d) inc += n;
-        }
-        const int wsum = __shfl_sync(ZRK_FULL, inc, 31);
-        if (TEAM == 32) {
-            total = wsum;
-            return inc - v;
-        }
-        return across_warps(wsum, total) + inc - v;
     }
     __device__ __forceinline__ int min(int v) {
         v = __reduce_min_sync(ZRK_FULL, v);
@@ -719,7 +699,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
     tm.sync();
 
     const int *chdr = ZRK_CST_I(c_hdr);
-    const int nR = chdr[C_NR], nL = chdr[C_NL], nC = chdr[C_NC], T = o.T;
+    const int nR = chdr[C_NR], nC = chdr[C_NC], T = o.T;
     const int ccp_id = chdr[C_CCP_ID];
     const int tick_limit = chdr[C_TICK_LIMIT];
     const bool has_ccp = ccp_id != ZRK_NONE;

@@ -207,6 +207,8 @@ def run_ours(args, rank, world, local_rank):
             kern_ms.append(ms1 - ms0)
             launches += n1 - n0
         if i == args.warmup + args.steps - 1:
+            from zrk_modulation_b200.distributed import local_stats_device
+            dev_stats = local_stats_device(eng.torch_view("summary")).clone()  # stays on the GPU for NCCL
             counts = eng.counts()
             fc, ft, nr = eng.status()
         eng.close()
@@ -246,7 +248,8 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- final statistics gather: the one collective of the path (NCCL all-reduce over NVLink)
     from zrk_modulation_b200.distributed import describe_stats, gather_stats, local_stats
-    stats = gather_stats(local_stats(counts, fc), device=torch.device("cuda", dev))
+    assert np.array_equal(dev_stats.cpu().numpy(), local_stats(counts, fc)), "device-side statistics differ"
+    stats = gather_stats(dev_stats, device=torch.device("cuda", dev))
 
     if rank == 0:
         value = units * world * args.steps / (total_ms * 1e-3)

@@ -283,7 +283,7 @@ int zrk_read_messages(zrk_handle *h, int scenario, int tick0, int tick1, zrk_msg
                       size_t *n, int32_t *ids, size_t ids_cap, size_t *n_ids);
 int zrk_read_state(zrk_handle *h, const zrk_state_view *view);
 /* Device pointers for zero-copy consumers (torch): borrowed, valid until zrk_destroy. */
-int zrk_device_ptr(zrk_handle *h, const char *name, void **ptr, size_t *bytes); /* "dyn", "cst", "rec", "masks" */
+int zrk_device_ptr(zrk_handle *h, const char *name, void **ptr, size_t *bytes); /* "dyn", "cst", "rec", "masks", "summary" */
 /* Checkpoint / resume (absent in the reference): the complete device state of the
  * batch (scenario state, record log, mask history, clock) as one opaque host blob.
  * zrk_state_bytes gives the size; zrk_load_state needs a handle created from the same

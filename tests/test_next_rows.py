@@ -87,3 +87,19 @@ def test_checkpoint_roundtrip_cuda(request):
 def test_outcomes_and_perturbed_cuda(request):
     _outcomes(_lib(request))
     _perturbed(_lib(request))
+
+
+@pytest.mark.gpu
+def test_zero_copy_torch_view_of_the_summary(request):
+    """PyTorch as plumbing: the per-scenario counters as a CUDA tensor without a host hop
+    (what a NCCL statistics all-reduce consumes)."""
+    import torch
+    b = synthetic_batch(64, 12, n_radars=1, n_launchers=2, missiles_per_launcher=2, noise_period=8)
+    with Engine(b) as eng:
+        eng.step(50)
+        t = eng.torch_view("summary")
+        assert t.is_cuda and tuple(t.shape) == (64, 34) and t.dtype == torch.int32
+        assert np.array_equal(t[:, 16:].cpu().numpy().astype(np.int64), eng.counts())
+        assert int(t[:, 0].min()) <= 50  # H_TICK
+        raw = eng.torch_view("dyn")
+        assert raw.dtype == torch.uint8 and raw.numel() == eng.device_ptr("dyn")[1]

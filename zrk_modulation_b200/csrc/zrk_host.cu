@@ -899,6 +899,12 @@ extern "C" int zrk_device_ptr(zrk_handle *h, const char *name, void **ptr, size_
     if (n == "dyn") { p = P.dyn; sz = (size_t)o.B * o.dyn_bytes; }
     else if (n == "cst") { p = (void *)P.cst; sz = (size_t)o.B * o.cst_bytes; }
     else if (n == "rec") { p = P.rec; sz = (size_t)o.B * P.log_cap * sizeof(zrk_msg); }
+    else if (n == "summary") {  // [B][H_WORDS + NTYPES] int32: header + message counters, refreshed here
+        int rc = fetch_summary(h);
+        if (rc) return rc;
+        p = h->d_summary;
+        sz = (size_t)o.B * ZRK_SUMMARY_WORDS * sizeof(int);
+    }
     else if (n == "masks") { p = P.masks; sz = (size_t)P.mask_ticks * o.B * (1 + o.RP) * P.mask_words * sizeof(unsigned); }
     else return ZRK_ERR_ARG;
     *ptr = p;

@@ -27,14 +27,28 @@ def local_stats(counts: np.ndarray, fault_code: np.ndarray) -> np.ndarray:
                                                 (fc == _cabi.FAULT_KEY_ERROR_CCP107).sum(), counts.shape[0]]]).astype(np.int64)
 
 
-def gather_stats(stats: np.ndarray, device=None) -> np.ndarray:
+def local_stats_device(summary):
+    """The same statistics vector computed on the GPU from Engine.torch_view("summary")
+    (int32 [B, 16 + 18]: header words, then the per-type counters): no host hop before NCCL."""
+    import torch
+    from .engine import Engine  # noqa: F401  (documentation pointer only)
+    H_FAULT = 5  # zrk_layout.h
+    counts = summary[:, 16:].to(torch.int64).sum(dim=0)
+    fc = summary[:, H_FAULT] & 63
+    extra = torch.stack([(fc != 0).sum(), (fc == _cabi.FAULT_ATTRIBUTE_ERROR_CCP259).sum(),
+                         (fc == _cabi.FAULT_KEY_ERROR_CCP107).sum(),
+                         torch.tensor(summary.shape[0], device=summary.device)]).to(torch.int64)
+    return torch.cat([counts, extra])
+
+
+def gather_stats(stats, device=None) -> np.ndarray:
     """Sum the statistics vectors of all ranks (torch.distributed must be initialised when
     world_size > 1)."""
     import torch
     import torch.distributed as dist
+    t = stats.clone() if torch.is_tensor(stats) else torch.from_numpy(np.array(stats, copy=True))
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return stats.copy()
-    t = torch.from_numpy(stats.copy())
+        return t.cpu().numpy()
     if device is not None:
         t = t.to(device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)

@@ -162,6 +162,25 @@ class Engine:
         self._ck(self.lib.zrk_launch_stats(self._h, C.byref(n), C.byref(ms)))
         return n.value, ms.value
 
+    def torch_view(self, name: str, dtype=None):
+        """Zero-copy torch tensor over a device buffer of the handle ("summary": int32
+        [B, 16 + 18] header words + per-type message counters; "dyn", "rec", "masks": raw state).
+        The view is borrowed: valid until the engine is closed."""
+        import torch
+        ptr, nbytes = self.device_ptr(name)
+        if name == "summary":
+            shape, typestr, td = (self.batch.n_scenarios, 16 + _cabi.ZRK_MSG_NTYPES), "<i4", torch.int32
+        else:
+            shape, typestr, td = (nbytes,), "|u1", torch.uint8
+
+        class _Buf:
+            __cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+        holder = _Buf()
+        t = torch.as_tensor(holder, device=torch.device("cuda", torch.cuda.current_device()))
+        t._zrk_owner = (holder, self)
+        return t if dtype is None else t.view(dtype)
+
     def device_ptr(self, name: str):
         p, sz = C.c_void_p(), C.c_size_t()
         self._ck(self.lib.zrk_device_ptr(self._h, name.encode(), C.byref(p), C.byref(sz)))

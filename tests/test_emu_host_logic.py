@@ -113,3 +113,18 @@ def test_read_messages_needs_full_log(lib):
         eng.step(2)
         with pytest.raises(ZrkError):
             eng.messages(0)
+
+
+def test_c_abi_example_on_the_emulated_build(lib, tmp_path):
+    """tests/c_abi/abi_example.c (plain C against include/zrk_b200.h) against the emulated build."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "abi_example")
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "c_abi", "abi_example.c"),
+                           "-o", exe, "-ldl"])
+    out = subprocess.run([exe, os.path.join(emu_lib.HERE, "_build", "libzrk_emu.so")], capture_output=True, text=True,
+                         check=True).stdout.splitlines()
+    g = parity.load_golden("shipped_simulation_config_nonoise")
+    assert [int(x) for x in out[0].split()] == list(g["counts"]) and out[1] == "total 685"
+    assert out[2:] == ["detonate tick 11 missile 3005 target 40", "detonate tick 13 missile 4005 target 39"]

@@ -173,3 +173,21 @@ def test_properties_at_scale():
     assert (c0[:, A.MSG_MISSILE_DETONATE] <= c0[:, A.MSG_NEW_MISSILE]).all()
     ok = (s0[0] & 63) == 0
     assert (c0[ok, A.MSG_ACTIVE_OBJECTS] == 120).all() and (c0[~ok, A.MSG_ACTIVE_OBJECTS] == s0[1][~ok] + 1).all()
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """The boundary is a C ABI: a plain C program (tests/c_abi/abi_example.c, no Python, no torch)
+    builds simulation_config.yaml by hand, runs it through libzrk_b200.so and must print the
+    reference's known answers (no radar noise: 685 messages, detonations at ticks 11 and 13)."""
+    import os
+    import subprocess
+    from zrk_modulation_b200 import _cabi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "abi_example")
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "c_abi", "abi_example.c"),
+                           "-o", exe, "-ldl"])
+    out = subprocess.run([exe, _cabi.lib_path()], capture_output=True, text=True, check=True).stdout.splitlines()
+    g = parity.load_golden("shipped_simulation_config_nonoise")
+    assert [int(x) for x in out[0].split()] == list(g["counts"])
+    assert out[1] == "total 685"
+    assert out[2:] == ["detonate tick 11 missile 3005 target 40", "detonate tick 13 missile 4005 target 39"]

@@ -99,6 +99,7 @@ struct Layout {
     int x_lf;          // float4[TEAM + MP]: the same position rounded to fp32 (scan pre-filter)
     int x_claim, x_detlist, x_wscr, x_need;  // x_need doubles as the launch result (x_ok)
     int x_ghead, x_gnext;  // int[TEAM], int[TEAM + MP]: hash grid over the entries' link positions
+    int x_mbar;            // one 8-byte mbarrier: completion of the bulk (TMA) load of the state
     int team_smem_bytes;
 };
 
@@ -181,6 +182,7 @@ static inline Layout make_layout(int B, int T, int M, int R, int L, int C) {
     o.x_need = take(4 * team);
     o.x_ghead = take(4 * team);
     o.x_gnext = take(4 * (team + o.MP));
+    o.x_mbar = take(8);
     o.team_smem_bytes = zrk_align(p, 16);
     return o;
 }

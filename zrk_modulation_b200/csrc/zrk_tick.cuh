@@ -152,6 +152,67 @@ __device__ __forceinline__ void radar_move(const double *q, double &caz, double 
     }
 }
 
+// ------------------------------------------------------------------ bulk (TMA) staging of the state
+//
+// The scenario's state blob moves between HBM and shared memory as ONE bulk asynchronous copy
+// per direction (cp.async.bulk, the non-tensor TMA path: UBLKCP in SASS), issued by one lane and
+// tracked by an mbarrier, instead of a loop of per-thread 16-byte loads and stores.
+#ifdef ZRK_EMU
+__device__ __forceinline__ void stage_in(unsigned char *sm, const unsigned char *g_dyn, int dyn_bytes,
+                                         const unsigned char *g_cst, int cst_bytes, void *, bool leader) {
+    if (leader) {
+        memcpy(sm, g_dyn, (size_t)dyn_bytes);
+        memcpy(sm + dyn_bytes, g_cst, (size_t)cst_bytes);
+    }
+}
+__device__ __forceinline__ void stage_wait(void *) {}
+__device__ __forceinline__ void stage_out(unsigned char *g_dyn, const unsigned char *sm, int dyn_bytes, bool leader) {
+    if (leader) memcpy(g_dyn, sm, (size_t)dyn_bytes);
+}
+#else
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+// The team's leader arms the mbarrier with the byte count and issues the two bulk loads.
+__device__ __forceinline__ void stage_in(unsigned char *sm, const unsigned char *g_dyn, int dyn_bytes,
+                                         const unsigned char *g_cst, int cst_bytes, void *mbar, bool leader) {
+    if (leader) {
+        const unsigned bar = smem_addr(mbar);
+        asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(dyn_bytes + cst_bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(sm)),
+                     "l"(g_dyn), "r"(dyn_bytes), "r"(bar)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_addr(sm + dyn_bytes)),
+                     "l"(g_cst), "r"(cst_bytes), "r"(bar)
+                     : "memory");
+    }
+}
+// Every lane waits for phase 0 of the barrier; bounded, so that a mistake traps instead of hanging.
+__device__ __forceinline__ void stage_wait(void *mbar) {
+    const unsigned bar = smem_addr(mbar);
+    for (int spin = 0; spin < (1 << 24); spin++) {
+        unsigned done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(0)
+                     : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void stage_out(unsigned char *g_dyn, const unsigned char *sm, int dyn_bytes, bool leader) {
+    if (leader) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copy
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g_dyn), "r"(smem_addr(sm)), "r"(dyn_bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+#endif
+
 // ------------------------------------------------------------------ team primitives
 
 // A TEAM of 32 is a warp (several per CTA, warp-synchronous); larger teams are exactly one CTA
@@ -687,14 +748,13 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
     float4 *lf = (float4 *)(sm + o.x_lf);
     int *ghead = (int *)(sm + o.x_ghead), *gnext = (int *)(sm + o.x_gnext);
 
-    // ---- prologue: HBM -> shared memory / registers
+    // ---- prologue: HBM -> shared memory, one bulk copy per blob
     {
-        const uint4 *gd = (const uint4 *)(P.dyn + (size_t)b * o.dyn_bytes);
-        uint4 *sd = (uint4 *)sm;
-        for (int i = lane; i < o.dyn_bytes / 16; i += TEAM) sd[i] = gd[i];
-        const uint4 *gc = (const uint4 *)(P.cst + (size_t)b * o.cst_bytes);
-        uint4 *sc = (uint4 *)(sm + o.dyn_bytes);
-        for (int i = lane; i < o.cst_bytes / 16; i += TEAM) sc[i] = gc[i];
+        void *mbar = sm + o.x_mbar;
+        stage_in(sm, P.dyn + (size_t)b * o.dyn_bytes, o.dyn_bytes, P.cst + (size_t)b * o.cst_bytes, o.cst_bytes, mbar,
+                 lane == 0);
+        tm.sync();  // the barrier is initialised before anyone polls it
+        stage_wait(mbar);
     }
     tm.sync();
 
@@ -1222,13 +1282,9 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
         tm.sync();
     }
 
-    // ---- epilogue: shared memory -> HBM
+    // ---- epilogue: shared memory -> HBM, one bulk copy
     tm.sync();
-    {
-        uint4 *gd = (uint4 *)(P.dyn + (size_t)b * o.dyn_bytes);
-        const uint4 *sd = (const uint4 *)sm;
-        for (int i = lane; i < o.dyn_bytes / 16; i += TEAM) gd[i] = sd[i];
-    }
+    stage_out(P.dyn + (size_t)b * o.dyn_bytes, sm, o.dyn_bytes, lane == 0);
 }
 
 }  // namespace zrk

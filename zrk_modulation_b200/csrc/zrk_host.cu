@@ -186,6 +186,7 @@ struct zrk_handle {
     zrk_batch_desc hd{};  // scalar fields only are meaningful after create
     int device = 0;
     cudaStream_t stream{};
+    bool has_stream = false;  // zrk_create got as far as creating the stream
     std::vector<void *> allocs;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;  // per-launch event pairs
     std::vector<cudaEvent_t> free_events;
@@ -277,6 +278,10 @@ extern "C" const char *zrk_last_error(zrk_handle *h) { return h ? h->err.c_str()
 
 extern "C" void zrk_destroy(zrk_handle *h) {
     if (!h) return;
+    if (!h->has_stream) {  // zrk_create failed before touching the device
+        delete h;
+        return;
+    }
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (auto &pr : h->pending) {
@@ -362,6 +367,7 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
     }
     CK(cudaSetDevice(h->device));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->has_stream = true;
     h->hd = *d;
     Params &P = h->P;
     P.lo = lo;

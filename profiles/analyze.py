@@ -9,7 +9,9 @@ import io
 import subprocess
 import sys
 
-SRC = "zrk_modulation_b200/csrc/zrk_tick.cuh"
+import os
+
+SRC = os.environ.get("ZRK_ANALYZE_SRC", "zrk_modulation_b200/csrc/zrk_tick.cuh")  # the source the profiled library was built from
 MARKS = [("helpers (dot3, pymod, tsec)", None), ("radar_sees", "SectorRadar.find_visible_objects for one object"),
          ("radar_move", "SectorRadar.move_to_next_sector_circular"), ("team primitives", "team primitives"),
          ("put_rec", "record log"), ("missile_solve", "Missile._calculate_trajectory_params"),

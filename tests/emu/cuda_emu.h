@@ -172,6 +172,9 @@ inline int atomicOr(int *p, int v) {
     return o;
 }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
+inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 inline float __fdividef(float a, float b) { return a / b; }
 inline int __reduce_min_sync(unsigned, int v) {
     zrk_emu::Warp &w = zrk_emu::my_warp();

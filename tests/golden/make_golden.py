@@ -50,8 +50,10 @@ def main():
             save(f"{fam}_{seed:02d}", cfg, noise)
 
 
-def special():
+def special(only=None):
     for kind in SPECIAL_KINDS:
+        if only and kind not in only:
+            continue
         cfg = special_config(kind)
         b = compile_batch(cfg)
         save(f"special_{kind}", cfg, make_noise(8, b.max_radars, b.n_slots, seed=5))
@@ -60,7 +62,7 @@ def special():
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "special":
-        special()
+        special(sys.argv[2:])  # optionally only the named kinds
     else:
         main()
         special()

@@ -87,11 +87,28 @@ def special_config(kind: str):
         t[1]["velocity"] = list(t[0]["velocity"])
         t[3]["position"] = [t[2]["position"][0], t[2]["position"][1] + 1e-9, t[2]["position"][2]]
         t[3]["velocity"] = list(t[2]["velocity"])
-    elif kind == "far_field":    # coordinates beyond the fp32-safe range of the scan pre-filter
+    elif kind == "far_field":    # large coordinates (hundreds of km): the fp32 pre-filter near the end of its range
         for i, tt in enumerate(t):
             tt["position"] = [2.0e5 + 3000.0 * i, -1.5e5 + 1000.0 * i, 9000.0]
         for r in cfg["radars"]:
             r["max_distance"] = 1.0e6
+            r.update(azimuth_start=0.0, azimuth_range=360.0, azimuth_speed=0.0, elevation_start=0.0,
+                     elevation_range=180.0, elevation_speed=0.0, scan_mode="horizontal")
+    elif kind == "far_close":    # near the end of the fp32 range AND tracks closer than fp32 resolves there
+        for i, tt in enumerate(t):
+            j = i // 2
+            tt["position"] = [9.0e5 + 4000.0 * j + 0.03 * (i % 2), -8.0e5 + 1500.0 * j - 0.05 * (i % 2), 9000.0 + 0.02 * (i % 2)]
+            if i % 2:
+                tt["velocity"] = list(t[i - 1]["velocity"])
+        for r in cfg["radars"]:
+            r["max_distance"] = 3.0e6
+            r.update(azimuth_start=0.0, azimuth_range=360.0, azimuth_speed=0.0, elevation_start=0.0,
+                     elevation_range=180.0, elevation_speed=0.0, scan_mode="horizontal")
+    elif kind == "beyond_f32":   # coordinates beyond the range the fp32 pre-filter is trusted in: exact scan only
+        for i, tt in enumerate(t):
+            tt["position"] = [3.0e6 + 3000.0 * i, -2.5e6 + 1000.0 * i, 9000.0]
+        for r in cfg["radars"]:
+            r["max_distance"] = 1.0e7
             r.update(azimuth_start=0.0, azimuth_range=360.0, azimuth_speed=0.0, elevation_start=0.0,
                      elevation_range=180.0, elevation_speed=0.0, scan_mode="horizontal")
     elif kind == "on_axis":      # objects exactly on sector edges / coordinate axes of the radar
@@ -122,4 +139,4 @@ def special_config(kind: str):
     return cfg
 
 
-SPECIAL_KINDS = ["twins", "near_twins", "far_field", "on_axis", "late_launch"]
+SPECIAL_KINDS = ["twins", "near_twins", "far_field", "far_close", "beyond_f32", "on_axis", "late_launch"]

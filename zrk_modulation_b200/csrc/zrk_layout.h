@@ -96,9 +96,10 @@ struct Layout {
     int cst_bytes;
     // scratch (shared memory only), offsets from the start of the team's region
     int x_lxy, x_lzd;  // double2[TEAM + MP]: per CCP entry, the position link_object measures to
-    int x_lf;          // float4[TEAM + MP]: the same position rounded to fp32 (scan pre-filter)
+    int x_lf;          // the same positions rounded to fp32: warp teams float[12][(TEAM + MP8) / 4], blocks of
+                       // x[4] y[4] z[4]; larger teams float4[TEAM + MP] = x, y, z, next entry in the grid chain
     int x_claim, x_detlist, x_wscr, x_need;  // x_need doubles as the launch result (x_ok)
-    int x_ghead, x_gnext;  // int[TEAM], int[TEAM + MP]: hash grid over the entries' link positions
+    int x_ghead;       // int[TEAM]: bucket heads of the hash grid over the entries' link positions
     int x_mbar;            // one 8-byte mbarrier: completion of the bulk (TMA) load of the state
     int team_smem_bytes;
 };
@@ -175,13 +176,12 @@ static inline Layout make_layout(int B, int T, int M, int R, int L, int C) {
     p = o.dyn_bytes + o.cst_bytes;
     o.x_lxy = take(16 * (team + o.MP));
     o.x_lzd = take(16 * (team + o.MP));
-    o.x_lf = take(16 * (team + o.MP));
+    o.x_lf = take(team > 32 ? 16 * (team + o.MP) : 12 * (team + zrk_align(o.MP, 8)));
     o.x_claim = take(4 * (team + o.MP));
     o.x_detlist = take(4 * team);
     o.x_wscr = take(4 * 64);
     o.x_need = take(4 * team);
     o.x_ghead = take(4 * team);
-    o.x_gnext = take(4 * (team + o.MP));
     o.x_mbar = take(8);
     o.team_smem_bytes = zrk_align(p, 16);
     return o;

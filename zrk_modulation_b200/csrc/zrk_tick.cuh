@@ -451,23 +451,117 @@ __device__ __forceinline__ double link_d2(const double2 *lxy, const double2 *lzd
     return dot3(ex, ey, ez, ex, ey, ez);
 }
 
-// fp32 pre-filter of the scan.  Link positions and the detection are rounded to fp32; for
-// |coordinate| <= 65536 m the fp32 distance differs from the fp64 one by < 0.05 m, so a pair whose
-// fp32 squared distance exceeds (sqrt(best) + 0.25 m)^2 cannot beat or tie the best.
-#define ZRK_F32_COORD_MAX 65536.0
-__device__ __forceinline__ float link_threshold(double best, bool f32ok) {
-    if (!f32ok || !(best < 1e30)) return INFINITY;
-    const double r = sqrt(best) + 0.25;
-    return (float)(r * r) * 1.000001f;
+// fp32 pre-filter of the scan.  Link positions and the detection are rounded to fp32.  For
+// |coordinate| <= C = 2^20 m each component of the fp32 difference vector is off by at most
+// 2 C 2^-24 (two roundings to fp32) plus a relative 2^-24, so the fp32 distance differs from the
+// fp64 one by less than sqrt(3) * 2^-3 = 0.22 m plus 2e-7 relative: a pair whose fp32 squared
+// distance exceeds (sqrt(best) + 0.5 m)^2 * (1 + 1e-6) cannot beat or tie the best (the margin
+// also absorbs the fp32 evaluation of that bound itself).  A detection
+// or an entry outside that range sends the detection (the whole team, for an entry) to link_exact.
+#define ZRK_F32_COORD_MAX 1048576.0
+#define ZRK_F32_MARGIN 0.5
+#define ZRK_F32_ALL 3.0e38f /* threshold "everything real": pads and skipped entries measure inf */
+__device__ __forceinline__ float link_threshold(double best) {
+    if (!(best < 1e30)) return ZRK_F32_ALL;
+    // an upper bound of (sqrt(best) + margin)^2 in fp32: every rounding below is covered by the factors
+    const float r = sqrtf((float)best) * 1.0000005f + (float)ZRK_F32_MARGIN;
+    return r * r * 1.000001f;
 }
-__device__ __forceinline__ float link_d2f(const float4 *lf, int ue, float fx, float fy, float fz) {
-    const float4 a = lf[ue];
+
+// The fp32 images live in blocks of four entries, x[4] y[4] z[4] (48 bytes), so that one block is
+// three 16-byte loads and the arithmetic runs on the packed fp32x2 pipe (FADD2 / FMUL2 / FFMA2):
+// two pairs per instruction, the same rounding as the scalar ex*ex -> fma -> fma chain.
+// Teams larger than a warp keep one float4 per entry instead (x, y, z, next entry of the hash-grid
+// chain): their scans mostly walk the grid, one 16-byte load per visited entry.
+template <int TEAM>
+__device__ __forceinline__ float &lf_x(float *lf, int ue) {
+    return TEAM > 32 ? lf[4 * ue] : lf[(ue >> 2) * 12 + (ue & 3)];
+}
+template <int TEAM>
+__device__ __forceinline__ void lf_store(float *lf, int ue, float x, float y, float z) {
+    if (TEAM > 32) {
+        reinterpret_cast<float4 *>(lf)[ue] = make_float4(x, y, z, 0.f);
+    } else {
+        float *q = &lf_x<TEAM>(lf, ue);
+        q[0] = x;
+        q[4] = y;
+        q[8] = z;
+    }
+}
+__device__ __forceinline__ float link_d2f(float4 a, float fx, float fy, float fz) {
     const float ex = a.x - fx, ey = a.y - fy, ez = a.z - fz;
     return fmaf(ez, ez, fmaf(ey, ey, ex * ex));
 }
 
+#ifdef ZRK_EMU
+struct F2 {
+    float lo, hi;
+};
+static inline F2 f2_dup(float a) { return F2{a, a}; }
+static inline F2 f2_add(F2 a, F2 b) { return F2{a.lo + b.lo, a.hi + b.hi}; }
+static inline F2 f2_mul(F2 a, F2 b) { return F2{a.lo * b.lo, a.hi * b.hi}; }
+static inline F2 f2_fma(F2 a, F2 b, F2 c) { return F2{fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)}; }
+static inline void f2_load4(const float *p, F2 &a, F2 &b) {
+    a = F2{p[0], p[1]};
+    b = F2{p[2], p[3]};
+}
+static inline void f2_split(F2 a, float &lo, float &hi) {
+    lo = a.lo;
+    hi = a.hi;
+}
+#else
+typedef unsigned long long F2;
+__device__ __forceinline__ F2 f2_dup(float a) {
+    F2 r;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(a));
+    return r;
+}
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) {
+    F2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
+    F2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) {
+    F2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ void f2_load4(const float *p, F2 &a, F2 &b) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p);
+    a = v.x;
+    b = v.y;
+}
+__device__ __forceinline__ void f2_split(F2 a, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+}
+#endif
+
+// fp32 squared distances of the four entries of block `blk` to the detection (nf* = -coordinate, twice)
+__device__ __forceinline__ void link_block(const float *lf, int blk, F2 nfx, F2 nfy, F2 nfz, float d[4]) {
+    const float *q = lf + blk * 12;
+    F2 x0, x1, y0, y1, z0, z1;
+    f2_load4(q, x0, x1);
+    f2_load4(q + 4, y0, y1);
+    f2_load4(q + 8, z0, z1);
+    x0 = f2_add(x0, nfx);
+    x1 = f2_add(x1, nfx);
+    y0 = f2_add(y0, nfy);
+    y1 = f2_add(y1, nfy);
+    z0 = f2_add(z0, nfz);
+    z1 = f2_add(z1, nfz);
+    const F2 s0 = f2_fma(z0, z0, f2_fma(y0, y0, f2_mul(x0, x0)));
+    const F2 s1 = f2_fma(z1, z1, f2_fma(y1, y1, f2_mul(x1, x1)));
+    f2_split(s0, d[0], d[1]);
+    f2_split(s1, d[2], d[3]);
+}
+
 // Hash grid over the entries' link positions (x, y of the fp32 image; cells of ZRK_CELL metres,
-// TEAM buckets, chained through gnext).  A detection whose acceptance radius sqrt(thr) is at most
+// TEAM buckets, chained through the w component of the images).  A detection whose acceptance radius sqrt(thr) is at most
 // one cell wide only has to look at the buckets of the <= 2 x 2 cells its radius touches: every
 // entry within that radius is in one of them (hash collisions only add harmless extra tests).
 #define ZRK_CELL 512.0f
@@ -477,8 +571,10 @@ __device__ __forceinline__ int grid_bucket(int ix, int iy) {
     return (int)(((unsigned)ix * 73856093u) ^ ((unsigned)iy * 19349663u)) & (TEAM - 1);
 }
 
+// Squared-domain scan of one detection.  `coords_ok`: the detection and every entry image are
+// inside the fp32-safe range (otherwise the caller runs link_exact).
 template <int TEAM>
-__device__ __forceinline__ void link_fast(const int *ghead, const int *gnext, bool grid_ok, const float4 *lf, const double2 *lxy, const double2 *lzd, int n_te, int n_me,
+__device__ __forceinline__ void link_fast(const int *ghead, bool grid_ok, const float *lf, const double2 *lxy, const double2 *lzd, int n_te, int n_me,
                                           int seed, double range_step, double px, double py, double pz, double speed,
                                           int &cls, int &cand, bool &unsure) {
     LinkAcc A;
@@ -489,59 +585,115 @@ __device__ __forceinline__ void link_fast(const int *ghead, const int *gnext, bo
     // Seed with the entry that tracked this slot last tick: it is almost always the nearest, and
     // with best = its d2 nearly every other pair fails the single fp32 compare below.
     if (seed >= 0) link_eval(A, seed, link_d2(lxy, lzd, seed, px, py, pz), lzd[seed].y, speed, range_step);
-    const bool f32ok = fabs(px) <= ZRK_F32_COORD_MAX && fabs(py) <= ZRK_F32_COORD_MAX && fabs(pz) <= ZRK_F32_COORD_MAX;
     const float fx = (float)px, fy = (float)py, fz = (float)pz;
-    float thr = link_threshold(A.best, f32ok);
-    if (grid_ok && thr <= ZRK_CELL * ZRK_CELL) {
-        // the common case: a seeded detection only visits the few entries near it
-        const float r = sqrtf(thr);
-        const int ix0 = grid_cell(fx - r), ix1 = grid_cell(fx + r), iy0 = grid_cell(fy - r), iy1 = grid_cell(fy + r);
-        for (int ix = ix0; ix <= ix1; ix++)
-            for (int iy = iy0; iy <= iy1; iy++)
-                for (int u = ghead[grid_bucket<TEAM>(ix, iy)]; u >= 0; u = gnext[u]) {
-                    if (u != seed && !(link_d2f(lf, u, fx, fy, fz) > thr)) {
-                        const double dk = link_d2(lxy, lzd, u, px, py, pz);
-                        if (!(dk > A.best)) {
-                            link_eval(A, u, dk, lzd[u].y, speed, range_step);
-                            thr = link_threshold(A.best, f32ok);
-                        }
-                    }
-                }
-    } else {
-        for (int pass = 0; pass < 2; pass++) {
-            const int n = pass ? n_me : n_te, base = pass ? TEAM : 0;
-            int e = 0;
-            // four pairs at a time; the common case is that none of them can beat the best
-            for (; e + 4 <= n; e += 4) {
-                const int u = base + e;
-                const float d0 = link_d2f(lf, u, fx, fy, fz), d1 = link_d2f(lf, u + 1, fx, fy, fz);
-                const float d2 = link_d2f(lf, u + 2, fx, fy, fz), d3 = link_d2f(lf, u + 3, fx, fy, fz);
-                // bitwise, not short-circuit: all four chains are issued before the one branch
-                const bool h = (!(d0 > thr) & (u != seed)) | (!(d1 > thr) & (u + 1 != seed)) |
-                               (!(d2 > thr) & (u + 2 != seed)) | (!(d3 > thr) & (u + 3 != seed));
-                if (h) {
-#pragma unroll 1
-                    for (int k = 0; k < 4; k++) {
-                        if (!(link_d2f(lf, u + k, fx, fy, fz) > thr) && u + k != seed) {
-                            const double dk = link_d2(lxy, lzd, u + k, px, py, pz);
+    float thr = link_threshold(A.best);
+    if (TEAM > 32) {
+        const float4 *lf4 = (const float4 *)lf;
+        if (grid_ok && thr <= ZRK_CELL * ZRK_CELL) {
+            // the common case: a seeded detection only visits the few entries near it
+            const float r = sqrtf(thr);
+            const int ix0 = grid_cell(fx - r), ix1 = grid_cell(fx + r), iy0 = grid_cell(fy - r), iy1 = grid_cell(fy + r);
+            for (int ix = ix0; ix <= ix1; ix++)
+                for (int iy = iy0; iy <= iy1; iy++)
+                    for (int u = ghead[grid_bucket<TEAM>(ix, iy)]; u >= 0;) {
+                        const float4 a = lf4[u];
+                        if (u != seed && !(link_d2f(a, fx, fy, fz) > thr)) {
+                            const double dk = link_d2(lxy, lzd, u, px, py, pz);
                             if (!(dk > A.best)) {
-                                link_eval(A, u + k, dk, lzd[u + k].y, speed, range_step);
-                                thr = link_threshold(A.best, f32ok);
+                                link_eval(A, u, dk, lzd[u].y, speed, range_step);
+                                thr = link_threshold(A.best);
+                            }
+                        }
+                        u = __float_as_int(a.w);
+                    }
+        } else {
+            for (int pass = 0; pass < 2; pass++) {
+                const int n = pass ? n_me : n_te, base = pass ? TEAM : 0;
+                int e = 0;
+                // four pairs at a time; the common case is that none of them can beat the best
+                for (; e + 4 <= n; e += 4) {
+                    const int u = base + e;
+                    const float d0 = link_d2f(lf4[u], fx, fy, fz), d1 = link_d2f(lf4[u + 1], fx, fy, fz);
+                    const float d2 = link_d2f(lf4[u + 2], fx, fy, fz), d3 = link_d2f(lf4[u + 3], fx, fy, fz);
+                    // bitwise, not short-circuit: all four chains are issued before the one branch
+                    const bool h = (!(d0 > thr) & (u != seed)) | (!(d1 > thr) & (u + 1 != seed)) |
+                                   (!(d2 > thr) & (u + 2 != seed)) | (!(d3 > thr) & (u + 3 != seed));
+                    if (h) {
+#pragma unroll 1
+                        for (int k = 0; k < 4; k++) {
+                            if (!(link_d2f(lf4[u + k], fx, fy, fz) > thr) && u + k != seed) {
+                                const double dk = link_d2(lxy, lzd, u + k, px, py, pz);
+                                if (!(dk > A.best)) {
+                                    link_eval(A, u + k, dk, lzd[u + k].y, speed, range_step);
+                                    thr = link_threshold(A.best);
+                                }
                             }
                         }
                     }
                 }
-            }
 #pragma unroll 1
-            for (; e < n; e++) {
-                const int u = base + e;
-                if (!(link_d2f(lf, u, fx, fy, fz) > thr) && u != seed) {
+                for (; e < n; e++) {
+                    const int u = base + e;
+                    if (!(link_d2f(lf4[u], fx, fy, fz) > thr) && u != seed) {
+                        const double dk = link_d2(lxy, lzd, u, px, py, pz);
+                        if (!(dk > A.best)) {
+                            link_eval(A, u, dk, lzd[u].y, speed, range_step);
+                            thr = link_threshold(A.best);
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        const F2 nfx = f2_dup(-fx), nfy = f2_dup(-fy), nfz = f2_dup(-fz);
+        // fp64 evaluation of the entries of step `blk` flagged in `hit`
+        auto visit = [&](int blk, unsigned hit) {
+            const int lim = blk < TEAM / 4 ? n_te : TEAM + n_me;
+            while (hit) {
+                const int u = blk * 4 + __ffs(hit) - 1;
+                hit &= hit - 1;
+                if (u < lim) {
                     const double dk = link_d2(lxy, lzd, u, px, py, pz);
                     if (!(dk > A.best)) {
                         link_eval(A, u, dk, lzd[u].y, speed, range_step);
-                        thr = link_threshold(A.best, f32ok);
+                        thr = link_threshold(A.best);
                     }
                 }
+            }
+        };
+        // Eight entries (two blocks) per step; both regions are padded with far images to a multiple
+        // of eight.  The step that holds the seed always has a pair within the threshold (the seed
+        // itself) and the seeds of the lanes are spread over all steps, so the sweep leaves that step
+        // out and all lanes visit theirs together afterwards, with the seed masked.
+        const int sblk = seed >= 0 ? (seed >> 3) * 2 : -2;
+        const int te_end = ((n_te + 7) >> 3) * 2, me_end = TEAM / 4 + ((n_me + 7) >> 3) * 2;
+        for (int blk = 0;; blk += 2) {
+            if (blk == te_end) blk = TEAM / 4;  // from the target entries to the missile entries
+            if (blk >= me_end) break;
+            float d[8];
+            link_block(lf, blk, nfx, nfy, nfz, d);
+            link_block(lf, blk + 1, nfx, nfy, nfz, d + 4);
+            const float m = fminf(fminf(fminf(d[0], d[1]), fminf(d[2], d[3])), fminf(fminf(d[4], d[5]), fminf(d[6], d[7])));
+            if (!(m > thr) && blk != sblk) {  // rare
+                unsigned hit = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) hit |= (unsigned)!(d[k] > thr) << k;
+                visit(blk, hit);
+            }
+        }
+        if (seed >= 0) {
+            float d[8];
+            link_block(lf, sblk, nfx, nfy, nfz, d);
+            link_block(lf, sblk + 1, nfx, nfy, nfz, d + 4);
+            const int ks = seed & 7;
+#pragma unroll
+            for (int k = 0; k < 8; k++) d[k] = k == ks ? INFINITY : d[k];
+            const float m = fminf(fminf(fminf(d[0], d[1]), fminf(d[2], d[3])), fminf(fminf(d[4], d[5]), fminf(d[6], d[7])));
+            if (!(m > thr)) {  // rare
+                unsigned hit = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) hit |= (unsigned)!(d[k] > thr) << k;
+                visit(sblk, hit);
             }
         }
     }
@@ -550,11 +702,9 @@ __device__ __forceinline__ void link_fast(const int *ghead, const int *gnext, bo
     cand = A.ue < 0 ? -1 : (A.ue >= TEAM ? A.ue - TEAM : A.ue);
 }
 
-// fp32 image of one link position: NaN (always a candidate) outside the fp32-safe range
-__device__ __forceinline__ float4 link_f32(double x, double y, double z) {
-    const bool ok = (x >= ZRK_FAR || fabs(x) <= ZRK_F32_COORD_MAX) && fabs(y) <= ZRK_F32_COORD_MAX &&
-                    fabs(z) <= ZRK_F32_COORD_MAX;
-    return ok ? make_float4(x >= ZRK_FAR ? 1e30f : (float)x, (float)y, (float)z, 0.f) : make_float4(NAN, NAN, NAN, 0.f);
+// is a link position (or a detection) inside the range where the fp32 image is trusted?
+__device__ __forceinline__ bool link_f32_ok(double x, double y, double z) {
+    return fabs(x) <= ZRK_F32_COORD_MAX && fabs(y) <= ZRK_F32_COORD_MAX && fabs(z) <= ZRK_F32_COORD_MAX;
 }
 
 // ------------------------------------------------------------------ lane 0 alone: launchers + CCP bookkeeping
@@ -732,7 +882,7 @@ template <int TEAM, int TPC, bool FAST>
 __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
     ZRK_SMEM_DECL;
     const Layout &o = P.lo;
-    const int MP = o.MP, Q = o.Q;
+    const int MP = o.MP, Q = o.Q, MP8 = (o.MP + 7) & ~7;
     Team<TEAM, TPC> tm;
     tm.tic = threadIdx.x / TEAM;
     tm.lane = threadIdx.x % TEAM;
@@ -745,8 +895,8 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
     tm.wscr = (int *)(sm + o.x_wscr);
     tm.flip = 0;
     double2 *lxy = (double2 *)(sm + o.x_lxy), *lzd = (double2 *)(sm + o.x_lzd);
-    float4 *lf = (float4 *)(sm + o.x_lf);
-    int *ghead = (int *)(sm + o.x_ghead), *gnext = (int *)(sm + o.x_gnext);
+    float *lf = (float *)(sm + o.x_lf);
+    int *ghead = (int *)(sm + o.x_ghead);
 
     // ---- prologue: HBM -> shared memory, one bulk copy per blob
     {
@@ -974,46 +1124,48 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
             // for a missile whose prev_pos is None) and d_t = now - upd_time
             // the hash grid pays off once a scan is long; warp-sized scenarios scan their few entries directly
             const bool want_grid = FAST && TEAM > 32 && n_te + n_me >= 48;
-            bool bad_image = false;  // an entry outside the fp32-safe range: no grid this tick
+            bool bad_image = false;  // an entry outside the fp32-safe range: the team scans exactly this tick
             if (want_grid) ghead[lane] = -1;
             if (lane < n_te) {
                 const int ref = H.te_ref()[lane], upd = H.te_upd()[lane];
                 const double2 a = H.qxy()[ref], c = H.qzw()[ref];
-                const double ax = upd == tick ? ZRK_FAR : a.x;
-                lxy[lane] = make_double2(ax, a.y);
+                const bool skip = upd == tick;
+                lxy[lane] = make_double2(skip ? ZRK_FAR : a.x, a.y);
                 lzd[lane] = make_double2(c.x, now_s - H.te_upds()[lane]);
                 if (FAST) {
-                    const float4 f = link_f32(ax, a.y, c.x);
-                    lf[lane] = f;
-                    bad_image = !(f.x == f.x);
+                    lf_store<TEAM>(lf, lane, skip ? 1e30f : (float)a.x, (float)a.y, (float)c.x);
+                    bad_image = !skip && !link_f32_ok(a.x, a.y, c.x);
                 }
+            } else if (FAST && TEAM == 32) {
+                lf_store<TEAM>(lf, lane, 1e30f, 0.f, 0.f);  // pad: measures inf to everything
             }
             if (lane < n_me) {
                 const int ref = ZRK_COLD_I(me_ref)[lane], upd = ZRK_COLD_I(me_upd)[lane];
                 const bool hp = (H.sflags()[ref] & F_HASPREV) != 0;
                 const double2 a = hp ? H.qxy()[ref] : H.pxy()[ref];
                 const double cz = hp ? H.qzw()[ref].x : H.pzs()[ref].x;
-                const double ax = upd == tick ? ZRK_FAR : a.x;
-                lxy[TEAM + lane] = make_double2(ax, a.y);
+                const bool skip = upd == tick;
+                lxy[TEAM + lane] = make_double2(skip ? ZRK_FAR : a.x, a.y);
                 lzd[TEAM + lane] = make_double2(cz, now_s - ZRK_COLD_D(me_upds)[lane]);
                 if (FAST) {
-                    const float4 f = link_f32(ax, a.y, cz);
-                    lf[TEAM + lane] = f;
-                    bad_image = bad_image || !(f.x == f.x);
+                    lf_store<TEAM>(lf, TEAM + lane, skip ? 1e30f : (float)a.x, (float)a.y, (float)cz);
+                    bad_image = bad_image || (!skip && !link_f32_ok(a.x, a.y, cz));
                 }
+            } else if (FAST && TEAM == 32 && lane < MP8) {
+                lf_store<TEAM>(lf, TEAM + lane, 1e30f, 0.f, 0.f);
             }
-            bool grid_ok = false;
+            bool grid_ok = false, any_bad = false;
             if (want_grid) {
-                grid_ok = !tm.any(bad_image);
-                tm.sync();  // bucket heads are reset, fp32 images are written
+                any_bad = tm.any(bad_image);  // also the barrier: bucket heads are reset, fp32 images are written
+                grid_ok = !any_bad;
                 if (grid_ok) {  // entries link_object skips (image x = 1e30) stay out of the grid
-                    if (lane < n_te && lf[lane].x < 1e29f) {
-                        const float4 f = lf[lane];
-                        gnext[lane] = atomicExch(&ghead[grid_bucket<TEAM>(grid_cell(f.x), grid_cell(f.y))], lane);
+                    if (lane < n_te && lf[4 * lane] < 1e29f) {
+                        float *q = lf + 4 * lane;
+                        q[3] = __int_as_float(atomicExch(&ghead[grid_bucket<TEAM>(grid_cell(q[0]), grid_cell(q[1]))], lane));
                     }
-                    if (lane < n_me && lf[TEAM + lane].x < 1e29f) {
-                        const float4 f = lf[TEAM + lane];
-                        gnext[TEAM + lane] = atomicExch(&ghead[grid_bucket<TEAM>(grid_cell(f.x), grid_cell(f.y))], TEAM + lane);
+                    if (lane < n_me && lf[4 * (TEAM + lane)] < 1e29f) {
+                        float *q = lf + 4 * (TEAM + lane);
+                        q[3] = __int_as_float(atomicExch(&ghead[grid_bucket<TEAM>(grid_cell(q[0]), grid_cell(q[1]))], TEAM + lane));
                     }
                 }
             }
@@ -1028,7 +1180,10 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
             }
             int *detlist = (int *)(sm + o.x_detlist);
             if (myrank >= 0) detlist[myrank] = lane;
-            tm.sync();
+            if (FAST && !want_grid)
+                any_bad = tm.any(bad_image);  // doubles as the barrier
+            else
+                tm.sync();
             const int i = lane;
             int slot = 0, did = 0, radar_id = 0, seed = -1;
             bool seed_own = false;
@@ -1048,13 +1203,15 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
                 // does the seed entry still refer to this very slot?  (then distinct slots have distinct seeds)
                 if (seed >= 0) seed_own = (seed >= TEAM ? ZRK_COLD_I(me_ref)[seed - TEAM] : H.te_ref()[seed]) == slot;
             }
+            const bool coords_ok = FAST && !any_bad && link_f32_ok(dpx, dpy, dpz);
             int lo_rank = 0;
             for (;;) {
                 int cls = 0, cand = -1, claim = -1;
                 if (unresolved) {
                     if (FAST) {
-                        bool unsure;
-                        link_fast<TEAM>(ghead, gnext, grid_ok, lf, lxy, lzd, n_te, n_me, seed, P.range_step, dpx, dpy, dpz, dspeed, cls, cand, unsure);
+                        bool unsure = !coords_ok;
+                        if (coords_ok)
+                            link_fast<TEAM>(ghead, grid_ok, lf, lxy, lzd, n_te, n_me, seed, P.range_step, dpx, dpy, dpz, dspeed, cls, cand, unsure);
                         if (unsure) link_exact<TEAM>(lxy, lzd, n_te, n_me, P.range_step, dpx, dpy, dpz, dspeed, cls, cand);
                     } else {
                         link_exact<TEAM>(lxy, lzd, n_te, n_me, P.range_step, dpx, dpy, dpz, dspeed, cls, cand);
@@ -1196,14 +1353,14 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
                         if (!following) H.te_follow()[cand] = ok != 0;
                         H.own()[slot] = cand;
                         lxy[cand].x = ZRK_FAR;
-                        if (FAST) lf[cand].x = 1e30f;
+                        if (FAST) lf_x<TEAM>(lf, cand) = 1e30f;
                     } else if (cls == 2) {  // old_rocket (CCP.py:361-366)
                         ZRK_COLD_I(me_ref)[cand] = slot;
                         ZRK_COLD_I(me_upd)[cand] = tick;
                         ZRK_COLD_D(me_upds)[cand] = now_s;
                         H.own()[slot] = TEAM + cand;
                         lxy[TEAM + cand].x = ZRK_FAR;
-                        if (FAST) lf[TEAM + cand].x = 1e30f;
+                        if (FAST) lf_x<TEAM>(lf, TEAM + cand) = 1e30f;
                     } else {  // new_target + add_target (CCP.py:322-330, :88-93)
                         const int e = claim >= 0 ? claim : n_te + r_app;
                         H.te_key()[e] = did;
@@ -1214,7 +1371,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
                         H.te_mid()[e] = ZRK_NONE;
                         H.own()[slot] = e;
                         lxy[e].x = ZRK_FAR;
-                        if (FAST) lf[e] = make_float4(1e30f, 0.f, 0.f, 0.f);
+                        if (FAST) lf_x<TEAM>(lf, e) = 1e30f;
                     }
                     unresolved = false;
                 }

@@ -104,32 +104,35 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def profiled(workload, ticks_per_launch, key, what):
-    """`key` of the committed ncu summary of this workload as a labelled dict, else None."""
+def _profile_summaries(workload, ticks_per_launch):
+    """Committed ncu summaries (profiles/*_summary.json) of this workload, newest kernel version first."""
     import glob
-    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_summary.json")), reverse=True):
-        try:
-            d = json.load(open(p))
-        except ValueError:
-            continue
-        if d.get("workload") == workload and abs(d.get("ticks_per_launch", 0) - ticks_per_launch) < 1e-9 and key in d:
-            return {"what": what, key: d[key], "source": os.path.relpath(p, ROOT)}
-    return None
-
-
-def profiled_traffic(workload, ticks_per_launch):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one tick-kernel launch, from the committed
-    `ncu --set full` summary of the same workload (profiles/*_summary.json), else None."""
-    import glob
-    best = None
-    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_summary.json"))):
+    out = []
+    for p in glob.glob(os.path.join(ROOT, "profiles", "*_summary.json")):
         try:
             d = json.load(open(p))
         except ValueError:
             continue
         if d.get("workload") == workload and abs(d.get("ticks_per_launch", 0) - ticks_per_launch) < 1e-9:
-            best = d.get("dram_bytes_per_launch")
-    return best
+            out.append((d.get("seq", 0), p, d))
+    return [(p, d) for _, p, d in sorted(out, key=lambda t: -t[0])]
+
+
+def profiled(workload, ticks_per_launch, key, what):
+    """`key` of the newest committed ncu summary of this workload as a labelled dict, else None."""
+    for p, d in _profile_summaries(workload, ticks_per_launch):
+        if key in d:
+            return {"what": what, key: d[key], "source": os.path.relpath(p, ROOT)}
+    return None
+
+
+def profiled_traffic(workload, ticks_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one tick-kernel launch, from the newest committed
+    `ncu --set full` summary of the same workload (profiles/*_summary.json), else None."""
+    for _, d in _profile_summaries(workload, ticks_per_launch):
+        if d.get("dram_bytes_per_launch") is not None:
+            return d["dram_bytes_per_launch"]
+    return None
 
 
 def cpu_reference_throughput(name, n_scen_per_core, cores, ticks=None):

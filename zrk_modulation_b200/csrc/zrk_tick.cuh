@@ -461,10 +461,19 @@ __device__ __forceinline__ double link_d2(const double2 *lxy, const double2 *lzd
 #define ZRK_F32_COORD_MAX 1048576.0
 #define ZRK_F32_MARGIN 0.5
 #define ZRK_F32_ALL 3.0e38f /* threshold "everything real": pads and skipped entries measure inf */
+__device__ __forceinline__ float sqrt_fast(float x) {  // relative error <= 2^-23 (sqrt.approx.f32)
+#ifdef ZRK_EMU
+    return sqrtf(x);
+#else
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
 __device__ __forceinline__ float link_threshold(double best) {
     if (!(best < 1e30)) return ZRK_F32_ALL;
     // an upper bound of (sqrt(best) + margin)^2 in fp32: every rounding below is covered by the factors
-    const float r = sqrtf((float)best) * 1.0000005f + (float)ZRK_F32_MARGIN;
+    const float r = sqrt_fast((float)best) * 1.000001f + (float)ZRK_F32_MARGIN;
     return r * r * 1.000001f;
 }
 
@@ -1180,10 +1189,12 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
             }
             int *detlist = (int *)(sm + o.x_detlist);
             if (myrank >= 0) detlist[myrank] = lane;
-            if (FAST && !want_grid)
-                any_bad = tm.any(bad_image);  // doubles as the barrier
-            else
+            if (FAST && !want_grid) {
+                any_bad = tm.any(bad_image);  // for teams larger than a warp this is the barrier as well
+                if (TEAM == 32) tm.sync();     // a ballot orders nothing: the images and detlist are read next
+            } else {
                 tm.sync();
+            }
             const int i = lane;
             int slot = 0, did = 0, radar_id = 0, seed = -1;
             bool seed_own = false;

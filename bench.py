@@ -245,7 +245,7 @@ def run_ours(args, rank, world, local_rank):
     for i in range(args.warmup + args.steps):
         barrier()
         t0 = time.perf_counter()
-        eng = Engine(batch, device=dev, ticks_per_launch=args.ticks_per_launch)
+        eng = Engine(batch, device=dev, ticks_per_launch=args.ticks_per_launch, waves=args.waves)
         ta = time.perf_counter()
         eng.step(ticks)
         c2 = eng.counts()  # per-scenario message counters + status: the step's result
@@ -281,7 +281,8 @@ def run_ours(args, rank, world, local_rank):
             "config": dict(describe(args.workload, world), ticks_per_launch=ticks_per_launch),
             "scenario_ticks_per_s": value / NS,
             "e2e": {"value": e2e_value, "unit": "object-updates/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t_e2e.item()) / args.steps * 1e3},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t_e2e.item()) / args.steps * 1e3,
+                    "waves": args.waves},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -318,6 +319,8 @@ def main():
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--ticks", type=int, default=0)
     ap.add_argument("--ticks-per-launch", type=int, default=0)
+    ap.add_argument("--waves", type=int, default=8,
+                    help="scenario waves of the end-to-end leg (zrk_options.waves): the H2D copy of one wave overlaps the kernels of the others")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()

@@ -227,8 +227,18 @@ typedef struct zrk_options {
     int32_t log_capacity;      /* records per scenario; 0 = bound for ZRK_LOG_EVENTS computed from the batch */
     int32_t mask_ticks;        /* ticks of mask history to keep when ZRK_LOG_MASKS (ring if smaller than the run) */
     int32_t ticks_per_launch;  /* ticks fused into one kernel launch; 0 = library default */
-    int32_t reserved[3];
+    uint32_t flags;            /* ZRK_OPT_* */
+    int32_t waves;             /* > 1: split the batch into that many contiguous scenario ranges ("waves"), each uploaded,
+                                  initialised and stepped on its own CUDA stream, so that the host-to-device copy of a
+                                  wave overlaps the kernels of the waves before it.  zrk_create then returns without
+                                  waiting: the arrays of the zrk_batch_desc must stay valid and unchanged until the first
+                                  call that synchronises (zrk_sync or any zrk_read_*), and a per-scenario validation
+                                  error is reported by that call (and by every call after it) instead of zrk_create.
+                                  Page-locked host arrays are needed for the copies to overlap.  0 or 1 = off. */
+    int32_t reserved;
 } zrk_options;
+
+#define ZRK_OPT_EXACT_ONLY 1u  /* run the tick without the fp32 / squared-distance pre-filters (same results, slower) */
 
 /* Caller-provided host buffers for zrk_read_state; any pointer may be NULL (skipped).
  * NS = max_targets + max_missiles slots / static indices, E = NS track entries per dict. */

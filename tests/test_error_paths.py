@@ -80,7 +80,44 @@ def _ragged_durations(lib):
     check_batch_full(b, 50, lib=lib if lib is not _cabi._LIB else None, step_chunks=[3, 40, 7])
 
 
-CASES = [_log_overflow, _mask_ring, _bad_descriptors, _ragged_durations]
+def _waves_agree(lib):
+    """zrk_options.waves: scenario ranges on separate streams give the very same run."""
+    b = synthetic_batch(300, 6, n_radars=1, n_launchers=1, missiles_per_launcher=2, noise_period=8, box_km=6.0)
+    outs = []
+    for waves in (0, 3, 64):   # 300 scenarios -> ranges of 128, 128, 44; 64 asks for more waves than there are ranges
+        with Engine(b, waves=waves, ticks_per_launch=7, lib=lib) as eng:
+            eng.step(5)
+            eng.step(25)
+            fc, ft, nr = eng.status()
+            recs, n = eng.records()
+            live = np.arange(recs.shape[1])[None, :] < n[:, None]
+            outs.append((eng.counts(), fc, ft, nr, np.where(live, recs["type"], -1), eng.state()))
+    ref = outs[0]
+    assert ref[0][:, _cabi.MSG_LAUNCH_MISSILE].sum() > 0   # the runs are not trivial
+    for o in outs[1:]:
+        for a, c in zip(ref[:5], o[:5]):
+            assert np.array_equal(a, c)
+        for k in ref[5]:
+            assert np.array_equal(ref[5][k], o[5][k], equal_nan=True), k
+
+
+def _waves_defer_validation(lib):
+    """With waves zrk_create does not wait for the init kernel: its verdict arrives with the first
+    synchronising call and stays."""
+    b = synthetic_batch(260, 4, n_radars=1, n_launchers=2, missiles_per_launcher=1, noise_period=4)
+    b.launcher_id[200, 1] = b.launcher_id[200, 0]          # in the second wave
+    with pytest.raises(ZrkError):
+        Engine(b, lib=lib)                                  # without waves: at create
+    eng = Engine(b, waves=2, lib=lib)                       # with waves: accepted ...
+    eng.step(3)
+    for call in (eng.sync, eng.counts, eng.status, lambda: eng.step(1)):
+        with pytest.raises(ZrkError) as e:                  # ... and reported from then on
+            call()
+        assert e.value.rc == _cabi.ERR_UNSUPPORTED and "unique" in str(e.value)
+    eng.close()
+
+
+CASES = [_log_overflow, _mask_ring, _bad_descriptors, _ragged_durations, _waves_agree, _waves_defer_validation]
 
 
 @pytest.mark.parametrize("fn", CASES, ids=lambda f: f.__name__.strip("_"))

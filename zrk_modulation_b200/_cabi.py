@@ -80,10 +80,13 @@ class ZrkBatchDesc(C.Structure):
     ]
 
 
+OPT_EXACT_ONLY = 1
+
+
 class ZrkOptions(C.Structure):
     _fields_ = [("device", C.c_int32), ("log_types", C.c_uint32), ("log_capacity", C.c_int32),
                 ("mask_ticks", C.c_int32), ("ticks_per_launch", C.c_int32),
-                ("reserved", C.c_int32 * 3)]
+                ("flags", C.c_uint32), ("waves", C.c_int32), ("reserved", C.c_int32)]
 
 
 STATE_FIELDS = [

@@ -42,11 +42,14 @@ struct DevDesc {  // zrk_batch_desc with device pointers
     const double *ccp_launcher_pos;
 };
 
-// One thread per scenario: main.create_objects_from_config (main.py:35-149) into the device layout.
-__global__ void zrk_init_kernel(const Params P, const DevDesc d, int *err) {
+// One warp per scenario (lanes stride over the slots, so the blob is written coalesced):
+// main.create_objects_from_config (main.py:35-149) into the device layout.
+#define ZRK_INIT_BLOCK 128
+__global__ void zrk_init_kernel(const Params P, const DevDesc d, int *err, int b0, int b1) {
     const Layout &o = P.lo;
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= o.B) return;
+    const int lane = threadIdx.x & 31;
+    const int b = b0 + (blockIdx.x * blockDim.x + threadIdx.x) / 32;
+    if (b >= b1) return;  // whole warp
     const int NSP = o.team, MP = o.MP;
     const HotOff &ho = o.hot;
     unsigned char *sm = P.dyn + (size_t)b * o.dyn_bytes;
@@ -55,17 +58,16 @@ __global__ void zrk_init_kernel(const Params P, const DevDesc d, int *err) {
     const int nL = d.n_launchers ? d.n_launchers[b] : d.L, nM = d.n_missiles ? d.n_missiles[b] : d.M;
     const int nC = d.n_ccp_launchers ? d.n_ccp_launchers[b] : d.C;
     if (nT < 0 || nT > d.T || nR < 0 || nR > d.R || nL < 0 || nL > d.L || nM < 0 || nM > d.M || nC < 0 || nC > d.C) {
-        atomicOr(err, 1);
+        if (lane == 0) atomicOr(err, 1);
         return;
     }
     int *hdr = (int *)(sm + ho.hdr);
-    hdr[H_NSLOTS] = nT;
     double2 *pxy = (double2 *)(sm + ho.pxy), *pzs = (double2 *)(sm + ho.pzs);
     double2 *txy = (double2 *)(sm + ho.txy), *tzt = (double2 *)(sm + ho.tzt), *vxy = (double2 *)(sm + ho.vxy),
             *qzw = (double2 *)(sm + ho.qzw);
     int *sid = (int *)(sm + ho.sid), *sflags = (int *)(sm + ho.sflags), *srf = (int *)(sm + ho.srf),
         *own = (int *)(sm + ho.own);
-    for (int t = 0; t < nT; t++) {
+    for (int t = lane; t < nT; t += 32) {
         size_t g = (size_t)b * d.T + t;
         double vx = d.target_vel[3 * g], vy = d.target_vel[3 * g + 1], vz = d.target_vel[3 * g + 2];
         double sp = sqrt(dot3(vx, vy, vz, vx, vy, vz));  // np.linalg.norm (AirObject.py:36)
@@ -80,20 +82,23 @@ __global__ void zrk_init_kernel(const Params P, const DevDesc d, int *err) {
         sflags[t] = F_ALIVE | ((tt & 3) << F_TTYPE_SHIFT) | (t << F_STATIC_SHIFT);
     }
     int *te_mid = (int *)(sm + ho.te_mid);
-    for (int k = 0; k < NSP; k++) {
+    for (int k = lane; k < NSP; k += 32) {
         srf[k] = -1;
         own[k] = -1;
         te_mid[k] = ZRK_NONE;
     }
-    int *chdr = (int *)(cs + o.c_hdr);
-    chdr[C_NT] = nT; chdr[C_NR] = nR; chdr[C_NL] = nL; chdr[C_NM] = nM; chdr[C_NC] = nC;
-    chdr[C_AIRENV_ID] = d.airenv_id ? d.airenv_id[b] : 1;
-    chdr[C_CCP_ID] = d.ccp_id ? d.ccp_id[b] : 0;
-    chdr[C_TICK_LIMIT] = d.tick_limit ? d.tick_limit[b] : -1;
+    if (lane == 0) {
+        hdr[H_NSLOTS] = nT;
+        int *chdr = (int *)(cs + o.c_hdr);
+        chdr[C_NT] = nT; chdr[C_NR] = nR; chdr[C_NL] = nL; chdr[C_NM] = nM; chdr[C_NC] = nC;
+        chdr[C_AIRENV_ID] = d.airenv_id ? d.airenv_id[b] : 1;
+        chdr[C_CCP_ID] = d.ccp_id ? d.ccp_id[b] : 0;
+        chdr[C_TICK_LIMIT] = d.tick_limit ? d.tick_limit[b] : -1;
+    }
     double *rad_cur = (double *)(sm + o.rad_cur);
     int *c_rad_id = (int *)(cs + o.c_rad_id);
     double *c_rad_pos = (double *)(cs + o.c_rad_pos), *c_rad_par = (double *)(cs + o.c_rad_par);
-    for (int r = 0; r < nR; r++) {
+    for (int r = lane; r < nR; r += 32) {
         size_t g = (size_t)b * d.R + r;
         c_rad_id[r] = d.radar_id[g];
         for (int k = 0; k < 3; k++) c_rad_pos[3 * r + k] = d.radar_pos[3 * g + k];
@@ -101,25 +106,23 @@ __global__ void zrk_init_kernel(const Params P, const DevDesc d, int *err) {
         double md = d.radar_par[8 * g + 2], md2 = md * md;
         c_rad_par[RAD_PAR_STRIDE * r + 8] = md >= 0 ? md2 * (1.0 - 1e-14) : -1.0;
         c_rad_par[RAD_PAR_STRIDE * r + 9] = md >= 0 ? md2 * (1.0 + 1e-14) : -1.0;
-        rad_cur[2 * r] = d.radar_par[8 * g + 0];
-        rad_cur[2 * r + 1] = d.radar_par[8 * g + 1];
+        const double az0 = d.radar_par[8 * g + 0], el0 = d.radar_par[8 * g + 1];
+        rad_cur[2 * r] = az0;
+        rad_cur[2 * r + 1] = el0;
         // a start sector that the sweep maps onto itself stays there forever: skip the sweep
-        double caz = rad_cur[2 * r], cel = rad_cur[2 * r + 1];
+        double caz = az0, cel = el0;
         radar_move(c_rad_par + RAD_PAR_STRIDE * r, caz, cel);
-        const bool fixed = caz == rad_cur[2 * r] && cel == rad_cur[2 * r + 1] &&
-                           !(caz == 0.0 && signbit(caz) != signbit(rad_cur[2 * r])) &&
-                           !(cel == 0.0 && signbit(cel) != signbit(rad_cur[2 * r + 1]));
+        const bool fixed = caz == az0 && cel == el0 && !(caz == 0.0 && signbit(caz) != signbit(az0)) &&
+                           !(cel == 0.0 && signbit(cel) != signbit(el0));
         c_rad_par[RAD_PAR_STRIDE * r + 10] = fixed ? 1.0 : 0.0;
         c_rad_par[RAD_PAR_STRIDE * r + 11] = 0.0;
     }
     int *c_l_id = (int *)(cs + o.c_l_id);
     double *c_l_pos = (double *)(cs + o.c_l_pos);
-    for (int l = 0; l < nL; l++) {
+    for (int l = lane; l < nL; l += 32) {
         size_t g = (size_t)b * d.L + l;
         c_l_id[l] = d.launcher_id[g];
         for (int k = 0; k < 3; k++) c_l_pos[3 * l + k] = d.launcher_pos[3 * g + k];
-        for (int j = 0; j < l; j++)
-            if (c_l_id[j] == c_l_id[l]) atomicOr(err, 2);
     }
     int *st_n = (int *)(sm + o.st_n), *st = (int *)(sm + o.st);
     int *m_status = (int *)(sm + o.m_status), *m_target = (int *)(sm + o.m_target), *m_slot = (int *)(sm + o.m_slot),
@@ -128,12 +131,13 @@ __global__ void zrk_init_kernel(const Params P, const DevDesc d, int *err) {
     int *c_m_id = (int *)(cs + o.c_m_id), *c_m_launcher = (int *)(cs + o.c_m_launcher);
     double *c_m_v0 = (double *)(cs + o.c_m_v0), *c_m_v0sq = (double *)(cs + o.c_m_v0sq),
            *c_m_radius = (double *)(cs + o.c_m_radius);
-    for (int m = 0; m < nM; m++) {
+    bool bad = false;
+    for (int m = lane; m < nM; m += 32) {
         size_t g = (size_t)b * d.M + m;
         int l = d.missile_launcher[g];
         if (l < 0 || l >= nL) {
-            atomicOr(err, 1);
-            return;
+            bad = true;
+            break;
         }
         c_m_id[m] = d.missile_id[g];
         c_m_launcher[m] = l;
@@ -145,10 +149,22 @@ __global__ void zrk_init_kernel(const Params P, const DevDesc d, int *err) {
         m_target[m] = -1;
         m_slot[m] = -1;
         m_birth[m] = -1;
-        st[l * MP + st_n[l]++] = m;  // MissileLauncher.add_missile (MissileLauncher.py:36-48)
     }
+    if (__ballot_sync(0xffffffffu, bad)) {
+        if (lane == 0) atomicOr(err, 1);
+        return;
+    }
+    __syncwarp();  // ids, launchers and missiles are written: the checks below read other lanes' entries
+    if (lane == 0)  // MissileLauncher.add_missile (MissileLauncher.py:36-48): the stacks fill in list order
+        for (int m = 0; m < nM; m++) {
+            const int l = c_m_launcher[m];
+            st[l * MP + st_n[l]++] = m;
+        }
+    for (int l = lane; l < nL; l += 32)
+        for (int j = 0; j < l; j++)
+            if (c_l_id[j] == c_l_id[l]) atomicOr(err, 2);
     // air-object ids must be unique (the tick resolves object identity by slot)
-    for (int i = 0; i < nT + nM; i++) {
+    for (int i = lane; i < nT + nM; i += 32) {
         int a = i < nT ? sid[i] : c_m_id[i - nT];
         for (int j = 0; j < i; j++) {
             int c = j < nT ? sid[j] : c_m_id[j - nT];
@@ -157,7 +173,7 @@ __global__ void zrk_init_kernel(const Params P, const DevDesc d, int *err) {
     }
     int *c_cl_id = (int *)(cs + o.c_cl_id), *c_cl_launcher = (int *)(cs + o.c_cl_launcher);
     double *c_cl_pos = (double *)(cs + o.c_cl_pos);
-    for (int c = 0; c < nC; c++) {
+    for (int c = lane; c < nC; c += 32) {
         size_t g = (size_t)b * d.C + c;
         c_cl_id[c] = d.ccp_launcher_id[g];
         for (int k = 0; k < 3; k++) c_cl_pos[3 * c + k] = d.ccp_launcher_pos[3 * g + k];
@@ -204,6 +220,16 @@ struct zrk_handle {
     std::vector<int> h_summary;
     double *d_tsec = nullptr;
     Params *d_self = nullptr;
+    // Scenario waves (zrk_options.waves > 1): contiguous scenario ranges, each uploaded,
+    // initialised and stepped on its own stream, so that the host-to-device copy of one wave
+    // overlaps the kernels of the waves before it.
+    std::vector<cudaStream_t> wave_stream;  // empty = everything on `stream`
+    std::vector<int> wave_b;                // wave w covers scenarios [wave_b[w], wave_b[w + 1])
+    std::vector<cudaEvent_t> wave_done;
+    cudaEvent_t fork_ev{};
+    int *pin_err = nullptr;   // pinned: the init kernel's verdict when zrk_create did not wait for it
+    bool deferred = false;    // that verdict has not been looked at yet
+    int sticky_rc = ZRK_OK;   // a deferred create error: every later call returns it
 };
 
 static thread_local std::string g_create_err;
@@ -254,7 +280,7 @@ static int dev_alloc(zrk_handle *h, size_t n, T **dst, bool zero) {
     return ZRK_OK;
 }
 
-typedef void (*tick_fn)(const Params, int);
+typedef void (*tick_fn)(const Params, int, int, int);
 
 template <int TEAM, int TPC>
 static tick_fn pick_fast(bool fast) {
@@ -289,6 +315,13 @@ extern "C" void zrk_destroy(zrk_handle *h) {
         cudaEventDestroy(pr.second);
     }
     for (auto e : h->free_events) cudaEventDestroy(e);
+    for (auto ws : h->wave_stream) {
+        cudaStreamSynchronize(ws);
+        cudaStreamDestroy(ws);
+    }
+    for (auto e : h->wave_done) cudaEventDestroy(e);
+    if (!h->wave_stream.empty()) cudaEventDestroy(h->fork_ev);
+    if (h->pin_err) cudaFreeHost(h->pin_err);
     for (void *p : h->allocs) cudaFreeAsync(p, h->stream);
     cudaStreamSynchronize(h->stream);
     cudaStreamDestroy(h->stream);
@@ -326,6 +359,18 @@ static int ensure_tsec(zrk_handle *h, long long upto) {
     h->P.tsec = p;
     h->P.tsec_n = (int)n;
     return push_params(h);
+}
+
+static int init_verdict(zrk_handle *h, int herr) {
+    if (herr & 1) {
+        h->err = "per-scenario count exceeds the batch maximum, or missile_launcher out of range";
+        return ZRK_ERR_ARG;
+    }
+    if (herr & 2) {
+        h->err = "unsupported scenario: air-object ids and launcher ids must be unique within a scenario";
+        return ZRK_ERR_UNSUPPORTED;
+    }
+    return ZRK_OK;
 }
 
 static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options *opt) {
@@ -382,21 +427,47 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
     if (P.mask_words < 1) P.mask_words = 1;
     P.mask_ticks = (P.log_types & ZRK_LOG_MASKS) ? ((opt && opt->mask_ticks > 0) ? opt->mask_ticks : 1024) : 0;
     h->ticks_per_launch = (opt && opt->ticks_per_launch > 0) ? opt->ticks_per_launch : 256;
-    h->fast = !(opt && (opt->reserved[0] & 1));  // reserved[0] bit 0: exact-only kernel (no pre-filters)
+    h->fast = !(opt && (opt->flags & ZRK_OPT_EXACT_ONLY));
+
+    // scenario waves: whole CTAs and whole init blocks per wave
+    int n_waves = opt ? opt->waves : 0;
+    if (n_waves < 1) n_waves = 1;
+    if (n_waves > 64) n_waves = 64;
+    {
+        const int quantum = 128;
+        const int per = ((B + n_waves - 1) / n_waves + quantum - 1) / quantum * quantum;
+        h->wave_b.clear();
+        for (int b0 = 0; b0 < B; b0 += per) h->wave_b.push_back(b0);
+        h->wave_b.push_back(B);
+        n_waves = (int)h->wave_b.size() - 1;
+    }
 
     DevDesc dd{};
     dd.B = B; dd.T = T; dd.R = R; dd.L = L; dd.M = M; dd.C = C;
     int rc;
-#define UP(field, n) if ((rc = dev_upload(h, d->field, (size_t)(n), &dd.field)) != ZRK_OK) return rc
-    UP(n_targets, B); UP(n_radars, B); UP(n_launchers, B); UP(n_missiles, B); UP(n_ccp_launchers, B);
-    UP(airenv_id, B); UP(ccp_id, B); UP(tick_limit, B);
-    UP(target_id, (size_t)B * T); UP(target_type, (size_t)B * T);
-    UP(target_pos, (size_t)B * T * 3); UP(target_vel, (size_t)B * T * 3);
-    UP(radar_id, (size_t)B * R); UP(radar_pos, (size_t)B * R * 3); UP(radar_par, (size_t)B * R * 8);
-    UP(launcher_id, (size_t)B * L); UP(launcher_pos, (size_t)B * L * 3);
-    UP(missile_id, (size_t)B * M); UP(missile_launcher, (size_t)B * M); UP(missile_v0, (size_t)B * M);
-    UP(missile_v0sq, (size_t)B * M); UP(missile_radius, (size_t)B * M); UP(missile_life, (size_t)B * M);
-    UP(ccp_launcher_id, (size_t)B * C); UP(ccp_launcher_pos, (size_t)B * C * 3);
+    // device copies of the description: allocated whole, filled wave by wave
+    struct Field {
+        const char *src;
+        char *dst;
+        size_t per_scenario;  // bytes
+    };
+    std::vector<Field> fields;
+#define UP(field, n)                                                                                   \
+    if (d->field && (n)) {                                                                             \
+        void *q_ = nullptr;                                                                            \
+        if ((rc = pool_alloc(h, &q_, (size_t)B * (n) * sizeof(*d->field))) != ZRK_OK) return rc;       \
+        dd.field = (decltype(dd.field))q_;                                                             \
+        fields.push_back({(const char *)d->field, (char *)q_, (size_t)(n) * sizeof(*d->field)});       \
+    }
+    UP(n_targets, 1); UP(n_radars, 1); UP(n_launchers, 1); UP(n_missiles, 1); UP(n_ccp_launchers, 1);
+    UP(airenv_id, 1); UP(ccp_id, 1); UP(tick_limit, 1);
+    UP(target_id, T); UP(target_type, T);
+    UP(target_pos, (size_t)T * 3); UP(target_vel, (size_t)T * 3);
+    UP(radar_id, R); UP(radar_pos, (size_t)R * 3); UP(radar_par, (size_t)R * 8);
+    UP(launcher_id, L); UP(launcher_pos, (size_t)L * 3);
+    UP(missile_id, M); UP(missile_launcher, M); UP(missile_v0, M);
+    UP(missile_v0sq, M); UP(missile_radius, M); UP(missile_life, M);
+    UP(ccp_launcher_id, C); UP(ccp_launcher_pos, (size_t)C * 3);
 #undef UP
     const size_t n_desc_allocs = h->allocs.size();
     if (d->noise) {
@@ -420,30 +491,9 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
     int *derr = nullptr;
     if ((rc = dev_alloc(h, 1, &derr, true)) != ZRK_OK) return rc;
     if ((rc = dev_alloc(h, (size_t)B * ZRK_SUMMARY_WORDS, &h->d_summary, false)) != ZRK_OK) return rc;
-    ZRK_LAUNCH(zrk_init_kernel, (B + 127) / 128, 128, 0, h->stream, P, dd, derr);
-    CK(cudaGetLastError());
-    int herr = 0;
-    CK(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    // the uploaded description is no longer needed on the device
-    for (size_t i = 0; i < n_desc_allocs; i++) cudaFreeAsync(h->allocs[i], h->stream);
-    h->allocs.erase(h->allocs.begin(), h->allocs.begin() + n_desc_allocs);
-    if (herr & 1) {
-        h->err = "per-scenario count exceeds the batch maximum, or missile_launcher out of range";
-        return ZRK_ERR_ARG;
-    }
-    if (herr & 2) {
-        h->err = "unsupported scenario: air-object ids and launcher ids must be unique within a scenario";
-        return ZRK_ERR_UNSUPPORTED;
-    }
-    // small host copies used by zrk_read_messages
-    h->h_radar_id.assign(d->radar_id ? d->radar_id : nullptr, d->radar_id ? d->radar_id + (size_t)B * R : nullptr);
-    h->h_n_radars.resize(B);
-    h->h_airenv_id.resize(B);
-    for (int b = 0; b < B; b++) {
-        h->h_n_radars[b] = d->n_radars ? d->n_radars[b] : R;
-        h->h_airenv_id[b] = d->airenv_id ? d->airenv_id[b] : 1;
-    }
+
+    // launch configuration, clock table and the device copy of Params: everything that has to
+    // synchronise does so before the first wave is queued
     h->block = lo.team * lo.teams_per_cta;
     h->grid = (B + lo.teams_per_cta - 1) / lo.teams_per_cta;
     h->smem_bytes = (size_t)lo.team_smem_bytes * lo.teams_per_cta;
@@ -465,7 +515,60 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
         if (pct < 8) pct = 8;
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
-    return ensure_tsec(h, 1024);
+    if ((rc = ensure_tsec(h, 1024)) != ZRK_OK) return rc;
+
+    // upload + init, wave by wave
+    if (n_waves > 1) {
+        CK(cudaHostAlloc((void **)&h->pin_err, sizeof(int), cudaHostAllocDefault));
+        *h->pin_err = 0;
+        CK(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+        CK(cudaEventRecord(h->fork_ev, h->stream));  // allocations and memsets above
+        for (int w = 0; w < n_waves; w++) {
+            cudaStream_t ws;
+            cudaEvent_t ev;
+            CK(cudaStreamCreateWithFlags(&ws, cudaStreamNonBlocking));
+            h->wave_stream.push_back(ws);
+            CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            h->wave_done.push_back(ev);
+            CK(cudaStreamWaitEvent(ws, h->fork_ev, 0));
+        }
+    }
+    for (int w = 0; w < n_waves; w++) {
+        const int b0 = h->wave_b[w], b1 = h->wave_b[w + 1];
+        cudaStream_t ws = n_waves > 1 ? h->wave_stream[w] : h->stream;
+        for (const Field &f : fields)
+            CK(cudaMemcpyAsync(f.dst + (size_t)b0 * f.per_scenario, f.src + (size_t)b0 * f.per_scenario,
+                               (size_t)(b1 - b0) * f.per_scenario, cudaMemcpyHostToDevice, ws));
+        ZRK_LAUNCH(zrk_init_kernel, (b1 - b0 + ZRK_INIT_BLOCK / 32 - 1) / (ZRK_INIT_BLOCK / 32), ZRK_INIT_BLOCK, 0, ws, P, dd, derr, b0, b1);
+        CK(cudaGetLastError());
+        if (n_waves > 1) {
+            CK(cudaEventRecord(h->wave_done[w], ws));
+            CK(cudaStreamWaitEvent(h->stream, h->wave_done[w], 0));
+        }
+    }
+    // small host copies used by zrk_read_messages
+    h->h_radar_id.assign(d->radar_id ? d->radar_id : nullptr, d->radar_id ? d->radar_id + (size_t)B * R : nullptr);
+    h->h_n_radars.resize(B);
+    h->h_airenv_id.resize(B);
+    for (int b = 0; b < B; b++) {
+        h->h_n_radars[b] = d->n_radars ? d->n_radars[b] : R;
+        h->h_airenv_id[b] = d->airenv_id ? d->airenv_id[b] : 1;
+    }
+    if (n_waves > 1) {
+        // do not wait: the verdict of the init kernel is looked at by the first call that synchronises
+        CK(cudaMemcpyAsync(h->pin_err, derr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        for (size_t i = 0; i < n_desc_allocs; i++) cudaFreeAsync(h->allocs[i], h->stream);
+        h->allocs.erase(h->allocs.begin(), h->allocs.begin() + n_desc_allocs);
+        h->deferred = true;
+        return ZRK_OK;
+    }
+    int herr = 0;
+    CK(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    // the uploaded description is no longer needed on the device
+    for (size_t i = 0; i < n_desc_allocs; i++) cudaFreeAsync(h->allocs[i], h->stream);
+    h->allocs.erase(h->allocs.begin(), h->allocs.begin() + n_desc_allocs);
+    return init_verdict(h, herr);
 }
 
 extern "C" int zrk_create(const zrk_batch_desc *desc, const zrk_options *opt, zrk_handle **out) {
@@ -509,6 +612,7 @@ static int get_event(zrk_handle *h, cudaEvent_t *e) {
 
 extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
     if (!h || n_ticks < 0) return ZRK_ERR_ARG;
+    if (h->sticky_rc) return h->sticky_rc;
     CK(cudaSetDevice(h->device));
     tick_fn fn = pick_kernel(h->P.lo.team, h->fast);
     if (h->pending.size() > 4096) {
@@ -516,22 +620,36 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
         if (rc) return rc;
     }
     {
-        int rc = ensure_tsec(h, h->tick + n_ticks + 1);
+        int rc = ensure_tsec(h, h->tick + n_ticks + 1);  // (synchronises only when the table has to grow)
         if (rc) return rc;
     }
-    int left = n_ticks;
-    while (left > 0) {
-        int k = left < h->ticks_per_launch ? left : h->ticks_per_launch;
-        cudaEvent_t e0, e1;
-        int rc;
-        if ((rc = get_event(h, &e0)) || (rc = get_event(h, &e1))) return rc;
-        CK(cudaEventRecord(e0, h->stream));
-        ZRK_LAUNCH(fn, h->grid, h->block, h->smem_bytes, h->stream, h->P, k);
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(e1, h->stream));
-        h->pending.push_back({e0, e1});
-        h->n_launches++;
-        left -= k;
+    const int n_waves = h->wave_stream.empty() ? 1 : (int)h->wave_stream.size();
+    const int tpc = h->P.lo.teams_per_cta;
+    // Every call that queues work on the main stream also waits for it (reads, table growth), so a
+    // wave never has to wait for the main stream here — and must not: right after zrk_create the
+    // main stream is queued behind the uploads of ALL waves, which is exactly what a wave's first
+    // kernels are meant to overlap.
+    for (int w = 0; w < n_waves; w++) {
+        const int b0 = n_waves > 1 ? h->wave_b[w] : 0, b1 = n_waves > 1 ? h->wave_b[w + 1] : h->P.lo.B;
+        cudaStream_t ws = n_waves > 1 ? h->wave_stream[w] : h->stream;
+        int left = n_ticks;
+        while (left > 0) {
+            int k = left < h->ticks_per_launch ? left : h->ticks_per_launch;
+            cudaEvent_t e0, e1;
+            int rc;
+            if ((rc = get_event(h, &e0)) || (rc = get_event(h, &e1))) return rc;
+            CK(cudaEventRecord(e0, ws));
+            ZRK_LAUNCH(fn, (b1 - b0 + tpc - 1) / tpc, h->block, h->smem_bytes, ws, h->P, k, b0, b1);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(e1, ws));
+            h->pending.push_back({e0, e1});
+            h->n_launches++;
+            left -= k;
+        }
+        if (n_waves > 1) {  // and the main stream continues after all of them
+            CK(cudaEventRecord(h->wave_done[w], ws));
+            CK(cudaStreamWaitEvent(h->stream, h->wave_done[w], 0));
+        }
     }
     h->tick += n_ticks;
     return ZRK_OK;
@@ -539,8 +657,17 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
 
 extern "C" int zrk_sync(zrk_handle *h) {
     if (!h) return ZRK_ERR_ARG;
+    if (h->sticky_rc) return h->sticky_rc;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->deferred) {  // zrk_create with waves did not wait for the init kernel's verdict
+        h->deferred = false;
+        int rc = init_verdict(h, *h->pin_err);
+        if (rc) {
+            h->sticky_rc = rc;
+            return rc;
+        }
+    }
     return resolve_events(h);
 }
 

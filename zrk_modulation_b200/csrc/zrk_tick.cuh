@@ -888,7 +888,7 @@ constexpr int min_blocks(int threads) { return threads <= 64 ? 8 : (threads <= 1
 #define ZRK_KERNEL_ATTR __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC))
 #endif
 template <int TEAM, int TPC, bool FAST>
-__global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
+__global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int b_first, int b_end) {
     ZRK_SMEM_DECL;
     const Layout &o = P.lo;
     const int MP = o.MP, Q = o.Q, MP8 = (o.MP + 7) & ~7;
@@ -896,8 +896,8 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks) {
     tm.tic = threadIdx.x / TEAM;
     tm.lane = threadIdx.x % TEAM;
     const int lane = tm.lane;
-    const int b = blockIdx.x * TPC + tm.tic;
-    if (b >= o.B) return;  // whole team leaves together
+    const int b = b_first + blockIdx.x * TPC + tm.tic;  // this launch covers scenarios [b_first, b_end)
+    if (b >= b_end) return;  // whole team leaves together
     unsigned char *sm = zrk_smem + (size_t)tm.tic * o.team_smem_bytes;
     Hot<TEAM> H;
     H.sm = sm;

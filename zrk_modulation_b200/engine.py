@@ -19,11 +19,13 @@ class ZrkError(RuntimeError):
 class Engine:
     """Device state of a batch of scenarios plus the tick loop.
 
-    `lib` defaults to the CUDA library (libzrk_b200.so); there is no CPU fallback."""
+    `lib` defaults to the CUDA library (libzrk_b200.so); there is no CPU fallback.  With `waves` > 1
+    the constructor returns while the batch is still being copied (keep the Batch alive and
+    unchanged until the first sync / read; an invalid scenario is reported there)."""
 
     def __init__(self, batch: Batch, log_types: int = _cabi.LOG_EVENTS, log_capacity: int = 0,
                  mask_ticks: int = 0, ticks_per_launch: int = 0, device: int = 0, exact_only: bool = False,
-                 lib=None):
+                 waves: int = 0, lib=None):
         self.lib = lib if lib is not None else _cabi.load()
         self.batch = batch
         self._h = C.c_void_p()
@@ -33,7 +35,8 @@ class Engine:
         opt.log_capacity = log_capacity
         opt.mask_ticks = mask_ticks
         opt.ticks_per_launch = ticks_per_launch
-        opt.reserved[0] = 1 if exact_only else 0
+        opt.flags = _cabi.OPT_EXACT_ONLY if exact_only else 0
+        opt.waves = waves  # > 1: upload / init / step in scenario waves on separate streams (see zrk_options.waves)
         self.log_types = log_types
         desc = batch.desc()
         rc = self.lib.zrk_create(C.byref(desc), C.byref(opt), C.byref(self._h))

@@ -217,7 +217,7 @@ struct zrk_handle {
     // host copies kept for reconstruction
     std::vector<int> h_radar_id, h_n_radars, h_airenv_id;
     int *d_summary = nullptr;
-    std::vector<int> h_summary;
+    int *h_summary = nullptr;  // page-locked [B][ZRK_SUMMARY_WORDS], allocated while the first step runs
     double *d_tsec = nullptr;
     Params *d_self = nullptr;
     // Scenario waves (zrk_options.waves > 1): contiguous scenario ranges, each uploaded,
@@ -322,6 +322,7 @@ extern "C" void zrk_destroy(zrk_handle *h) {
     for (auto e : h->wave_done) cudaEventDestroy(e);
     if (!h->wave_stream.empty()) cudaEventDestroy(h->fork_ev);
     if (h->pin_err) cudaFreeHost(h->pin_err);
+    if (h->h_summary) cudaFreeHost(h->h_summary);
     for (void *p : h->allocs) cudaFreeAsync(p, h->stream);
     cudaStreamSynchronize(h->stream);
     cudaStreamDestroy(h->stream);
@@ -652,6 +653,8 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
         }
     }
     h->tick += n_ticks;
+    if (!h->h_summary && n_ticks > 0)  // page-lock the read-back buffer while the GPU is busy
+        CK(cudaHostAlloc((void **)&h->h_summary, (size_t)h->P.lo.B * ZRK_SUMMARY_WORDS * sizeof(int), cudaHostAllocDefault));
     return ZRK_OK;
 }
 
@@ -706,8 +709,8 @@ static int fetch_summary(zrk_handle *h) {
     const long long n = (long long)o.B * ZRK_SUMMARY_WORDS;
     ZRK_LAUNCH(zrk_summary_kernel, (unsigned)((n + 255) / 256), 256, 0, h->stream, h->P, h->d_summary);
     CK(cudaGetLastError());
-    h->h_summary.resize((size_t)n);
-    CK(cudaMemcpyAsync(h->h_summary.data(), h->d_summary, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (!h->h_summary) CK(cudaHostAlloc((void **)&h->h_summary, (size_t)n * sizeof(int), cudaHostAllocDefault));
+    CK(cudaMemcpyAsync(h->h_summary, h->d_summary, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     return zrk_sync(h);
 }
 
@@ -716,7 +719,7 @@ extern "C" int zrk_read_status(zrk_handle *h, int32_t *fault_code, int32_t *faul
     int rc = fetch_summary(h);
     if (rc) return rc;
     for (int s = 0; s < h->P.lo.B; s++) {
-        const int *hdr = h->h_summary.data() + (size_t)s * ZRK_SUMMARY_WORDS;
+        const int *hdr = h->h_summary + (size_t)s * ZRK_SUMMARY_WORDS;
         if (fault_code) fault_code[s] = hdr[H_FAULT];
         if (fault_tick) fault_tick[s] = hdr[H_FAULT_TICK];
         if (n_records) n_records[s] = hdr[H_NREC];
@@ -729,7 +732,7 @@ extern "C" int zrk_read_counts(zrk_handle *h, int64_t *counts) {
     int rc = fetch_summary(h);
     if (rc) return rc;
     for (int s = 0; s < h->P.lo.B; s++) {
-        const unsigned *c = (const unsigned *)(h->h_summary.data() + (size_t)s * ZRK_SUMMARY_WORDS + H_WORDS);
+        const unsigned *c = (const unsigned *)(h->h_summary + (size_t)s * ZRK_SUMMARY_WORDS + H_WORDS);
         for (int t = 0; t < ZRK_MSG_NTYPES; t++) counts[(size_t)s * ZRK_MSG_NTYPES + t] = c[t];
     }
     return ZRK_OK;
@@ -740,7 +743,7 @@ extern "C" int zrk_read_records(zrk_handle *h, int s0, int s1, zrk_msg *recs, in
     int rc = fetch_summary(h);
     if (rc) return rc;
     for (int s = s0; s < s1; s++) {
-        const int *hdr = h->h_summary.data() + (size_t)s * ZRK_SUMMARY_WORDS;
+        const int *hdr = h->h_summary + (size_t)s * ZRK_SUMMARY_WORDS;
         if (n) n[s - s0] = std::min(hdr[H_NREC], h->P.log_cap);
     }
     if (recs && s1 > s0)

@@ -267,6 +267,82 @@ struct Team {
         }
         return across_warps(__popc(bal), total) + below;
     }
+    // Several ranks for the price of one barrier: per-warp counts packed into one word (field k at
+    // bit SHk; the caller guarantees that every team-wide total fits its field), combined like
+    // across_warps.  `orin` is OR-reduced over the team by the same barrier (__syncthreads_or).
+    __device__ __forceinline__ unsigned across_warps_or(unsigned v, unsigned &total, bool orin, bool &orout) {
+        const int l32 = lane & 31, w = lane >> 5;
+        int *r = row();
+        if (l32 == 0) r[w] = (int)v;
+        orout = __syncthreads_or(orin) != 0;
+        const unsigned x = l32 < WARPS ? (unsigned)r[l32] : 0u;
+        unsigned inc = x;
+#pragma unroll
+        for (int d = 1; d < WARPS; d <<= 1) {
+            const unsigned n = __shfl_up_sync(ZRK_FULL, inc, d);
+            if (l32 >= d) inc += n;
+        }
+        total = __shfl_sync(ZRK_FULL, inc, WARPS - 1);
+        return __shfl_sync(ZRK_FULL, inc - x, w);
+    }
+    // rank of p and the team-wide OR of `orin`
+    __device__ __forceinline__ int rank_or(bool p, int &total, bool orin, bool &orout) {
+        const unsigned bal = __ballot_sync(ZRK_FULL, p);
+        const int below = __popc(bal & ((1u << (lane & 31)) - 1u));
+        if (TEAM == 32) {
+            total = __popc(bal);
+            orout = __ballot_sync(ZRK_FULL, orin) != 0;
+            return below;
+        }
+        unsigned tot;
+        const unsigned ex = across_warps_or((unsigned)__popc(bal), tot, orin, orout);
+        total = (int)tot;
+        return (int)ex + below;
+    }
+    // ranks of p0 and p1 (totals < 65536 each) and the team-wide OR of `orin`
+    __device__ __forceinline__ void rank2(bool p0, bool p1, int &r0, int &r1, int &t0, int &t1, bool orin, bool &orout) {
+        const unsigned b0 = __ballot_sync(ZRK_FULL, p0), b1 = __ballot_sync(ZRK_FULL, p1);
+        const unsigned lt = (1u << (lane & 31)) - 1u;
+        r0 = __popc(b0 & lt);
+        r1 = __popc(b1 & lt);
+        if (TEAM == 32) {
+            t0 = __popc(b0);
+            t1 = __popc(b1);
+            orout = __ballot_sync(ZRK_FULL, orin) != 0;
+            return;
+        }
+        unsigned tot;
+        const unsigned ex = across_warps_or((unsigned)__popc(b0) | ((unsigned)__popc(b1) << 16), tot, orin, orout);
+        r0 += (int)(ex & 0xffffu);
+        r1 += (int)(ex >> 16);
+        t0 = (int)(tot & 0xffffu);
+        t1 = (int)(tot >> 16);
+    }
+    // ranks of p0 (total < 1024), p1 and p2 (totals <= 1024 each) and the team-wide OR of `orin`
+    __device__ __forceinline__ void rank3(bool p0, bool p1, bool p2, int &r0, int &r1, int &r2, int &t0, int &t1, int &t2,
+                                          bool orin, bool &orout) {
+        const unsigned b0 = __ballot_sync(ZRK_FULL, p0), b1 = __ballot_sync(ZRK_FULL, p1), b2 = __ballot_sync(ZRK_FULL, p2);
+        const unsigned lt = (1u << (lane & 31)) - 1u;
+        r0 = __popc(b0 & lt);
+        r1 = __popc(b1 & lt);
+        r2 = __popc(b2 & lt);
+        if (TEAM == 32) {
+            t0 = __popc(b0);
+            t1 = __popc(b1);
+            t2 = __popc(b2);
+            orout = __ballot_sync(ZRK_FULL, orin) != 0;
+            return;
+        }
+        unsigned tot;
+        const unsigned ex =
+            across_warps_or((unsigned)__popc(b0) | ((unsigned)__popc(b1) << 10) | ((unsigned)__popc(b2) << 21), tot, orin, orout);
+        r0 += (int)(ex & 0x3ffu);
+        r1 += (int)((ex >> 10) & 0x7ffu);
+        r2 += (int)(ex >> 21);
+        t0 = (int)(tot & 0x3ffu);
+        t1 = (int)((tot >> 10) & 0x7ffu);
+        t2 = (int)(tot >> 21);
+    }
     __device__ __forceinline__ int min(int v) {
         v = __reduce_min_sync(ZRK_FULL, v);
         if (TEAM == 32) return v;
@@ -1000,7 +1076,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
         // Missile.step, status 'active' (Missile.py:162-193), in slot order
         {
             const bool msl = alive && (fl & F_MISSILE);
-            if (tm.any(msl)) {
+            if ((TEAM == 32 || chdr[C_NM] > 0) && tm.any(msl)) {  // (uniform: a large team without missiles skips the barrier)
                 int det = 0, det_tid = ZRK_NONE;
                 if (msl) {
                     const int m = (fl >> F_STATIC_SHIFT) - T;
@@ -1181,20 +1257,30 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
             // processing order: FOUND_OBJECTS messages in radar order, objects in list order,
             // each id once -> (first radar that saw it, slot)
             int n_det = 0, myrank = -1;
-            for (int r = 0; r < nR; r++) {
-                int tot;
-                const int ex = tm.rank(rf == r, tot);
-                if (rf == r) myrank = n_det + ex;
-                n_det += tot;
+            bool any_seen = false;  // OR of bad_image over the team, taken along with the first ranks
+            if (TEAM == 32) {
+                for (int r = 0; r < nR; r++) {
+                    int tot;
+                    const int ex = tm.rank(rf == r, tot);
+                    if (rf == r) myrank = n_det + ex;
+                    n_det += tot;
+                }
+                any_seen = tm.any(bad_image);
+            } else {
+                for (int r = 0; r < nR; r += 2) {  // two radars per barrier
+                    int e0, e1, t0, t1;
+                    bool orv;
+                    tm.rank2(rf == r, rf == r + 1, e0, e1, t0, t1, r == 0 && bad_image, orv);
+                    if (r == 0) any_seen = orv;
+                    if (rf == r) myrank = n_det + e0;
+                    if (rf == r + 1) myrank = n_det + t0 + e1;
+                    n_det += t0 + t1;
+                }
             }
             int *detlist = (int *)(sm + o.x_detlist);
             if (myrank >= 0) detlist[myrank] = lane;
-            if (FAST && !want_grid) {
-                any_bad = tm.any(bad_image);  // for teams larger than a warp this is the barrier as well
-                if (TEAM == 32) tm.sync();     // a ballot orders nothing: the images and detlist are read next
-            } else {
-                tm.sync();
-            }
+            if (FAST && !want_grid) any_bad = nR > 0 ? any_seen : false;  // (no radar: no detection, nothing scans)
+            tm.sync();
             const int i = lane;
             int slot = 0, did = 0, radar_id = 0, seed = -1;
             bool seed_own = false;
@@ -1245,10 +1331,19 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 // capacity left nothing can be launched: the whole round reduces to stamping the entries.
                 if (lo_rank == 0 && hdr[H_FREECAP] <= 0) {
                     const bool quiet = !unresolved || (cls != 0 && claim == seed && seed_own);
-                    if (!tm.any(!quiet)) {
-                        const bool upd_msg = unresolved && cls == 1 && H.te_follow()[cand] != 0;
-                        int n_upd;
-                        const int r_upd = tm.rank(upd_msg, n_upd);
+                    bool upd_msg = false, noisy;
+                    int n_upd = 0, r_upd = 0;
+                    if (TEAM == 32) {
+                        noisy = tm.any(!quiet);
+                        if (!noisy) {
+                            upd_msg = unresolved && cls == 1 && H.te_follow()[cand] != 0;
+                            r_upd = tm.rank(upd_msg, n_upd);
+                        }
+                    } else {  // one barrier: the vote rides on the rank's
+                        upd_msg = quiet && unresolved && cls == 1 && H.te_follow()[cand] != 0;
+                        r_upd = tm.rank_or(upd_msg, n_upd, !quiet, noisy);
+                    }
+                    if (!noisy) {
                         if (unresolved) {
                             if (cls == 1) {  // old_target, already followed or no missile to send (CCP.py:332-359)
                                 if (upd_msg && logged(P, ZRK_MSG_CCP_UPDATE_TARGET))
@@ -1412,13 +1507,27 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                     dt = H.srf()[tref] >= 0;
                     bad = dt && (H.sflags()[tref] & F_MISSILE);  // .type on a Missile (CCP.py:259)
                 }
-                const int efault = tm.any(bad) ? tm.min(bad ? lane : ZRK_IMAX) : ZRK_IMAX;
-                dt = dt && lane < efault;
-                const bool dother = efault == ZRK_IMAX && alive && rf < 0 && nR > 0;
-                int tot_m, tot_t, tot_o;
-                const int ex_m = tm.rank(dm, tot_m);
-                const int ex_t = tm.rank(dt, tot_t);
-                const int ex_o = tm.rank(dother, tot_o);
+                int tot_m, tot_t, tot_o, ex_m, ex_t, ex_o, efault = ZRK_IMAX;
+                bool dother;
+                if (TEAM == 32) {
+                    efault = tm.any(bad) ? tm.min(bad ? lane : ZRK_IMAX) : ZRK_IMAX;
+                    dt = dt && lane < efault;
+                    dother = efault == ZRK_IMAX && alive && rf < 0 && nR > 0;
+                    ex_m = tm.rank(dm, tot_m);
+                    ex_t = tm.rank(dt, tot_t);
+                    ex_o = tm.rank(dother, tot_o);
+                } else {  // one barrier for the three ranks and the fault vote
+                    bool any_fault;
+                    dother = alive && rf < 0 && nR > 0;
+                    tm.rank3(dm, dt, dother, ex_m, ex_t, ex_o, tot_m, tot_t, tot_o, bad, any_fault);
+                    if (any_fault) {  // rare: the entries before the faulting one are still drawn, nothing after it
+                        efault = tm.min(bad ? lane : ZRK_IMAX);
+                        dt = dt && lane < efault;
+                        dother = false;
+                        ex_t = tm.rank(dt, tot_t);
+                        tot_o = 0;
+                    }
+                }
                 if (ldr) {
                     if (dm)
                         put_rec(P, rec, nrec + ex_m, tick, ZRK_MSG_DRAW_OBJECTS, 1, ccp_id, ZRK_MANAGER_ID, H.sid()[mref], ZRK_ZUR,

@@ -1017,12 +1017,8 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
         const int det_prev = hdr[H_DETN0 + prv];
         const int mb_prev = hdr[H_MBN0 + prv];
         int nrec = hdr[H_NREC];  // records written so far; kept uniform across the team
-        tm.sync();               // everyone has read the header before lane 0 resets the per-tick lists
-        if (lane == 0) {
-            hdr[H_MBN0 + par] = 0;
-            hdr[H_DETN0 + par] = 0;
-            hdr[H_LN] = 0;
-        }
+        // (the per-tick lists of this parity were emptied at the end of the previous tick; nobody
+        // writes a header word read above before the barrier that ends AirEnv.step)
 
         // ============ AirEnv.step (AirEnv.py:26-53)
         int fl = 0, my_id = 0;
@@ -1553,7 +1549,13 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
         if (lane == 0) {
             hdr[H_NREC] = nrec;
             if (nrec > P.log_cap) hdr[H_FAULT] |= ZRK_FAULT_LOG_OVERFLOW;
-            if (!(hdr[H_FAULT] & 63)) hdr[H_TICK] = tick + 1;
+            if (!(hdr[H_FAULT] & 63)) {
+                hdr[H_TICK] = tick + 1;
+                // the lists consumed during this tick become the next tick's output lists
+                hdr[H_MBN0 + prv] = 0;
+                hdr[H_DETN0 + prv] = 0;
+                hdr[H_LN] = 0;
+            }
         }
         if (++noise_w == P.noise_period) noise_w = 0;
         tm.sync();

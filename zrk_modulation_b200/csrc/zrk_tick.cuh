@@ -1236,20 +1236,6 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 lf_store<TEAM>(lf, TEAM + lane, 1e30f, 0.f, 0.f);
             }
             bool grid_ok = false, any_bad = false;
-            if (want_grid) {
-                any_bad = tm.any(bad_image);  // also the barrier: bucket heads are reset, fp32 images are written
-                grid_ok = !any_bad;
-                if (grid_ok) {  // entries link_object skips (image x = 1e30) stay out of the grid
-                    if (lane < n_te && lf[4 * lane] < 1e29f) {
-                        float *q = lf + 4 * lane;
-                        q[3] = __int_as_float(atomicExch(&ghead[grid_bucket<TEAM>(grid_cell(q[0]), grid_cell(q[1]))], lane));
-                    }
-                    if (lane < n_me && lf[4 * (TEAM + lane)] < 1e29f) {
-                        float *q = lf + 4 * (TEAM + lane);
-                        q[3] = __int_as_float(atomicExch(&ghead[grid_bucket<TEAM>(grid_cell(q[0]), grid_cell(q[1]))], TEAM + lane));
-                    }
-                }
-            }
             // processing order: FOUND_OBJECTS messages in radar order, objects in list order,
             // each id once -> (first radar that saw it, slot)
             int n_det = 0, myrank = -1;
@@ -1275,7 +1261,21 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
             }
             int *detlist = (int *)(sm + o.x_detlist);
             if (myrank >= 0) detlist[myrank] = lane;
-            if (FAST && !want_grid) any_bad = nR > 0 ? any_seen : false;  // (no radar: no detection, nothing scans)
+            if (FAST) any_bad = nR > 0 ? any_seen : false;  // (no radar: no detection, nothing scans)
+            if (want_grid && nR > 0) {
+                // the barrier of the first ranks also published the images and the reset bucket heads
+                grid_ok = !any_bad;
+                if (grid_ok) {  // entries link_object skips (image x = 1e30) stay out of the grid
+                    if (lane < n_te && lf[4 * lane] < 1e29f) {
+                        float *q = lf + 4 * lane;
+                        q[3] = __int_as_float(atomicExch(&ghead[grid_bucket<TEAM>(grid_cell(q[0]), grid_cell(q[1]))], lane));
+                    }
+                    if (lane < n_me && lf[4 * (TEAM + lane)] < 1e29f) {
+                        float *q = lf + 4 * (TEAM + lane);
+                        q[3] = __int_as_float(atomicExch(&ghead[grid_bucket<TEAM>(grid_cell(q[0]), grid_cell(q[1]))], TEAM + lane));
+                    }
+                }
+            }
             tm.sync();
             const int i = lane;
             int slot = 0, did = 0, radar_id = 0, seed = -1;

@@ -227,6 +227,7 @@ def run_ours(args, rank, world, local_rank):
             dev_stats = local_stats_device(eng.torch_view("summary")).clone()  # stays on the GPU for NCCL
             counts = eng.counts()
             fc, ft, nr = eng.status()
+            alive_ticks = int(eng.alive_slot_ticks().sum())
         eng.close()
     clocks = sampler.stop() if sampler else None
     t_dev = torch.tensor([sum(kern_ms)], dtype=torch.float64, device="cuda")
@@ -266,6 +267,7 @@ def run_ours(args, rank, world, local_rank):
     from zrk_modulation_b200.distributed import describe_stats, gather_stats, local_stats
     assert np.array_equal(dev_stats.cpu().numpy(), local_stats(counts, fc)), "device-side statistics differ"
     stats = gather_stats(dev_stats, device=torch.device("cuda", dev))
+    alive_all = int(gather_stats(torch.tensor([alive_ticks], dtype=torch.int64), device=torch.device("cuda", dev))[0])
 
     if rank == 0:
         value = units * world * args.steps / (total_ms * 1e-3)
@@ -280,6 +282,7 @@ def run_ours(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(describe(args.workload, world), ticks_per_launch=ticks_per_launch),
             "scenario_ticks_per_s": value / NS,
+            "active_slot_fraction": alive_all / float(units * world),  # alive objects / (scenarios x slots x ticks), SURVEY 8d
             "e2e": {"value": e2e_value, "unit": "object-updates/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t_e2e.item()) / args.steps * 1e3,
                     "waves": args.waves},

@@ -22,6 +22,7 @@
  * zrk_get_time                     Timer.get_time                   Timer.py:20-22
  * zrk_read_messages                Manager.give_messages            Manager.py:60-70
  * zrk_read_counts                  sum(len(messages))               main.py:171
+ * zrk_read_activity                sum(len(ActiveObjectsMessage.active_objects))  AirEnv.py:50-53
  * zrk_read_state                   model attributes (pos, prev_pos, current_azimuth,
  *                                  _target_dict ...)                BaseModel.py:28-36, CCP.py:80-86
  * zrk_read_status                  exception propagation            (CCP.py:259, CCP.py:107)
@@ -282,6 +283,10 @@ int zrk_get_time(zrk_handle *h, int64_t *tick, int64_t *time_ms);
 int zrk_read_status(zrk_handle *h, int32_t *fault_code, int32_t *fault_tick, int32_t *n_records);
 /* Messages emitted so far per scenario and type: counts[B][ZRK_MSG_NTYPES]. */
 int zrk_read_counts(zrk_handle *h, int64_t *counts);
+/* Per scenario: alive air objects summed over the ticks started so far, i.e. the total length of
+ * the active_objects lists AirEnv.step published (AirEnv.py:50-53); divided by slots x ticks it is
+ * the active-slot fraction of the run.  Counted modulo 2^32. */
+int zrk_read_activity(zrk_handle *h, int64_t *alive_slot_ticks);
 /* Copy the explicit records of scenarios [s0, s1) to host: recs[(s - s0) * cap + i] for
  * i < n[s - s0], cap = zrk_log_capacity().  Records of one scenario are in emission order. */
 int zrk_read_records(zrk_handle *h, int s0, int s1, zrk_msg *recs, int32_t *n);

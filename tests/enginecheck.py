@@ -25,9 +25,13 @@ def check_batch_full(batch, n_ticks, lib=None, ticks_per_launch=0, exact_only=Fa
         eng.sync()
         fc, ft, nr = eng.status()
         counts = eng.counts()
+        alive = eng.alive_slot_ticks()
         st = eng.state()
+        from zrk_modulation_b200 import _cabi as A
         for s in scenarios:
             r = O.run(batch, s, n_ticks)
+            act = r["msgs"][r["msgs"]["type"] == A.MSG_ACTIVE_OBJECTS]
+            assert int(alive[s]) == int(act["b"].sum()), f"scenario {s}: alive slot-ticks"
             msgs, ids = eng.messages(s, 0, n_ticks)
             d = parity.diff_msgs(r["msgs"], r["ids"], msgs, ids)
             assert d == "", f"scenario {s}: {d}"

@@ -738,6 +738,15 @@ extern "C" int zrk_read_counts(zrk_handle *h, int64_t *counts) {
     return ZRK_OK;
 }
 
+extern "C" int zrk_read_activity(zrk_handle *h, int64_t *alive_slot_ticks) {
+    if (!h || !alive_slot_ticks) return ZRK_ERR_ARG;
+    int rc = fetch_summary(h);
+    if (rc) return rc;
+    for (int s = 0; s < h->P.lo.B; s++)
+        alive_slot_ticks[s] = (unsigned)h->h_summary[(size_t)s * ZRK_SUMMARY_WORDS + H_ALIVE];
+    return ZRK_OK;
+}
+
 extern "C" int zrk_read_records(zrk_handle *h, int s0, int s1, zrk_msg *recs, int32_t *n) {
     if (!h || s0 < 0 || s1 > h->P.lo.B || s0 > s1) return ZRK_ERR_ARG;
     int rc = fetch_summary(h);

@@ -21,7 +21,7 @@ enum { F_ALIVE = 1, F_PENDING = 2, F_HASPREV = 4, F_MISSILE = 8, F_TTYPE_SHIFT =
 // header words (ints) at dyn.hdr
 enum {
     H_TICK = 0, H_NSLOTS, H_NTE, H_NME, H_CCP_INIT, H_FAULT, H_FAULT_TICK, H_NREC,
-    H_DETN0, H_DETN1, H_MBN0, H_MBN1, H_LN, H_FREECAP, H_TMP0, H_TMP1, H_WORDS = 16
+    H_DETN0, H_DETN1, H_MBN0, H_MBN1, H_LN, H_FREECAP, H_ALIVE /* alive slot-ticks so far (mod 2^32) */, H_TMP1, H_WORDS = 16
 };
 enum { MB_COMMAND = 0, MB_SUCCESS = 1, MB_CANCEL = 2, MB_COUNTREQ = 3 };
 enum { ST_READY = 0, ST_ACTIVE = 1, ST_DETONATED = 2 };

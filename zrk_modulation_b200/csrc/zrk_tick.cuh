@@ -1067,6 +1067,14 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
             H.sflags()[lane] = fl;
         }
         const bool alive = (fl & F_ALIVE) != 0;
+        {  // activity counter: alive slots summed over the ticks started (the "active-slot fraction" of a run)
+            const unsigned live = __ballot_sync(ZRK_FULL, alive);
+            if (TEAM == 32) {
+                if (lane == 0) hdr[H_ALIVE] += __popc(live);
+            } else if ((lane & 31) == 0 && live) {
+                atomicAdd(&hdr[H_ALIVE], __popc(live));
+            }
+        }
         tm.sync();
 
         // Missile.step, status 'active' (Missile.py:162-193), in slot order

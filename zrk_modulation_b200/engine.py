@@ -94,6 +94,13 @@ class Engine:
         self._ck(self.lib.zrk_read_counts(self._h, c.ctypes.data_as(C.POINTER(C.c_int64))))
         return c
 
+    def alive_slot_ticks(self) -> np.ndarray:
+        """Per scenario: alive air objects summed over the ticks run (the total length of the
+        active_objects lists AirEnv.step published)."""
+        a = np.zeros(self.batch.n_scenarios, dtype=np.int64)
+        self._ck(self.lib.zrk_read_activity(self._h, a.ctypes.data_as(C.POINTER(C.c_int64))))
+        return a
+
     def log_capacity(self) -> int:
         return int(self.lib.zrk_log_capacity(self._h))
 

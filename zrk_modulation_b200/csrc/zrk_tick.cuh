@@ -646,9 +646,10 @@ __device__ __forceinline__ void link_block(const float *lf, int blk, F2 nfx, F2 
 }
 
 // Hash grid over the entries' link positions (x, y of the fp32 image; cells of ZRK_CELL metres,
-// TEAM buckets, chained through the w component of the images).  A detection whose acceptance radius sqrt(thr) is at most
-// one cell wide only has to look at the buckets of the <= 2 x 2 cells its radius touches: every
-// entry within that radius is in one of them (hash collisions only add harmless extra tests).
+// TEAM buckets, chained through the w component of the images).  A detection whose acceptance
+// radius sqrt(thr) is at most one cell wide only has to look at the buckets of the <= 2 x 2 cells
+// its radius touches: every entry within that radius is in one of them (hash collisions only add
+// harmless extra tests).
 #define ZRK_CELL 512.0f
 __device__ __forceinline__ int grid_cell(float v) { return (int)floorf(v * (1.0f / ZRK_CELL)); }
 template <int TEAM>
@@ -656,8 +657,8 @@ __device__ __forceinline__ int grid_bucket(int ix, int iy) {
     return (int)(((unsigned)ix * 73856093u) ^ ((unsigned)iy * 19349663u)) & (TEAM - 1);
 }
 
-// Squared-domain scan of one detection.  `coords_ok`: the detection and every entry image are
-// inside the fp32-safe range (otherwise the caller runs link_exact).
+// Squared-domain scan of one detection.  The caller has checked that the detection and every
+// entry image are inside the fp32-safe range (otherwise it runs link_exact).
 template <int TEAM>
 __device__ __forceinline__ void link_fast(const int *ghead, bool grid_ok, const float *lf, const double2 *lxy, const double2 *lzd, int n_te, int n_me,
                                           int seed, double range_step, double px, double py, double pz, double speed,

@@ -94,10 +94,10 @@ def special_config(kind: str):
             r["max_distance"] = 1.0e6
             r.update(azimuth_start=0.0, azimuth_range=360.0, azimuth_speed=0.0, elevation_start=0.0,
                      elevation_range=180.0, elevation_speed=0.0, scan_mode="horizontal")
-    elif kind == "far_close":    # near the end of the fp32 range AND tracks closer than fp32 resolves there
+    elif kind == "far_close":    # near the end of the fp32 range (|x| + |y| + |z| just under 2^20) AND tracks closer than fp32 resolves there
         for i, tt in enumerate(t):
             j = i // 2
-            tt["position"] = [9.0e5 + 4000.0 * j + 0.03 * (i % 2), -8.0e5 + 1500.0 * j - 0.05 * (i % 2), 9000.0 + 0.02 * (i % 2)]
+            tt["position"] = [5.2e5 + 4000.0 * j + 0.03 * (i % 2), -4.6e5 + 1500.0 * j - 0.05 * (i % 2), 9000.0 + 0.02 * (i % 2)]
             if i % 2:
                 tt["velocity"] = list(t[i - 1]["velocity"])
         for r in cfg["radars"]:

@@ -70,6 +70,17 @@ __device__ __forceinline__ double tick_seconds(const Params &P, int tick) {
 
 #define ZRK_RAD2DEG 57.29577951308232 /* 180.0 / pi, as np.degrees multiplies */
 
+// fp32 square root for the conservative pre-filters only (never for a value that reaches state)
+__device__ __forceinline__ float sqrt_fast(float x) {  // relative error <= 2^-23 (sqrt.approx.f32)
+#ifdef ZRK_EMU
+    return sqrtf(x);
+#else
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
+
 // SectorRadar.find_visible_objects for one object (Radar.py:53-71), exact path.
 __device__ ZRK_NOINLINE bool radar_sees_exact(double dx, double dy, double dz, double max_dist, double az_lo,
                                               double az_hi, double el_lo, double el_hi) {
@@ -91,7 +102,8 @@ __device__ __forceinline__ float atan2_deg_approx(float y, float x) {
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
     const float a = __fdividef(mn, mx);  // 0/0 -> NaN -> every comparison false -> exact path
     const float q = a * a;
-    float r = ((((0.0208351f * q - 0.085133f) * q + 0.180141f) * q - 0.3302995f) * q + 0.999866f) * a;
+    // (explicit fmaf: the file is compiled without contraction for the sake of the fp64 path)
+    float r = fmaf(fmaf(fmaf(fmaf(0.0208351f, q, -0.085133f), q, 0.180141f), q, -0.3302995f), q, 0.999866f) * a;
     if (ay > ax) r = 1.57079637f - r;
     if (x < 0.f) r = 3.14159274f - r;
     if (y < 0.f) r = -r;
@@ -117,7 +129,7 @@ __device__ __forceinline__ bool radar_sees(double dx, double dy, double dz, cons
             sure_out = sure_out || az < a0 - M || az > a1 + M;
         }
         if (!(el_lo <= 0.0 && el_hi >= 180.0)) {
-            float el = atan2_deg_approx(fz, sqrtf(fx * fx + fy * fy));  // == asin(dz / distance), well conditioned
+            float el = atan2_deg_approx(fz, sqrt_fast(fmaf(fy, fy, fx * fx)));  // == asin(dz / distance), well conditioned
             if (el < 0.f) el += 180.f;
             const float e0 = (float)el_lo, e1 = (float)el_hi;
             ok = ok && el > M && el < 180.f - M && fabsf(e0) < 1e4f && fabsf(e1) < 1e4f;
@@ -537,15 +549,6 @@ __device__ __forceinline__ double link_d2(const double2 *lxy, const double2 *lzd
 #define ZRK_F32_COORD_MAX 1048576.0
 #define ZRK_F32_MARGIN 0.5
 #define ZRK_F32_ALL 3.0e38f /* threshold "everything real": pads and skipped entries measure inf */
-__device__ __forceinline__ float sqrt_fast(float x) {  // relative error <= 2^-23 (sqrt.approx.f32)
-#ifdef ZRK_EMU
-    return sqrtf(x);
-#else
-    float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-#endif
-}
 __device__ __forceinline__ float link_threshold(double best) {
     if (!(best < 1e30)) return ZRK_F32_ALL;
     // an upper bound of (sqrt(best) + margin)^2 in fp32: every rounding below is covered by the factors
@@ -788,9 +791,11 @@ __device__ __forceinline__ void link_fast(const int *ghead, bool grid_ok, const 
     cand = A.ue < 0 ? -1 : (A.ue >= TEAM ? A.ue - TEAM : A.ue);
 }
 
-// is a link position (or a detection) inside the range where the fp32 image is trusted?
-__device__ __forceinline__ bool link_f32_ok(double x, double y, double z) {
-    return fabs(x) <= ZRK_F32_COORD_MAX && fabs(y) <= ZRK_F32_COORD_MAX && fabs(z) <= ZRK_F32_COORD_MAX;
+// Is a link position (or a detection) inside the range where the fp32 image is trusted?  Tested on
+// the image itself, branch-free: |x| + |y| + |z| <= C implies every |coordinate| <= C (+ a quarter
+// metre of rounding, nothing against the margins above); NaN and inf fail the compare.
+__device__ __forceinline__ bool link_f32_ok(float x, float y, float z) {
+    return fabsf(x) + fabsf(y) + fabsf(z) <= (float)ZRK_F32_COORD_MAX;
 }
 
 // ------------------------------------------------------------------ lane 0 alone: launchers + CCP bookkeeping
@@ -1224,7 +1229,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 lzd[lane] = make_double2(c.x, now_s - H.te_upds()[lane]);
                 if (FAST) {
                     lf_store<TEAM>(lf, lane, skip ? 1e30f : (float)a.x, (float)a.y, (float)c.x);
-                    bad_image = !skip && !link_f32_ok(a.x, a.y, c.x);
+                    bad_image = !skip & !link_f32_ok((float)a.x, (float)a.y, (float)c.x);
                 }
             } else if (FAST && TEAM == 32) {
                 lf_store<TEAM>(lf, lane, 1e30f, 0.f, 0.f);  // pad: measures inf to everything
@@ -1239,7 +1244,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 lzd[TEAM + lane] = make_double2(cz, now_s - ZRK_COLD_D(me_upds)[lane]);
                 if (FAST) {
                     lf_store<TEAM>(lf, TEAM + lane, skip ? 1e30f : (float)a.x, (float)a.y, (float)cz);
-                    bad_image = bad_image || (!skip && !link_f32_ok(a.x, a.y, cz));
+                    bad_image = bad_image | (!skip & !link_f32_ok((float)a.x, (float)a.y, (float)cz));
                 }
             } else if (FAST && TEAM == 32 && lane < MP8) {
                 lf_store<TEAM>(lf, TEAM + lane, 1e30f, 0.f, 0.f);
@@ -1305,7 +1310,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 // does the seed entry still refer to this very slot?  (then distinct slots have distinct seeds)
                 if (seed >= 0) seed_own = (seed >= TEAM ? ZRK_COLD_I(me_ref)[seed - TEAM] : H.te_ref()[seed]) == slot;
             }
-            const bool coords_ok = FAST && !any_bad && link_f32_ok(dpx, dpy, dpz);
+            const bool coords_ok = FAST && !any_bad && link_f32_ok((float)dpx, (float)dpy, (float)dpz);
             int lo_rank = 0;
             for (;;) {
                 int cls = 0, cand = -1, claim = -1;

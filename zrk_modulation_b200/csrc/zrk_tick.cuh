@@ -1292,21 +1292,22 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
             }
             tm.sync();
             const int i = lane;
-            int slot = 0, did = 0, radar_id = 0, seed = -1;
+            int slot = 0, seed = -1;
+            // id of the detected object and of the radar that reported it: only messages and new tracks need them
+            auto det_id = [&]() { return H.sid()[slot]; };
+            auto det_radar = [&]() { return ZRK_CST_I(c_rad_id)[H.srf()[slot]]; };
             bool seed_own = false;
             double dpx = 0, dpy = 0, dpz = 0, dspeed = 0;
             bool unresolved = i < n_det;
             if (unresolved) {
                 slot = detlist[i];
-                did = H.sid()[slot];
-                radar_id = ZRK_CST_I(c_rad_id)[H.srf()[slot]];
                 const double2 a = H.pxy()[slot], c = H.pzs()[slot];
                 dpx = a.x;
                 dpy = a.y;
                 dpz = c.x;
                 dspeed = c.y;
                 seed = H.own()[slot];
-                if (seed >= 0 && (seed >= TEAM ? seed - TEAM >= n_me : seed >= n_te)) seed = -1;
+                // (entries are never removed — CCP's dicts only grow, CCP.py:88-109 — so a stored seed stays in range)
                 // does the seed entry still refer to this very slot?  (then distinct slots have distinct seeds)
                 if (seed >= 0) seed_own = (seed >= TEAM ? ZRK_COLD_I(me_ref)[seed - TEAM] : H.te_ref()[seed]) == slot;
             }
@@ -1329,8 +1330,9 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                         claim = TEAM + cand;
                     else {  // add_target overwrites an existing key in place (CCP.py:92)
                         const int *te_key = H.te_key();
+                        const int did_ = det_id();
                         for (int e = 0; e < n_te; e++)
-                            if (te_key[e] == did) {
+                            if (te_key[e] == did_) {
                                 claim = e;
                                 break;
                             }
@@ -1357,7 +1359,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                         if (unresolved) {
                             if (cls == 1) {  // old_target, already followed or no missile to send (CCP.py:332-359)
                                 if (upd_msg && logged(P, ZRK_MSG_CCP_UPDATE_TARGET))
-                                    put_rec(P, rec, nrec + r_upd, tick, ZRK_MSG_CCP_UPDATE_TARGET, 0, ccp_id, radar_id, did,
+                                    put_rec(P, rec, nrec + r_upd, tick, ZRK_MSG_CCP_UPDATE_TARGET, 0, ccp_id, det_radar(), det_id(),
                                             H.te_mid()[cand], 0, 0, 0);
                                 H.te_upd()[cand] = tick;
                                 H.te_upds()[cand] = now_s;
@@ -1457,9 +1459,9 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                     r_wr = tm.rank(wr, n_wr);
                 if (wr) {
                     if (mtype == ZRK_MSG_LAUNCH_COMMAND)
-                        put_rec(P, rec, nrec + r_wr, tick, mtype, 0, ccp_id, ZRK_CST_I(c_cl_id)[ok - 1], did, radar_id, dpx, dpy, dpz);
+                        put_rec(P, rec, nrec + r_wr, tick, mtype, 0, ccp_id, ZRK_CST_I(c_cl_id)[ok - 1], det_id(), det_radar(), dpx, dpy, dpz);
                     else
-                        put_rec(P, rec, nrec + r_wr, tick, mtype, 0, ccp_id, radar_id, did, old_mid, 0, 0, 0);
+                        put_rec(P, rec, nrec + r_wr, tick, mtype, 0, ccp_id, det_radar(), det_id(), old_mid, 0, 0, 0);
                 }
                 if (fin) {
                     if (cls == 1) {  // old_target (CCP.py:332-359)
@@ -1479,7 +1481,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                         if (FAST) lf_x<TEAM>(lf, TEAM + cand) = 1e30f;
                     } else {  // new_target + add_target (CCP.py:322-330, :88-93)
                         const int e = claim >= 0 ? claim : n_te + r_app;
-                        H.te_key()[e] = did;
+                        H.te_key()[e] = det_id();
                         H.te_ref()[e] = slot;
                         H.te_upd()[e] = tick;
                         H.te_upds()[e] = now_s;

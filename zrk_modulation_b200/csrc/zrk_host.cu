@@ -282,18 +282,18 @@ static int dev_alloc(zrk_handle *h, size_t n, T **dst, bool zero) {
 
 typedef void (*tick_fn)(const Params, int, int, int);
 
-template <int TEAM, int TPC>
+template <int TEAM, int TPC, int MPB>
 static tick_fn pick_fast(bool fast) {
-    return fast ? (tick_fn)zrk_tick_kernel<TEAM, TPC, true> : (tick_fn)zrk_tick_kernel<TEAM, TPC, false>;
+    return fast ? (tick_fn)zrk_tick_kernel<TEAM, TPC, true, MPB> : (tick_fn)zrk_tick_kernel<TEAM, TPC, false, MPB>;
 }
-static tick_fn pick_kernel(int team, bool fast) {
-    switch (team) {
-    case 32: return pick_fast<32, ZRK_CTA_THREADS / 32>(fast);
-    case 64: return pick_fast<64, 1>(fast);
-    case 128: return pick_fast<128, 1>(fast);
-    case 256: return pick_fast<256, 1>(fast);
-    case 512: return pick_fast<512, 1>(fast);
-    case 1024: return pick_fast<1024, 1>(fast);
+static tick_fn pick_kernel(const Layout &lo, bool fast) {
+    switch (lo.team) {
+    case 32: return lo.MP == 8 ? pick_fast<32, ZRK_CTA_THREADS / 32, 8>(fast) : pick_fast<32, ZRK_CTA_THREADS / 32, 32>(fast);
+    case 64: return pick_fast<64, 1, 0>(fast);
+    case 128: return pick_fast<128, 1, 0>(fast);
+    case 256: return pick_fast<256, 1, 0>(fast);
+    case 512: return pick_fast<512, 1, 0>(fast);
+    case 1024: return pick_fast<1024, 1, 0>(fast);
     }
     return nullptr;
 }
@@ -502,7 +502,7 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
         h->err = "unsupported: scenario state does not fit in shared memory";
         return ZRK_ERR_UNSUPPORTED;
     }
-    tick_fn fn = pick_kernel(lo.team, h->fast);
+    tick_fn fn = pick_kernel(lo, h->fast);
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     {
         // shared-memory carve-out: what the resident CTAs need (registers bound their number), so
@@ -615,7 +615,7 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
     if (!h || n_ticks < 0) return ZRK_ERR_ARG;
     if (h->sticky_rc) return h->sticky_rc;
     CK(cudaSetDevice(h->device));
-    tick_fn fn = pick_kernel(h->P.lo.team, h->fast);
+    tick_fn fn = pick_kernel(h->P.lo, h->fast);
     if (h->pending.size() > 4096) {
         int rc = resolve_events(h);
         if (rc) return rc;

@@ -78,6 +78,49 @@ ZRK_HD constexpr HotOff hot_off(int team) {
 #define ZRK_CTA_THREADS 128
 #endif
 
+// Scratch of one team (shared memory only).  It sits in front of the dyn blob, so that its
+// offsets from the blob base depend on the team size and the missile capacity only — compile-time
+// constants for warp teams, whose kernel is instantiated per capacity bucket.
+struct ScratchOff {
+    int x_lxy, x_lzd, x_lf, x_claim, x_detlist, x_wscr, x_need, x_ghead, x_mbar;
+    int bytes;
+};
+ZRK_HD constexpr int zrk_align_c(int x, int a) { return (x + a - 1) / a * a; }
+ZRK_HD constexpr ScratchOff scratch_off(int team, int mp) {
+    ScratchOff x{};
+    int p = 0;
+    x.x_lxy = p; p += 16 * (team + mp);
+    x.x_lzd = p; p += 16 * (team + mp);
+    x.x_lf = p; p += team > 32 ? 16 * (team + mp) : 12 * (team + zrk_align_c(mp, 8));
+    x.x_claim = p; p += zrk_align_c(4 * (team + mp), 8);
+    x.x_detlist = p; p += 4 * team;
+    x.x_wscr = p; p += 4 * 64;
+    x.x_need = p; p += 4 * team;
+    x.x_ghead = p; p += 4 * team;
+    x.x_mbar = p; p += 8;
+    x.bytes = zrk_align_c(p, 16);
+    return x;
+}
+// Byte offsets of the CCP missile entries, the first arrays of the cold part: hot_off(team).end + ...
+struct MeOff {
+    int me_key, me_ref, me_upd, me_tid, me_upds, end;
+};
+ZRK_HD constexpr MeOff me_off(int team, int mp) {
+    MeOff m{};
+    int p = hot_off(team).end;
+    m.me_key = p; p += zrk_align_c(4 * mp, 8);
+    m.me_ref = p; p += zrk_align_c(4 * mp, 8);
+    m.me_upd = p; p += zrk_align_c(4 * mp, 8);
+    m.me_tid = p; p += zrk_align_c(4 * mp, 8);
+    m.me_upds = p; p += 8 * mp;
+    m.end = p;
+    return m;
+}
+// missile capacity of a scenario's arrays: warp teams use one of two buckets
+ZRK_HD constexpr int zrk_mp_for(int team, int M) {
+    return team == 32 ? (M <= 8 ? 8 : 32) : zrk_align_c(M > 0 ? M : 1, 2);
+}
+
 struct Layout {
     int B, T, M, NS, R, L, C;
     int MP, RP, LP, CP, Q;
@@ -94,7 +137,8 @@ struct Layout {
     int c_m_id, c_m_launcher, c_m_v0, c_m_v0sq, c_m_radius;
     int c_cl_id, c_cl_launcher, c_cl_pos;
     int cst_bytes;
-    // scratch (shared memory only), offsets from the start of the team's region
+    int scratch_bytes;  // the team's region is [scratch][dyn blob][cst blob]; `sm` in the kernel is the dyn base
+    // scratch (shared memory only): offsets from the dyn base, all negative (scratch_off(...) - scratch_bytes)
     int x_lxy, x_lzd;  // double2[TEAM + MP]: per CCP entry, the position link_object measures to
     int x_lf;          // the same positions rounded to fp32: warp teams float[12][(TEAM + MP8) / 4], blocks of
                        // x[4] y[4] z[4]; larger teams float4[TEAM + MP] = x, y, z, next entry in the grid chain
@@ -139,7 +183,7 @@ static inline Layout make_layout(int B, int T, int M, int R, int L, int C) {
     o.team = zrk_team_for(o.NS);
     const int team = o.team ? o.team : 32;
     o.teams_per_cta = team > 32 ? 1 : ZRK_CTA_THREADS / 32;  // teams larger than a warp own their CTA
-    o.MP = zrk_align(M > 0 ? M : 1, 2);
+    o.MP = zrk_mp_for(team, M);
     o.RP = R > 0 ? R : 1;
     o.LP = zrk_align(L > 0 ? L : 1, 2);
     o.CP = zrk_align(C > 0 ? C : 1, 2);
@@ -147,8 +191,11 @@ static inline Layout make_layout(int B, int T, int M, int R, int L, int C) {
     o.hot = hot_off(team);
     int p = o.hot.end;
     auto take = [&p](int bytes) { int at = p; p += zrk_align(bytes, 8); return at; };
-    o.me_key = take(4 * o.MP); o.me_ref = take(4 * o.MP); o.me_upd = take(4 * o.MP); o.me_tid = take(4 * o.MP);
-    o.me_upds = take(8 * o.MP);
+    {
+        const MeOff m = me_off(team, o.MP);
+        o.me_key = m.me_key; o.me_ref = m.me_ref; o.me_upd = m.me_upd; o.me_tid = m.me_tid; o.me_upds = m.me_upds;
+        p = m.end;
+    }
     o.rad_cur = take(8 * 2 * o.RP);
     o.st_n = take(4 * o.LP);
     o.st = take(4 * o.LP * o.MP);
@@ -173,17 +220,14 @@ static inline Layout make_layout(int B, int T, int M, int R, int L, int C) {
     o.c_cl_id = take(4 * o.CP); o.c_cl_launcher = take(4 * o.CP);
     o.c_cl_pos = take(8 * 3 * o.CP);
     o.cst_bytes = zrk_align(p, 16);
-    p = o.dyn_bytes + o.cst_bytes;
-    o.x_lxy = take(16 * (team + o.MP));
-    o.x_lzd = take(16 * (team + o.MP));
-    o.x_lf = take(team > 32 ? 16 * (team + o.MP) : 12 * (team + zrk_align(o.MP, 8)));
-    o.x_claim = take(4 * (team + o.MP));
-    o.x_detlist = take(4 * team);
-    o.x_wscr = take(4 * 64);
-    o.x_need = take(4 * team);
-    o.x_ghead = take(4 * team);
-    o.x_mbar = take(8);
-    o.team_smem_bytes = zrk_align(p, 16);
+    {
+        const ScratchOff x = scratch_off(team, o.MP);
+        o.scratch_bytes = x.bytes;
+        o.x_lxy = x.x_lxy - x.bytes; o.x_lzd = x.x_lzd - x.bytes; o.x_lf = x.x_lf - x.bytes;
+        o.x_claim = x.x_claim - x.bytes; o.x_detlist = x.x_detlist - x.bytes; o.x_wscr = x.x_wscr - x.bytes;
+        o.x_need = x.x_need - x.bytes; o.x_ghead = x.x_ghead - x.bytes; o.x_mbar = x.x_mbar - x.bytes;
+        o.team_smem_bytes = zrk_align(x.bytes + o.dyn_bytes + o.cst_bytes, 16);
+    }
     return o;
 }
 

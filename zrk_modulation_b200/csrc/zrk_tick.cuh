@@ -969,29 +969,36 @@ constexpr int min_blocks(int threads) { return threads <= 64 ? 8 : (threads <= 1
 #else
 #define ZRK_KERNEL_ATTR __launch_bounds__(TEAM *TPC, min_blocks(TEAM *TPC))
 #endif
-template <int TEAM, int TPC, bool FAST>
+// MPB: missile capacity bucket of a warp team (Layout::MP as a compile-time constant, so that the
+// scratch and track-entry offsets below are immediates); 0 = offsets from the Layout at run time.
+template <int TEAM, int TPC, bool FAST, int MPB>
 __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int b_first, int b_end) {
     ZRK_SMEM_DECL;
     const Layout &o = P.lo;
-    const int MP = o.MP, Q = o.Q, MP8 = (o.MP + 7) & ~7;
+    constexpr ScratchOff XS = scratch_off(TEAM, MPB ? MPB : 2);
+    constexpr MeOff XM = me_off(TEAM, MPB ? MPB : 2);
+#define ZRK_X(name) (MPB ? XS.name - XS.bytes : o.name)   /* scratch offset from the dyn base */
+#define ZRK_ME_I(name) ((int *)(sm + (MPB ? XM.name : o.name)))
+#define ZRK_ME_D(name) ((double *)(sm + (MPB ? XM.name : o.name)))
+    const int MP = MPB ? MPB : o.MP, Q = o.Q, MP8 = (MP + 7) & ~7;
     Team<TEAM, TPC> tm;
     tm.tic = threadIdx.x / TEAM;
     tm.lane = threadIdx.x % TEAM;
     const int lane = tm.lane;
     const int b = b_first + blockIdx.x * TPC + tm.tic;  // this launch covers scenarios [b_first, b_end)
     if (b >= b_end) return;  // whole team leaves together
-    unsigned char *sm = zrk_smem + (size_t)tm.tic * o.team_smem_bytes;
+    unsigned char *sm = zrk_smem + (size_t)tm.tic * o.team_smem_bytes + (MPB ? XS.bytes : o.scratch_bytes);  // the dyn blob; scratch in front of it
     Hot<TEAM> H;
     H.sm = sm;
-    tm.wscr = (int *)(sm + o.x_wscr);
+    tm.wscr = (int *)(sm + ZRK_X(x_wscr));
     tm.flip = 0;
-    double2 *lxy = (double2 *)(sm + o.x_lxy), *lzd = (double2 *)(sm + o.x_lzd);
-    float *lf = (float *)(sm + o.x_lf);
-    int *ghead = (int *)(sm + o.x_ghead);
+    double2 *lxy = (double2 *)(sm + ZRK_X(x_lxy)), *lzd = (double2 *)(sm + ZRK_X(x_lzd));
+    float *lf = (float *)(sm + ZRK_X(x_lf));
+    int *ghead = (int *)(sm + ZRK_X(x_ghead));
 
     // ---- prologue: HBM -> shared memory, one bulk copy per blob
     {
-        void *mbar = sm + o.x_mbar;
+        void *mbar = sm + ZRK_X(x_mbar);
         stage_in(sm, P.dyn + (size_t)b * o.dyn_bytes, o.dyn_bytes, P.cst + (size_t)b * o.cst_bytes, o.cst_bytes, mbar,
                  lane == 0);
         tm.sync();  // the barrier is initialised before anyone polls it
@@ -1235,13 +1242,13 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 lf_store<TEAM>(lf, lane, 1e30f, 0.f, 0.f);  // pad: measures inf to everything
             }
             if (lane < n_me) {
-                const int ref = ZRK_COLD_I(me_ref)[lane], upd = ZRK_COLD_I(me_upd)[lane];
+                const int ref = ZRK_ME_I(me_ref)[lane], upd = ZRK_ME_I(me_upd)[lane];
                 const bool hp = (H.sflags()[ref] & F_HASPREV) != 0;
                 const double2 a = hp ? H.qxy()[ref] : H.pxy()[ref];
                 const double cz = hp ? H.qzw()[ref].x : H.pzs()[ref].x;
                 const bool skip = upd == tick;
                 lxy[TEAM + lane] = make_double2(skip ? ZRK_FAR : a.x, a.y);
-                lzd[TEAM + lane] = make_double2(cz, now_s - ZRK_COLD_D(me_upds)[lane]);
+                lzd[TEAM + lane] = make_double2(cz, now_s - ZRK_ME_D(me_upds)[lane]);
                 if (FAST) {
                     lf_store<TEAM>(lf, TEAM + lane, skip ? 1e30f : (float)a.x, (float)a.y, (float)cz);
                     bad_image = bad_image | (!skip & !link_f32_ok((float)a.x, (float)a.y, (float)cz));
@@ -1273,7 +1280,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                     n_det += t0 + t1;
                 }
             }
-            int *detlist = (int *)(sm + o.x_detlist);
+            int *detlist = (int *)(sm + ZRK_X(x_detlist));
             if (myrank >= 0) detlist[myrank] = lane;
             if (FAST) any_bad = nR > 0 ? any_seen : false;  // (no radar: no detection, nothing scans)
             if (want_grid && nR > 0) {
@@ -1309,7 +1316,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 seed = H.own()[slot];
                 // (entries are never removed — CCP's dicts only grow, CCP.py:88-109 — so a stored seed stays in range)
                 // does the seed entry still refer to this very slot?  (then distinct slots have distinct seeds)
-                if (seed >= 0) seed_own = (seed >= TEAM ? ZRK_COLD_I(me_ref)[seed - TEAM] : H.te_ref()[seed]) == slot;
+                if (seed >= 0) seed_own = (seed >= TEAM ? ZRK_ME_I(me_ref)[seed - TEAM] : H.te_ref()[seed]) == slot;
             }
             const bool coords_ok = FAST && !any_bad && link_f32_ok((float)dpx, (float)dpy, (float)dpz);
             int lo_rank = 0;
@@ -1364,8 +1371,8 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                                 H.te_upd()[cand] = tick;
                                 H.te_upds()[cand] = now_s;
                             } else {  // old_rocket (CCP.py:361-366)
-                                ZRK_COLD_I(me_upd)[cand] = tick;
-                                ZRK_COLD_D(me_upds)[cand] = now_s;
+                                ZRK_ME_I(me_upd)[cand] = tick;
+                                ZRK_ME_D(me_upds)[cand] = now_s;
                             }
                         }
                         if (logged(P, ZRK_MSG_CCP_UPDATE_TARGET)) nrec += n_upd;
@@ -1386,7 +1393,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                     }
                     conflict = has && (same & ((1u << lane) - 1u)) != 0;
                 } else {
-                    int *x_claim = (int *)(sm + o.x_claim);
+                    int *x_claim = (int *)(sm + ZRK_X(x_claim));
                     for (int x = lane; x < TEAM + MP; x += TEAM) x_claim[x] = ZRK_IMAX;
                     tm.sync();
                     if (unresolved && claim >= 0) atomicMin(&x_claim[claim], i);
@@ -1402,7 +1409,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 int ok = 0;
                 // hdr[H_FREECAP] = sum over launchers of max(0, capacity - launched), kept by lane 0
                 if (hdr[H_FREECAP] > 0 && tm.any(need)) {  // try_to_launch_missile (CCP.py:287-320), in order
-                    int *x_need = (int *)(sm + o.x_need);
+                    int *x_need = (int *)(sm + ZRK_X(x_need));
                     x_need[i] = need;
                     tm.sync();
                     if (lane == 0) {
@@ -1473,9 +1480,9 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                         lxy[cand].x = ZRK_FAR;
                         if (FAST) lf_x<TEAM>(lf, cand) = 1e30f;
                     } else if (cls == 2) {  // old_rocket (CCP.py:361-366)
-                        ZRK_COLD_I(me_ref)[cand] = slot;
-                        ZRK_COLD_I(me_upd)[cand] = tick;
-                        ZRK_COLD_D(me_upds)[cand] = now_s;
+                        ZRK_ME_I(me_ref)[cand] = slot;
+                        ZRK_ME_I(me_upd)[cand] = tick;
+                        ZRK_ME_D(me_upds)[cand] = now_s;
                         H.own()[slot] = TEAM + cand;
                         lxy[TEAM + cand].x = ZRK_FAR;
                         if (FAST) lf_x<TEAM>(lf, TEAM + cand) = 1e30f;
@@ -1511,7 +1518,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 int mref = -1, tref = -1;
                 bool dm = false, dt = false, bad = false;
                 if (lane < n_me) {
-                    mref = ZRK_COLD_I(me_ref)[lane];
+                    mref = ZRK_ME_I(me_ref)[lane];
                     dm = H.srf()[mref] >= 0;
                 }
                 if (lane < n_te) {
@@ -1581,6 +1588,10 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
     tm.sync();
     stage_out(P.dyn + (size_t)b * o.dyn_bytes, sm, o.dyn_bytes, lane == 0);
 }
+
+#undef ZRK_X
+#undef ZRK_ME_I
+#undef ZRK_ME_D
 
 }  // namespace zrk
 #endif

@@ -103,7 +103,7 @@ ZRK_HD constexpr ScratchOff scratch_off(int team, int mp) {
 }
 // Byte offsets of the CCP missile entries, the first arrays of the cold part: hot_off(team).end + ...
 struct MeOff {
-    int me_key, me_ref, me_upd, me_tid, me_upds, end;
+    int me_key, me_ref, me_upd, me_tid, me_upds, rad_cur /* the array after them */, end;
 };
 ZRK_HD constexpr MeOff me_off(int team, int mp) {
     MeOff m{};
@@ -113,6 +113,7 @@ ZRK_HD constexpr MeOff me_off(int team, int mp) {
     m.me_upd = p; p += zrk_align_c(4 * mp, 8);
     m.me_tid = p; p += zrk_align_c(4 * mp, 8);
     m.me_upds = p; p += 8 * mp;
+    m.rad_cur = p;
     m.end = p;
     return m;
 }

@@ -982,7 +982,8 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
 #define ZRK_ME_D(name) ((double *)(sm + (MPB ? XM.name : o.name)))
     const int MP = MPB ? MPB : o.MP, Q = o.Q, MP8 = (MP + 7) & ~7;
     Team<TEAM, TPC> tm;
-    tm.tic = threadIdx.x / TEAM;
+    // (a warp team's index is the same in all its lanes: say so, the addresses built from it can then be uniform)
+    tm.tic = TEAM == 32 ? __shfl_sync(ZRK_FULL, (int)(threadIdx.x / TEAM), 0) : (int)(threadIdx.x / TEAM);
     tm.lane = threadIdx.x % TEAM;
     const int lane = tm.lane;
     const int b = b_first + blockIdx.x * TPC + tm.tic;  // this launch covers scenarios [b_first, b_end)
@@ -1143,7 +1144,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
         // ============ SectorRadar.step for every radar (Radar.py:144-205)
         int rf = -1;
         {
-            const double *rad_cur = ZRK_COLD_D(rad_cur), *c_rad_pos = ZRK_CST_D(c_rad_pos), *c_rad_par = ZRK_CST_D(c_rad_par);
+            const double *rad_cur = ZRK_ME_D(rad_cur), *c_rad_pos = ZRK_CST_D(c_rad_pos), *c_rad_par = ZRK_CST_D(c_rad_par);
             for (int r = 0; r < nR; r++) {
                 const double *par_r = c_rad_par + RAD_PAR_STRIDE * r;
                 bool vis = false;
@@ -1198,7 +1199,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
 
         // ============ lane 0: sector sweep, MissileLauncher.step, CCP bookkeeping
         if (lane == 0) {
-            double *rad_cur = ZRK_COLD_D(rad_cur);
+            double *rad_cur = ZRK_ME_D(rad_cur);
             const double *c_rad_par = ZRK_CST_D(c_rad_par);
             for (int r = 0; r < nR; r++) {  // move_to_next_sector_circular (Radar.py:96-117)
                 const double *q = c_rad_par + RAD_PAR_STRIDE * r;

@@ -243,6 +243,49 @@ static thread_local std::string g_create_err;
         }                                                                                \
     } while (0)
 
+// Page-locked host buffers are expensive to create (the pages are pinned one by one, under a
+// lock that the ranks of a multi-GPU job share), so freed ones are kept for the next handle of
+// the process: a handle created per step, as bench.py's end-to-end leg does, pins nothing after
+// the first one.  At most ZRK_PINNED_KEEP blocks are kept.
+#include <mutex>
+#define ZRK_PINNED_KEEP 8
+struct PinnedBlock {
+    void *p;
+    size_t bytes;
+};
+static std::mutex g_pinned_mu;
+static std::vector<PinnedBlock> g_pinned_free;
+static size_t pinned_class(size_t bytes) {  // powers of two up to 1 MiB, whole MiB above
+    if (bytes > (1u << 20)) return (bytes + (1u << 20) - 1) >> 20 << 20;
+    size_t c = 64;
+    while (c < bytes) c <<= 1;
+    return c;
+}
+static cudaError_t pinned_get(void **p, size_t bytes) {
+    const size_t c = pinned_class(bytes);
+    {
+        std::lock_guard<std::mutex> g(g_pinned_mu);
+        for (size_t i = 0; i < g_pinned_free.size(); i++)
+            if (g_pinned_free[i].bytes == c) {
+                *p = g_pinned_free[i].p;
+                g_pinned_free.erase(g_pinned_free.begin() + i);
+                return cudaSuccess;
+            }
+    }
+    return cudaHostAlloc(p, c, cudaHostAllocDefault);
+}
+static void pinned_put(void *p, size_t bytes) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> g(g_pinned_mu);
+        if (g_pinned_free.size() < ZRK_PINNED_KEEP) {
+            g_pinned_free.push_back({p, pinned_class(bytes)});
+            return;
+        }
+    }
+    cudaFreeHost(p);
+}
+
 // Stream-ordered allocations from the device's default memory pool, which is told to keep
 // freed memory: creating and destroying handles in a loop then costs no cudaMalloc/cudaFree.
 static int pool_alloc(zrk_handle *h, void **p, size_t bytes) {
@@ -321,8 +364,8 @@ extern "C" void zrk_destroy(zrk_handle *h) {
     }
     for (auto e : h->wave_done) cudaEventDestroy(e);
     if (!h->wave_stream.empty()) cudaEventDestroy(h->fork_ev);
-    if (h->pin_err) cudaFreeHost(h->pin_err);
-    if (h->h_summary) cudaFreeHost(h->h_summary);
+    pinned_put(h->pin_err, sizeof(int));
+    pinned_put(h->h_summary, (size_t)h->P.lo.B * ZRK_SUMMARY_WORDS * sizeof(int));
     for (void *p : h->allocs) cudaFreeAsync(p, h->stream);
     cudaStreamSynchronize(h->stream);
     cudaStreamDestroy(h->stream);
@@ -520,7 +563,7 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
 
     // upload + init, wave by wave
     if (n_waves > 1) {
-        CK(cudaHostAlloc((void **)&h->pin_err, sizeof(int), cudaHostAllocDefault));
+        CK(pinned_get((void **)&h->pin_err, sizeof(int)));
         *h->pin_err = 0;
         CK(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
         CK(cudaEventRecord(h->fork_ev, h->stream));  // allocations and memsets above
@@ -654,7 +697,7 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
     }
     h->tick += n_ticks;
     if (!h->h_summary && n_ticks > 0)  // page-lock the read-back buffer while the GPU is busy
-        CK(cudaHostAlloc((void **)&h->h_summary, (size_t)h->P.lo.B * ZRK_SUMMARY_WORDS * sizeof(int), cudaHostAllocDefault));
+        CK(pinned_get((void **)&h->h_summary, (size_t)h->P.lo.B * ZRK_SUMMARY_WORDS * sizeof(int)));
     return ZRK_OK;
 }
 
@@ -709,7 +752,7 @@ static int fetch_summary(zrk_handle *h) {
     const long long n = (long long)o.B * ZRK_SUMMARY_WORDS;
     ZRK_LAUNCH(zrk_summary_kernel, (unsigned)((n + 255) / 256), 256, 0, h->stream, h->P, h->d_summary);
     CK(cudaGetLastError());
-    if (!h->h_summary) CK(cudaHostAlloc((void **)&h->h_summary, (size_t)n * sizeof(int), cudaHostAllocDefault));
+    if (!h->h_summary) CK(pinned_get((void **)&h->h_summary, (size_t)n * sizeof(int)));
     CK(cudaMemcpyAsync(h->h_summary, h->d_summary, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     return zrk_sync(h);
 }

@@ -128,3 +128,21 @@ def test_c_abi_example_on_the_emulated_build(lib, tmp_path):
     g = parity.load_golden("shipped_simulation_config_nonoise")
     assert [int(x) for x in out[0].split()] == list(g["counts"]) and out[1] == "total 685"
     assert out[2:] == ["detonate tick 11 missile 3005 target 40", "detonate tick 13 missile 4005 target 39"]
+
+
+def test_handles_in_a_loop_reuse_host_buffers(lib):
+    """Create / step / read / destroy in a loop with changing batch sizes and wave counts: the
+    page-locked read-back buffers are handed from handle to handle; results never change."""
+    ref = {}
+    for it in range(16):
+        B = [3, 130, 260, 17][it % 4]
+        b = synthetic_batch(B, 6, n_radars=1, n_launchers=1, missiles_per_launcher=2, noise_period=8, box_km=6.0)
+        eng = Engine(b, waves=[0, 2, 3, 0, 5][it % 5], lib=lib)
+        eng.step(12)
+        got = (eng.counts(), eng.alive_slot_ticks(), eng.status()[0])
+        if B in ref:
+            assert all(np.array_equal(x, y) for x, y in zip(ref[B], got))
+        else:
+            ref[B] = got
+        if it % 3:
+            eng.close()   # the others are left to the garbage collector

@@ -146,3 +146,13 @@ def test_handles_in_a_loop_reuse_host_buffers(lib):
             ref[B] = got
         if it % 3:
             eng.close()   # the others are left to the garbage collector
+
+
+@pytest.mark.parametrize("shape", [(2, 200, 3, 2, 10, 20, 12.0), (2, 70, 4, 3, 6, 30, 6.0), (1, 400, 2, 2, 20, 12, 15.0)],
+                         ids=["256x3radars", "128x4radars", "512x2radars"])
+def test_large_teams_odd_and_even_radar_counts(lib, shape):
+    """Teams larger than a warp rank two radars per barrier: odd and even radar counts, launchers
+    and missiles in flight, dense boxes (conflicting claims)."""
+    B, T, R, L, mpl, ticks, box = shape
+    b = synthetic_batch(B, T, n_radars=R, n_launchers=L, missiles_per_launcher=mpl, seed0=7 * T, noise_period=8, box_km=box)
+    check_batch_full(b, ticks, lib=lib, ticks_per_launch=3)

@@ -79,6 +79,8 @@ def test_exact_only_kernel():
     (120, 2, 1, 8, 40, 20.0),    # team of 128
     (256, 2, 0, 0, 12, 20.0),    # config 4 shape (team of 256)
     (300, 1, 2, 8, 10, 20.0),    # team of 512
+    (200, 3, 2, 10, 20, 12.0),   # team of 256, three radars (two radars per barrier + an odd one)
+    (70, 4, 3, 6, 30, 6.0),      # team of 128, four radars, dense box
 ])
 def test_synthetic_families_full_log(n_targets, radars, launchers, mpl, ticks, box):
     b = synthetic_batch(6, n_targets, n_radars=radars, n_launchers=launchers, missiles_per_launcher=mpl,

@@ -306,7 +306,9 @@ int zrk_device_ptr(zrk_handle *h, const char *name, void **ptr, size_t *bytes); 
 int zrk_state_bytes(zrk_handle *h, size_t *bytes);
 int zrk_save_state(zrk_handle *h, void *buf, size_t cap);
 int zrk_load_state(zrk_handle *h, const void *buf, size_t bytes);
-/* Kernel launches issued by this handle and device time spent in them (CUDA events), ms. */
+/* Kernel launches issued by this handle and device time spent in them (CUDA events), ms.
+ * With zrk_options.waves > 1 the launches of different waves overlap: the figure is then the sum
+ * of the per-launch durations, not the elapsed time. */
 int zrk_launch_stats(zrk_handle *h, int64_t *n_launches, double *kernel_ms);
 const char *zrk_last_error(zrk_handle *h); /* h may be NULL: error of the last failed zrk_create */
 void zrk_destroy(zrk_handle *h);

@@ -497,7 +497,7 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
     };
     std::vector<Field> fields;
 #define UP(field, n)                                                                                   \
-    if (d->field && (n)) {                                                                             \
+    if (d->field && (size_t)(n) != 0) {                                                                             \
         void *q_ = nullptr;                                                                            \
         if ((rc = pool_alloc(h, &q_, (size_t)B * (n) * sizeof(*d->field))) != ZRK_OK) return rc;       \
         dd.field = (decltype(dd.field))q_;                                                             \

@@ -208,7 +208,7 @@ def run_ours(args, rank, world, local_rank):
     kern_ms, launches = [], 0
     sampler = None
     for i in range(args.warmup + args.steps):
-        eng = Engine(batch, device=dev, ticks_per_launch=args.ticks_per_launch)
+        eng = Engine(batch, device=dev, ticks_per_launch=args.ticks_per_launch, certificate=not args.no_certificate)
         eng.sync()
         flush.fill_(i & 0xff)  # evict the freshly written state from L2
         if i == 0 and rank == 0:  # same load during warm-up and timed steps: sample across both
@@ -228,6 +228,7 @@ def run_ours(args, rank, world, local_rank):
             counts = eng.counts()
             fc, ft, nr = eng.status()
             alive_ticks = int(eng.alive_slot_ticks().sum())
+            cert_ticks = int(eng.certified_ticks().sum())
         eng.close()
     clocks = sampler.stop() if sampler else None
     t_dev = torch.tensor([sum(kern_ms)], dtype=torch.float64, device="cuda")
@@ -246,7 +247,8 @@ def run_ours(args, rank, world, local_rank):
     for i in range(args.warmup + args.steps):
         barrier()
         t0 = time.perf_counter()
-        eng = Engine(batch, device=dev, ticks_per_launch=args.ticks_per_launch, waves=args.waves)
+        eng = Engine(batch, device=dev, ticks_per_launch=args.ticks_per_launch, waves=args.waves,
+                     certificate=not args.no_certificate)
         ta = time.perf_counter()
         eng.step(ticks)
         c2 = eng.counts()  # per-scenario message counters + status: the step's result
@@ -283,6 +285,7 @@ def run_ours(args, rank, world, local_rank):
             "config": dict(describe(args.workload, world), ticks_per_launch=ticks_per_launch),
             "scenario_ticks_per_s": value / NS,
             "active_slot_fraction": alive_all / float(units * world),  # alive objects / (scenarios x slots x ticks), SURVEY 8d
+            "certified_tick_fraction": cert_ticks / float(B * ticks),  # rank 0's shard: ticks whose link_object scan was proven away
             "e2e": {"value": e2e_value, "unit": "object-updates/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t_e2e.item()) / args.steps * 1e3,
                     "waves": args.waves},
@@ -325,6 +328,7 @@ def main():
     ap.add_argument("--waves", type=int, default=8,
                     help="scenario waves of the end-to-end leg (zrk_options.waves): the H2D copy of one wave overlaps the kernels of the others")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-certificate", action="store_true", help="A/B: always run CCP.link_object's scan (ZRK_OPT_NO_CERTIFICATE)")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

@@ -23,6 +23,7 @@
  * zrk_read_messages                Manager.give_messages            Manager.py:60-70
  * zrk_read_counts                  sum(len(messages))               main.py:171
  * zrk_read_activity                sum(len(ActiveObjectsMessage.active_objects))  AirEnv.py:50-53
+ * zrk_read_certified               (diagnostic: ticks on which CCP.link_object's scan, CCP.py:171-219, was proven away)
  * zrk_read_state                   model attributes (pos, prev_pos, current_azimuth,
  *                                  _target_dict ...)                BaseModel.py:28-36, CCP.py:80-86
  * zrk_read_status                  exception propagation            (CCP.py:259, CCP.py:107)
@@ -240,6 +241,8 @@ typedef struct zrk_options {
 } zrk_options;
 
 #define ZRK_OPT_EXACT_ONLY 1u  /* run the tick without the fp32 / squared-distance pre-filters (same results, slower) */
+#define ZRK_OPT_NO_CERTIFICATE 2u /* always run CCP.link_object's scan, even on ticks whose outcome the association
+                                     certificate proves in advance (same results, slower; for A/B measurements) */
 
 /* Caller-provided host buffers for zrk_read_state; any pointer may be NULL (skipped).
  * NS = max_targets + max_missiles slots / static indices, E = NS track entries per dict. */
@@ -287,6 +290,10 @@ int zrk_read_counts(zrk_handle *h, int64_t *counts);
  * the active_objects lists AirEnv.step published (AirEnv.py:50-53); divided by slots x ticks it is
  * the active-slot fraction of the run.  Counted modulo 2^32. */
 int zrk_read_activity(zrk_handle *h, int64_t *alive_slot_ticks);
+/* Per scenario: ticks whose CombatControlPoint.step (CCP.py:368-431) took the certified path, i.e.
+ * skipped link_object's scan because its outcome was proven in advance.  A diagnostic: results do not
+ * depend on it.  Counted modulo 2^32. */
+int zrk_read_certified(zrk_handle *h, int64_t *certified_ticks);
 /* Copy the explicit records of scenarios [s0, s1) to host: recs[(s - s0) * cap + i] for
  * i < n[s - s0], cap = zrk_log_capacity().  Records of one scenario are in emission order. */
 int zrk_read_records(zrk_handle *h, int s0, int s1, zrk_msg *recs, int32_t *n);

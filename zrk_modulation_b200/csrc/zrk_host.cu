@@ -522,7 +522,26 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
         size_t one = (size_t)d->noise_period * d->noise_radars * d->noise_objects * 3;
         size_t n = d->noise_scenario_stride ? (size_t)d->noise_scenario_stride * (B - 1) + one : one;
         if ((rc = dev_upload(h, d->noise, n, &P.noise)) != ZRK_OK) return rc;
+        // the association certificate's bound on what the radars can move an object by in one tick:
+        // sum over radars of the largest |noise vector| anywhere in the table (NaN / inf: certificate off)
+        std::vector<double> mx2((size_t)d->noise_radars, 0.0);
+        bool finite = true;
+        const size_t per_w = (size_t)d->noise_radars * d->noise_objects;
+        const int nsc = d->noise_scenario_stride ? B : 1;
+        for (int sc = 0; sc < nsc; sc++) {
+            const double *t = d->noise + (size_t)sc * d->noise_scenario_stride;
+            for (size_t i = 0; i < (size_t)d->noise_period * per_w; i++) {
+                const double x = t[3 * i], y = t[3 * i + 1], z = t[3 * i + 2], n2 = x * x + y * y + z * z;
+                if (!(n2 < 1e300)) finite = false;
+                double &m = mx2[(i % per_w) / (size_t)d->noise_objects];
+                if (n2 > m) m = n2;
+            }
+        }
+        double nb = 0.0;
+        for (double m : mx2) nb += sqrt(m) * (1.0 + 1e-12);
+        P.noise_bound = finite ? nb : -1.0;
     }
+    P.cert = (opt && (opt->flags & (ZRK_OPT_EXACT_ONLY | ZRK_OPT_NO_CERTIFICATE))) || P.noise_bound < 0 ? 0 : 1;
     if ((rc = dev_alloc(h, (size_t)B * lo.dyn_bytes, &P.dyn, true)) != ZRK_OK) return rc;
     unsigned char *cst = nullptr;
     if ((rc = dev_alloc(h, (size_t)B * lo.cst_bytes, &cst, true)) != ZRK_OK) return rc;
@@ -787,6 +806,15 @@ extern "C" int zrk_read_activity(zrk_handle *h, int64_t *alive_slot_ticks) {
     if (rc) return rc;
     for (int s = 0; s < h->P.lo.B; s++)
         alive_slot_ticks[s] = (unsigned)h->h_summary[(size_t)s * ZRK_SUMMARY_WORDS + H_ALIVE];
+    return ZRK_OK;
+}
+
+extern "C" int zrk_read_certified(zrk_handle *h, int64_t *certified_ticks) {
+    if (!h || !certified_ticks) return ZRK_ERR_ARG;
+    int rc = fetch_summary(h);
+    if (rc) return rc;
+    for (int s = 0; s < h->P.lo.B; s++)
+        certified_ticks[s] = (unsigned)h->h_summary[(size_t)s * ZRK_SUMMARY_WORDS + H_FAST];
     return ZRK_OK;
 }
 

@@ -21,7 +21,7 @@ enum { F_ALIVE = 1, F_PENDING = 2, F_HASPREV = 4, F_MISSILE = 8, F_TTYPE_SHIFT =
 // header words (ints) at dyn.hdr
 enum {
     H_TICK = 0, H_NSLOTS, H_NTE, H_NME, H_CCP_INIT, H_FAULT, H_FAULT_TICK, H_NREC,
-    H_DETN0, H_DETN1, H_MBN0, H_MBN1, H_LN, H_FREECAP, H_ALIVE /* alive slot-ticks so far (mod 2^32) */, H_TMP1, H_WORDS = 16
+    H_DETN0, H_DETN1, H_MBN0, H_MBN1, H_LN, H_FREECAP, H_ALIVE /* alive slot-ticks so far (mod 2^32) */, H_FAST /* ticks whose CCP step took the certified path */, H_WORDS = 16
 };
 enum { MB_COMMAND = 0, MB_SUCCESS = 1, MB_CANCEL = 2, MB_COUNTREQ = 3 };
 enum { ST_READY = 0, ST_ACTIVE = 1, ST_DETONATED = 2 };
@@ -83,6 +83,7 @@ ZRK_HD constexpr HotOff hot_off(int team) {
 // constants for warp teams, whose kernel is instantiated per capacity bucket.
 struct ScratchOff {
     int x_lxy, x_lzd, x_lf, x_claim, x_detlist, x_wscr, x_need, x_ghead, x_mbar;
+    int x_cin, x_cout, x_refc, x_cflag;  // association certificate (see zrk_tick.cuh): per-slot window, reference counts, dirty flag
     int bytes;
 };
 ZRK_HD constexpr int zrk_align_c(int x, int a) { return (x + a - 1) / a * a; }
@@ -98,6 +99,11 @@ ZRK_HD constexpr ScratchOff scratch_off(int team, int mp) {
     x.x_need = p; p += 4 * team;
     x.x_ghead = p; p += 4 * team;
     x.x_mbar = p; p += 8;
+    const int ct = team <= 256 ? team : 0;  // (larger teams run without the certificate)
+    x.x_cin = p; p += 4 * ct;
+    x.x_cout = p; p += 4 * ct;
+    x.x_refc = p; p += 4 * ct;
+    x.x_cflag = p; p += 8;
     x.bytes = zrk_align_c(p, 16);
     return x;
 }
@@ -146,6 +152,7 @@ struct Layout {
     int x_claim, x_detlist, x_wscr, x_need;  // x_need doubles as the launch result (x_ok)
     int x_ghead;       // int[TEAM]: bucket heads of the hash grid over the entries' link positions
     int x_mbar;            // one 8-byte mbarrier: completion of the bulk (TMA) load of the state
+    int x_cin, x_cout, x_refc, x_cflag;  // int[TEAM] x 3 + one flag word: the association certificate
     int team_smem_bytes;
 };
 
@@ -159,6 +166,9 @@ struct Params {
     int mask_ticks, mask_words;  // words per mask row; a tick's row set is (1 + R) rows
     int noise_period, noise_radars, noise_objects;
     long long noise_stride;
+    double noise_bound;  // upper bound of the displacement the radars' noise can give an object in one tick (sum over radars of the
+                         // largest |noise vector| of the table); < 0 = unknown: the association certificate is off
+    int cert;            // association certificate enabled (zrk_tick.cuh)
     unsigned char *dyn;
     const unsigned char *cst;
     zrk_msg *rec;
@@ -227,6 +237,7 @@ static inline Layout make_layout(int B, int T, int M, int R, int L, int C) {
         o.x_lxy = x.x_lxy - x.bytes; o.x_lzd = x.x_lzd - x.bytes; o.x_lf = x.x_lf - x.bytes;
         o.x_claim = x.x_claim - x.bytes; o.x_detlist = x.x_detlist - x.bytes; o.x_wscr = x.x_wscr - x.bytes;
         o.x_need = x.x_need - x.bytes; o.x_ghead = x.x_ghead - x.bytes; o.x_mbar = x.x_mbar - x.bytes;
+        o.x_cin = x.x_cin - x.bytes; o.x_cout = x.x_cout - x.bytes; o.x_refc = x.x_refc - x.bytes; o.x_cflag = x.x_cflag - x.bytes;
         o.team_smem_bytes = zrk_align(x.bytes + o.dyn_bytes + o.cst_bytes, 16);
     }
     return o;

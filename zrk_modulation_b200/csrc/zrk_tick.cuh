@@ -117,7 +117,7 @@ __device__ __forceinline__ bool radar_sees(double dx, double dy, double dz, cons
         const float M = 1e-2f;  // decision margin in degrees, 10x the approximation error
         const double d2 = dot3(dx, dy, dz, dx, dy, dz);
         if (d2 > par[9]) return false;  // certainly farther than max_distance
-        bool sure_in = d2 <= par[8], sure_out = false, ok = true;
+        bool sure_in = d2 > 0.0 && d2 <= par[8], sure_out = false, ok = true;  // (an object AT the radar: arcsin(0/0) is NaN, exact path)
         const float fx = (float)dx, fy = (float)dy, fz = (float)dz;
         // azimuth % 360 lies in [0, 360]: a sector covering all of it needs no angle at all
         if (!(az_lo <= 0.0 && az_hi >= 360.0)) {
@@ -178,6 +178,7 @@ __device__ __forceinline__ void stage_in(unsigned char *sm, const unsigned char 
     }
 }
 __device__ __forceinline__ void stage_wait(void *) {}
+__device__ __forceinline__ void stage_fence() {}
 __device__ __forceinline__ void stage_out(unsigned char *g_dyn, const unsigned char *sm, int dyn_bytes, bool leader) {
     if (leader) memcpy(g_dyn, sm, (size_t)dyn_bytes);
 }
@@ -214,9 +215,12 @@ __device__ __forceinline__ void stage_wait(void *mbar) {
     }
     __trap();
 }
+// every lane that wrote the blob through the generic proxy fences before the team's last barrier ...
+__device__ __forceinline__ void stage_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// ... and the leader then issues the one bulk store
 __device__ __forceinline__ void stage_out(unsigned char *g_dyn, const unsigned char *sm, int dyn_bytes, bool leader) {
     if (leader) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g_dyn), "r"(smem_addr(sm)), "r"(dyn_bytes)
                      : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -798,6 +802,134 @@ __device__ __forceinline__ bool link_f32_ok(float x, float y, float z) {
     return fabsf(x) + fabsf(y) + fabsf(z) <= (float)ZRK_F32_COORD_MAX;
 }
 
+// ------------------------------------------------------------------ association certificate
+//
+// Nearly every tick of nearly every scenario is "quiet": each detection re-acquires the track that
+// followed its own slot last tick (CCP.link_object returns that entry), nothing is appended and
+// nothing can be launched.  link_object still scans every track to find that out — O(detections x
+// tracks) distance tests, the dominant cost of the tick.  The certificate proves the outcome of the
+// scan without running it.
+//
+// Every air object flies a straight line from the tick it is created (Trajectory.get_pos,
+// AirObject.py:23-25; mid-course retargeting is dead code), a radar moves it by at
+// most `nb` metres per tick (sum over radars of the largest |noise vector| of the table), and the
+// position link_object measures a track to is the tracked object's previous position
+// (CCP.py:181-183).  So for the detection of slot i at tick t, with c(.) the noise-free positions:
+//     distance to its own track     = |p_i(t) - p_i(t-1)|               <= |v_i| dt + 2 nb
+//     distance to a track on slot j >= |c_j(t) - c_i(t)| - |v_j| dt - 2 nb   (j moving)
+//                                   >= |F_j - c_i(t)| - nb                   (j removed or not yet born: frozen at F_j)
+// and the own track is strictly the nearest whenever |c_j(t) - c_i(t)| > R_ij = (|v_i| + |v_j|) dt + 6 nb
+// + slack for every other slot j (the extra 2 nb: the quadratic below starts from the current noisy
+// positions).  cert_recompute solves |dp + dv tau| <= R_ij for every j in fp64 and keeps, per slot,
+// the first window of ticks [cin, cout] in which some pair is that close: the slot is "certified"
+// while tick < cin and looks again once tick > cout.  Anything that changes the picture — a launch,
+// a birth, a removal, a track changing hands or being created — clears all windows (x_cflag); ticks
+// on which that happens and detections that are not certified take the ordinary scan, so the
+// certificate can only ever skip work, never change a result.
+#define ZRK_CERT_NEVER 0x3fffffff
+template <int TEAM>
+__device__ __forceinline__ void team_barrier() {
+    if (TEAM == 32) {
+        __syncwarp();
+    } else {
+        __syncthreads();
+    }
+}
+// All lanes of the team call this together.  full: after a structural change — also recount how many
+// tracks refer to each slot (a slot followed by two tracks measures the same distance to both: never
+// certified); otherwise only the lanes whose window has passed look again.
+template <int TEAM>
+__device__ ZRK_NOINLINE void cert_recompute(unsigned char *sm, const int *me_ref, int lane, int n_slots, int tick, int n_te,
+                                            int n_me, bool full, double dt_s, double nb, int *cin, int *cout, int *refc) {
+    Hot<TEAM> H;
+    H.sm = sm;
+    if (full) {
+        refc[lane] = 0;
+        team_barrier<TEAM>();
+        if (lane < n_te) atomicAdd(&refc[H.te_ref()[lane]], 1);
+        if (lane < n_me) atomicAdd(&refc[me_ref[lane]], 1);
+        team_barrier<TEAM>();
+    }
+    const int fl = lane < n_slots ? H.sflags()[lane] : 0;
+    if (!(fl & F_ALIVE)) {
+        if (full) {
+            cin[lane] = ZRK_CERT_NEVER;
+            cout[lane] = ZRK_CERT_NEVER;
+        }
+        return;
+    }
+    if (!full && !(cout[lane] < tick)) return;
+    int best_in = ZRK_CERT_NEVER, best_out = ZRK_CERT_NEVER;
+    if (refc[lane] != 1) {  // untracked, or followed by several tracks: not certifiable until the next structural change
+        best_in = 0;
+    } else if (!(fl & F_HASPREV)) {
+        best_in = 0;
+        best_out = tick;
+    } else {
+        const double2 pi = H.pxy()[lane], zi = H.pzs()[lane], vi = H.vxy()[lane];
+        const double viz = H.qzw()[lane].y, spi = fabs(zi.y);
+        for (int j = 0; j < n_slots; j++) {
+            if (j == lane) continue;
+            const int flj = H.sflags()[j];
+            double bx, by, bz, ux, uy, uz, spj;
+            if (flj & F_ALIVE) {
+                if (!(flj & F_HASPREV)) {  // (its first tick: its tracks still measure to an older position)
+                    best_in = 0;
+                    best_out = tick;
+                    break;
+                }
+                const double2 pj = H.pxy()[j], zj = H.pzs()[j], vj = H.vxy()[j];
+                bx = pj.x - pi.x, by = pj.y - pi.y, bz = zj.x - zi.x;
+                ux = vj.x - vi.x, uy = vj.y - vi.y, uz = H.qzw()[j].y - viz;
+                spj = fabs(zj.y);
+            } else {
+                double fx, fy, fz;
+                if (flj & F_PENDING) {  // on the launcher until NEW_MISSILE is consumed (its track measures to pos)
+                    fx = H.pxy()[j].x, fy = H.pxy()[j].y, fz = H.pzs()[j].x;
+                } else if (flj & F_HASPREV) {  // removed: prev_pos stays what it was
+                    fx = H.qxy()[j].x, fy = H.qxy()[j].y, fz = H.qzw()[j].x;
+                } else {
+                    best_in = 0;
+                    break;
+                }
+                bx = fx - pi.x, by = fy - pi.y, bz = fz - zi.x;
+                ux = -vi.x, uy = -vi.y, uz = -viz;
+                spj = 0.0;
+            }
+            const double R = ((spi + spj) * dt_s * 1.000000001 + 6.0 * nb + 1.0) * 1.000001;
+            const double a = dot3(ux, uy, uz, ux, uy, uz), bq = dot3(bx, by, bz, ux, uy, uz);
+            const double c = dot3(bx, by, bz, bx, by, bz) - R * R;
+            const double disc = bq * bq - a * c;
+            if (c > 0 && (bq >= 0 || disc < 0)) continue;  // never within R of each other from now on
+            int kin = 0, kout = ZRK_CERT_NEVER;            // (also what every NaN ends up with)
+            if (a > 0 && disc >= 0) {
+                const double sq = sqrt(disc);
+                const double qo = (-bq + sq) / a / dt_s;
+                if (qo < 1e9) kout = tick + (int)qo + 2;
+                if (c > 0) {  // approaching: within R during [tin, tout], both ahead
+                    const double qi = (-bq - sq) / a / dt_s;
+                    kin = ZRK_CERT_NEVER;
+                    if (qi < 1e9) {
+                        const int k = (int)qi - 1;
+                        kin = tick + (k > 0 ? k : 0);
+                    }
+                    if (!(qi >= 0)) kin = 0;
+                }
+            }
+            if (kin > ZRK_CERT_NEVER) kin = ZRK_CERT_NEVER;
+            if (kout > ZRK_CERT_NEVER) kout = ZRK_CERT_NEVER;
+            if (kin < best_in) {
+                best_in = kin;
+                best_out = kout;
+            } else if (kin == best_in && kout > best_out) {
+                best_out = kout;
+            }
+        }
+    }
+    cin[lane] = best_in;
+    cout[lane] = best_out;
+}
+
 // ------------------------------------------------------------------ lane 0 alone: launchers + CCP bookkeeping
 
 // MissileLauncher.step for every launcher (MissileLauncher.py:82-138) and the CCP's first-tick
@@ -996,6 +1128,12 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
     double2 *lxy = (double2 *)(sm + ZRK_X(x_lxy)), *lzd = (double2 *)(sm + ZRK_X(x_lzd));
     float *lf = (float *)(sm + ZRK_X(x_lf));
     int *ghead = (int *)(sm + ZRK_X(x_ghead));
+    // association certificate (teams up to 256 slots: the pair loop is O(slots) per lane)
+    constexpr bool CERT = FAST && TEAM <= 256;
+    int *const c_in = (int *)(sm + ZRK_X(x_cin)), *const c_out = (int *)(sm + ZRK_X(x_cout));
+    int *const c_flag = (int *)(sm + ZRK_X(x_cflag));
+    const bool use_cert = CERT && P.cert && n_ticks >= 4;  // (windows live in scratch: a short launch would only pay for them)
+    if (CERT && lane == 0) *c_flag = 1;  // nothing is known yet
 
     // ---- prologue: HBM -> shared memory, one bulk copy per blob
     {
@@ -1038,8 +1176,10 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
         int fl = 0, my_id = 0;
         double px = 0, py = 0, pz = 0;
         double nz0 = 0, nz1 = 0, nz2 = 0;  // radar 0's noise for this slot, fetched early
+        bool odd = false;  // a slot whose tracks do not follow the certificate's model this tick (not yet born / first tick)
         if (lane < n_slots) {
             fl = H.sflags()[lane];
+            odd = (fl & F_PENDING) != 0;
             my_id = H.sid()[lane];
             if (noise && nR) {
                 const double *nz = noise + (size_t)noise_w * noise_row + (fl >> F_STATIC_SHIFT) * 3;
@@ -1081,6 +1221,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
             H.sflags()[lane] = fl;
         }
         const bool alive = (fl & F_ALIVE) != 0;
+        odd = odd || (alive && !(fl & F_HASPREV));
         {  // activity counter: alive slots summed over the ticks started (the "active-slot fraction" of a run)
             const unsigned live = __ballot_sync(ZRK_FULL, alive);
             if (TEAM == 32) {
@@ -1089,7 +1230,16 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 atomicAdd(&hdr[H_ALIVE], __popc(live));
             }
         }
-        tm.sync();
+        // A tick on which the certificate's model does not hold: removals, launcher / CCP bookkeeping, a
+        // missile between launch and its first step, an object on its first tick.  (uniform)
+        bool event = true;
+        if (use_cert) {
+            event = det_prev != 0 || mb_prev != 0 || (has_ccp && !hdr[H_CCP_INIT]);
+            event = tm.any(odd) || event;  // (a team larger than a warp: this is the barrier that ends AirEnv.step)
+            if (TEAM == 32) tm.sync();
+        } else {
+            tm.sync();
+        }
 
         // Missile.step, status 'active' (Missile.py:162-193), in slot order
         {
@@ -1195,7 +1345,26 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 H.counts()[ZRK_MSG_DESTROYED_MISSILE] += nR * det_prev;
             }
         }
-        tm.sync();
+        // Certificate upkeep: an event tick clears every window; otherwise the lanes whose window has
+        // passed (all of them after an event) look again.  The vote is the barrier that ends the radars.
+        bool cert_ok = false;  // this tick may take the certified CCP path (uniform)
+        if (CERT && use_cert && !event && has_ccp) {
+            const bool again = tm.any(alive && c_out[lane] < tick) || *c_flag != 0;
+            if (TEAM == 32) tm.sync();
+            if (again) {
+                const bool full = *c_flag != 0;
+                cert_recompute<TEAM>(sm, ZRK_ME_I(me_ref), lane, n_slots, tick, hdr[H_NTE], hdr[H_NME], full, P.dt_s,
+                                     P.noise_bound, c_in, c_out, (int *)(sm + ZRK_X(x_refc)));
+                if (full) {
+                    tm.sync();  // everybody has read the flag
+                    if (lane == 0) *c_flag = 0;
+                }
+            }
+            cert_ok = true;
+        } else {
+            if (CERT && use_cert && lane == 0) *c_flag = 1;
+            tm.sync();
+        }
 
         // ============ lane 0: sector sweep, MissileLauncher.step, CCP bookkeeping
         if (lane == 0) {
@@ -1223,6 +1392,81 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
         if (has_ccp && !(hdr[H_FAULT] & 63)) {
             int n_te = hdr[H_NTE];
             const int n_me = hdr[H_NME];
+            // ---- certified path: every detection provably re-acquires the track of its own slot (see
+            // "association certificate" above), so link_object's scan, the processing order and the conflict
+            // rounds are skipped: evaluate the own track exactly, stamp it, count the messages.
+            bool fast_done = false;
+            if (CERT && cert_ok && (TEAM == 32 || !logged(P, ZRK_MSG_CCP_UPDATE_TARGET))) {
+                const bool det = alive && rf >= 0;
+                bool okc = true, is_me = false, follow = false;
+                int e = 0;
+                if (det) {
+                    const int seed = H.own()[lane];
+                    okc = seed >= 0 && (fl & F_HASPREV) && tick < c_in[lane];
+                    if (okc) {
+                        is_me = seed >= TEAM;
+                        e = is_me ? seed - TEAM : seed;
+                        const int ref = is_me ? ZRK_ME_I(me_ref)[e] : H.te_ref()[e];
+                        const double upds = is_me ? ZRK_ME_D(me_upds)[e] : H.te_upds()[e];
+                        follow = is_me || H.te_follow()[e] != 0;
+                        // the own track measures to this slot's prev_pos: the same d2 link_d2 computes
+                        const double2 q = H.qxy()[lane];
+                        const double qz = H.qzw()[lane].x, speed = H.pzs()[lane].y;
+                        const double ex = q.x - px, ey = q.y - py, ez = qz - pz;
+                        const double d2 = dot3(ex, ey, ez, ex, ey, ez);
+                        double lo, hi;
+                        calc_range(speed, now_s - upds, P.range_step, lo, hi);
+                        const double EPS = 4e-15;  // as link_eval: inside [lo, hi] beyond doubt
+                        const double l2 = lo * lo, h2 = hi * hi;
+                        const bool in_sure = d2 >= l2 * (1.0 + EPS) && d2 <= h2 * (1.0 - EPS);
+                        // the certificate's premise on the own track's distance, checked rather than assumed
+                        const double dm = fabs(speed) * P.dt_s * 1.000000001 + 2.0 * P.noise_bound + 1e-3;
+                        // a target nobody follows yet would ask for a launch while capacity is left (CCP.py:332-348)
+                        okc = ref == lane && in_sure && d2 <= dm * dm && (follow || hdr[H_FREECAP] <= 0);
+                    }
+                }
+                if (!tm.any(det && !okc)) {
+                    const bool upd_msg = det && !is_me && follow;  // old_target, followed: CCP_UPDATE_TARGET (CCP.py:350-357)
+                    const bool lu = logged(P, ZRK_MSG_CCP_UPDATE_TARGET);
+                    int r_upd = 0, n_upd = 0;
+                    if (TEAM == 32) {
+                        if (lu) {  // message order = detection order: first radar that saw the object, then slot
+                            for (int r = 0; r < nR; r++) {
+                                int tot;
+                                const int ex_ = tm.rank(upd_msg && rf == r, tot);
+                                if (rf == r) r_upd = n_upd + ex_;
+                                n_upd += tot;
+                            }
+                        } else {
+                            n_upd = __popc(__ballot_sync(ZRK_FULL, upd_msg));
+                        }
+                        if (lane == 0) {
+                            H.counts()[ZRK_MSG_CCP_UPDATE_TARGET] += (unsigned)n_upd;
+                            hdr[H_FAST] += 1;
+                        }
+                    } else {
+                        const int c = __popc(__ballot_sync(ZRK_FULL, upd_msg));
+                        if ((lane & 31) == 0 && c) atomicAdd((int *)&H.counts()[ZRK_MSG_CCP_UPDATE_TARGET], c);
+                        if (lane == 0) hdr[H_FAST] += 1;
+                    }
+                    if (det) {
+                        if (!is_me) {
+                            if (upd_msg && lu)
+                                put_rec(P, rec, nrec + r_upd, tick, ZRK_MSG_CCP_UPDATE_TARGET, 0, ccp_id, ZRK_CST_I(c_rad_id)[rf], my_id,
+                                        H.te_mid()[e], 0, 0, 0);
+                            H.te_upd()[e] = tick;
+                            H.te_upds()[e] = now_s;
+                        } else {
+                            ZRK_ME_I(me_upd)[e] = tick;
+                            ZRK_ME_D(me_upds)[e] = now_s;
+                        }
+                    }
+                    if (lu) nrec += n_upd;
+                    fast_done = true;
+                }
+            }
+            if (!fast_done) {
+            bool structural = false;  // this tick's rounds went beyond re-stamping own tracks
             // what link_object measures to, per entry: prev_pos of the tracked object (or pos
             // for a missile whose prev_pos is None) and d_t = now - upd_time
             // the hash grid pays off once a scan is long; warp-sized scenarios scan their few entries directly
@@ -1381,6 +1625,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                         break;
                     }
                 }
+                structural = true;
                 // a detection is final once no earlier unresolved detection touches the same entry
                 bool conflict;
                 if (TEAM == 32) {
@@ -1511,6 +1756,8 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 lo_rank = istar;
                 tm.sync();  // entry updates of this round are visible to the next
             }
+            if (CERT && structural && lane == 0) *c_flag = 1;  // tracks changed hands or were created: windows are void
+            }  // !fast_done
             tm.sync();
 
             // ============ send_objects_to_GUI (CCP.py:237-284)
@@ -1586,6 +1833,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
     }
 
     // ---- epilogue: shared memory -> HBM, one bulk copy
+    stage_fence();
     tm.sync();
     stage_out(P.dyn + (size_t)b * o.dyn_bytes, sm, o.dyn_bytes, lane == 0);
 }

@@ -25,7 +25,7 @@ class Engine:
 
     def __init__(self, batch: Batch, log_types: int = _cabi.LOG_EVENTS, log_capacity: int = 0,
                  mask_ticks: int = 0, ticks_per_launch: int = 0, device: int = 0, exact_only: bool = False,
-                 waves: int = 0, lib=None):
+                 waves: int = 0, certificate: bool = True, lib=None):
         self.lib = lib if lib is not None else _cabi.load()
         self.batch = batch
         self._h = C.c_void_p()
@@ -35,7 +35,7 @@ class Engine:
         opt.log_capacity = log_capacity
         opt.mask_ticks = mask_ticks
         opt.ticks_per_launch = ticks_per_launch
-        opt.flags = _cabi.OPT_EXACT_ONLY if exact_only else 0
+        opt.flags = (_cabi.OPT_EXACT_ONLY if exact_only else 0) | (0 if certificate else _cabi.OPT_NO_CERTIFICATE)
         opt.waves = waves  # > 1: upload / init / step in scenario waves on separate streams (see zrk_options.waves)
         self.log_types = log_types
         desc = batch.desc()
@@ -99,6 +99,13 @@ class Engine:
         active_objects lists AirEnv.step published)."""
         a = np.zeros(self.batch.n_scenarios, dtype=np.int64)
         self._ck(self.lib.zrk_read_activity(self._h, a.ctypes.data_as(C.POINTER(C.c_int64))))
+        return a
+
+    def certified_ticks(self) -> np.ndarray:
+        """Per scenario: ticks whose CCP step skipped link_object's scan because the association
+        certificate proved its outcome (a diagnostic; results do not depend on it)."""
+        a = np.zeros(self.batch.n_scenarios, dtype=np.int64)
+        self._ck(self.lib.zrk_read_certified(self._h, a.ctypes.data_as(C.POINTER(C.c_int64))))
         return a
 
     def log_capacity(self) -> int:

@@ -835,32 +835,47 @@ __device__ __forceinline__ void team_barrier() {
         __syncthreads();
     }
 }
-// All lanes of the team call this together.  full: after a structural change — also recount how many
-// tracks refer to each slot (a slot followed by two tracks measures the same distance to both: never
-// certified); otherwise only the lanes whose window has passed look again.
+// All lanes of the team call this together.  It recounts how many tracks refer to each slot (a slot
+// followed by two tracks measures the same distance to both: never certified) and rebuilds every
+// window.  Nearly all pairs never come near each other: they are dismissed by an fp32 evaluation of
+// the quadratic whose margins (1e-4 relative, 2 m) are far wider than its rounding errors; the
+// others are solved in fp64.  fp / fv: scratch for the fp32 images (position + speed, velocity).
 template <int TEAM>
 __device__ ZRK_NOINLINE void cert_recompute(unsigned char *sm, const int *me_ref, int lane, int n_slots, int tick, int n_te,
-                                            int n_me, bool full, double dt_s, double nb, int *cin, int *cout, int *refc) {
+                                            int n_me, double dt_s, double nb, int *cin, int *cout, int *refc, float4 *fp,
+                                            float4 *fv) {
     Hot<TEAM> H;
     H.sm = sm;
-    if (full) {
-        refc[lane] = 0;
-        team_barrier<TEAM>();
-        if (lane < n_te) atomicAdd(&refc[H.te_ref()[lane]], 1);
-        if (lane < n_me) atomicAdd(&refc[me_ref[lane]], 1);
-        team_barrier<TEAM>();
-    }
+    refc[lane] = 0;
     const int fl = lane < n_slots ? H.sflags()[lane] : 0;
-    if (!(fl & F_ALIVE)) {
-        if (full) {
-            cin[lane] = ZRK_CERT_NEVER;
-            cout[lane] = ZRK_CERT_NEVER;
+    {   // this slot as the others see it: where its tracks measure to, and how that moves
+        const float qn = __int_as_float(0x7fc00000);
+        float4 p4 = make_float4(qn, qn, qn, 0.f), v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((fl & F_ALIVE) && (fl & F_HASPREV)) {
+            const double2 a = H.pxy()[lane], z = H.pzs()[lane], v = H.vxy()[lane];
+            p4 = make_float4((float)a.x, (float)a.y, (float)z.x, fabsf((float)z.y) * 1.000001f);
+            v4 = make_float4((float)v.x, (float)v.y, (float)H.qzw()[lane].y, 0.f);
+        } else if (!(fl & F_ALIVE) && (fl & F_PENDING)) {
+            p4 = make_float4((float)H.pxy()[lane].x, (float)H.pxy()[lane].y, (float)H.pzs()[lane].x, 0.f);
+        } else if (!(fl & F_ALIVE) && (fl & F_HASPREV)) {
+            p4 = make_float4((float)H.qxy()[lane].x, (float)H.qxy()[lane].y, (float)H.qzw()[lane].x, 0.f);
         }
+        if (lane < n_slots) {
+            fp[lane] = p4;
+            fv[lane] = v4;
+        }
+    }
+    team_barrier<TEAM>();
+    if (lane < n_te) atomicAdd(&refc[H.te_ref()[lane]], 1);
+    if (lane < n_me) atomicAdd(&refc[me_ref[lane]], 1);
+    team_barrier<TEAM>();
+    if (!(fl & F_ALIVE)) {
+        cin[lane] = ZRK_CERT_NEVER;
+        cout[lane] = ZRK_CERT_NEVER;
         return;
     }
-    if (!full && !(cout[lane] < tick)) return;
     int best_in = ZRK_CERT_NEVER, best_out = ZRK_CERT_NEVER;
-    if (refc[lane] != 1) {  // untracked, or followed by several tracks: not certifiable until the next structural change
+    if (refc[lane] != 1) {  // untracked, or followed by several tracks: not certifiable until the tracks change
         best_in = 0;
     } else if (!(fl & F_HASPREV)) {
         best_in = 0;
@@ -868,8 +883,20 @@ __device__ ZRK_NOINLINE void cert_recompute(unsigned char *sm, const int *me_ref
     } else {
         const double2 pi = H.pxy()[lane], zi = H.pzs()[lane], vi = H.vxy()[lane];
         const double viz = H.qzw()[lane].y, spi = fabs(zi.y);
+        const float4 fpi = fp[lane], fvi = fv[lane];
+        const float fdt = (float)dt_s * 1.000001f, fnb = 6.0f * (float)nb * 1.000001f + 3.0f;
         for (int j = 0; j < n_slots; j++) {
             if (j == lane) continue;
+            {   // fp32: never within R of each other from now on?
+                const float4 pj = fp[j], vj = fv[j];
+                const float bx = pj.x - fpi.x, by = pj.y - fpi.y, bz = pj.z - fpi.z;
+                const float ux = vj.x - fvi.x, uy = vj.y - fvi.y, uz = vj.z - fvi.z;
+                const float R = fmaf(fpi.w + pj.w, fdt, fnb) * 1.0001f;
+                const float a = fmaf(uz, uz, fmaf(uy, uy, ux * ux)), bq = fmaf(bz, uz, fmaf(by, uy, bx * ux));
+                const float p2 = fmaf(bz, bz, fmaf(by, by, bx * bx)), c = fmaf(-R, R, p2);
+                const float b2 = bq * bq;
+                if (c > 1e-4f * p2 && (bq >= 0.f || fmaf(-a, c, b2) < -1e-4f * fmaf(a, p2, b2))) continue;
+            }
             const int flj = H.sflags()[j];
             double bx, by, bz, ux, uy, uz, spj;
             if (flj & F_ALIVE) {
@@ -903,17 +930,16 @@ __device__ ZRK_NOINLINE void cert_recompute(unsigned char *sm, const int *me_ref
             if (c > 0 && (bq >= 0 || disc < 0)) continue;  // never within R of each other from now on
             int kin = 0, kout = ZRK_CERT_NEVER;            // (also what every NaN ends up with)
             if (a > 0 && disc >= 0) {
-                const double sq = sqrt(disc);
-                const double qo = (-bq + sq) / a / dt_s;
-                if (qo < 1e9) kout = tick + (int)qo + 2;
-                if (c > 0) {  // approaching: within R during [tin, tout], both ahead
-                    const double qi = (-bq - sq) / a / dt_s;
+                // within R for tau in [tin, tout]; tick + k is tau = k dt away (the clock table deviates from
+                // that by rounding only, which the 1e-9 relative + 1e-6 absolute allowance swallows)
+                const double sq = sqrt(disc), ia = 1.0 / (a * dt_s);
+                const double qo = (-bq + sq) * ia * 1.000000001 + 1e-6;
+                if (qo < 1e9) kout = tick + (int)qo;  // the last tick inside
+                if (c > 0) {                          // approaching: tin is ahead; ticks k < tin / dt are outside
+                    const double qi = (-bq - sq) * ia * 0.999999999 - 1e-6;
                     kin = ZRK_CERT_NEVER;
-                    if (qi < 1e9) {
-                        const int k = (int)qi - 1;
-                        kin = tick + (k > 0 ? k : 0);
-                    }
-                    if (!(qi >= 0)) kin = 0;
+                    if (qi < 1e9) kin = tick + (qi > 0 ? (int)qi + 1 : 0);
+                    if (!(qi >= -1.0)) kin = 0;  // (NaN)
                 }
             }
             if (kin > ZRK_CERT_NEVER) kin = ZRK_CERT_NEVER;
@@ -1230,11 +1256,13 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 atomicAdd(&hdr[H_ALIVE], __popc(live));
             }
         }
-        // A tick on which the certificate's model does not hold: removals, launcher / CCP bookkeeping, a
-        // missile between launch and its first step, an object on its first tick.  (uniform)
+        // A tick on which the certificate's model does not hold: launcher / CCP bookkeeping, a missile
+        // between launch and its first step, an object on its first tick.  (uniform)  A removal is not one:
+        // the removed objects' tracks stay where they were from this very tick on, so the windows are rebuilt
+        // now and the tick goes on as usual.
         bool event = true;
         if (use_cert) {
-            event = det_prev != 0 || mb_prev != 0 || (has_ccp && !hdr[H_CCP_INIT]);
+            event = mb_prev != 0 || (has_ccp && !hdr[H_CCP_INIT]);
             event = tm.any(odd) || event;  // (a team larger than a warp: this is the barrier that ends AirEnv.step)
             if (TEAM == 32) tm.sync();
         } else {
@@ -1349,16 +1377,15 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
         // passed (all of them after an event) look again.  The vote is the barrier that ends the radars.
         bool cert_ok = false;  // this tick may take the certified CCP path (uniform)
         if (CERT && use_cert && !event && has_ccp) {
-            const bool again = tm.any(alive && c_out[lane] < tick) || *c_flag != 0;
+            // (windows that have passed are looked at again every 16th tick: until then their slots are
+            // merely not certified, which costs them a check against every track but is always right)
+            const bool stale = tm.any((tick & 15) == 0 && alive && c_out[lane] < tick);
             if (TEAM == 32) tm.sync();
-            if (again) {
-                const bool full = *c_flag != 0;
-                cert_recompute<TEAM>(sm, ZRK_ME_I(me_ref), lane, n_slots, tick, hdr[H_NTE], hdr[H_NME], full, P.dt_s,
-                                     P.noise_bound, c_in, c_out, (int *)(sm + ZRK_X(x_refc)));
-                if (full) {
-                    tm.sync();  // everybody has read the flag
-                    if (lane == 0) *c_flag = 0;
-                }
+            if (*c_flag != 0 || det_prev != 0 || stale) {
+                cert_recompute<TEAM>(sm, ZRK_ME_I(me_ref), lane, n_slots, tick, hdr[H_NTE], hdr[H_NME], P.dt_s, P.noise_bound,
+                                     c_in, c_out, (int *)(sm + ZRK_X(x_refc)), (float4 *)lxy, (float4 *)lzd);
+                tm.sync();  // everybody has read the flag
+                if (lane == 0) *c_flag = 0;
             }
             cert_ok = true;
         } else {
@@ -1398,12 +1425,14 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
             bool fast_done = false;
             if (CERT && cert_ok && (TEAM == 32 || !logged(P, ZRK_MSG_CCP_UPDATE_TARGET))) {
                 const bool det = alive && rf >= 0;
-                bool okc = true, is_me = false, follow = false;
+                // hard: this detection needs the ordinary rounds (no own track, out of its range, a launch to
+                // decide); doubt: its own track is fine but not certified to be the nearest
+                bool hard = false, doubt = false, is_me = false, follow = false;
                 int e = 0;
                 if (det) {
                     const int seed = H.own()[lane];
-                    okc = seed >= 0 && (fl & F_HASPREV) && tick < c_in[lane];
-                    if (okc) {
+                    hard = !(seed >= 0 && (fl & F_HASPREV));
+                    if (!hard) {
                         is_me = seed >= TEAM;
                         e = is_me ? seed - TEAM : seed;
                         const int ref = is_me ? ZRK_ME_I(me_ref)[e] : H.te_ref()[e];
@@ -1419,13 +1448,56 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                         const double EPS = 4e-15;  // as link_eval: inside [lo, hi] beyond doubt
                         const double l2 = lo * lo, h2 = hi * hi;
                         const bool in_sure = d2 >= l2 * (1.0 + EPS) && d2 <= h2 * (1.0 - EPS);
-                        // the certificate's premise on the own track's distance, checked rather than assumed
-                        const double dm = fabs(speed) * P.dt_s * 1.000000001 + 2.0 * P.noise_bound + 1e-3;
                         // a target nobody follows yet would ask for a launch while capacity is left (CCP.py:332-348)
-                        okc = ref == lane && in_sure && d2 <= dm * dm && (follow || hdr[H_FREECAP] <= 0);
+                        hard = !(ref == lane && in_sure && (follow || hdr[H_FREECAP] <= 0));
+                        // the certificate's premise on the own track's distance is checked rather than assumed
+                        const double dm = fabs(speed) * P.dt_s * 1.000000001 + 2.0 * P.noise_bound + 1e-3;
+                        doubt = !(tick < c_in[lane] && d2 <= dm * dm);
                     }
                 }
-                if (!tm.any(det && !okc)) {
+                bool slow;
+                if (TEAM == 32) {
+                    slow = __ballot_sync(ZRK_FULL, hard) != 0;
+                    const unsigned dmask = __ballot_sync(ZRK_FULL, doubt);
+                    if (!slow && dmask) {
+                        // The few uncertified detections are checked against every track, all lanes at once
+                        // (lane k: _target_dict entry k and _missile_dict entry k): is any other track as
+                        // near as the own one?  If so the ordinary scan decides; if not, link_object returns
+                        // the own track (the nearest one in range).
+                        const bool hte = lane < n_te, hme = lane < n_me;
+                        double tx = 0, ty = 0, tz = 0, mx = 0, my = 0, mz = 0;
+                        if (hte) {
+                            const int ref = H.te_ref()[lane];
+                            tx = H.qxy()[ref].x, ty = H.qxy()[ref].y, tz = H.qzw()[ref].x;
+                        }
+                        if (hme) {
+                            const int ref = ZRK_ME_I(me_ref)[lane];
+                            const bool hp = (H.sflags()[ref] & F_HASPREV) != 0;
+                            mx = hp ? H.qxy()[ref].x : H.pxy()[ref].x, my = hp ? H.qxy()[ref].y : H.pxy()[ref].y;
+                            mz = hp ? H.qzw()[ref].x : H.pzs()[ref].x;
+                        }
+                        bool rival = false;
+                        for (unsigned m = dmask; m; m &= m - 1) {
+                            const int d = __ffs(m) - 1, sd = H.own()[d];
+                            const double2 p = H.pxy()[d], q = H.qxy()[d];
+                            const double pz_ = H.pzs()[d].x, qz_ = H.qzw()[d].x;
+                            const double ox = q.x - p.x, oy = q.y - p.y, oz = qz_ - pz_;
+                            const double thr = dot3(ox, oy, oz, ox, oy, oz) * (1.0 + 1e-12);
+                            if (hte && lane != sd) {
+                                const double ax = tx - p.x, ay = ty - p.y, az = tz - pz_;
+                                rival = rival || !(dot3(ax, ay, az, ax, ay, az) > thr);
+                            }
+                            if (hme && TEAM + lane != sd) {
+                                const double ax = mx - p.x, ay = my - p.y, az = mz - pz_;
+                                rival = rival || !(dot3(ax, ay, az, ax, ay, az) > thr);
+                            }
+                        }
+                        slow = __ballot_sync(ZRK_FULL, rival) != 0;
+                    }
+                } else {
+                    slow = tm.any(hard || doubt);
+                }
+                if (!slow) {
                     const bool upd_msg = det && !is_me && follow;  // old_target, followed: CCP_UPDATE_TARGET (CCP.py:350-357)
                     const bool lu = logged(P, ZRK_MSG_CCP_UPDATE_TARGET);
                     int r_upd = 0, n_upd = 0;

@@ -435,7 +435,18 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
         h->err = "missing array in zrk_batch_desc";
         return ZRK_ERR_ARG;
     }
-    Layout lo = make_layout(B, T, M, R, L, C);
+    int ns_used = 0, m_used = 0;  // what the scenarios really have (the maxima may be padding)
+    for (int b = 0; b < B; b++) {
+        const int nt = d->n_targets ? d->n_targets[b] : T, nm = d->n_missiles ? d->n_missiles[b] : M;
+        if (nt >= 0 && nt <= T && nm >= 0 && nm <= M) {  // (anything else is reported by the init kernel)
+            ns_used = std::max(ns_used, nt + nm);
+            m_used = std::max(m_used, nm);
+        } else {
+            ns_used = T + M;
+            m_used = M;
+        }
+    }
+    Layout lo = make_layout(B, T, M, R, L, C, ns_used, m_used);
     if (!lo.team || T + M > 1024 || M > 1023) {
         h->err = "unsupported: more than 1024 air-object slots per scenario";
         return ZRK_ERR_UNSUPPORTED;

@@ -188,13 +188,18 @@ static inline int zrk_team_for(int ns) {
     return 0;
 }
 
-static inline Layout make_layout(int B, int T, int M, int R, int L, int C) {
+// ns_used / m_used: the largest number of air-object slots (targets + missiles) and of missiles any
+// scenario of the batch really has (the batch maxima T, M may be padding): they size the team and
+// the per-missile arrays.  T and M stay the strides of the caller's arrays and of the static index.
+static inline Layout make_layout(int B, int T, int M, int R, int L, int C, int ns_used = -1, int m_used = -1) {
     Layout o{};
     o.B = B; o.T = T; o.M = M; o.NS = T + M; o.R = R; o.L = L; o.C = C;
-    o.team = zrk_team_for(o.NS);
+    if (ns_used < 0 || ns_used > o.NS) ns_used = o.NS;
+    if (m_used < 0 || m_used > M) m_used = M;
+    o.team = zrk_team_for(ns_used > 0 ? ns_used : 1);
     const int team = o.team ? o.team : 32;
     o.teams_per_cta = team > 32 ? 1 : ZRK_CTA_THREADS / 32;  // teams larger than a warp own their CTA
-    o.MP = zrk_mp_for(team, M);
+    o.MP = zrk_mp_for(team, m_used);
     o.RP = R > 0 ? R : 1;
     o.LP = zrk_align(L > 0 ? L : 1, 2);
     o.CP = zrk_align(C > 0 ? C : 1, 2);

@@ -835,11 +835,95 @@ __device__ __forceinline__ void team_barrier() {
         __syncthreads();
     }
 }
+// One pair of the certificate: slot `lane` (exact position / velocity pi, zi, vi, viz; fp32 images fpi, fvi)
+// against slot j, whose tracks measure to the fp32 image pj and move with vj.  Merges the window in
+// which the two are within R of each other into [best_in, best_out].  Nearly all pairs never come near
+// each other: they are dismissed by an fp32 evaluation of the quadratic whose margins (1e-4 relative,
+// 3 m) are far wider than its rounding errors; the others are solved in fp64.
+// Returns false if slot j cannot be modelled (the caller then gives up on this lane).
+template <int TEAM>
+__device__ __forceinline__ bool cert_pair(const Hot<TEAM> &H, int j, float4 pj, float4 vj, float4 fpi, float4 fvi, double2 pi,
+                                          double2 zi, double2 vi, double viz, int tick, double dt_s, double nb, float fdt,
+                                          float fnb, int &best_in, int &best_out) {
+    {   // fp32: never within R of each other from now on?
+        const float bx = pj.x - fpi.x, by = pj.y - fpi.y, bz = pj.z - fpi.z;
+        const float ux = vj.x - fvi.x, uy = vj.y - fvi.y, uz = vj.z - fvi.z;
+        const float R = fmaf(fpi.w + pj.w, fdt, fnb) * 1.0001f;
+        const float a = fmaf(uz, uz, fmaf(uy, uy, ux * ux)), bq = fmaf(bz, uz, fmaf(by, uy, bx * ux));
+        const float p2 = fmaf(bz, bz, fmaf(by, by, bx * bx)), c = fmaf(-R, R, p2);
+        const float b2 = bq * bq;
+        if (c > 1e-4f * p2 && (bq >= 0.f || fmaf(-a, c, b2) < -1e-4f * fmaf(a, p2, b2))) return true;
+    }
+    const int flj = H.sflags()[j];
+    const double spi = fabs(zi.y);
+    double bx, by, bz, ux, uy, uz, spj;
+    if (flj & F_ALIVE) {
+        if (!(flj & F_HASPREV)) return false;  // (its first tick: its tracks still measure to an older position)
+        const double2 pj2 = H.pxy()[j], zj = H.pzs()[j], vj2 = H.vxy()[j];
+        bx = pj2.x - pi.x, by = pj2.y - pi.y, bz = zj.x - zi.x;
+        ux = vj2.x - vi.x, uy = vj2.y - vi.y, uz = H.qzw()[j].y - viz;
+        spj = fabs(zj.y);
+    } else {
+        double fx, fy, fz;
+        if (flj & F_PENDING) {  // on the launcher until NEW_MISSILE is consumed (its track measures to pos)
+            fx = H.pxy()[j].x, fy = H.pxy()[j].y, fz = H.pzs()[j].x;
+        } else if (flj & F_HASPREV) {  // removed: prev_pos stays what it was
+            fx = H.qxy()[j].x, fy = H.qxy()[j].y, fz = H.qzw()[j].x;
+        } else {
+            return false;
+        }
+        bx = fx - pi.x, by = fy - pi.y, bz = fz - zi.x;
+        ux = -vi.x, uy = -vi.y, uz = -viz;
+        spj = 0.0;
+    }
+    const double R = ((spi + spj) * dt_s * 1.000000001 + 6.0 * nb + 1.0) * 1.000001;
+    const double a = dot3(ux, uy, uz, ux, uy, uz), bq = dot3(bx, by, bz, ux, uy, uz);
+    const double c = dot3(bx, by, bz, bx, by, bz) - R * R;
+    const double disc = bq * bq - a * c;
+    if (c > 0 && (bq >= 0 || disc < 0)) return true;  // never within R of each other from now on
+    int kin = 0, kout = ZRK_CERT_NEVER;                // (also what every NaN ends up with)
+    if (a > 0 && disc >= 0) {
+        // within R for tau in [tin, tout]; tick + k is tau = k dt away (the clock table deviates from
+        // that by rounding only, which the 1e-9 relative + 1e-6 absolute allowance swallows)
+        const double sq = sqrt(disc), ia = 1.0 / (a * dt_s);
+        const double qo = (-bq + sq) * ia * 1.000000001 + 1e-6;
+        if (qo < 1e9) kout = tick + (int)qo;  // the last tick inside
+        if (c > 0) {                          // approaching: tin is ahead; ticks k < tin / dt are outside
+            const double qi = (-bq - sq) * ia * 0.999999999 - 1e-6;
+            kin = ZRK_CERT_NEVER;
+            if (qi < 1e9) kin = tick + (qi > 0 ? (int)qi + 1 : 0);
+            if (!(qi >= -1.0)) kin = 0;  // (NaN)
+        }
+    }
+    if (kin > ZRK_CERT_NEVER) kin = ZRK_CERT_NEVER;
+    if (kout > ZRK_CERT_NEVER) kout = ZRK_CERT_NEVER;
+    if (kin < best_in) {
+        best_in = kin;
+        best_out = kout;
+    } else if (kin == best_in && kout > best_out) {
+        best_out = kout;
+    }
+    return true;
+}
+// this slot as the others see it: where its tracks measure to (+ its speed), and how that moves
+template <int TEAM>
+__device__ __forceinline__ void cert_image(const Hot<TEAM> &H, int lane, int fl, float4 &p4, float4 &v4) {
+    const float qn = __int_as_float(0x7fc00000);
+    p4 = make_float4(qn, qn, qn, 0.f);
+    v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((fl & F_ALIVE) && (fl & F_HASPREV)) {
+        const double2 a = H.pxy()[lane], z = H.pzs()[lane], v = H.vxy()[lane];
+        p4 = make_float4((float)a.x, (float)a.y, (float)z.x, fabsf((float)z.y) * 1.000001f);
+        v4 = make_float4((float)v.x, (float)v.y, (float)H.qzw()[lane].y, 0.f);
+    } else if (!(fl & F_ALIVE) && (fl & F_PENDING)) {
+        p4 = make_float4((float)H.pxy()[lane].x, (float)H.pxy()[lane].y, (float)H.pzs()[lane].x, 0.f);
+    } else if (!(fl & F_ALIVE) && (fl & F_HASPREV)) {
+        p4 = make_float4((float)H.qxy()[lane].x, (float)H.qxy()[lane].y, (float)H.qzw()[lane].x, 0.f);
+    }
+}
 // All lanes of the team call this together.  It recounts how many tracks refer to each slot (a slot
 // followed by two tracks measures the same distance to both: never certified) and rebuilds every
-// window.  Nearly all pairs never come near each other: they are dismissed by an fp32 evaluation of
-// the quadratic whose margins (1e-4 relative, 2 m) are far wider than its rounding errors; the
-// others are solved in fp64.  fp / fv: scratch for the fp32 images (position + speed, velocity).
+// window.  fp / fv: scratch for the fp32 images.
 template <int TEAM>
 __device__ ZRK_NOINLINE void cert_recompute(unsigned char *sm, const int *me_ref, int lane, int n_slots, int tick, int n_te,
                                             int n_me, double dt_s, double nb, int *cin, int *cout, int *refc, float4 *fp,
@@ -848,22 +932,11 @@ __device__ ZRK_NOINLINE void cert_recompute(unsigned char *sm, const int *me_ref
     H.sm = sm;
     refc[lane] = 0;
     const int fl = lane < n_slots ? H.sflags()[lane] : 0;
-    {   // this slot as the others see it: where its tracks measure to, and how that moves
-        const float qn = __int_as_float(0x7fc00000);
-        float4 p4 = make_float4(qn, qn, qn, 0.f), v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if ((fl & F_ALIVE) && (fl & F_HASPREV)) {
-            const double2 a = H.pxy()[lane], z = H.pzs()[lane], v = H.vxy()[lane];
-            p4 = make_float4((float)a.x, (float)a.y, (float)z.x, fabsf((float)z.y) * 1.000001f);
-            v4 = make_float4((float)v.x, (float)v.y, (float)H.qzw()[lane].y, 0.f);
-        } else if (!(fl & F_ALIVE) && (fl & F_PENDING)) {
-            p4 = make_float4((float)H.pxy()[lane].x, (float)H.pxy()[lane].y, (float)H.pzs()[lane].x, 0.f);
-        } else if (!(fl & F_ALIVE) && (fl & F_HASPREV)) {
-            p4 = make_float4((float)H.qxy()[lane].x, (float)H.qxy()[lane].y, (float)H.qzw()[lane].x, 0.f);
-        }
-        if (lane < n_slots) {
-            fp[lane] = p4;
-            fv[lane] = v4;
-        }
+    float4 fpi, fvi;
+    cert_image<TEAM>(H, lane, fl, fpi, fvi);
+    if (lane < n_slots) {
+        fp[lane] = fpi;
+        fv[lane] = fvi;
     }
     team_barrier<TEAM>();
     if (lane < n_te) atomicAdd(&refc[H.te_ref()[lane]], 1);
@@ -882,74 +955,43 @@ __device__ ZRK_NOINLINE void cert_recompute(unsigned char *sm, const int *me_ref
         best_out = tick;
     } else {
         const double2 pi = H.pxy()[lane], zi = H.pzs()[lane], vi = H.vxy()[lane];
-        const double viz = H.qzw()[lane].y, spi = fabs(zi.y);
-        const float4 fpi = fp[lane], fvi = fv[lane];
+        const double viz = H.qzw()[lane].y;
         const float fdt = (float)dt_s * 1.000001f, fnb = 6.0f * (float)nb * 1.000001f + 3.0f;
         for (int j = 0; j < n_slots; j++) {
             if (j == lane) continue;
-            {   // fp32: never within R of each other from now on?
-                const float4 pj = fp[j], vj = fv[j];
-                const float bx = pj.x - fpi.x, by = pj.y - fpi.y, bz = pj.z - fpi.z;
-                const float ux = vj.x - fvi.x, uy = vj.y - fvi.y, uz = vj.z - fvi.z;
-                const float R = fmaf(fpi.w + pj.w, fdt, fnb) * 1.0001f;
-                const float a = fmaf(uz, uz, fmaf(uy, uy, ux * ux)), bq = fmaf(bz, uz, fmaf(by, uy, bx * ux));
-                const float p2 = fmaf(bz, bz, fmaf(by, by, bx * bx)), c = fmaf(-R, R, p2);
-                const float b2 = bq * bq;
-                if (c > 1e-4f * p2 && (bq >= 0.f || fmaf(-a, c, b2) < -1e-4f * fmaf(a, p2, b2))) continue;
+            if (!cert_pair<TEAM>(H, j, fp[j], fv[j], fpi, fvi, pi, zi, vi, viz, tick, dt_s, nb, fdt, fnb, best_in, best_out)) {
+                best_in = 0;
+                best_out = tick;
+                break;
             }
-            const int flj = H.sflags()[j];
-            double bx, by, bz, ux, uy, uz, spj;
-            if (flj & F_ALIVE) {
-                if (!(flj & F_HASPREV)) {  // (its first tick: its tracks still measure to an older position)
-                    best_in = 0;
-                    best_out = tick;
-                    break;
-                }
-                const double2 pj = H.pxy()[j], zj = H.pzs()[j], vj = H.vxy()[j];
-                bx = pj.x - pi.x, by = pj.y - pi.y, bz = zj.x - zi.x;
-                ux = vj.x - vi.x, uy = vj.y - vi.y, uz = H.qzw()[j].y - viz;
-                spj = fabs(zj.y);
-            } else {
-                double fx, fy, fz;
-                if (flj & F_PENDING) {  // on the launcher until NEW_MISSILE is consumed (its track measures to pos)
-                    fx = H.pxy()[j].x, fy = H.pxy()[j].y, fz = H.pzs()[j].x;
-                } else if (flj & F_HASPREV) {  // removed: prev_pos stays what it was
-                    fx = H.qxy()[j].x, fy = H.qxy()[j].y, fz = H.qzw()[j].x;
-                } else {
-                    best_in = 0;
-                    break;
-                }
-                bx = fx - pi.x, by = fy - pi.y, bz = fz - zi.x;
-                ux = -vi.x, uy = -vi.y, uz = -viz;
-                spj = 0.0;
-            }
-            const double R = ((spi + spj) * dt_s * 1.000000001 + 6.0 * nb + 1.0) * 1.000001;
-            const double a = dot3(ux, uy, uz, ux, uy, uz), bq = dot3(bx, by, bz, ux, uy, uz);
-            const double c = dot3(bx, by, bz, bx, by, bz) - R * R;
-            const double disc = bq * bq - a * c;
-            if (c > 0 && (bq >= 0 || disc < 0)) continue;  // never within R of each other from now on
-            int kin = 0, kout = ZRK_CERT_NEVER;            // (also what every NaN ends up with)
-            if (a > 0 && disc >= 0) {
-                // within R for tau in [tin, tout]; tick + k is tau = k dt away (the clock table deviates from
-                // that by rounding only, which the 1e-9 relative + 1e-6 absolute allowance swallows)
-                const double sq = sqrt(disc), ia = 1.0 / (a * dt_s);
-                const double qo = (-bq + sq) * ia * 1.000000001 + 1e-6;
-                if (qo < 1e9) kout = tick + (int)qo;  // the last tick inside
-                if (c > 0) {                          // approaching: tin is ahead; ticks k < tin / dt are outside
-                    const double qi = (-bq - sq) * ia * 0.999999999 - 1e-6;
-                    kin = ZRK_CERT_NEVER;
-                    if (qi < 1e9) kin = tick + (qi > 0 ? (int)qi + 1 : 0);
-                    if (!(qi >= -1.0)) kin = 0;  // (NaN)
-                }
-            }
-            if (kin > ZRK_CERT_NEVER) kin = ZRK_CERT_NEVER;
-            if (kout > ZRK_CERT_NEVER) kout = ZRK_CERT_NEVER;
-            if (kin < best_in) {
-                best_in = kin;
-                best_out = kout;
-            } else if (kin == best_in && kout > best_out) {
-                best_out = kout;
-            }
+        }
+    }
+    cin[lane] = best_in;
+    cout[lane] = best_out;
+}
+// A removal (AirEnv.py:33-40) only turns moving objects into fixed ones: the windows of the other
+// slots stay valid (wider than needed where they were due to a removed object) once the pairs with
+// the removed slots — the bits of `removed`, now frozen at their prev_pos — are merged in.  Warp teams.
+template <int TEAM>
+__device__ ZRK_NOINLINE void cert_removed(unsigned char *sm, int lane, int fl, unsigned removed, int tick, double dt_s, double nb,
+                                          int *cin, int *cout) {
+    Hot<TEAM> H;
+    H.sm = sm;
+    if (!(fl & F_ALIVE) || !(fl & F_HASPREV)) return;
+    int best_in = cin[lane], best_out = cout[lane];
+    float4 fpi, fvi;
+    cert_image<TEAM>(H, lane, fl, fpi, fvi);
+    const double2 pi = H.pxy()[lane], zi = H.pzs()[lane], vi = H.vxy()[lane];
+    const double viz = H.qzw()[lane].y;
+    const float fdt = (float)dt_s * 1.000001f, fnb = 6.0f * (float)nb * 1.000001f + 3.0f;
+    for (unsigned m = removed; m; m &= m - 1) {
+        const int j = __ffs(m) - 1;
+        float4 pj, vj;
+        cert_image<TEAM>(H, j, H.sflags()[j], pj, vj);
+        if (!cert_pair<TEAM>(H, j, pj, vj, fpi, fvi, pi, zi, vi, viz, tick, dt_s, nb, fdt, fnb, best_in, best_out)) {
+            best_in = 0;
+            best_out = tick;
+            break;
         }
     }
     cin[lane] = best_in;
@@ -1203,6 +1245,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
         double px = 0, py = 0, pz = 0;
         double nz0 = 0, nz1 = 0, nz2 = 0;  // radar 0's noise for this slot, fetched early
         bool odd = false;  // a slot whose tracks do not follow the certificate's model this tick (not yet born / first tick)
+        bool was_alive = false;
         if (lane < n_slots) {
             fl = H.sflags()[lane];
             odd = (fl & F_PENDING) != 0;
@@ -1213,6 +1256,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 nz1 = ZRK_LD_EARLY(nz + 1);
                 nz2 = ZRK_LD_EARLY(nz + 2);
             }
+            was_alive = (fl & F_ALIVE) != 0;
             if ((fl & F_ALIVE) && det_prev) {  // :33-40 removal by id
                 const int *dm = ZRK_COLD_I(det_mid) + prv * MP, *dt = ZRK_COLD_I(det_tid) + prv * MP;
                 for (int i = 0; i < det_prev; i++) {
@@ -1377,15 +1421,20 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
         // passed (all of them after an event) look again.  The vote is the barrier that ends the radars.
         bool cert_ok = false;  // this tick may take the certified CCP path (uniform)
         if (CERT && use_cert && !event && has_ccp) {
-            // (windows that have passed are looked at again every 16th tick: until then their slots are
-            // merely not certified, which costs them a check against every track but is always right)
-            const bool stale = tm.any((tick & 15) == 0 && alive && c_out[lane] < tick);
-            if (TEAM == 32) tm.sync();
-            if (*c_flag != 0 || det_prev != 0 || stale) {
+            unsigned removed = 0;
+            if (TEAM == 32) {
+                if (det_prev) removed = __ballot_sync(ZRK_FULL, was_alive && !alive);
+                tm.sync();
+            } else {
+                tm.sync();
+            }
+            if (*c_flag != 0 || (TEAM > 32 && det_prev != 0)) {
                 cert_recompute<TEAM>(sm, ZRK_ME_I(me_ref), lane, n_slots, tick, hdr[H_NTE], hdr[H_NME], P.dt_s, P.noise_bound,
                                      c_in, c_out, (int *)(sm + ZRK_X(x_refc)), (float4 *)lxy, (float4 *)lzd);
                 tm.sync();  // everybody has read the flag
                 if (lane == 0) *c_flag = 0;
+            } else if (removed) {
+                cert_removed<TEAM>(sm, lane, fl, removed, tick, P.dt_s, P.noise_bound, c_in, c_out);
             }
             cert_ok = true;
         } else {
@@ -1493,9 +1542,12 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                             }
                         }
                         slow = __ballot_sync(ZRK_FULL, rival) != 0;
+                        // a window that has passed keeps its slot uncertified: look again (every 8th tick at most)
+                        if ((tick & 7) == 0 && __ballot_sync(ZRK_FULL, doubt && c_out[lane] < tick) != 0 && lane == 0) *c_flag = 1;
                     }
                 } else {
                     slow = tm.any(hard || doubt);
+                    if ((tick & 7) == 0 && doubt && c_out[lane] < tick) *c_flag = 1;  // (as above)
                 }
                 if (!slow) {
                     const bool upd_msg = det && !is_me && follow;  // old_target, followed: CCP_UPDATE_TARGET (CCP.py:350-357)

@@ -41,6 +41,16 @@ __device__ __forceinline__ double zrk_ld_early(const double *p) {
 
 #include <math.h>
 
+// branch hints: the rare side is moved out of the straight-line code (the hot loop has to stay
+// within the instruction cache)
+#if defined(__GNUC__) || defined(__CUDACC__)
+#define ZRK_RARE(x) __builtin_expect(!!(x), 0)
+#define ZRK_OFTEN(x) __builtin_expect(!!(x), 1)
+#else
+#define ZRK_RARE(x) (x)
+#define ZRK_OFTEN(x) (x)
+#endif
+
 namespace zrk {
 
 #define ZRK_FULL 0xffffffffu
@@ -136,9 +146,9 @@ __device__ __forceinline__ bool radar_sees(double dx, double dy, double dz, cons
             sure_in = sure_in && el > e0 + M && el < e1 - M;
             sure_out = sure_out || el < e0 - M || el > e1 + M;
         }
-        if (ok) {
+        if (ZRK_OFTEN(ok)) {
             if (sure_out) return false;
-            if (sure_in) return true;
+            if (ZRK_OFTEN(sure_in)) return true;
         }
     }
     return radar_sees_exact(dx, dy, dz, par[2], az_lo, az_hi, el_lo, el_hi);
@@ -921,16 +931,28 @@ __device__ __forceinline__ void cert_image(const Hot<TEAM> &H, int lane, int fl,
         p4 = make_float4((float)H.qxy()[lane].x, (float)H.qxy()[lane].y, (float)H.qzw()[lane].x, 0.f);
     }
 }
-// All lanes of the team call this together.  It recounts how many tracks refer to each slot (a slot
-// followed by two tracks measures the same distance to both: never certified) and rebuilds every
-// window.  fp / fv: scratch for the fp32 images.
+// How many tracks refer to each slot: a slot followed by two tracks measures the same distance to
+// both, an untracked one has no own track — neither is certified.  The windows do not depend on the
+// tracks (every slot counts as an obstacle, tracked or not), so when tracks change hands or are
+// created this recount is all that is needed.  All lanes of the team call it together.
+template <int TEAM>
+__device__ __forceinline__ void cert_recount(unsigned char *sm, const int *me_ref, int lane, int n_te, int n_me, int *refc) {
+    Hot<TEAM> H;
+    H.sm = sm;
+    refc[lane] = 0;
+    team_barrier<TEAM>();
+    if (lane < n_te) atomicAdd(&refc[H.te_ref()[lane]], 1);
+    if (lane < n_me) atomicAdd(&refc[me_ref[lane]], 1);
+    team_barrier<TEAM>();
+}
+// Rebuilds every window (and the reference counts).  All lanes of the team call this together.
+// fp / fv: scratch for the fp32 images.
 template <int TEAM>
 __device__ ZRK_NOINLINE void cert_recompute(unsigned char *sm, const int *me_ref, int lane, int n_slots, int tick, int n_te,
                                             int n_me, double dt_s, double nb, int *cin, int *cout, int *refc, float4 *fp,
                                             float4 *fv) {
     Hot<TEAM> H;
     H.sm = sm;
-    refc[lane] = 0;
     const int fl = lane < n_slots ? H.sflags()[lane] : 0;
     float4 fpi, fvi;
     cert_image<TEAM>(H, lane, fl, fpi, fvi);
@@ -938,19 +960,14 @@ __device__ ZRK_NOINLINE void cert_recompute(unsigned char *sm, const int *me_ref
         fp[lane] = fpi;
         fv[lane] = fvi;
     }
-    team_barrier<TEAM>();
-    if (lane < n_te) atomicAdd(&refc[H.te_ref()[lane]], 1);
-    if (lane < n_me) atomicAdd(&refc[me_ref[lane]], 1);
-    team_barrier<TEAM>();
+    cert_recount<TEAM>(sm, me_ref, lane, n_te, n_me, refc);  // (its barriers also publish the images)
     if (!(fl & F_ALIVE)) {
         cin[lane] = ZRK_CERT_NEVER;
         cout[lane] = ZRK_CERT_NEVER;
         return;
     }
     int best_in = ZRK_CERT_NEVER, best_out = ZRK_CERT_NEVER;
-    if (refc[lane] != 1) {  // untracked, or followed by several tracks: not certifiable until the tracks change
-        best_in = 0;
-    } else if (!(fl & F_HASPREV)) {
+    if (!(fl & F_HASPREV)) {
         best_in = 0;
         best_out = tick;
     } else {
@@ -996,6 +1013,244 @@ __device__ ZRK_NOINLINE void cert_removed(unsigned char *sm, int lane, int fl, u
     }
     cin[lane] = best_in;
     cout[lane] = best_out;
+}
+
+// ------------------------------------------------------------------ quiet streak
+//
+// A run of consecutive ticks on which nothing happens but flying and tracking: no launcher or CCP
+// bookkeeping, no removal, no missile about to be born or to detonate, every visibility decision made
+// by the fp32 pre-filter or the exact path as usual, and every detection certified to re-acquire the
+// track of its own slot (see "association certificate").  On such a tick the lanes exchange nothing
+// but votes (and, with missiles in flight, the targets' positions by shuffle), so the slot's state —
+// position, previous position, trajectory, the own track's update time, a missile's remaining
+// detonate_period — stays in registers from tick to tick, nothing is written to shared memory, and
+// the message counters are settled when the streak ends.  Every value is computed by the same fp64
+// operations as in the general tick below; a tick is committed only if no lane objects, otherwise the
+// streak ends BEFORE that tick with nothing of it applied and the general tick runs it from the
+// state written back here.  Returns the number of ticks committed.
+template <int TEAM, int MPB>
+__device__ ZRK_NOINLINE int quiet_streak(const Params *Pg, unsigned char *sm, int lane, int b, int max_ticks, int noise_w,
+                                         const int *c_in, const int *c_refc) {
+    const Params &P = *Pg;
+    const Layout &o = P.lo;
+    constexpr MeOff XM = me_off(TEAM, MPB ? MPB : 2);
+#define ZRK_QME_I(name) ((int *)(sm + (MPB ? XM.name : o.name)))
+#define ZRK_QME_D(name) ((double *)(sm + (MPB ? XM.name : o.name)))
+    Hot<TEAM> H;
+    H.sm = sm;
+    int *const hdr = H.hdr();
+    const int *chdr = ZRK_CST_I(c_hdr);
+    const int nR = chdr[C_NR], T = o.T, tick_limit = chdr[C_TICK_LIMIT], n_slots = hdr[H_NSLOTS];
+    int tick = hdr[H_TICK];
+    const bool nolaunch = hdr[H_FREECAP] <= 0;
+    const int fl = lane < n_slots ? H.sflags()[lane] : 0;
+    const bool alive = (fl & F_ALIVE) != 0, msl = alive && (fl & F_MISSILE);
+    // lanes the streak cannot carry at all
+    bool bail0 = (fl & F_PENDING) != 0 || (alive && !(fl & F_HASPREV)) || (TEAM > 32 && msl);
+    double px = 0, py = 0, pz = 0, qx = 0, qy = 0, qz = 0, sx = 0, sy = 0, sz = 0, t0 = 0, vx = 0, vy = 0, vz = 0, speed = 0;
+    if (lane < n_slots) {
+        const double2 a = H.pxy()[lane], c = H.pzs()[lane];
+        px = a.x, py = a.y, pz = c.x, speed = c.y;
+    }
+    if (alive) {
+        const double2 q = H.qxy()[lane], w = H.qzw()[lane], s0 = H.txy()[lane], s1 = H.tzt()[lane], v = H.vxy()[lane];
+        qx = q.x, qy = q.y, qz = w.x, vz = w.y;
+        sx = s0.x, sy = s0.y, sz = s1.x, t0 = s1.y;
+        vx = v.x, vy = v.y;
+    }
+    // the own track
+    bool seed_ok = false, is_me = false, follow = false;
+    int e = 0, updt = -1;
+    double upds = 0;
+    if (alive) {
+        const int seed = H.own()[lane];
+        if (seed >= 0) {
+            is_me = seed >= TEAM;
+            e = is_me ? seed - TEAM : seed;
+            seed_ok = (is_me ? ZRK_QME_I(me_ref)[e] : H.te_ref()[e]) == lane;
+            upds = is_me ? ZRK_QME_D(me_upds)[e] : H.te_upds()[e];
+            follow = is_me || H.te_follow()[e] != 0;
+        }
+    }
+    const int cin = c_in[lane];
+    const bool refc1 = c_refc[lane] == 1;
+    const double dm = fabs(speed) * P.dt_s * 1.000000001 + 2.0 * P.noise_bound + 1e-3, dm2 = dm * dm;
+    // a missile in flight: no detonation as long as it stays surely outside its radius of its target
+    int m = 0, tg = 0;
+    double period = 0, r2hi = 0;
+    if (msl) {
+        m = (fl >> F_STATIC_SHIFT) - T;
+        tg = ZRK_COLD_I(m_target)[m];
+        period = ZRK_COLD_D(m_period)[m];
+        const double r = ZRK_CST_D(c_m_radius)[m];
+        r2hi = r * r * (1.0 + 1e-15);
+        if (!(r >= 0.0) || tg < 0 || tg >= n_slots) bail0 = true;
+    }
+    const unsigned alive_mask = __ballot_sync(ZRK_FULL, alive), msl_mask = __ballot_sync(ZRK_FULL, msl);
+    const double *noise = P.noise ? P.noise + (size_t)b * P.noise_stride + (fl >> F_STATIC_SHIFT) * 3 : nullptr;
+    const int noise_row = P.noise_radars * P.noise_objects * 3;
+    const double *rad_cur = ZRK_QME_D(rad_cur), *c_rad_pos = ZRK_CST_D(c_rad_pos), *c_rad_par = ZRK_CST_D(c_rad_par);
+    bool sweeping = false;
+    for (int r = 0; r < nR; r++) sweeping = sweeping || c_rad_par[RAD_PAR_STRIDE * r + 10] == 0.0;
+    int n_q = 0, n_upd = 0;
+    double now_s = tick_seconds(P, tick);
+    while (n_q < max_ticks) {
+        if (tick_limit >= 0 && tick >= tick_limit) break;
+        const double now_next = tick_seconds(P, tick + 1);
+        bool bail = bail0;
+        // AirObject.step (AirObject.py:39-42): the new position; the old one becomes prev_pos at commit
+        double nx = px, ny = py, nz = pz;
+        if (alive) {
+            const double dtm = now_s - t0;
+            nx = sx + vx * dtm;
+            ny = sy + vy * dtm;
+            nz = sz + vz * dtm;
+        }
+        // Missile.step (Missile.py:162-193): target's position of this tick, before any radar touches it
+        double per = period;
+        if (TEAM == 32 && msl_mask) {
+            const double tx = __shfl_sync(ZRK_FULL, nx, tg), ty = __shfl_sync(ZRK_FULL, ny, tg), tz = __shfl_sync(ZRK_FULL, nz, tg);
+            if (msl) {
+                const double ex = tx - nx, ey = ty - ny, ez = tz - nz;
+                if (!(dot3(ex, ey, ez, ex, ey, ez) > r2hi)) bail = true;  // (may be) within the radius: detonation
+                per = period - P.dt_s;
+                if (!(per > 0)) bail = true;  // self-detonation
+            }
+        }
+        // SectorRadar.step (Radar.py:144-205)
+        int rf = -1;
+        unsigned *mrow = nullptr;
+        if (P.masks) {
+            mrow = P.masks + ((size_t)(tick % P.mask_ticks) * o.B + b) * (size_t)((1 + o.RP) * P.mask_words);
+            if ((lane & 31) == 0 && (lane >> 5) < P.mask_words) mrow[lane >> 5] = TEAM == 32 ? alive_mask : __ballot_sync(ZRK_FULL, alive);
+        }
+        for (int r = 0; r < nR; r++) {
+            const double *par_r = c_rad_par + RAD_PAR_STRIDE * r;
+            bool vis = false;
+            if (alive) {
+                const double caz = rad_cur[2 * r], cel = rad_cur[2 * r + 1];
+                const double dx = nx - c_rad_pos[3 * r], dy = ny - c_rad_pos[3 * r + 1], dz = nz - c_rad_pos[3 * r + 2];
+                vis = radar_sees<true>(dx, dy, dz, par_r, caz, caz + par_r[3], cel, cel + par_r[4]);
+                if (vis) {  // smooth_objects (Radar.py:138-142)
+                    if (noise) {
+                        const double *q = noise + (size_t)noise_w * noise_row + (size_t)r * P.noise_objects * 3;
+                        nx += q[0];
+                        ny += q[1];
+                        nz += q[2];
+                    }
+                    if (rf < 0) rf = r;
+                }
+            }
+            if (mrow) {
+                const unsigned bal = __ballot_sync(ZRK_FULL, vis);
+                if ((lane & 31) == 0 && (lane >> 5) < P.mask_words) mrow[(1 + r) * P.mask_words + (lane >> 5)] = bal;
+            }
+        }
+        // CombatControlPoint.step: the own track, exactly as link_d2 / link_eval measure it
+        const bool det = alive && rf >= 0;
+        bool upd_msg = false;
+        if (det) {
+            const double ex = px - nx, ey = py - ny, ez = pz - nz;
+            const double d2 = dot3(ex, ey, ez, ex, ey, ez);
+            double lo, hi;
+            calc_range(speed, now_s - upds, P.range_step, lo, hi);
+            const double EPS = 4e-15;
+            const double l2 = lo * lo, h2 = hi * hi;
+            const bool in_sure = d2 >= l2 * (1.0 + EPS) && d2 <= h2 * (1.0 - EPS);
+            // (a Missile followed by a target track is the reference's AttributeError, CCP.py:259)
+            const bool hard = !(seed_ok && in_sure && (follow || nolaunch)) || (msl && !is_me);
+            const bool doubt = !(tick < cin && refc1 && d2 <= dm2);
+            bail = bail || hard || doubt;
+            upd_msg = !is_me && follow;
+        }
+        if (TEAM == 32 ? __ballot_sync(ZRK_FULL, bail) != 0 : __syncthreads_or(bail) != 0) break;
+        // ---- commit
+        if (alive) {
+            qx = px, qy = py, qz = pz;
+            px = nx, py = ny, pz = nz;
+        }
+        if (det) {
+            upds = now_s;
+            updt = tick;
+        }
+        period = per;
+        n_upd += __popc(__ballot_sync(ZRK_FULL, upd_msg));
+        if (sweeping) {  // move_to_next_sector_circular (Radar.py:96-117)
+            team_barrier<TEAM>();
+            if (lane == 0) {
+                double *rc = ZRK_QME_D(rad_cur);
+                for (int r = 0; r < nR; r++) {
+                    const double *q = c_rad_par + RAD_PAR_STRIDE * r;
+                    if (q[10] != 0.0) continue;
+                    double caz = rc[2 * r], cel = rc[2 * r + 1];
+                    radar_move(q, caz, cel);
+                    rc[2 * r] = caz;
+                    rc[2 * r + 1] = cel;
+                }
+            }
+            team_barrier<TEAM>();
+        }
+        tick++;
+        n_q++;
+        now_s = now_next;
+        if (++noise_w == P.noise_period) noise_w = 0;
+    }
+    if (n_q) {  // the state the general tick expects, and the messages of the committed ticks
+        if (alive) {
+            H.qxy()[lane] = make_double2(qx, qy);
+            H.qzw()[lane].x = qz;
+            H.pxy()[lane] = make_double2(px, py);
+            H.pzs()[lane].x = pz;
+        }
+        if (updt >= 0) {
+            if (is_me) {
+                ZRK_QME_I(me_upd)[e] = updt;
+                ZRK_QME_D(me_upds)[e] = upds;
+            } else {
+                H.te_upd()[e] = updt;
+                H.te_upds()[e] = upds;
+            }
+        }
+        if (msl) ZRK_COLD_D(m_period)[m] = period;
+        if (TEAM == 32) {
+            if (lane == 0) {
+                const int na = __popc(alive_mask);
+                unsigned *cnt = H.counts();
+                hdr[H_TICK] = tick;
+                hdr[H_FAST] += n_q;
+                hdr[H_ALIVE] += n_q * na;
+                cnt[ZRK_MSG_ACTIVE_OBJECTS] += (unsigned)n_q;
+                cnt[ZRK_MSG_MISSILE_POS] += (unsigned)(n_q * __popc(msl_mask));
+                cnt[ZRK_MSG_CCP_UPDATE_TARGET] += (unsigned)n_upd;
+                if (nR) {
+                    cnt[ZRK_MSG_ALL_OBJECTS] += (unsigned)(n_q * nR);
+                    cnt[ZRK_MSG_FOUND_OBJECTS] += (unsigned)(n_q * nR);
+                    cnt[ZRK_MSG_DRAW_OBJECTS] += (unsigned)(n_q * na);
+                }
+            }
+        } else {
+            if ((lane & 31) == 0) {
+                const int na = __popc(alive_mask);
+                if (na) atomicAdd(&hdr[H_ALIVE], n_q * na);
+                if (n_upd) atomicAdd((int *)&H.counts()[ZRK_MSG_CCP_UPDATE_TARGET], n_upd);
+                if (nR && na) atomicAdd((int *)&H.counts()[ZRK_MSG_DRAW_OBJECTS], n_q * na);
+            }
+            if (lane == 0) {
+                unsigned *cnt = H.counts();
+                hdr[H_TICK] = tick;
+                hdr[H_FAST] += n_q;
+                cnt[ZRK_MSG_ACTIVE_OBJECTS] += (unsigned)n_q;
+                if (nR) {
+                    cnt[ZRK_MSG_ALL_OBJECTS] += (unsigned)(n_q * nR);
+                    cnt[ZRK_MSG_FOUND_OBJECTS] += (unsigned)(n_q * nR);
+                }
+            }
+        }
+    }
+    team_barrier<TEAM>();
+    return n_q;
+#undef ZRK_QME_I
+#undef ZRK_QME_D
 }
 
 // ------------------------------------------------------------------ lane 0 alone: launchers + CCP bookkeeping
@@ -1199,7 +1454,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
     // association certificate (teams up to 256 slots: the pair loop is O(slots) per lane)
     constexpr bool CERT = FAST && TEAM <= 256;
     int *const c_in = (int *)(sm + ZRK_X(x_cin)), *const c_out = (int *)(sm + ZRK_X(x_cout));
-    int *const c_flag = (int *)(sm + ZRK_X(x_cflag));
+    int *const c_flag = (int *)(sm + ZRK_X(x_cflag)), *const c_refc = (int *)(sm + ZRK_X(x_refc));
     const bool use_cert = CERT && P.cert && n_ticks >= 4;  // (windows live in scratch: a short launch would only pay for them)
     if (CERT && lane == 0) *c_flag = 1;  // nothing is known yet
 
@@ -1226,7 +1481,23 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
     // row of the noise table for this tick: (tick % period), advanced incrementally
     int noise_w = noise ? hdr[H_TICK] % P.noise_period : 0;
     const int noise_row = P.noise_radars * P.noise_objects * 3;  // doubles per tick row
+    int streak_wait = 0;  // ticks to go before the next attempt at a quiet streak (after one that ended at once)
     for (int it = 0; it < n_ticks; it++) {
+        if (CERT && use_cert && has_ccp && --streak_wait < 0) {
+            const int prv0 = (hdr[H_TICK] & 1) ^ 1;
+            if (*c_flag == 0 && hdr[H_DETN0 + prv0] == 0 && hdr[H_MBN0 + prv0] == 0 && hdr[H_CCP_INIT] && !(hdr[H_FAULT] & 63) &&
+                !(P.log_types & ZRK_LOG_BULK)) {
+                const int nq = quiet_streak<TEAM, MPB>(P.self, sm, lane, b, n_ticks - it, noise_w, c_in, c_refc);
+                if (nq) {
+                    it += nq;
+                    if (it >= n_ticks) break;
+                    noise_w = (noise_w + nq) % P.noise_period;
+                    now_next = tick_seconds(P, hdr[H_TICK]);
+                } else {
+                    streak_wait = 3;
+                }
+            }
+        }
         const int tick = hdr[H_TICK];
         if (hdr[H_FAULT] & 63) break;  // the reference run aborted here
         if (tick_limit >= 0 && tick >= tick_limit) break;
@@ -1257,14 +1528,14 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 nz2 = ZRK_LD_EARLY(nz + 2);
             }
             was_alive = (fl & F_ALIVE) != 0;
-            if ((fl & F_ALIVE) && det_prev) {  // :33-40 removal by id
+            if (ZRK_RARE((fl & F_ALIVE) && det_prev)) {  // :33-40 removal by id
                 const int *dm = ZRK_COLD_I(det_mid) + prv * MP, *dt = ZRK_COLD_I(det_tid) + prv * MP;
                 for (int i = 0; i < det_prev; i++) {
                     int tid = dt[i];
                     if (my_id == dm[i] || (tid != ZRK_NONE && my_id == tid)) fl &= ~F_ALIVE;
                 }
             }
-            if (fl & F_PENDING) {  // :42-43 NEW_MISSILE of the previous tick
+            if (ZRK_RARE(fl & F_PENDING)) {  // :42-43 NEW_MISSILE of the previous tick
                 int m = (fl >> F_STATIC_SHIFT) - T;
                 if (ZRK_COLD_I(m_birth)[m] == tick) {
                     fl = (fl & ~F_PENDING) | F_ALIVE;
@@ -1395,7 +1666,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                     if ((lane & 31) == 0 && (lane >> 5) < P.mask_words) mrow[(1 + r) * P.mask_words + (lane >> 5)] = bal;
                 }
                 // :193-203 one DESTROYED_MISSILE per MISSILE_DETONATE of the previous tick
-                if (det_prev && logged(P, ZRK_MSG_DESTROYED_MISSILE) && lane < det_prev)
+                if (ZRK_RARE(det_prev && logged(P, ZRK_MSG_DESTROYED_MISSILE) && lane < det_prev))
                     put_rec(P, rec, nrec + r * det_prev + lane, tick, ZRK_MSG_DESTROYED_MISSILE,
                             ZRK_COLD_I(det_flag)[prv * MP + lane], ZRK_CST_I(c_rad_id)[r], ZRK_CCP_ID,
                             ZRK_COLD_I(det_mid)[prv * MP + lane], ZRK_NONE, 0, 0, 0);
@@ -1428,13 +1699,17 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
             } else {
                 tm.sync();
             }
-            if (*c_flag != 0 || (TEAM > 32 && det_prev != 0)) {
+            const int cf = *c_flag;  // bit 0: the windows are void; bit 1: tracks changed hands or were created
+            if (ZRK_RARE((cf & 1) || (TEAM > 32 && det_prev != 0))) {
                 cert_recompute<TEAM>(sm, ZRK_ME_I(me_ref), lane, n_slots, tick, hdr[H_NTE], hdr[H_NME], P.dt_s, P.noise_bound,
-                                     c_in, c_out, (int *)(sm + ZRK_X(x_refc)), (float4 *)lxy, (float4 *)lzd);
+                                     c_in, c_out, c_refc, (float4 *)lxy, (float4 *)lzd);
+            } else {
+                if (ZRK_RARE(cf)) cert_recount<TEAM>(sm, ZRK_ME_I(me_ref), lane, hdr[H_NTE], hdr[H_NME], c_refc);
+                if (ZRK_RARE(removed)) cert_removed<TEAM>(sm, lane, fl, removed, tick, P.dt_s, P.noise_bound, c_in, c_out);
+            }
+            if (ZRK_RARE(cf)) {
                 tm.sync();  // everybody has read the flag
                 if (lane == 0) *c_flag = 0;
-            } else if (removed) {
-                cert_removed<TEAM>(sm, lane, fl, removed, tick, P.dt_s, P.noise_bound, c_in, c_out);
             }
             cert_ok = true;
         } else {
@@ -1455,7 +1730,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 rad_cur[2 * r + 1] = cel;
             }
         }
-        if (serial) {
+        if (ZRK_RARE(serial)) {
             if (lane == 0) {
                 nrec = serial_section<TEAM>(P.self, sm, rec, tick, now_s, mb_prev, nrec);
                 hdr[H_NREC] = nrec;
@@ -1501,14 +1776,14 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                         hard = !(ref == lane && in_sure && (follow || hdr[H_FREECAP] <= 0));
                         // the certificate's premise on the own track's distance is checked rather than assumed
                         const double dm = fabs(speed) * P.dt_s * 1.000000001 + 2.0 * P.noise_bound + 1e-3;
-                        doubt = !(tick < c_in[lane] && d2 <= dm * dm);
+                        doubt = !(tick < c_in[lane] && c_refc[lane] == 1 && d2 <= dm * dm);
                     }
                 }
                 bool slow;
                 if (TEAM == 32) {
                     slow = __ballot_sync(ZRK_FULL, hard) != 0;
                     const unsigned dmask = __ballot_sync(ZRK_FULL, doubt);
-                    if (!slow && dmask) {
+                    if (ZRK_RARE(!slow && dmask)) {
                         // The few uncertified detections are checked against every track, all lanes at once
                         // (lane k: _target_dict entry k and _missile_dict entry k): is any other track as
                         // near as the own one?  If so the ordinary scan decides; if not, link_object returns
@@ -1543,13 +1818,13 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                         }
                         slow = __ballot_sync(ZRK_FULL, rival) != 0;
                         // a window that has passed keeps its slot uncertified: look again (every 8th tick at most)
-                        if ((tick & 7) == 0 && __ballot_sync(ZRK_FULL, doubt && c_out[lane] < tick) != 0 && lane == 0) *c_flag = 1;
+                        if ((tick & 7) == 0 && __ballot_sync(ZRK_FULL, doubt && c_out[lane] < tick) != 0 && lane == 0) *c_flag |= 1;
                     }
                 } else {
                     slow = tm.any(hard || doubt);
-                    if ((tick & 7) == 0 && doubt && c_out[lane] < tick) *c_flag = 1;  // (as above)
+                    if ((tick & 7) == 0 && doubt && c_out[lane] < tick) atomicOr(c_flag, 1);  // (as above)
                 }
-                if (!slow) {
+                if (ZRK_OFTEN(!slow)) {
                     const bool upd_msg = det && !is_me && follow;  // old_target, followed: CCP_UPDATE_TARGET (CCP.py:350-357)
                     const bool lu = logged(P, ZRK_MSG_CCP_UPDATE_TARGET);
                     int r_upd = 0, n_upd = 0;
@@ -1589,7 +1864,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                     fast_done = true;
                 }
             }
-            if (!fast_done) {
+            if (ZRK_RARE(!fast_done)) {
             bool structural = false;  // this tick's rounds went beyond re-stamping own tracks
             // what link_object measures to, per entry: prev_pos of the tracked object (or pos
             // for a missile whose prev_pos is None) and d_t = now - upd_time
@@ -1880,7 +2155,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 lo_rank = istar;
                 tm.sync();  // entry updates of this round are visible to the next
             }
-            if (CERT && structural && lane == 0) *c_flag = 1;  // tracks changed hands or were created: windows are void
+            if (CERT && structural && lane == 0) *c_flag |= 2;  // tracks changed hands or were created
             }  // !fast_done
             tm.sync();
 

@@ -74,8 +74,9 @@ __device__ __forceinline__ double pymod(double a, double m) {
 }
 __device__ __forceinline__ double to_seconds(long long ms) { return (double)ms / 1000.0; }
 // to_seconds(tick * dt) from the table the host fills with exactly that expression
+__device__ ZRK_NOINLINE double tick_seconds_beyond(long long tick, int dt_ms) { return to_seconds(tick * dt_ms); }
 __device__ __forceinline__ double tick_seconds(const Params &P, int tick) {
-    return (tick >= 0 && tick < P.tsec_n) ? ZRK_LD_EARLY(&P.tsec[tick]) : to_seconds((long long)tick * P.dt_ms);
+    return ZRK_OFTEN(tick >= 0 && tick < P.tsec_n) ? ZRK_LD_EARLY(&P.tsec[tick]) : tick_seconds_beyond(tick, P.dt_ms);
 }
 
 #define ZRK_RAD2DEG 57.29577951308232 /* 180.0 / pi, as np.degrees multiplies */
@@ -1030,7 +1031,7 @@ __device__ ZRK_NOINLINE void cert_removed(unsigned char *sm, int lane, int fl, u
 // state written back here.  Returns the number of ticks committed.
 template <int TEAM, int MPB>
 __device__ ZRK_NOINLINE int quiet_streak(const Params *Pg, unsigned char *sm, int lane, int b, int max_ticks, int noise_w,
-                                         const int *c_in, const int *c_refc) {
+                                         const int *c_in, const int *c_out, const int *c_refc, int *c_flag) {
     const Params &P = *Pg;
     const Layout &o = P.lo;
     constexpr MeOff XM = me_off(TEAM, MPB ? MPB : 2);
@@ -1052,18 +1053,25 @@ __device__ ZRK_NOINLINE int quiet_streak(const Params *Pg, unsigned char *sm, in
         const double2 a = H.pxy()[lane], c = H.pzs()[lane];
         px = a.x, py = a.y, pz = c.x, speed = c.y;
     }
-    if (alive) {
-        const double2 q = H.qxy()[lane], w = H.qzw()[lane], s0 = H.txy()[lane], s1 = H.tzt()[lane], v = H.vxy()[lane];
+    if (lane < n_slots) {
+        const double2 q = H.qxy()[lane], w = H.qzw()[lane];
         qx = q.x, qy = q.y, qz = w.x, vz = w.y;
+    }
+    if (alive) {
+        const double2 s0 = H.txy()[lane], s1 = H.tzt()[lane], v = H.vxy()[lane];
         sx = s0.x, sy = s0.y, sz = s1.x, t0 = s1.y;
         vx = v.x, vy = v.y;
     }
+    // tracks number `lane` of the two dicts: the slots they follow (fixed during a streak)
+    const int n_te = hdr[H_NTE], n_me = hdr[H_NME];
+    const int r_te = lane < n_te ? H.te_ref()[lane] : 0, r_me = lane < n_me ? ZRK_QME_I(me_ref)[lane] : 0;
     // the own track
     bool seed_ok = false, is_me = false, follow = false;
-    int e = 0, updt = -1;
+    int e = 0, updt = -1, seedu = -1;
     double upds = 0;
     if (alive) {
         const int seed = H.own()[lane];
+        seedu = seed;
         if (seed >= 0) {
             is_me = seed >= TEAM;
             e = is_me ? seed - TEAM : seed;
@@ -1072,7 +1080,7 @@ __device__ ZRK_NOINLINE int quiet_streak(const Params *Pg, unsigned char *sm, in
             follow = is_me || H.te_follow()[e] != 0;
         }
     }
-    const int cin = c_in[lane];
+    const int cin = c_in[lane], cout = c_out[lane];
     const bool refc1 = c_refc[lane] == 1;
     const double dm = fabs(speed) * P.dt_s * 1.000000001 + 2.0 * P.noise_bound + 1e-3, dm2 = dm * dm;
     // a missile in flight: no detonation as long as it stays surely outside its radius of its target
@@ -1148,10 +1156,11 @@ __device__ ZRK_NOINLINE int quiet_streak(const Params *Pg, unsigned char *sm, in
         }
         // CombatControlPoint.step: the own track, exactly as link_d2 / link_eval measure it
         const bool det = alive && rf >= 0;
-        bool upd_msg = false;
+        bool upd_msg = false, doubt = false;
+        double d2 = 0;
         if (det) {
             const double ex = px - nx, ey = py - ny, ez = pz - nz;
-            const double d2 = dot3(ex, ey, ez, ex, ey, ez);
+            d2 = dot3(ex, ey, ez, ex, ey, ez);
             double lo, hi;
             calc_range(speed, now_s - upds, P.range_step, lo, hi);
             const double EPS = 4e-15;
@@ -1159,11 +1168,48 @@ __device__ ZRK_NOINLINE int quiet_streak(const Params *Pg, unsigned char *sm, in
             const bool in_sure = d2 >= l2 * (1.0 + EPS) && d2 <= h2 * (1.0 - EPS);
             // (a Missile followed by a target track is the reference's AttributeError, CCP.py:259)
             const bool hard = !(seed_ok && in_sure && (follow || nolaunch)) || (msl && !is_me);
-            const bool doubt = !(tick < cin && refc1 && d2 <= dm2);
-            bail = bail || hard || doubt;
+            doubt = !(tick < cin && refc1 && d2 <= dm2);
+            bail = bail || hard;
             upd_msg = !is_me && follow;
         }
-        if (TEAM == 32 ? __ballot_sync(ZRK_FULL, bail) != 0 : __syncthreads_or(bail) != 0) break;
+        if (TEAM == 32) {
+            if (__ballot_sync(ZRK_FULL, bail) != 0) break;
+            const unsigned dmask = __ballot_sync(ZRK_FULL, doubt);
+            if (ZRK_RARE(dmask)) {
+                // The few detections that are not certified are checked against every track, all lanes at
+                // once (lane k: entry k of _target_dict and of _missile_dict): is any other track as near
+                // as the own one?  If not, link_object returns the own track; if so, the general tick decides.
+                // What a slot's tracks measure to: its prev_pos — the position still in p while the tick is
+                // not committed — or, for a slot that is gone, what was frozen there.
+                const double ax = alive || !(fl & F_HASPREV) ? px : qx, ay = alive || !(fl & F_HASPREV) ? py : qy,
+                             az = alive || !(fl & F_HASPREV) ? pz : qz;
+                const double tx = __shfl_sync(ZRK_FULL, ax, r_te), ty = __shfl_sync(ZRK_FULL, ay, r_te), tz = __shfl_sync(ZRK_FULL, az, r_te);
+                const double mx = __shfl_sync(ZRK_FULL, ax, r_me), my = __shfl_sync(ZRK_FULL, ay, r_me), mz = __shfl_sync(ZRK_FULL, az, r_me);
+                bool rival = false;
+                for (unsigned mm = dmask; mm; mm &= mm - 1) {
+                    const int d = __ffs(mm) - 1;
+                    const double cx = __shfl_sync(ZRK_FULL, nx, d), cy = __shfl_sync(ZRK_FULL, ny, d), cz = __shfl_sync(ZRK_FULL, nz, d);
+                    const double thr = __shfl_sync(ZRK_FULL, d2, d) * (1.0 + 1e-12);
+                    const int sd = __shfl_sync(ZRK_FULL, seedu, d);
+                    if (lane < n_te && lane != sd) {
+                        const double ex = tx - cx, ey = ty - cy, ez = tz - cz;
+                        rival = rival || !(dot3(ex, ey, ez, ex, ey, ez) > thr);
+                    }
+                    if (lane < n_me && TEAM + lane != sd) {
+                        const double ex = mx - cx, ey = my - cy, ez = mz - cz;
+                        rival = rival || !(dot3(ex, ey, ez, ex, ey, ez) > thr);
+                    }
+                }
+                if (__ballot_sync(ZRK_FULL, rival) != 0) break;
+                // a window that has passed keeps its slot uncertified: have the windows rebuilt (every 8th tick at most)
+                if ((tick & 7) == 0 && __ballot_sync(ZRK_FULL, doubt && cout < tick) != 0) {
+                    if (lane == 0) *c_flag |= 1;
+                    break;
+                }
+            }
+        } else if (__syncthreads_or(bail || doubt) != 0) {
+            break;
+        }
         // ---- commit
         if (alive) {
             qx = px, qy = py, qz = pz;
@@ -1487,11 +1533,11 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
             const int prv0 = (hdr[H_TICK] & 1) ^ 1;
             if (*c_flag == 0 && hdr[H_DETN0 + prv0] == 0 && hdr[H_MBN0 + prv0] == 0 && hdr[H_CCP_INIT] && !(hdr[H_FAULT] & 63) &&
                 !(P.log_types & ZRK_LOG_BULK)) {
-                const int nq = quiet_streak<TEAM, MPB>(P.self, sm, lane, b, n_ticks - it, noise_w, c_in, c_refc);
+                const int nq = quiet_streak<TEAM, MPB>(P.self, sm, lane, b, n_ticks - it, noise_w, c_in, c_out, c_refc, c_flag);
                 if (nq) {
                     it += nq;
                     if (it >= n_ticks) break;
-                    noise_w = (noise_w + nq) % P.noise_period;
+                    if (noise) noise_w = (noise_w + nq) % P.noise_period;
                     now_next = tick_seconds(P, hdr[H_TICK]);
                 } else {
                     streak_wait = 3;
@@ -1866,10 +1912,14 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
             }
             if (ZRK_RARE(!fast_done)) {
             bool structural = false;  // this tick's rounds went beyond re-stamping own tracks
+            // With the quiet streak carrying the ordinary ticks, a warp team comes here on the rare eventful
+            // tick only, and what it costs then is the code it has to fetch, not the arithmetic: it scans
+            // with link_exact (a small loop) rather than the unrolled fp32 sweep.
+            const bool scan_fast = FAST && !(TEAM == 32 && use_cert);
             // what link_object measures to, per entry: prev_pos of the tracked object (or pos
             // for a missile whose prev_pos is None) and d_t = now - upd_time
             // the hash grid pays off once a scan is long; warp-sized scenarios scan their few entries directly
-            const bool want_grid = FAST && TEAM > 32 && n_te + n_me >= 48;
+            const bool want_grid = scan_fast && TEAM > 32 && n_te + n_me >= 48;
             bool bad_image = false;  // an entry outside the fp32-safe range: the team scans exactly this tick
             if (want_grid) ghead[lane] = -1;
             if (lane < n_te) {
@@ -1878,11 +1928,11 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 const bool skip = upd == tick;
                 lxy[lane] = make_double2(skip ? ZRK_FAR : a.x, a.y);
                 lzd[lane] = make_double2(c.x, now_s - H.te_upds()[lane]);
-                if (FAST) {
+                if (scan_fast) {
                     lf_store<TEAM>(lf, lane, skip ? 1e30f : (float)a.x, (float)a.y, (float)c.x);
                     bad_image = !skip & !link_f32_ok((float)a.x, (float)a.y, (float)c.x);
                 }
-            } else if (FAST && TEAM == 32) {
+            } else if (scan_fast && TEAM == 32) {
                 lf_store<TEAM>(lf, lane, 1e30f, 0.f, 0.f);  // pad: measures inf to everything
             }
             if (lane < n_me) {
@@ -1893,11 +1943,11 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 const bool skip = upd == tick;
                 lxy[TEAM + lane] = make_double2(skip ? ZRK_FAR : a.x, a.y);
                 lzd[TEAM + lane] = make_double2(cz, now_s - ZRK_ME_D(me_upds)[lane]);
-                if (FAST) {
+                if (scan_fast) {
                     lf_store<TEAM>(lf, TEAM + lane, skip ? 1e30f : (float)a.x, (float)a.y, (float)cz);
                     bad_image = bad_image | (!skip & !link_f32_ok((float)a.x, (float)a.y, (float)cz));
                 }
-            } else if (FAST && TEAM == 32 && lane < MP8) {
+            } else if (scan_fast && TEAM == 32 && lane < MP8) {
                 lf_store<TEAM>(lf, TEAM + lane, 1e30f, 0.f, 0.f);
             }
             bool grid_ok = false, any_bad = false;
@@ -1926,7 +1976,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
             }
             int *detlist = (int *)(sm + ZRK_X(x_detlist));
             if (myrank >= 0) detlist[myrank] = lane;
-            if (FAST) any_bad = nR > 0 ? any_seen : false;  // (no radar: no detection, nothing scans)
+            if (scan_fast) any_bad = nR > 0 ? any_seen : false;  // (no radar: no detection, nothing scans)
             if (want_grid && nR > 0) {
                 // the barrier of the first ranks also published the images and the reset bucket heads
                 grid_ok = !any_bad;
@@ -1962,12 +2012,12 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 // does the seed entry still refer to this very slot?  (then distinct slots have distinct seeds)
                 if (seed >= 0) seed_own = (seed >= TEAM ? ZRK_ME_I(me_ref)[seed - TEAM] : H.te_ref()[seed]) == slot;
             }
-            const bool coords_ok = FAST && !any_bad && link_f32_ok((float)dpx, (float)dpy, (float)dpz);
+            const bool coords_ok = scan_fast && !any_bad && link_f32_ok((float)dpx, (float)dpy, (float)dpz);
             int lo_rank = 0;
             for (;;) {
                 int cls = 0, cand = -1, claim = -1;
                 if (unresolved) {
-                    if (FAST) {
+                    if (scan_fast) {
                         bool unsure = !coords_ok;
                         if (coords_ok)
                             link_fast<TEAM>(ghead, grid_ok, lf, lxy, lzd, n_te, n_me, seed, P.range_step, dpx, dpy, dpz, dspeed, cls, cand, unsure);
@@ -2123,14 +2173,14 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                         if (!following) H.te_follow()[cand] = ok != 0;
                         H.own()[slot] = cand;
                         lxy[cand].x = ZRK_FAR;
-                        if (FAST) lf_x<TEAM>(lf, cand) = 1e30f;
+                        if (scan_fast) lf_x<TEAM>(lf, cand) = 1e30f;
                     } else if (cls == 2) {  // old_rocket (CCP.py:361-366)
                         ZRK_ME_I(me_ref)[cand] = slot;
                         ZRK_ME_I(me_upd)[cand] = tick;
                         ZRK_ME_D(me_upds)[cand] = now_s;
                         H.own()[slot] = TEAM + cand;
                         lxy[TEAM + cand].x = ZRK_FAR;
-                        if (FAST) lf_x<TEAM>(lf, TEAM + cand) = 1e30f;
+                        if (scan_fast) lf_x<TEAM>(lf, TEAM + cand) = 1e30f;
                     } else {  // new_target + add_target (CCP.py:322-330, :88-93)
                         const int e = claim >= 0 ? claim : n_te + r_app;
                         H.te_key()[e] = det_id();
@@ -2141,7 +2191,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                         H.te_mid()[e] = ZRK_NONE;
                         H.own()[slot] = e;
                         lxy[e].x = ZRK_FAR;
-                        if (FAST) lf_x<TEAM>(lf, e) = 1e30f;
+                        if (scan_fast) lf_x<TEAM>(lf, e) = 1e30f;
                     }
                     unresolved = false;
                 }

@@ -847,15 +847,16 @@ __device__ __forceinline__ void team_barrier() {
     }
 }
 // One pair of the certificate: slot `lane` (exact position / velocity pi, zi, vi, viz; fp32 images fpi, fvi)
-// against slot j, whose tracks measure to the fp32 image pj and move with vj.  Merges the window in
+// against slot j, whose tracks measure to the fp32 image pj and move with vj; the positions are those of
+// `tick`, the answer is wanted from tick_now on.  Merges the window in
 // which the two are within R of each other into [best_in, best_out].  Nearly all pairs never come near
 // each other: they are dismissed by an fp32 evaluation of the quadratic whose margins (1e-4 relative,
 // 3 m) are far wider than its rounding errors; the others are solved in fp64.
 // Returns false if slot j cannot be modelled (the caller then gives up on this lane).
 template <int TEAM>
 __device__ __forceinline__ bool cert_pair(const Hot<TEAM> &H, int j, float4 pj, float4 vj, float4 fpi, float4 fvi, double2 pi,
-                                          double2 zi, double2 vi, double viz, int tick, double dt_s, double nb, float fdt,
-                                          float fnb, int &best_in, int &best_out) {
+                                          double2 zi, double2 vi, double viz, int tick, int tick_now, double dt_s, double nb,
+                                          float fdt, float fnb, int &best_in, int &best_out) {
     {   // fp32: never within R of each other from now on?
         const float bx = pj.x - fpi.x, by = pj.y - fpi.y, bz = pj.z - fpi.z;
         const float ux = vj.x - fvi.x, uy = vj.y - fvi.y, uz = vj.z - fvi.z;
@@ -908,6 +909,7 @@ __device__ __forceinline__ bool cert_pair(const Hot<TEAM> &H, int j, float4 pj, 
     }
     if (kin > ZRK_CERT_NEVER) kin = ZRK_CERT_NEVER;
     if (kout > ZRK_CERT_NEVER) kout = ZRK_CERT_NEVER;
+    if (kout < tick_now) return true;  // (positions of an older tick: this window has already passed)
     if (kin < best_in) {
         best_in = kin;
         best_out = kout;
@@ -949,8 +951,8 @@ __device__ __forceinline__ void cert_recount(unsigned char *sm, const int *me_re
 // Rebuilds every window (and the reference counts).  All lanes of the team call this together.
 // fp / fv: scratch for the fp32 images.
 template <int TEAM>
-__device__ ZRK_NOINLINE void cert_recompute(unsigned char *sm, const int *me_ref, int lane, int n_slots, int tick, int n_te,
-                                            int n_me, double dt_s, double nb, int *cin, int *cout, int *refc, float4 *fp,
+__device__ ZRK_NOINLINE void cert_recompute(unsigned char *sm, const int *me_ref, int lane, int n_slots, int tick, int tick_now,
+                                            int n_te, int n_me, double dt_s, double nb, int *cin, int *cout, int *refc, float4 *fp,
                                             float4 *fv) {
     Hot<TEAM> H;
     H.sm = sm;
@@ -977,7 +979,7 @@ __device__ ZRK_NOINLINE void cert_recompute(unsigned char *sm, const int *me_ref
         const float fdt = (float)dt_s * 1.000001f, fnb = 6.0f * (float)nb * 1.000001f + 3.0f;
         for (int j = 0; j < n_slots; j++) {
             if (j == lane) continue;
-            if (!cert_pair<TEAM>(H, j, fp[j], fv[j], fpi, fvi, pi, zi, vi, viz, tick, dt_s, nb, fdt, fnb, best_in, best_out)) {
+            if (!cert_pair<TEAM>(H, j, fp[j], fv[j], fpi, fvi, pi, zi, vi, viz, tick, tick_now, dt_s, nb, fdt, fnb, best_in, best_out)) {
                 best_in = 0;
                 best_out = tick;
                 break;
@@ -1006,7 +1008,7 @@ __device__ ZRK_NOINLINE void cert_removed(unsigned char *sm, int lane, int fl, u
         const int j = __ffs(m) - 1;
         float4 pj, vj;
         cert_image<TEAM>(H, j, H.sflags()[j], pj, vj);
-        if (!cert_pair<TEAM>(H, j, pj, vj, fpi, fvi, pi, zi, vi, viz, tick, dt_s, nb, fdt, fnb, best_in, best_out)) {
+        if (!cert_pair<TEAM>(H, j, pj, vj, fpi, fvi, pi, zi, vi, viz, tick, tick + 1, dt_s, nb, fdt, fnb, best_in, best_out)) {
             best_in = 0;
             best_out = tick;
             break;
@@ -1029,9 +1031,54 @@ __device__ ZRK_NOINLINE void cert_removed(unsigned char *sm, int lane, int fl, u
 // operations as in the general tick below; a tick is committed only if no lane objects, otherwise the
 // streak ends BEFORE that tick with nothing of it applied and the general tick runs it from the
 // state written back here.  Returns the number of ticks committed.
+// The few detections of a streak tick that are not certified (bits of dmask) are checked against every
+// track, all lanes at once (lane k: entry k of _target_dict and of _missile_dict): is any other track
+// as near as the own one?  If not, link_object returns the own track; if so (returns true), the general
+// tick decides.  What a slot's tracks measure to is its prev_pos — the position still in p while the
+// tick is not committed (use_p) — or, for a slot that is gone, what was frozen in q.  Rare: out of line.
+template <int TEAM>
+__device__ ZRK_NOINLINE bool streak_rivals(unsigned dmask, int lane, bool use_p, double px, double py, double pz, double qx,
+                                           double qy, double qz, int r_te, int r_me, int n_te, int n_me, double nx, double ny,
+                                           double nz, double d2, int seedu) {
+    const double ax = use_p ? px : qx, ay = use_p ? py : qy, az = use_p ? pz : qz;
+    const double tx = __shfl_sync(ZRK_FULL, ax, r_te), ty = __shfl_sync(ZRK_FULL, ay, r_te), tz = __shfl_sync(ZRK_FULL, az, r_te);
+    const double mx = __shfl_sync(ZRK_FULL, ax, r_me), my = __shfl_sync(ZRK_FULL, ay, r_me), mz = __shfl_sync(ZRK_FULL, az, r_me);
+    bool rival = false;
+    for (unsigned mm = dmask; mm; mm &= mm - 1) {
+        const int d = __ffs(mm) - 1;
+        const double cx = __shfl_sync(ZRK_FULL, nx, d), cy = __shfl_sync(ZRK_FULL, ny, d), cz = __shfl_sync(ZRK_FULL, nz, d);
+        const double thr = __shfl_sync(ZRK_FULL, d2, d) * (1.0 + 1e-12);
+        const int sd = __shfl_sync(ZRK_FULL, seedu, d);
+        if (lane < n_te && lane != sd) {
+            const double ex = tx - cx, ey = ty - cy, ez = tz - cz;
+            rival = rival || !(dot3(ex, ey, ez, ex, ey, ez) > thr);
+        }
+        if (lane < n_me && TEAM + lane != sd) {
+            const double ex = mx - cx, ey = my - cy, ez = mz - cz;
+            rival = rival || !(dot3(ex, ey, ez, ex, ey, ez) > thr);
+        }
+    }
+    return __ballot_sync(ZRK_FULL, rival) != 0;
+}
+// move_to_next_sector_circular for the radars of a streak tick that sweep (Radar.py:96-117): out of line
+template <int TEAM>
+__device__ ZRK_NOINLINE void streak_sweep(double *rc, const double *c_rad_par, int nR, int lane) {
+    team_barrier<TEAM>();
+    if (lane == 0) {
+        for (int r = 0; r < nR; r++) {
+            const double *q = c_rad_par + RAD_PAR_STRIDE * r;
+            if (q[10] != 0.0) continue;
+            double caz = rc[2 * r], cel = rc[2 * r + 1];
+            radar_move(q, caz, cel);
+            rc[2 * r] = caz;
+            rc[2 * r + 1] = cel;
+        }
+    }
+    team_barrier<TEAM>();
+}
 template <int TEAM, int MPB>
 __device__ ZRK_NOINLINE int quiet_streak(const Params *Pg, unsigned char *sm, int lane, int b, int max_ticks, int noise_w,
-                                         const int *c_in, const int *c_out, const int *c_refc, int *c_flag) {
+                                         int *c_in, int *c_out, int *c_refc, float4 *fp, float4 *fv) {
     const Params &P = *Pg;
     const Layout &o = P.lo;
     constexpr MeOff XM = me_off(TEAM, MPB ? MPB : 2);
@@ -1080,8 +1127,9 @@ __device__ ZRK_NOINLINE int quiet_streak(const Params *Pg, unsigned char *sm, in
             follow = is_me || H.te_follow()[e] != 0;
         }
     }
-    const int cin = c_in[lane], cout = c_out[lane];
-    const bool refc1 = c_refc[lane] == 1;
+    int cin = c_in[lane], cout = c_out[lane];
+    bool refc1 = c_refc[lane] == 1;
+    const int tick0 = tick;  // shared memory keeps the state of tick0 - 1 for as long as the streak lasts
     const double dm = fabs(speed) * P.dt_s * 1.000000001 + 2.0 * P.noise_bound + 1e-3, dm2 = dm * dm;
     // a missile in flight: no detonation as long as it stays surely outside its radius of its target
     int m = 0, tg = 0;
@@ -1101,6 +1149,7 @@ __device__ ZRK_NOINLINE int quiet_streak(const Params *Pg, unsigned char *sm, in
     bool sweeping = false;
     for (int r = 0; r < nR; r++) sweeping = sweeping || c_rad_par[RAD_PAR_STRIDE * r + 10] == 0.0;
     int n_q = 0, n_upd = 0;
+    bool looked = false;  // the windows have been rebuilt during this streak's first tick
     double now_s = tick_seconds(P, tick);
     while (n_q < max_ticks) {
         if (tick_limit >= 0 && tick >= tick_limit) break;
@@ -1176,38 +1225,29 @@ __device__ ZRK_NOINLINE int quiet_streak(const Params *Pg, unsigned char *sm, in
             if (__ballot_sync(ZRK_FULL, bail) != 0) break;
             const unsigned dmask = __ballot_sync(ZRK_FULL, doubt);
             if (ZRK_RARE(dmask)) {
-                // The few detections that are not certified are checked against every track, all lanes at
-                // once (lane k: entry k of _target_dict and of _missile_dict): is any other track as near
-                // as the own one?  If not, link_object returns the own track; if so, the general tick decides.
-                // What a slot's tracks measure to: its prev_pos — the position still in p while the tick is
-                // not committed — or, for a slot that is gone, what was frozen there.
-                const double ax = alive || !(fl & F_HASPREV) ? px : qx, ay = alive || !(fl & F_HASPREV) ? py : qy,
-                             az = alive || !(fl & F_HASPREV) ? pz : qz;
-                const double tx = __shfl_sync(ZRK_FULL, ax, r_te), ty = __shfl_sync(ZRK_FULL, ay, r_te), tz = __shfl_sync(ZRK_FULL, az, r_te);
-                const double mx = __shfl_sync(ZRK_FULL, ax, r_me), my = __shfl_sync(ZRK_FULL, ay, r_me), mz = __shfl_sync(ZRK_FULL, az, r_me);
-                bool rival = false;
-                for (unsigned mm = dmask; mm; mm &= mm - 1) {
-                    const int d = __ffs(mm) - 1;
-                    const double cx = __shfl_sync(ZRK_FULL, nx, d), cy = __shfl_sync(ZRK_FULL, ny, d), cz = __shfl_sync(ZRK_FULL, nz, d);
-                    const double thr = __shfl_sync(ZRK_FULL, d2, d) * (1.0 + 1e-12);
-                    const int sd = __shfl_sync(ZRK_FULL, seedu, d);
-                    if (lane < n_te && lane != sd) {
-                        const double ex = tx - cx, ey = ty - cy, ez = tz - cz;
-                        rival = rival || !(dot3(ex, ey, ez, ex, ey, ez) > thr);
-                    }
-                    if (lane < n_me && TEAM + lane != sd) {
-                        const double ex = mx - cx, ey = my - cy, ez = mz - cz;
-                        rival = rival || !(dot3(ex, ey, ez, ex, ey, ez) > thr);
-                    }
-                }
-                if (__ballot_sync(ZRK_FULL, rival) != 0) break;
-                // a window that has passed keeps its slot uncertified: have the windows rebuilt (every 8th tick at most)
-                if ((tick & 7) == 0 && __ballot_sync(ZRK_FULL, doubt && cout < tick) != 0) {
-                    if (lane == 0) *c_flag |= 1;
+                if (streak_rivals<TEAM>(dmask, lane, alive || !(fl & F_HASPREV), px, py, pz, qx, qy, qz, r_te, r_me, n_te, n_me, nx, ny,
+                                        nz, d2, seedu))
                     break;
+                // a window that has passed keeps its slot uncertified: rebuild the windows (on the streak's
+                // first tick, then every 16th at most) from the state shared memory still holds, and look at
+                // this tick again
+                if (((tick & 15) == 0 || (n_q == 0 && !looked)) && __ballot_sync(ZRK_FULL, doubt && cout < tick) != 0) {
+                    looked = true;
+                    cert_recompute<TEAM>(sm, ZRK_QME_I(me_ref), lane, n_slots, tick0 - 1, tick, n_te, n_me, P.dt_s, P.noise_bound, c_in,
+                                         c_out, c_refc, fp, fv);
+                    cin = c_in[lane], cout = c_out[lane], refc1 = c_refc[lane] == 1;
+                    continue;
                 }
             }
         } else if (__syncthreads_or(bail || doubt) != 0) {
+            if (((tick & 15) == 0 || (n_q == 0 && !looked)) && __syncthreads_or(!bail && doubt && cout < tick) != 0) {  // (as above)
+                looked = true;
+                cert_recompute<TEAM>(sm, ZRK_QME_I(me_ref), lane, n_slots, tick0 - 1, tick, n_te, n_me, P.dt_s, P.noise_bound, c_in, c_out,
+                                     c_refc, fp, fv);
+                cin = c_in[lane], cout = c_out[lane], refc1 = c_refc[lane] == 1;
+                if (__syncthreads_or(bail || !(tick < cin)) != 0) break;  // still not a quiet tick
+                continue;
+            }
             break;
         }
         // ---- commit
@@ -1221,21 +1261,7 @@ __device__ ZRK_NOINLINE int quiet_streak(const Params *Pg, unsigned char *sm, in
         }
         period = per;
         n_upd += __popc(__ballot_sync(ZRK_FULL, upd_msg));
-        if (sweeping) {  // move_to_next_sector_circular (Radar.py:96-117)
-            team_barrier<TEAM>();
-            if (lane == 0) {
-                double *rc = ZRK_QME_D(rad_cur);
-                for (int r = 0; r < nR; r++) {
-                    const double *q = c_rad_par + RAD_PAR_STRIDE * r;
-                    if (q[10] != 0.0) continue;
-                    double caz = rc[2 * r], cel = rc[2 * r + 1];
-                    radar_move(q, caz, cel);
-                    rc[2 * r] = caz;
-                    rc[2 * r + 1] = cel;
-                }
-            }
-            team_barrier<TEAM>();
-        }
+        if (ZRK_RARE(sweeping)) streak_sweep<TEAM>(ZRK_QME_D(rad_cur), c_rad_par, nR, lane);
         tick++;
         n_q++;
         now_s = now_next;
@@ -1528,12 +1554,35 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
     int noise_w = noise ? hdr[H_TICK] % P.noise_period : 0;
     const int noise_row = P.noise_radars * P.noise_objects * 3;  // doubles per tick row
     int streak_wait = 0;  // ticks to go before the next attempt at a quiet streak (after one that ended at once)
+    unsigned removed_carry = 0;  // slots the last general tick removed (warp teams)
     for (int it = 0; it < n_ticks; it++) {
+        if (CERT && use_cert && has_ccp) {
+            // Certificate upkeep, on the state the last tick left (positions of tick H_TICK - 1): after an
+            // event every window is rebuilt; after tracks changed hands the reference counts; after a removal
+            // the pairs with the removed slots are merged in.
+            const int cf = *c_flag;  // bit 0: the windows are void; bit 1: tracks changed hands or were created
+            if (ZRK_RARE(cf != 0 || removed_carry != 0)) {
+                const int tprev = hdr[H_TICK] - 1, ns = hdr[H_NSLOTS];
+                if (cf & 1) {
+                    cert_recompute<TEAM>(sm, ZRK_ME_I(me_ref), lane, ns, tprev, tprev + 1, hdr[H_NTE], hdr[H_NME], P.dt_s,
+                                         P.noise_bound, c_in, c_out, c_refc, (float4 *)lxy, (float4 *)lzd);
+                } else {
+                    if (cf) cert_recount<TEAM>(sm, ZRK_ME_I(me_ref), lane, hdr[H_NTE], hdr[H_NME], c_refc);
+                    if (removed_carry)
+                        cert_removed<TEAM>(sm, lane, lane < ns ? H.sflags()[lane] : 0, removed_carry, tprev, P.dt_s, P.noise_bound,
+                                           c_in, c_out);
+                }
+                removed_carry = 0;
+                tm.sync();  // everybody has read the flag
+                if (lane == 0) *c_flag = 0;
+            }
+        }
         if (CERT && use_cert && has_ccp && --streak_wait < 0) {
             const int prv0 = (hdr[H_TICK] & 1) ^ 1;
-            if (*c_flag == 0 && hdr[H_DETN0 + prv0] == 0 && hdr[H_MBN0 + prv0] == 0 && hdr[H_CCP_INIT] && !(hdr[H_FAULT] & 63) &&
+            if (hdr[H_DETN0 + prv0] == 0 && hdr[H_MBN0 + prv0] == 0 && hdr[H_CCP_INIT] && !(hdr[H_FAULT] & 63) &&
                 !(P.log_types & ZRK_LOG_BULK)) {
-                const int nq = quiet_streak<TEAM, MPB>(P.self, sm, lane, b, n_ticks - it, noise_w, c_in, c_out, c_refc, c_flag);
+                const int nq = quiet_streak<TEAM, MPB>(P.self, sm, lane, b, n_ticks - it, noise_w, c_in, c_out, c_refc, (float4 *)lxy,
+                                                       (float4 *)lzd);
                 if (nq) {
                     it += nq;
                     if (it >= n_ticks) break;
@@ -1734,34 +1783,17 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 H.counts()[ZRK_MSG_DESTROYED_MISSILE] += nR * det_prev;
             }
         }
-        // Certificate upkeep: an event tick clears every window; otherwise the lanes whose window has
-        // passed (all of them after an event) look again.  The vote is the barrier that ends the radars.
-        bool cert_ok = false;  // this tick may take the certified CCP path (uniform)
-        if (CERT && use_cert && !event && has_ccp) {
-            unsigned removed = 0;
+        // What this tick means for the certificate (the upkeep itself runs before the next tick, see the top of
+        // the loop): an event tick voids every window; a removal freezes the removed slots where they are.
+        if (CERT && use_cert) {
             if (TEAM == 32) {
-                if (det_prev) removed = __ballot_sync(ZRK_FULL, was_alive && !alive);
-                tm.sync();
-            } else {
-                tm.sync();
+                if (ZRK_RARE(det_prev)) removed_carry = __ballot_sync(ZRK_FULL, was_alive && !alive);
+                if (event && lane == 0) *c_flag |= 1;
+            } else if ((event || det_prev) && lane == 0) {
+                *c_flag |= 1;
             }
-            const int cf = *c_flag;  // bit 0: the windows are void; bit 1: tracks changed hands or were created
-            if (ZRK_RARE((cf & 1) || (TEAM > 32 && det_prev != 0))) {
-                cert_recompute<TEAM>(sm, ZRK_ME_I(me_ref), lane, n_slots, tick, hdr[H_NTE], hdr[H_NME], P.dt_s, P.noise_bound,
-                                     c_in, c_out, c_refc, (float4 *)lxy, (float4 *)lzd);
-            } else {
-                if (ZRK_RARE(cf)) cert_recount<TEAM>(sm, ZRK_ME_I(me_ref), lane, hdr[H_NTE], hdr[H_NME], c_refc);
-                if (ZRK_RARE(removed)) cert_removed<TEAM>(sm, lane, fl, removed, tick, P.dt_s, P.noise_bound, c_in, c_out);
-            }
-            if (ZRK_RARE(cf)) {
-                tm.sync();  // everybody has read the flag
-                if (lane == 0) *c_flag = 0;
-            }
-            cert_ok = true;
-        } else {
-            if (CERT && use_cert && lane == 0) *c_flag = 1;
-            tm.sync();
         }
+        tm.sync();
 
         // ============ lane 0: sector sweep, MissileLauncher.step, CCP bookkeeping
         if (lane == 0) {
@@ -1789,128 +1821,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
         if (has_ccp && !(hdr[H_FAULT] & 63)) {
             int n_te = hdr[H_NTE];
             const int n_me = hdr[H_NME];
-            // ---- certified path: every detection provably re-acquires the track of its own slot (see
-            // "association certificate" above), so link_object's scan, the processing order and the conflict
-            // rounds are skipped: evaluate the own track exactly, stamp it, count the messages.
-            bool fast_done = false;
-            if (CERT && cert_ok && (TEAM == 32 || !logged(P, ZRK_MSG_CCP_UPDATE_TARGET))) {
-                const bool det = alive && rf >= 0;
-                // hard: this detection needs the ordinary rounds (no own track, out of its range, a launch to
-                // decide); doubt: its own track is fine but not certified to be the nearest
-                bool hard = false, doubt = false, is_me = false, follow = false;
-                int e = 0;
-                if (det) {
-                    const int seed = H.own()[lane];
-                    hard = !(seed >= 0 && (fl & F_HASPREV));
-                    if (!hard) {
-                        is_me = seed >= TEAM;
-                        e = is_me ? seed - TEAM : seed;
-                        const int ref = is_me ? ZRK_ME_I(me_ref)[e] : H.te_ref()[e];
-                        const double upds = is_me ? ZRK_ME_D(me_upds)[e] : H.te_upds()[e];
-                        follow = is_me || H.te_follow()[e] != 0;
-                        // the own track measures to this slot's prev_pos: the same d2 link_d2 computes
-                        const double2 q = H.qxy()[lane];
-                        const double qz = H.qzw()[lane].x, speed = H.pzs()[lane].y;
-                        const double ex = q.x - px, ey = q.y - py, ez = qz - pz;
-                        const double d2 = dot3(ex, ey, ez, ex, ey, ez);
-                        double lo, hi;
-                        calc_range(speed, now_s - upds, P.range_step, lo, hi);
-                        const double EPS = 4e-15;  // as link_eval: inside [lo, hi] beyond doubt
-                        const double l2 = lo * lo, h2 = hi * hi;
-                        const bool in_sure = d2 >= l2 * (1.0 + EPS) && d2 <= h2 * (1.0 - EPS);
-                        // a target nobody follows yet would ask for a launch while capacity is left (CCP.py:332-348)
-                        hard = !(ref == lane && in_sure && (follow || hdr[H_FREECAP] <= 0));
-                        // the certificate's premise on the own track's distance is checked rather than assumed
-                        const double dm = fabs(speed) * P.dt_s * 1.000000001 + 2.0 * P.noise_bound + 1e-3;
-                        doubt = !(tick < c_in[lane] && c_refc[lane] == 1 && d2 <= dm * dm);
-                    }
-                }
-                bool slow;
-                if (TEAM == 32) {
-                    slow = __ballot_sync(ZRK_FULL, hard) != 0;
-                    const unsigned dmask = __ballot_sync(ZRK_FULL, doubt);
-                    if (ZRK_RARE(!slow && dmask)) {
-                        // The few uncertified detections are checked against every track, all lanes at once
-                        // (lane k: _target_dict entry k and _missile_dict entry k): is any other track as
-                        // near as the own one?  If so the ordinary scan decides; if not, link_object returns
-                        // the own track (the nearest one in range).
-                        const bool hte = lane < n_te, hme = lane < n_me;
-                        double tx = 0, ty = 0, tz = 0, mx = 0, my = 0, mz = 0;
-                        if (hte) {
-                            const int ref = H.te_ref()[lane];
-                            tx = H.qxy()[ref].x, ty = H.qxy()[ref].y, tz = H.qzw()[ref].x;
-                        }
-                        if (hme) {
-                            const int ref = ZRK_ME_I(me_ref)[lane];
-                            const bool hp = (H.sflags()[ref] & F_HASPREV) != 0;
-                            mx = hp ? H.qxy()[ref].x : H.pxy()[ref].x, my = hp ? H.qxy()[ref].y : H.pxy()[ref].y;
-                            mz = hp ? H.qzw()[ref].x : H.pzs()[ref].x;
-                        }
-                        bool rival = false;
-                        for (unsigned m = dmask; m; m &= m - 1) {
-                            const int d = __ffs(m) - 1, sd = H.own()[d];
-                            const double2 p = H.pxy()[d], q = H.qxy()[d];
-                            const double pz_ = H.pzs()[d].x, qz_ = H.qzw()[d].x;
-                            const double ox = q.x - p.x, oy = q.y - p.y, oz = qz_ - pz_;
-                            const double thr = dot3(ox, oy, oz, ox, oy, oz) * (1.0 + 1e-12);
-                            if (hte && lane != sd) {
-                                const double ax = tx - p.x, ay = ty - p.y, az = tz - pz_;
-                                rival = rival || !(dot3(ax, ay, az, ax, ay, az) > thr);
-                            }
-                            if (hme && TEAM + lane != sd) {
-                                const double ax = mx - p.x, ay = my - p.y, az = mz - pz_;
-                                rival = rival || !(dot3(ax, ay, az, ax, ay, az) > thr);
-                            }
-                        }
-                        slow = __ballot_sync(ZRK_FULL, rival) != 0;
-                        // a window that has passed keeps its slot uncertified: look again (every 8th tick at most)
-                        if ((tick & 7) == 0 && __ballot_sync(ZRK_FULL, doubt && c_out[lane] < tick) != 0 && lane == 0) *c_flag |= 1;
-                    }
-                } else {
-                    slow = tm.any(hard || doubt);
-                    if ((tick & 7) == 0 && doubt && c_out[lane] < tick) atomicOr(c_flag, 1);  // (as above)
-                }
-                if (ZRK_OFTEN(!slow)) {
-                    const bool upd_msg = det && !is_me && follow;  // old_target, followed: CCP_UPDATE_TARGET (CCP.py:350-357)
-                    const bool lu = logged(P, ZRK_MSG_CCP_UPDATE_TARGET);
-                    int r_upd = 0, n_upd = 0;
-                    if (TEAM == 32) {
-                        if (lu) {  // message order = detection order: first radar that saw the object, then slot
-                            for (int r = 0; r < nR; r++) {
-                                int tot;
-                                const int ex_ = tm.rank(upd_msg && rf == r, tot);
-                                if (rf == r) r_upd = n_upd + ex_;
-                                n_upd += tot;
-                            }
-                        } else {
-                            n_upd = __popc(__ballot_sync(ZRK_FULL, upd_msg));
-                        }
-                        if (lane == 0) {
-                            H.counts()[ZRK_MSG_CCP_UPDATE_TARGET] += (unsigned)n_upd;
-                            hdr[H_FAST] += 1;
-                        }
-                    } else {
-                        const int c = __popc(__ballot_sync(ZRK_FULL, upd_msg));
-                        if ((lane & 31) == 0 && c) atomicAdd((int *)&H.counts()[ZRK_MSG_CCP_UPDATE_TARGET], c);
-                        if (lane == 0) hdr[H_FAST] += 1;
-                    }
-                    if (det) {
-                        if (!is_me) {
-                            if (upd_msg && lu)
-                                put_rec(P, rec, nrec + r_upd, tick, ZRK_MSG_CCP_UPDATE_TARGET, 0, ccp_id, ZRK_CST_I(c_rad_id)[rf], my_id,
-                                        H.te_mid()[e], 0, 0, 0);
-                            H.te_upd()[e] = tick;
-                            H.te_upds()[e] = now_s;
-                        } else {
-                            ZRK_ME_I(me_upd)[e] = tick;
-                            ZRK_ME_D(me_upds)[e] = now_s;
-                        }
-                    }
-                    if (lu) nrec += n_upd;
-                    fast_done = true;
-                }
-            }
-            if (ZRK_RARE(!fast_done)) {
+            {
             bool structural = false;  // this tick's rounds went beyond re-stamping own tracks
             // With the quiet streak carrying the ordinary ticks, a warp team comes here on the rare eventful
             // tick only, and what it costs then is the code it has to fetch, not the arithmetic: it scans
@@ -2206,7 +2117,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 tm.sync();  // entry updates of this round are visible to the next
             }
             if (CERT && structural && lane == 0) *c_flag |= 2;  // tracks changed hands or were created
-            }  // !fast_done
+            }
             tm.sync();
 
             // ============ send_objects_to_GUI (CCP.py:237-284)

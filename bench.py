@@ -152,6 +152,37 @@ def cpu_reference_throughput(name, n_scen_per_core, cores, ticks=None):
     return n * (T + L * mpl) * ticks / dt, n, ticks, dt
 
 
+def python_loop(name):
+    """The reference's OWN Python tick loop (Manager.run_simulation, Manager.py:111-140) on all host cores.
+    Live when the reference tree is present (the build container; $ZRK_REFERENCE_DIR), else the committed
+    measurement profiles/ref_python_loop.json (made by profiles/ref_python_loop.py) is cited: the reference
+    is pure Python and does not travel to the GPU box."""
+    shape = name if name in ("c5", "c3", "c4") else "c5"
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        sys.path.insert(0, os.path.join(ROOT, "profiles"))
+        import refharness
+        if refharness.available():
+            import ref_python_loop
+            r = ref_python_loop.measure(shape, per_core=1)
+            return {"value": r["object_updates_per_s"], "unit": "object-updates/s", "cores": r["cores"], "kind": "reference",
+                    "per_core": r["object_updates_per_s_per_core"], "measured": "live, this host",
+                    "sample": f"{r['scenarios']} scenarios x {r['slots']} slots x {r['ticks']} ticks, one process per core"}
+    except Exception as e:  # the live leg is best effort
+        print(f"python_loop: live measurement failed: {e}", file=sys.stderr)
+    p = os.path.join(ROOT, "profiles", "ref_python_loop.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        for r in d["runs"]:
+            if r["workload"] == shape:
+                return {"value": r["object_updates_per_s"], "unit": "object-updates/s", "cores": r["cores"], "kind": "reference",
+                        "per_core": r["object_updates_per_s_per_core"],
+                        "measured": f"cited from profiles/ref_python_loop.json ({d['host']['where']}, "
+                                    f"{d['host']['cpu_count']} cores): the reference is pure Python and is not on this box",
+                        "sample": f"{r['scenarios']} scenarios x {r['slots']} slots x {r['ticks']} ticks, one process per core"}
+    return None
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -176,6 +207,7 @@ def run_reference(args, rank, world):
                                        f"reference tick (oracle/zrk_oracle.c) on {cores} host threads"},
             "e2e": {"value": value, "unit": "object-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "scenario_ticks_per_s": value / slots}
+    line["cpu_baseline"]["python_loop"] = python_loop(args.workload)
     print(json.dumps(line), flush=True)
 
 
@@ -228,6 +260,10 @@ def run_ours(args, rank, world, local_rank):
             counts = eng.counts()
             fc, ft, nr = eng.status()
             alive_ticks = int(eng.alive_slot_ticks().sum())
+            # a scenario the reference would have aborted freezes at its fault tick: only the
+            # ticks it really ran count as work
+            ran_ticks = np.where((fc & 63) != 0, np.minimum(ft.astype(np.int64) + 1, ticks), ticks)
+            units_done = int(NS * ran_ticks.sum())
             cert_ticks = int(eng.certified_ticks().sum())
         eng.close()
     clocks = sampler.stop() if sampler else None
@@ -269,15 +305,16 @@ def run_ours(args, rank, world, local_rank):
     from zrk_modulation_b200.distributed import describe_stats, gather_stats, local_stats
     assert np.array_equal(dev_stats.cpu().numpy(), local_stats(counts, fc)), "device-side statistics differ"
     stats = gather_stats(dev_stats, device=torch.device("cuda", dev))
-    alive_all = int(gather_stats(torch.tensor([alive_ticks], dtype=torch.int64), device=torch.device("cuda", dev))[0])
+    alive_all, units_all = (int(x) for x in gather_stats(torch.tensor([alive_ticks, units_done], dtype=torch.int64),
+                                                        device=torch.device("cuda", dev)))
 
     if rank == 0:
-        value = units * world * args.steps / (total_ms * 1e-3)
-        e2e_value = units * world * args.steps / float(t_e2e.item())
+        value = units_all * args.steps / (total_ms * 1e-3)
+        e2e_value = units_all * args.steps / float(t_e2e.item())
         peak, peak_src = measured_peak_gbs()
         per_launch_ms = sum(kern_ms) / max(1, launches)
         ticks_per_launch = ticks * args.steps / max(1, launches)
-        achieved = B * NS * ticks_per_launch * BYTES_PER_OBJECT_UPDATE / (per_launch_ms * 1e-3) / 1e9
+        achieved = (units_all / world) * (ticks_per_launch / ticks) * BYTES_PER_OBJECT_UPDATE / (per_launch_ms * 1e-3) / 1e9
         line = {
             "metric": "object-updates/sec", "value": value, "unit": "object-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -285,6 +322,8 @@ def run_ours(args, rank, world, local_rank):
             "config": dict(describe(args.workload, world), ticks_per_launch=ticks_per_launch),
             "scenario_ticks_per_s": value / NS,
             "active_slot_fraction": alive_all / float(units * world),  # alive objects / (scenarios x slots x ticks), SURVEY 8d
+            "object_updates_per_step": units_all,  # what `value` counts: slots x ticks really run (faulted scenarios stop early)
+            "object_updates_not_run": units * world - units_all,
             "certified_tick_fraction": cert_ticks / float(B * ticks),  # rank 0's shard: ticks whose link_object scan was proven away
             "e2e": {"value": e2e_value, "unit": "object-updates/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t_e2e.item()) / args.steps * 1e3,
@@ -302,15 +341,23 @@ def run_ours(args, rank, world, local_rank):
                                  "traffic is far lower (see profiles/)"},
             "stats": describe_stats(stats),
         }
+        # Where the kernel really lives: instruction issue.  Warp instructions per scenario-tick (ncu, committed
+        # summary of this workload) x scenario-ticks/s per GPU against SMs x 4 schedulers x the SM clock under load.
+        wi = profiled(args.workload, ticks_per_launch, "warp_instructions_per_scenario_tick", "ncu smsp__inst_executed.sum / scenario-ticks")
+        if wi and clocks and clocks.get("sm_mhz"):
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            peak_issue = sms * 4 * clocks["sm_mhz"] * 1e6
+            ach_issue = wi["warp_instructions_per_scenario_tick"] * (value / NS / world)
+            line["issue_roofline"] = {"bound": "issue", "achieved": ach_issue / 1e9, "peak": peak_issue / 1e9, "unit": "G warp-instr/s",
+                                      "frac": ach_issue / peak_issue, "warp_instructions_per_scenario_tick": wi["warp_instructions_per_scenario_tick"],
+                                      "source": wi["source"], "sms": sms, "sm_mhz": clocks["sm_mhz"]}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             v, n, tk, dt = cpu_reference_throughput(args.workload, 1024, cores, min(ticks, 250))
             line["cpu_baseline"] = {"value": v, "unit": "object-updates/s", "cores": cores, "kind": "port",
                                     "sample": f"{n} scenarios x {NS} slots x {tk} ticks in {dt:.2f}s, "
                                               f"oracle/zrk_oracle.c on {cores} host threads",
-                                    "note": "the reference itself is pure Python and cannot travel to this box; in the "
-                                            "build container its loop does 4.4e3 object-updates/s per core on this "
-                                            "workload (DESIGN.md section 5)"}
+                                    "python_loop": python_loop(args.workload)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -88,6 +88,7 @@ __global__ void zrk_init_kernel(const Params P, const DevDesc d, int *err, int b
         te_mid[k] = ZRK_NONE;
     }
     if (lane == 0) {
+        ((int *)(sm + ho.counts))[CW_FLAG] = CF_WINDOWS | CF_GENERAL;  // no certificate yet; tick 0 is a general tick
         hdr[H_NSLOTS] = nT;
         int *chdr = (int *)(cs + o.c_hdr);
         chdr[C_NT] = nT; chdr[C_NR] = nR; chdr[C_NL] = nL; chdr[C_NM] = nM; chdr[C_NC] = nC;
@@ -230,7 +231,15 @@ struct zrk_handle {
     int *pin_err = nullptr;   // pinned: the init kernel's verdict when zrk_create did not wait for it
     bool deferred = false;    // that verdict has not been looked at yet
     int sticky_rc = ZRK_OK;   // a deferred create error: every later call returns it
+    // two-kernel stepping (warp teams with the certificate): rounds of streak kernel + tick kernel
+    bool two_kernel = false;
+    int *d_pending = nullptr;  // [waves][ZRK_ROUND_SLOTS] scenarios still short of the target after a round
+    int *h_pending = nullptr;  // pinned [waves]
+    int round_no = 0;
+    long long n_rounds = 0;
 };
+#define ZRK_ROUND_SLOTS 1024
+#define ZRK_ROUND_BATCH 6  /* rounds queued between two looks at the pending counters */
 
 static thread_local std::string g_create_err;
 
@@ -323,7 +332,8 @@ static int dev_alloc(zrk_handle *h, size_t n, T **dst, bool zero) {
     return ZRK_OK;
 }
 
-typedef void (*tick_fn)(const Params, int, int, int);
+typedef void (*tick_fn)(const Params, int, int, int, int, int *);
+typedef void (*streak_fn)(const Params, int, int, int);
 
 template <int TEAM, int TPC, int MPB>
 static tick_fn pick_fast(bool fast) {
@@ -339,6 +349,10 @@ static tick_fn pick_kernel(const Layout &lo, bool fast) {
     case 1024: return pick_fast<1024, 1, 0>(fast);
     }
     return nullptr;
+}
+
+static streak_fn pick_streak(const Layout &lo) {
+    return lo.MP == 8 ? (streak_fn)zrk_streak_kernel<8> : (streak_fn)zrk_streak_kernel<32>;
 }
 
 extern "C" int zrk_abi_version(void) { return ZRK_ABI_VERSION; }
@@ -365,6 +379,7 @@ extern "C" void zrk_destroy(zrk_handle *h) {
     for (auto e : h->wave_done) cudaEventDestroy(e);
     if (!h->wave_stream.empty()) cudaEventDestroy(h->fork_ev);
     pinned_put(h->pin_err, sizeof(int));
+    pinned_put(h->h_pending, sizeof(int) * 64);
     pinned_put(h->h_summary, (size_t)h->P.lo.B * ZRK_SUMMARY_WORDS * sizeof(int));
     for (void *p : h->allocs) cudaFreeAsync(p, h->stream);
     cudaStreamSynchronize(h->stream);
@@ -590,6 +605,14 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
     if ((rc = ensure_tsec(h, 1024)) != ZRK_OK) return rc;
+    {
+        const char *env = getenv("ZRK_TWO_KERNEL");
+        h->two_kernel = lo.team == 32 && P.cert && h->fast && !(env && atoi(env) == 0);
+        if (h->two_kernel) {
+            if ((rc = dev_alloc(h, (size_t)n_waves * ZRK_ROUND_SLOTS, &h->d_pending, true)) != ZRK_OK) return rc;
+            CK(pinned_get((void **)&h->h_pending, sizeof(int) * 64));
+        }
+    }
 
     // upload + init, wave by wave
     if (n_waves > 1) {
@@ -699,6 +722,61 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
     }
     const int n_waves = h->wave_stream.empty() ? 1 : (int)h->wave_stream.size();
     const int tpc = h->P.lo.teams_per_cta;
+    if (h->two_kernel && n_ticks >= 8) {
+        // Two-kernel stepping: every round runs the streak kernel (quiet ticks, straight from HBM) and then the
+        // tick kernel (whatever else) over the batch; a scenario advances in whichever of the two its next
+        // tick belongs to, until all have reached the target.  The number of rounds depends on the data, so
+        // the host looks at the pending counters after every few rounds.
+        const int target = (int)(h->tick + n_ticks);
+        streak_fn sf = pick_streak(h->P.lo);
+        for (;;) {
+            if (h->round_no + ZRK_ROUND_BATCH > ZRK_ROUND_SLOTS) {
+                for (int w = 0; w < n_waves; w++)
+                    CK(cudaMemsetAsync(h->d_pending + (size_t)w * ZRK_ROUND_SLOTS, 0, sizeof(int) * ZRK_ROUND_SLOTS,
+                                       n_waves > 1 ? h->wave_stream[w] : h->stream));
+                h->round_no = 0;
+            }
+            for (int w = 0; w < n_waves; w++) {
+                const int b0 = n_waves > 1 ? h->wave_b[w] : 0, b1 = n_waves > 1 ? h->wave_b[w + 1] : h->P.lo.B;
+                cudaStream_t ws = n_waves > 1 ? h->wave_stream[w] : h->stream;
+                for (int r = 0; r < ZRK_ROUND_BATCH; r++) {
+                    cudaEvent_t e0, e1;
+                    int rc;
+                    if ((rc = get_event(h, &e0)) || (rc = get_event(h, &e1))) return rc;
+                    CK(cudaEventRecord(e0, ws));
+                    ZRK_LAUNCH(sf, (b1 - b0 + ZRK_STREAK_WARPS - 1) / ZRK_STREAK_WARPS, 32 * ZRK_STREAK_WARPS, ZRK_STREAK_SMEM, ws, h->P, b0, b1, target);
+                    ZRK_LAUNCH(fn, (b1 - b0 + tpc - 1) / tpc, h->block, h->smem_bytes, ws, h->P, 0, b0, b1, target,
+                               h->d_pending + (size_t)w * ZRK_ROUND_SLOTS + h->round_no + r);
+                    CK(cudaGetLastError());
+                    CK(cudaEventRecord(e1, ws));
+                    h->pending.push_back({e0, e1});
+                    h->n_launches += 2;
+                }
+                CK(cudaMemcpyAsync(h->h_pending + w, h->d_pending + (size_t)w * ZRK_ROUND_SLOTS + h->round_no + ZRK_ROUND_BATCH - 1,
+                                   sizeof(int), cudaMemcpyDeviceToHost, ws));
+            }
+            h->round_no += ZRK_ROUND_BATCH;
+            h->n_rounds += ZRK_ROUND_BATCH;
+            bool more = false;
+            for (int w = 0; w < n_waves; w++) {
+                CK(cudaStreamSynchronize(n_waves > 1 ? h->wave_stream[w] : h->stream));
+                more = more || h->h_pending[w] != 0;
+            }
+            if (h->pending.size() > 2048) {
+                int rc = resolve_events(h);
+                if (rc) return rc;
+            }
+            if (!more) break;
+        }
+        for (int w = 0; w < n_waves && n_waves > 1; w++) {
+            CK(cudaEventRecord(h->wave_done[w], h->wave_stream[w]));
+            CK(cudaStreamWaitEvent(h->stream, h->wave_done[w], 0));
+        }
+        h->tick += n_ticks;
+        if (!h->h_summary)
+            CK(pinned_get((void **)&h->h_summary, (size_t)h->P.lo.B * ZRK_SUMMARY_WORDS * sizeof(int)));
+        return ZRK_OK;
+    }
     // Every call that queues work on the main stream also waits for it (reads, table growth), so a
     // wave never has to wait for the main stream here — and must not: right after zrk_create the
     // main stream is queued behind the uploads of ALL waves, which is exactly what a wave's first
@@ -713,7 +791,7 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
             int rc;
             if ((rc = get_event(h, &e0)) || (rc = get_event(h, &e1))) return rc;
             CK(cudaEventRecord(e0, ws));
-            ZRK_LAUNCH(fn, (b1 - b0 + tpc - 1) / tpc, h->block, h->smem_bytes, ws, h->P, k, b0, b1);
+            ZRK_LAUNCH(fn, (b1 - b0 + tpc - 1) / tpc, h->block, h->smem_bytes, ws, h->P, k, b0, b1, -1, (int *)nullptr);
             CK(cudaGetLastError());
             CK(cudaEventRecord(e1, ws));
             h->pending.push_back({e0, e1});

@@ -45,7 +45,16 @@ struct HotOff {
     int sid, sflags, srf, own;                        // int[TEAM]
     int te_key, te_ref, te_upd, te_follow, te_mid;    // int[TEAM]  CCP._target_dict
     int te_upds;                                      // double[TEAM] TargetCCP.upd_time (seconds)
+    int c_in, c_out, c_refc;                          // int[TEAM] (teams up to 256 slots) association certificate, zrk_tick.cuh:
+                                                      // per slot the window of ticks it is not certified in, tracks per slot
     int end;
+};
+// words 18 and 19 of `counts` (after the 18 message counters) carry the certificate's flags
+enum { CW_FLAG = 18 /* CF_* */, CW_REMOVED = 19 /* slots the last general tick removed (bit mask, warp teams) */ };
+enum {
+    CF_WINDOWS = 1, /* the windows are void: rebuild them */
+    CF_TRACKS = 2,  /* tracks changed hands or were created: recount the tracks per slot */
+    CF_GENERAL = 4  /* (two-kernel stepping) the next tick of this scenario is not one the streak kernel can run */
 };
 ZRK_HD constexpr HotOff hot_off(int team) {
     HotOff h{};
@@ -69,6 +78,10 @@ ZRK_HD constexpr HotOff hot_off(int team) {
     h.te_follow = p; p += 4 * team;
     h.te_mid = p; p += 4 * team;
     h.te_upds = p; p += 8 * team;
+    const int ct = team <= 256 ? team : 0;  // (larger teams run without the certificate)
+    h.c_in = p; p += 4 * ct;
+    h.c_out = p; p += 4 * ct;
+    h.c_refc = p; p += 4 * ct;
     h.end = p;
     return h;
 }
@@ -83,7 +96,6 @@ ZRK_HD constexpr HotOff hot_off(int team) {
 // constants for warp teams, whose kernel is instantiated per capacity bucket.
 struct ScratchOff {
     int x_lxy, x_lzd, x_lf, x_claim, x_detlist, x_wscr, x_need, x_ghead, x_mbar;
-    int x_cin, x_cout, x_refc, x_cflag;  // association certificate (see zrk_tick.cuh): per-slot window, reference counts, dirty flag
     int bytes;
 };
 ZRK_HD constexpr int zrk_align_c(int x, int a) { return (x + a - 1) / a * a; }
@@ -99,11 +111,6 @@ ZRK_HD constexpr ScratchOff scratch_off(int team, int mp) {
     x.x_need = p; p += 4 * team;
     x.x_ghead = p; p += 4 * team;
     x.x_mbar = p; p += 8;
-    const int ct = team <= 256 ? team : 0;  // (larger teams run without the certificate)
-    x.x_cin = p; p += 4 * ct;
-    x.x_cout = p; p += 4 * ct;
-    x.x_refc = p; p += 4 * ct;
-    x.x_cflag = p; p += 8;
     x.bytes = zrk_align_c(p, 16);
     return x;
 }
@@ -152,7 +159,6 @@ struct Layout {
     int x_claim, x_detlist, x_wscr, x_need;  // x_need doubles as the launch result (x_ok)
     int x_ghead;       // int[TEAM]: bucket heads of the hash grid over the entries' link positions
     int x_mbar;            // one 8-byte mbarrier: completion of the bulk (TMA) load of the state
-    int x_cin, x_cout, x_refc, x_cflag;  // int[TEAM] x 3 + one flag word: the association certificate
     int team_smem_bytes;
 };
 
@@ -242,7 +248,6 @@ static inline Layout make_layout(int B, int T, int M, int R, int L, int C, int n
         o.x_lxy = x.x_lxy - x.bytes; o.x_lzd = x.x_lzd - x.bytes; o.x_lf = x.x_lf - x.bytes;
         o.x_claim = x.x_claim - x.bytes; o.x_detlist = x.x_detlist - x.bytes; o.x_wscr = x.x_wscr - x.bytes;
         o.x_need = x.x_need - x.bytes; o.x_ghead = x.x_ghead - x.bytes; o.x_mbar = x.x_mbar - x.bytes;
-        o.x_cin = x.x_cin - x.bytes; o.x_cout = x.x_cout - x.bytes; o.x_refc = x.x_refc - x.bytes; o.x_cflag = x.x_cflag - x.bytes;
         o.team_smem_bytes = zrk_align(x.bytes + o.dyn_bytes + o.cst_bytes, 16);
     }
     return o;

@@ -463,6 +463,11 @@ struct Hot {
     __device__ __forceinline__ int *te_follow() const { return (int *)(sm + O.te_follow); }
     __device__ __forceinline__ int *te_mid() const { return (int *)(sm + O.te_mid); }
     __device__ __forceinline__ double *te_upds() const { return (double *)(sm + O.te_upds); }
+    __device__ __forceinline__ int *c_in() const { return (int *)(sm + O.c_in); }
+    __device__ __forceinline__ int *c_out() const { return (int *)(sm + O.c_out); }
+    __device__ __forceinline__ int *c_refc() const { return (int *)(sm + O.c_refc); }
+    __device__ __forceinline__ int *c_flag() const { return (int *)(sm + O.counts) + CW_FLAG; }
+    __device__ __forceinline__ int *c_removed() const { return (int *)(sm + O.counts) + CW_REMOVED; }
 };
 
 // Cold arrays (run-time offsets), resolved on use.
@@ -1077,8 +1082,10 @@ __device__ ZRK_NOINLINE void streak_sweep(double *rc, const double *c_rad_par, i
     team_barrier<TEAM>();
 }
 template <int TEAM, int MPB>
-__device__ ZRK_NOINLINE int quiet_streak(const Params *Pg, unsigned char *sm, int lane, int b, int max_ticks, int noise_w,
-                                         int *c_in, int *c_out, int *c_refc, float4 *fp, float4 *fv) {
+__device__ ZRK_NOINLINE int quiet_streak(const Params *Pg, unsigned char *sm, const unsigned char *cs, int lane, int b,
+                                         int max_ticks, int noise_w, float4 *fp, float4 *fv) {
+    // sm: the scenario's state blob, cs: its parameter blob — in shared memory (the tick kernel) or in
+    // global memory (the streak kernel: a streak touches each word once at its beginning and its end)
     const Params &P = *Pg;
     const Layout &o = P.lo;
     constexpr MeOff XM = me_off(TEAM, MPB ? MPB : 2);
@@ -1087,7 +1094,8 @@ __device__ ZRK_NOINLINE int quiet_streak(const Params *Pg, unsigned char *sm, in
     Hot<TEAM> H;
     H.sm = sm;
     int *const hdr = H.hdr();
-    const int *chdr = ZRK_CST_I(c_hdr);
+    int *const c_in = H.c_in(), *const c_out = H.c_out(), *const c_refc = H.c_refc();
+    const int *chdr = (const int *)(cs + o.c_hdr);
     const int nR = chdr[C_NR], T = o.T, tick_limit = chdr[C_TICK_LIMIT], n_slots = hdr[H_NSLOTS];
     int tick = hdr[H_TICK];
     const bool nolaunch = hdr[H_FREECAP] <= 0;
@@ -1138,14 +1146,15 @@ __device__ ZRK_NOINLINE int quiet_streak(const Params *Pg, unsigned char *sm, in
         m = (fl >> F_STATIC_SHIFT) - T;
         tg = ZRK_COLD_I(m_target)[m];
         period = ZRK_COLD_D(m_period)[m];
-        const double r = ZRK_CST_D(c_m_radius)[m];
+        const double r = ((const double *)(cs + o.c_m_radius))[m];
         r2hi = r * r * (1.0 + 1e-15);
         if (!(r >= 0.0) || tg < 0 || tg >= n_slots) bail0 = true;
     }
     const unsigned alive_mask = __ballot_sync(ZRK_FULL, alive), msl_mask = __ballot_sync(ZRK_FULL, msl);
     const double *noise = P.noise ? P.noise + (size_t)b * P.noise_stride + (fl >> F_STATIC_SHIFT) * 3 : nullptr;
     const int noise_row = P.noise_radars * P.noise_objects * 3;
-    const double *rad_cur = ZRK_QME_D(rad_cur), *c_rad_pos = ZRK_CST_D(c_rad_pos), *c_rad_par = ZRK_CST_D(c_rad_par);
+    const double *rad_cur = ZRK_QME_D(rad_cur), *c_rad_pos = (const double *)(cs + o.c_rad_pos),
+                 *c_rad_par = (const double *)(cs + o.c_rad_par);
     bool sweeping = false;
     for (int r = 0; r < nR; r++) sweeping = sweeping || c_rad_par[RAD_PAR_STRIDE * r + 10] == 0.0;
     int n_q = 0, n_upd = 0;
@@ -1498,8 +1507,12 @@ constexpr int min_blocks(int threads) { return threads <= 64 ? 8 : (threads <= 1
 #endif
 // MPB: missile capacity bucket of a warp team (Layout::MP as a compile-time constant, so that the
 // scratch and track-entry offsets below are immediates); 0 = offsets from the Layout at run time.
+// target_tick < 0: run n_ticks ticks of every scenario (quiet streaks included, in this kernel).
+// target_tick >= 0 (warp teams, "two-kernel stepping"): this launch runs only the ticks the streak kernel
+// (zrk_streak_kernel below) cannot — of the scenarios flagged CF_GENERAL, until each of them is fit for a
+// streak again or has reached target_tick — and counts in *pending the scenarios still short of target_tick.
 template <int TEAM, int TPC, bool FAST, int MPB>
-__global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int b_first, int b_end) {
+__global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int b_first, int b_end, int target_tick, int *pending) {
     ZRK_SMEM_DECL;
     const Layout &o = P.lo;
     constexpr ScratchOff XS = scratch_off(TEAM, MPB ? MPB : 2);
@@ -1515,6 +1528,17 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
     const int lane = tm.lane;
     const int b = b_first + blockIdx.x * TPC + tm.tic;  // this launch covers scenarios [b_first, b_end)
     if (b >= b_end) return;  // whole team leaves together
+    const bool two = TEAM == 32 && target_tick >= 0;
+    if (two) {  // is there anything for this kernel to do?  (three words of the scenario's header, before any staging)
+        const unsigned char *g = P.dyn + (size_t)b * o.dyn_bytes;
+        const int *gh = (const int *)(g + Hot<TEAM>::O.hdr);
+        const int lim = ((const int *)(P.cst + (size_t)b * o.cst_bytes + o.c_hdr))[C_TICK_LIMIT];
+        if (gh[H_TICK] >= target_tick || (gh[H_FAULT] & 63) || (lim >= 0 && gh[H_TICK] >= lim)) return;
+        if (!(((const int *)(g + Hot<TEAM>::O.counts))[CW_FLAG] & CF_GENERAL)) {  // the streak kernel's turn
+            if (lane == 0) atomicAdd(pending, 1);
+            return;
+        }
+    }
     unsigned char *sm = zrk_smem + (size_t)tm.tic * o.team_smem_bytes + (MPB ? XS.bytes : o.scratch_bytes);  // the dyn blob; scratch in front of it
     Hot<TEAM> H;
     H.sm = sm;
@@ -1525,10 +1549,8 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
     int *ghead = (int *)(sm + ZRK_X(x_ghead));
     // association certificate (teams up to 256 slots: the pair loop is O(slots) per lane)
     constexpr bool CERT = FAST && TEAM <= 256;
-    int *const c_in = (int *)(sm + ZRK_X(x_cin)), *const c_out = (int *)(sm + ZRK_X(x_cout));
-    int *const c_flag = (int *)(sm + ZRK_X(x_cflag)), *const c_refc = (int *)(sm + ZRK_X(x_refc));
-    const bool use_cert = CERT && P.cert && n_ticks >= 4;  // (windows live in scratch: a short launch would only pay for them)
-    if (CERT && lane == 0) *c_flag = 1;  // nothing is known yet
+    int *const c_in = H.c_in(), *const c_out = H.c_out(), *const c_flag = H.c_flag(), *const c_refc = H.c_refc();
+    const bool use_cert = CERT && P.cert && (two || n_ticks >= 4);  // (a short launch would only pay for the upkeep)
 
     // ---- prologue: HBM -> shared memory, one bulk copy per blob
     {
@@ -1540,6 +1562,8 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
     }
     tm.sync();
 
+    // (a launch that does not keep the certificate up leaves word that the windows are void)
+    if (CERT && !use_cert && lane == 0) *c_flag |= CF_WINDOWS;
     const int *chdr = ZRK_CST_I(c_hdr);
     const int nR = chdr[C_NR], nC = chdr[C_NC], T = o.T;
     const int ccp_id = chdr[C_CCP_ID];
@@ -1554,16 +1578,18 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
     int noise_w = noise ? hdr[H_TICK] % P.noise_period : 0;
     const int noise_row = P.noise_radars * P.noise_objects * 3;  // doubles per tick row
     int streak_wait = 0;  // ticks to go before the next attempt at a quiet streak (after one that ended at once)
-    unsigned removed_carry = 0;  // slots the last general tick removed (warp teams)
+    if (two) n_ticks = target_tick - hdr[H_TICK];
+    int *const c_removed = H.c_removed();  // slots the last general tick removed (bit mask, warp teams)
     for (int it = 0; it < n_ticks; it++) {
         if (CERT && use_cert && has_ccp) {
             // Certificate upkeep, on the state the last tick left (positions of tick H_TICK - 1): after an
             // event every window is rebuilt; after tracks changed hands the reference counts; after a removal
             // the pairs with the removed slots are merged in.
-            const int cf = *c_flag;  // bit 0: the windows are void; bit 1: tracks changed hands or were created
+            const int cf = *c_flag & (CF_WINDOWS | CF_TRACKS);
+            const unsigned removed_carry = (unsigned)*c_removed;
             if (ZRK_RARE(cf != 0 || removed_carry != 0)) {
                 const int tprev = hdr[H_TICK] - 1, ns = hdr[H_NSLOTS];
-                if (cf & 1) {
+                if (cf & CF_WINDOWS) {
                     cert_recompute<TEAM>(sm, ZRK_ME_I(me_ref), lane, ns, tprev, tprev + 1, hdr[H_NTE], hdr[H_NME], P.dt_s,
                                          P.noise_bound, c_in, c_out, c_refc, (float4 *)lxy, (float4 *)lzd);
                 } else {
@@ -1572,16 +1598,25 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                         cert_removed<TEAM>(sm, lane, lane < ns ? H.sflags()[lane] : 0, removed_carry, tprev, P.dt_s, P.noise_bound,
                                            c_in, c_out);
                 }
-                removed_carry = 0;
-                tm.sync();  // everybody has read the flag
-                if (lane == 0) *c_flag = 0;
+                tm.sync();  // everybody has read the flags
+                if (lane == 0) {
+                    *c_flag &= ~(CF_WINDOWS | CF_TRACKS);
+                    *c_removed = 0;
+                }
             }
         }
-        if (CERT && use_cert && has_ccp && --streak_wait < 0) {
+        if (two) {  // hand the scenario back to the streak kernel as soon as its next tick is one for it
+            const int prv0 = (hdr[H_TICK] & 1) ^ 1;
+            if (it > 0 && use_cert && has_ccp && hdr[H_DETN0 + prv0] == 0 && hdr[H_MBN0 + prv0] == 0 && hdr[H_CCP_INIT] &&
+                !(hdr[H_FAULT] & 63) && !(P.log_types & ZRK_LOG_BULK)) {
+                if (lane == 0) *c_flag &= ~CF_GENERAL;
+                break;
+            }
+        } else if (CERT && use_cert && has_ccp && --streak_wait < 0) {
             const int prv0 = (hdr[H_TICK] & 1) ^ 1;
             if (hdr[H_DETN0 + prv0] == 0 && hdr[H_MBN0 + prv0] == 0 && hdr[H_CCP_INIT] && !(hdr[H_FAULT] & 63) &&
                 !(P.log_types & ZRK_LOG_BULK)) {
-                const int nq = quiet_streak<TEAM, MPB>(P.self, sm, lane, b, n_ticks - it, noise_w, c_in, c_out, c_refc, (float4 *)lxy,
+                const int nq = quiet_streak<TEAM, MPB>(P.self, sm, sm + o.dyn_bytes, lane, b, n_ticks - it, noise_w, (float4 *)lxy,
                                                        (float4 *)lzd);
                 if (nq) {
                     it += nq;
@@ -1787,10 +1822,13 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
         // the loop): an event tick voids every window; a removal freezes the removed slots where they are.
         if (CERT && use_cert) {
             if (TEAM == 32) {
-                if (ZRK_RARE(det_prev)) removed_carry = __ballot_sync(ZRK_FULL, was_alive && !alive);
-                if (event && lane == 0) *c_flag |= 1;
+                if (ZRK_RARE(det_prev)) {
+                    const unsigned rm = __ballot_sync(ZRK_FULL, was_alive && !alive);
+                    if (lane == 0) *c_removed = (int)rm;
+                }
+                if (event && lane == 0) *c_flag |= CF_WINDOWS;
             } else if ((event || det_prev) && lane == 0) {
-                *c_flag |= 1;
+                *c_flag |= CF_WINDOWS;
             }
         }
         tm.sync();
@@ -2116,7 +2154,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 lo_rank = istar;
                 tm.sync();  // entry updates of this round are visible to the next
             }
-            if (CERT && structural && lane == 0) *c_flag |= 2;  // tracks changed hands or were created
+            if (CERT && structural && lane == 0) *c_flag |= CF_TRACKS;  // tracks changed hands or were created
             }
             tm.sync();
 
@@ -2192,6 +2230,10 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
         tm.sync();
     }
 
+    if (two && lane == 0) {  // still short of the target: there will be another round
+        const int t = hdr[H_TICK];
+        if (t < target_tick && !(hdr[H_FAULT] & 63) && !(tick_limit >= 0 && t >= tick_limit)) atomicAdd(pending, 1);
+    }
     // ---- epilogue: shared memory -> HBM, one bulk copy
     stage_fence();
     tm.sync();
@@ -2201,6 +2243,48 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
 #undef ZRK_X
 #undef ZRK_ME_I
 #undef ZRK_ME_D
+
+// ------------------------------------------------------------------ the streak kernel (two-kernel stepping)
+//
+// Warp teams only.  One warp per scenario runs quiet ticks straight from the scenario's blob in global
+// memory: a streak reads each word of the state once when it begins (coalesced: the blob is a structure
+// of arrays, one element per lane) and writes back what changed when it ends, so the kernel streams the
+// batch through HBM once per launch and otherwise lives in registers.  Its code is a few KB — the reason
+// for a kernel of its own: with the streak inlined in the tick kernel, the two code paths evict each
+// other from the SM's instruction cache.  A scenario whose next tick is not a quiet one is flagged
+// CF_GENERAL for zrk_tick_kernel; the host alternates the two kernels until no scenario is pending.
+#define ZRK_STREAK_WARPS 4
+#ifndef ZRK_STREAK_MINB
+#define ZRK_STREAK_MINB 5 /* resident CTAs per SM the register allocation is bounded for */
+#endif
+#define ZRK_STREAK_SMEM (ZRK_STREAK_WARPS * 2 * 32 * 16)
+template <int MPB>
+__global__ void __launch_bounds__(32 * ZRK_STREAK_WARPS, ZRK_STREAK_MINB) zrk_streak_kernel(const Params P, int b_first, int b_end, int target_tick) {
+    const Layout &o = P.lo;
+    ZRK_SMEM_DECL;  // ZRK_STREAK_SMEM bytes: per warp, two rows of fp32 images for a window rebuild inside a streak
+    float4 *const scratch = (float4 *)zrk_smem;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = b_first + blockIdx.x * ZRK_STREAK_WARPS + w;
+    if (b >= b_end) return;
+    unsigned char *sm = P.dyn + (size_t)b * o.dyn_bytes;
+    const unsigned char *cs = P.cst + (size_t)b * o.cst_bytes;
+    Hot<32> H;
+    H.sm = sm;
+    int *const hdr = H.hdr();
+    const int tick = hdr[H_TICK], flag = *H.c_flag();
+    const int *chdr = (const int *)(cs + o.c_hdr);
+    const int lim = chdr[C_TICK_LIMIT];
+    if (tick >= target_tick || (hdr[H_FAULT] & 63) || (lim >= 0 && tick >= lim) || (flag & CF_GENERAL)) return;
+    const int prv0 = (tick & 1) ^ 1;
+    const bool fit = P.cert && chdr[C_CCP_ID] != ZRK_NONE && !(flag & (CF_WINDOWS | CF_TRACKS)) && *H.c_removed() == 0 &&
+                     hdr[H_DETN0 + prv0] == 0 && hdr[H_MBN0 + prv0] == 0 && hdr[H_CCP_INIT] && !(P.log_types & ZRK_LOG_BULK);
+    int done = 0;
+    if (fit) {
+        const int noise_w = P.noise ? tick % P.noise_period : 0;
+        done = quiet_streak<32, MPB>(P.self, sm, cs, lane, b, target_tick - tick, noise_w, scratch + (2 * w) * 32, scratch + (2 * w + 1) * 32);
+    }
+    if (tick + done < target_tick && lane == 0) *H.c_flag() |= CF_GENERAL;  // (also when the streak ended before its first tick)
+}
 
 }  // namespace zrk
 #endif

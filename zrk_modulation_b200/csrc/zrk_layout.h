@@ -54,7 +54,8 @@ enum { CW_FLAG = 18 /* CF_* */, CW_REMOVED = 19 /* slots the last general tick r
 enum {
     CF_WINDOWS = 1, /* the windows are void: rebuild them */
     CF_TRACKS = 2,  /* tracks changed hands or were created: recount the tracks per slot */
-    CF_GENERAL = 4  /* (two-kernel stepping) the next tick of this scenario is not one the streak kernel can run */
+    CF_GENERAL = 4, /* (two-kernel stepping) the next tick of this scenario is not one the streak kernel can run */
+    CF_HOLD_SHIFT = 8 /* bits 8..14: general ticks to run before the streak kernel is tried again */
 };
 ZRK_HD constexpr HotOff hot_off(int team) {
     HotOff h{};

@@ -1082,11 +1082,11 @@ __device__ ZRK_NOINLINE void streak_sweep(double *rc, const double *c_rad_par, i
     team_barrier<TEAM>();
 }
 template <int TEAM, int MPB>
-__device__ ZRK_NOINLINE int quiet_streak(const Params *Pg, unsigned char *sm, const unsigned char *cs, int lane, int b,
-                                         int max_ticks, int noise_w, float4 *fp, float4 *fv) {
+__device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, const unsigned char *cs, int lane, int b,
+                                            int max_ticks, int noise_w, float4 *fp, float4 *fv) {
     // sm: the scenario's state blob, cs: its parameter blob — in shared memory (the tick kernel) or in
-    // global memory (the streak kernel: a streak touches each word once at its beginning and its end)
-    const Params &P = *Pg;
+    // global memory (the streak kernel: a streak touches each word once at its beginning and its end).
+    // Inlined into its kernel: P is then the kernel parameter, read from the constant bank.
     const Layout &o = P.lo;
     constexpr MeOff XM = me_off(TEAM, MPB ? MPB : 2);
 #define ZRK_QME_I(name) ((int *)(sm + (MPB ? XM.name : o.name)))
@@ -1607,7 +1607,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
         }
         if (two) {  // hand the scenario back to the streak kernel as soon as its next tick is one for it
             const int prv0 = (hdr[H_TICK] & 1) ^ 1;
-            if (it > 0 && use_cert && has_ccp && hdr[H_DETN0 + prv0] == 0 && hdr[H_MBN0 + prv0] == 0 && hdr[H_CCP_INIT] &&
+            if (it > ((*c_flag >> CF_HOLD_SHIFT) & 127) && use_cert && has_ccp && hdr[H_DETN0 + prv0] == 0 && hdr[H_MBN0 + prv0] == 0 && hdr[H_CCP_INIT] &&
                 !(hdr[H_FAULT] & 63) && !(P.log_types & ZRK_LOG_BULK)) {
                 if (lane == 0) *c_flag &= ~CF_GENERAL;
                 break;
@@ -1616,7 +1616,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
             const int prv0 = (hdr[H_TICK] & 1) ^ 1;
             if (hdr[H_DETN0 + prv0] == 0 && hdr[H_MBN0 + prv0] == 0 && hdr[H_CCP_INIT] && !(hdr[H_FAULT] & 63) &&
                 !(P.log_types & ZRK_LOG_BULK)) {
-                const int nq = quiet_streak<TEAM, MPB>(P.self, sm, sm + o.dyn_bytes, lane, b, n_ticks - it, noise_w, (float4 *)lxy,
+                const int nq = quiet_streak<TEAM, MPB>(P, sm, sm + o.dyn_bytes, lane, b, n_ticks - it, noise_w, (float4 *)lxy,
                                                        (float4 *)lzd);
                 if (nq) {
                     it += nq;
@@ -1861,10 +1861,11 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
             const int n_me = hdr[H_NME];
             {
             bool structural = false;  // this tick's rounds went beyond re-stamping own tracks
-            // With the quiet streak carrying the ordinary ticks, a warp team comes here on the rare eventful
-            // tick only, and what it costs then is the code it has to fetch, not the arithmetic: it scans
-            // with link_exact (a small loop) rather than the unrolled fp32 sweep.
-            const bool scan_fast = FAST && !(TEAM == 32 && use_cert);
+            // With the quiet streak carrying the ordinary ticks inside this kernel, a warp team comes here on
+            // the rare eventful tick only, and what it costs then is the code it has to fetch, not the
+            // arithmetic: it scans with link_exact (a small loop) rather than the unrolled fp32 sweep.  (Under
+            // two-kernel stepping every warp of this kernel runs general ticks: the sweep's code stays cached.)
+            const bool scan_fast = FAST && !(TEAM == 32 && use_cert && !two);
             // what link_object measures to, per entry: prev_pos of the tracked object (or pos
             // for a missile whose prev_pos is None) and d_t = now - upd_time
             // the hash grid pays off once a scan is long; warp-sized scenarios scan their few entries directly
@@ -2281,9 +2282,16 @@ __global__ void __launch_bounds__(32 * ZRK_STREAK_WARPS, ZRK_STREAK_MINB) zrk_st
     int done = 0;
     if (fit) {
         const int noise_w = P.noise ? tick % P.noise_period : 0;
-        done = quiet_streak<32, MPB>(P.self, sm, cs, lane, b, target_tick - tick, noise_w, scratch + (2 * w) * 32, scratch + (2 * w + 1) * 32);
+        done = quiet_streak<32, MPB>(P, sm, cs, lane, b, target_tick - tick, noise_w, scratch + (2 * w) * 32, scratch + (2 * w + 1) * 32);
     }
-    if (tick + done < target_tick && lane == 0) *H.c_flag() |= CF_GENERAL;  // (also when the streak ended before its first tick)
+    if (tick + done < target_tick && lane == 0) {
+        // the tick kernel's turn.  A streak that ended before its first tick doubles the number of ticks the
+        // scenario then stays there (bits CF_HOLD_SHIFT.. of the flag word; up to 64), one that got going resets it.
+        int f = *H.c_flag();
+        int hold = (f >> CF_HOLD_SHIFT) & 127;
+        hold = fit && done == 0 ? (hold ? (hold * 2 > 64 ? 64 : hold * 2) : 1) : (done >= 4 ? 0 : hold);
+        *H.c_flag() = (f & ((1 << CF_HOLD_SHIFT) - 1)) | (hold << CF_HOLD_SHIFT) | CF_GENERAL;
+    }
 }
 
 }  // namespace zrk

@@ -235,6 +235,7 @@ struct zrk_handle {
     bool two_kernel = false;
     int *d_pending = nullptr;  // [waves][ZRK_ROUND_SLOTS] scenarios still short of the target after a round
     int *h_pending = nullptr;  // pinned [waves]
+    int *d_work = nullptr;     // [2][B] worklists: the scenarios a batch of rounds found pending (per wave: its own range)
     int round_no = 0;
     long long n_rounds = 0;
 };
@@ -332,8 +333,8 @@ static int dev_alloc(zrk_handle *h, size_t n, T **dst, bool zero) {
     return ZRK_OK;
 }
 
-typedef void (*tick_fn)(const Params, int, int, int, int, int *);
-typedef void (*streak_fn)(const Params, int, int, int);
+typedef void (*tick_fn)(const Params, int, int, int, int, int *, const int *, int *);
+typedef void (*streak_fn)(const Params, int, int, int, const int *);
 
 template <int TEAM, int TPC, int MPB>
 static tick_fn pick_fast(bool fast) {
@@ -611,6 +612,7 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
         if (h->two_kernel) {
             if ((rc = dev_alloc(h, (size_t)n_waves * ZRK_ROUND_SLOTS, &h->d_pending, true)) != ZRK_OK) return rc;
             CK(pinned_get((void **)&h->h_pending, sizeof(int) * 64));
+            if ((rc = dev_alloc(h, (size_t)2 * B, &h->d_work, false)) != ZRK_OK) return rc;
         }
     }
 
@@ -729,6 +731,9 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
         // the host looks at the pending counters after every few rounds.
         const int target = (int)(h->tick + n_ticks);
         streak_fn sf = pick_streak(h->P.lo);
+        // per wave: how many scenarios the last batch left pending (-1: all of the wave's range, no worklist yet),
+        // and which of the two worklist buffers holds them
+        std::vector<int> n_work(n_waves, -1), cur(n_waves, 0);
         for (;;) {
             if (h->round_no + ZRK_ROUND_BATCH > ZRK_ROUND_SLOTS) {
                 for (int w = 0; w < n_waves; w++)
@@ -737,16 +742,23 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
                 h->round_no = 0;
             }
             for (int w = 0; w < n_waves; w++) {
+                if (n_work[w] == 0) continue;
                 const int b0 = n_waves > 1 ? h->wave_b[w] : 0, b1 = n_waves > 1 ? h->wave_b[w + 1] : h->P.lo.B;
                 cudaStream_t ws = n_waves > 1 ? h->wave_stream[w] : h->stream;
+                const int *wl = n_work[w] < 0 ? nullptr : h->d_work + (size_t)cur[w] * h->P.lo.B + b0;
+                int *wl_out = h->d_work + (size_t)(cur[w] ^ 1) * h->P.lo.B + b0;
+                const int f0 = wl ? 0 : b0, f1 = wl ? n_work[w] : b1;  // index range of the launch
                 for (int r = 0; r < ZRK_ROUND_BATCH; r++) {
                     cudaEvent_t e0, e1;
                     int rc;
                     if ((rc = get_event(h, &e0)) || (rc = get_event(h, &e1))) return rc;
                     CK(cudaEventRecord(e0, ws));
-                    ZRK_LAUNCH(sf, (b1 - b0 + ZRK_STREAK_WARPS - 1) / ZRK_STREAK_WARPS, 32 * ZRK_STREAK_WARPS, ZRK_STREAK_SMEM, ws, h->P, b0, b1, target);
-                    ZRK_LAUNCH(fn, (b1 - b0 + tpc - 1) / tpc, h->block, h->smem_bytes, ws, h->P, 0, b0, b1, target,
-                               h->d_pending + (size_t)w * ZRK_ROUND_SLOTS + h->round_no + r);
+                    ZRK_LAUNCH(sf, (f1 - f0 + ZRK_STREAK_WARPS - 1) / ZRK_STREAK_WARPS, 32 * ZRK_STREAK_WARPS, ZRK_STREAK_SMEM, ws, h->P,
+                               f0, f1, target, wl);
+                    // (only the batch's last round writes the next worklist)
+                    ZRK_LAUNCH(fn, (f1 - f0 + tpc - 1) / tpc, h->block, h->smem_bytes, ws, h->P, 0, f0, f1, target,
+                               h->d_pending + (size_t)w * ZRK_ROUND_SLOTS + h->round_no + r, wl,
+                               r == ZRK_ROUND_BATCH - 1 ? wl_out : (int *)nullptr);
                     CK(cudaGetLastError());
                     CK(cudaEventRecord(e1, ws));
                     h->pending.push_back({e0, e1});
@@ -759,8 +771,11 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
             h->n_rounds += ZRK_ROUND_BATCH;
             bool more = false;
             for (int w = 0; w < n_waves; w++) {
+                if (n_work[w] == 0) continue;
                 CK(cudaStreamSynchronize(n_waves > 1 ? h->wave_stream[w] : h->stream));
-                more = more || h->h_pending[w] != 0;
+                n_work[w] = h->h_pending[w];
+                cur[w] ^= 1;
+                more = more || n_work[w] != 0;
             }
             if (h->pending.size() > 2048) {
                 int rc = resolve_events(h);
@@ -791,7 +806,8 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
             int rc;
             if ((rc = get_event(h, &e0)) || (rc = get_event(h, &e1))) return rc;
             CK(cudaEventRecord(e0, ws));
-            ZRK_LAUNCH(fn, (b1 - b0 + tpc - 1) / tpc, h->block, h->smem_bytes, ws, h->P, k, b0, b1, -1, (int *)nullptr);
+            ZRK_LAUNCH(fn, (b1 - b0 + tpc - 1) / tpc, h->block, h->smem_bytes, ws, h->P, k, b0, b1, -1, (int *)nullptr,
+                       (const int *)nullptr, (int *)nullptr);
             CK(cudaGetLastError());
             CK(cudaEventRecord(e1, ws));
             h->pending.push_back({e0, e1});

@@ -958,7 +958,7 @@ __device__ __forceinline__ void cert_recount(unsigned char *sm, const int *me_re
 template <int TEAM>
 __device__ ZRK_NOINLINE void cert_recompute(unsigned char *sm, const int *me_ref, int lane, int n_slots, int tick, int tick_now,
                                             int n_te, int n_me, double dt_s, double nb, int *cin, int *cout, int *refc, float4 *fp,
-                                            float4 *fv) {
+                                            float4 *fv, bool stale_only = false) {
     Hot<TEAM> H;
     H.sm = sm;
     const int fl = lane < n_slots ? H.sflags()[lane] : 0;
@@ -974,6 +974,8 @@ __device__ ZRK_NOINLINE void cert_recompute(unsigned char *sm, const int *me_ref
         cout[lane] = ZRK_CERT_NEVER;
         return;
     }
+    // stale_only (nothing has changed since the windows were built): a window that has not passed stays
+    if (stale_only && !(cout[lane] < tick_now)) return;
     int best_in = ZRK_CERT_NEVER, best_out = ZRK_CERT_NEVER;
     if (!(fl & F_HASPREV)) {
         best_in = 0;
@@ -1243,7 +1245,7 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
                 if (((tick & 15) == 0 || (n_q == 0 && !looked)) && __ballot_sync(ZRK_FULL, doubt && cout < tick) != 0) {
                     looked = true;
                     cert_recompute<TEAM>(sm, ZRK_QME_I(me_ref), lane, n_slots, tick0 - 1, tick, n_te, n_me, P.dt_s, P.noise_bound, c_in,
-                                         c_out, c_refc, fp, fv);
+                                         c_out, c_refc, fp, fv, true);
                     cin = c_in[lane], cout = c_out[lane], refc1 = c_refc[lane] == 1;
                     continue;
                 }
@@ -1252,7 +1254,7 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
             if (((tick & 15) == 0 || (n_q == 0 && !looked)) && __syncthreads_or(!bail && doubt && cout < tick) != 0) {  // (as above)
                 looked = true;
                 cert_recompute<TEAM>(sm, ZRK_QME_I(me_ref), lane, n_slots, tick0 - 1, tick, n_te, n_me, P.dt_s, P.noise_bound, c_in, c_out,
-                                     c_refc, fp, fv);
+                                     c_refc, fp, fv, true);
                 cin = c_in[lane], cout = c_out[lane], refc1 = c_refc[lane] == 1;
                 if (__syncthreads_or(bail || !(tick < cin)) != 0) break;  // still not a quiet tick
                 continue;
@@ -1498,7 +1500,10 @@ __device__ ZRK_NOINLINE int serial_section(const Params *Pg, unsigned char *sm, 
 #ifndef ZRK_MINB_256
 #define ZRK_MINB_256 2
 #endif
-constexpr int min_blocks(int threads) { return threads <= 64 ? 8 : (threads <= 128 ? ZRK_MINB_SMALL : (threads == 256 ? ZRK_MINB_256 : 1)); }
+#ifndef ZRK_MINB_TINY
+#define ZRK_MINB_TINY 8
+#endif
+constexpr int min_blocks(int threads) { return threads <= 32 ? ZRK_MINB_TINY : threads <= 64 ? 8 : (threads <= 128 ? ZRK_MINB_SMALL : (threads == 256 ? ZRK_MINB_256 : 1)); }
 
 #ifdef ZRK_MAXNREG
 #define ZRK_KERNEL_ATTR __maxnreg__(ZRK_MAXNREG)
@@ -1511,8 +1516,12 @@ constexpr int min_blocks(int threads) { return threads <= 64 ? 8 : (threads <= 1
 // target_tick >= 0 (warp teams, "two-kernel stepping"): this launch runs only the ticks the streak kernel
 // (zrk_streak_kernel below) cannot — of the scenarios flagged CF_GENERAL, until each of them is fit for a
 // streak again or has reached target_tick — and counts in *pending the scenarios still short of target_tick.
+// work (two-kernel stepping, may be null): the scenarios to look at, n = b_end - b_first of them, instead of
+// [b_first, b_end); work_out (may be null): the scenarios still pending are appended here, at the index
+// the pending counter hands out.
 template <int TEAM, int TPC, bool FAST, int MPB>
-__global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int b_first, int b_end, int target_tick, int *pending) {
+__global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int b_first, int b_end, int target_tick, int *pending,
+                                                const int *work, int *work_out) {
     ZRK_SMEM_DECL;
     const Layout &o = P.lo;
     constexpr ScratchOff XS = scratch_off(TEAM, MPB ? MPB : 2);
@@ -1526,16 +1535,20 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
     tm.tic = TEAM == 32 ? __shfl_sync(ZRK_FULL, (int)(threadIdx.x / TEAM), 0) : (int)(threadIdx.x / TEAM);
     tm.lane = threadIdx.x % TEAM;
     const int lane = tm.lane;
-    const int b = b_first + blockIdx.x * TPC + tm.tic;  // this launch covers scenarios [b_first, b_end)
+    int b = b_first + blockIdx.x * TPC + tm.tic;  // this launch covers scenarios [b_first, b_end)
     if (b >= b_end) return;  // whole team leaves together
     const bool two = TEAM == 32 && target_tick >= 0;
+    if (two && work) b = work[b - b_first];
     if (two) {  // is there anything for this kernel to do?  (three words of the scenario's header, before any staging)
         const unsigned char *g = P.dyn + (size_t)b * o.dyn_bytes;
         const int *gh = (const int *)(g + Hot<TEAM>::O.hdr);
         const int lim = ((const int *)(P.cst + (size_t)b * o.cst_bytes + o.c_hdr))[C_TICK_LIMIT];
         if (gh[H_TICK] >= target_tick || (gh[H_FAULT] & 63) || (lim >= 0 && gh[H_TICK] >= lim)) return;
         if (!(((const int *)(g + Hot<TEAM>::O.counts))[CW_FLAG] & CF_GENERAL)) {  // the streak kernel's turn
-            if (lane == 0) atomicAdd(pending, 1);
+            if (lane == 0) {
+                const int k = atomicAdd(pending, 1);
+                if (work_out) work_out[k] = b;
+            }
             return;
         }
     }
@@ -2233,7 +2246,10 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
 
     if (two && lane == 0) {  // still short of the target: there will be another round
         const int t = hdr[H_TICK];
-        if (t < target_tick && !(hdr[H_FAULT] & 63) && !(tick_limit >= 0 && t >= tick_limit)) atomicAdd(pending, 1);
+        if (t < target_tick && !(hdr[H_FAULT] & 63) && !(tick_limit >= 0 && t >= tick_limit)) {
+            const int k = atomicAdd(pending, 1);
+            if (work_out) work_out[k] = b;
+        }
     }
     // ---- epilogue: shared memory -> HBM, one bulk copy
     stage_fence();
@@ -2254,19 +2270,23 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
 // for a kernel of its own: with the streak inlined in the tick kernel, the two code paths evict each
 // other from the SM's instruction cache.  A scenario whose next tick is not a quiet one is flagged
 // CF_GENERAL for zrk_tick_kernel; the host alternates the two kernels until no scenario is pending.
+#ifndef ZRK_STREAK_WARPS
 #define ZRK_STREAK_WARPS 4
+#endif
 #ifndef ZRK_STREAK_MINB
 #define ZRK_STREAK_MINB 5 /* resident CTAs per SM the register allocation is bounded for */
 #endif
 #define ZRK_STREAK_SMEM (ZRK_STREAK_WARPS * 2 * 32 * 16)
 template <int MPB>
-__global__ void __launch_bounds__(32 * ZRK_STREAK_WARPS, ZRK_STREAK_MINB) zrk_streak_kernel(const Params P, int b_first, int b_end, int target_tick) {
+__global__ void __launch_bounds__(32 * ZRK_STREAK_WARPS, ZRK_STREAK_MINB) zrk_streak_kernel(const Params P, int b_first, int b_end, int target_tick,
+                                                                                           const int *work) {
     const Layout &o = P.lo;
     ZRK_SMEM_DECL;  // ZRK_STREAK_SMEM bytes: per warp, two rows of fp32 images for a window rebuild inside a streak
     float4 *const scratch = (float4 *)zrk_smem;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = b_first + blockIdx.x * ZRK_STREAK_WARPS + w;
+    int b = b_first + blockIdx.x * ZRK_STREAK_WARPS + w;
     if (b >= b_end) return;
+    if (work) b = work[b - b_first];  // (the scenarios the last look at the batch found pending)
     unsigned char *sm = P.dyn + (size_t)b * o.dyn_bytes;
     const unsigned char *cs = P.cst + (size_t)b * o.cst_bytes;
     Hot<32> H;

@@ -772,9 +772,27 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
             bool more = false;
             for (int w = 0; w < n_waves; w++) {
                 if (n_work[w] == 0) continue;
-                CK(cudaStreamSynchronize(n_waves > 1 ? h->wave_stream[w] : h->stream));
+                cudaStream_t ws = n_waves > 1 ? h->wave_stream[w] : h->stream;
+                CK(cudaStreamSynchronize(ws));
                 n_work[w] = h->h_pending[w];
                 cur[w] ^= 1;
+                const int span = (n_waves > 1 ? h->wave_b[w + 1] - h->wave_b[w] : h->P.lo.B);
+                if (n_work[w] > 0 && n_work[w] <= span / 64) {
+                    // the tail: a few scenarios with many rounds still to go (one tick per round, in the worst
+                    // case) are finished by one launch of the tick kernel on its own
+                    const int b0 = n_waves > 1 ? h->wave_b[w] : 0;
+                    cudaEvent_t e0, e1;
+                    int rc;
+                    if ((rc = get_event(h, &e0)) || (rc = get_event(h, &e1))) return rc;
+                    CK(cudaEventRecord(e0, ws));
+                    ZRK_LAUNCH(fn, (n_work[w] + tpc - 1) / tpc, h->block, h->smem_bytes, ws, h->P, 0, 0, n_work[w], target, (int *)nullptr,
+                               (const int *)(h->d_work + (size_t)cur[w] * h->P.lo.B + b0), (int *)nullptr);
+                    CK(cudaGetLastError());
+                    CK(cudaEventRecord(e1, ws));
+                    h->pending.push_back({e0, e1});
+                    h->n_launches++;
+                    n_work[w] = 0;
+                }
                 more = more || n_work[w] != 0;
             }
             if (h->pending.size() > 2048) {

@@ -139,7 +139,15 @@ __device__ __forceinline__ bool radar_sees(double dx, double dy, double dz, cons
             sure_in = sure_in && az > a0 + M && az < a1 - M;
             sure_out = sure_out || az < a0 - M || az > a1 + M;
         }
-        if (!(el_lo <= 0.0 && el_hi >= 180.0)) {
+        if (el_lo == 0.0 && el_hi == 90.0) {
+            // the upper hemisphere: degrees(arcsin(dz / d)) % 180 lies in [0, 90] iff dz >= 0 (a negative angle maps
+            // beyond 90).  Decided here unless dz is within 1e-3 of zero relative to the horizontal range
+            // (elevation within 0.06 deg of the horizon) or straight overhead (within 0.06 deg of 90).
+            const float hz = sqrt_fast(fmaf(fy, fy, fx * fx));
+            ok = ok && fabsf(fz) > 1e-3f * hz && hz > 1e-3f * fabsf(fz);
+            sure_in = sure_in && fz > 0.f;
+            sure_out = sure_out || fz < 0.f;
+        } else if (!(el_lo <= 0.0 && el_hi >= 180.0)) {
             float el = atan2_deg_approx(fz, sqrt_fast(fmaf(fy, fy, fx * fx)));  // == asin(dz / distance), well conditioned
             if (el < 0.f) el += 180.f;
             const float e0 = (float)el_lo, e1 = (float)el_hi;
@@ -1242,8 +1250,8 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
                 // a window that has passed keeps its slot uncertified: rebuild the windows (on the streak's
                 // first tick, then every 16th at most) from the state shared memory still holds, and look at
                 // this tick again
-                if (((tick & 15) == 0 || (n_q == 0 && !looked)) && __ballot_sync(ZRK_FULL, doubt && cout < tick) != 0) {
-                    looked = true;
+                if ((tick & 15) == 0 && !looked && __ballot_sync(ZRK_FULL, doubt && cout < tick) != 0) {
+                    looked = true;  // (once per streak: the next one starts from the rebuilt windows anyway)
                     cert_recompute<TEAM>(sm, ZRK_QME_I(me_ref), lane, n_slots, tick0 - 1, tick, n_te, n_me, P.dt_s, P.noise_bound, c_in,
                                          c_out, c_refc, fp, fv, true);
                     cin = c_in[lane], cout = c_out[lane], refc1 = c_refc[lane] == 1;
@@ -1513,7 +1521,7 @@ constexpr int min_blocks(int threads) { return threads <= 32 ? ZRK_MINB_TINY : t
 // MPB: missile capacity bucket of a warp team (Layout::MP as a compile-time constant, so that the
 // scratch and track-entry offsets below are immediates); 0 = offsets from the Layout at run time.
 // target_tick < 0: run n_ticks ticks of every scenario (quiet streaks included, in this kernel).
-// target_tick >= 0 (warp teams, "two-kernel stepping"): this launch runs only the ticks the streak kernel
+// target_tick >= 0 and pending != null (warp teams, "two-kernel stepping"): this launch runs only the ticks the streak kernel
 // (zrk_streak_kernel below) cannot — of the scenarios flagged CF_GENERAL, until each of them is fit for a
 // streak again or has reached target_tick — and counts in *pending the scenarios still short of target_tick.
 // work (two-kernel stepping, may be null): the scenarios to look at, n = b_end - b_first of them, instead of
@@ -1537,8 +1545,11 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
     const int lane = tm.lane;
     int b = b_first + blockIdx.x * TPC + tm.tic;  // this launch covers scenarios [b_first, b_end)
     if (b >= b_end) return;  // whole team leaves together
-    const bool two = TEAM == 32 && target_tick >= 0;
-    if (two && work) b = work[b - b_first];
+    const bool two = TEAM == 32 && target_tick >= 0 && pending != nullptr;
+    // (target_tick >= 0 without a pending counter: "finish" — run the listed scenarios up to target_tick
+    // in this one launch, quiet streaks included; the host's way to end the tail of a step)
+    const bool finish = TEAM == 32 && target_tick >= 0 && pending == nullptr;
+    if ((two || finish) && work) b = work[b - b_first];
     if (two) {  // is there anything for this kernel to do?  (three words of the scenario's header, before any staging)
         const unsigned char *g = P.dyn + (size_t)b * o.dyn_bytes;
         const int *gh = (const int *)(g + Hot<TEAM>::O.hdr);
@@ -1563,7 +1574,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
     // association certificate (teams up to 256 slots: the pair loop is O(slots) per lane)
     constexpr bool CERT = FAST && TEAM <= 256;
     int *const c_in = H.c_in(), *const c_out = H.c_out(), *const c_flag = H.c_flag(), *const c_refc = H.c_refc();
-    const bool use_cert = CERT && P.cert && (two || n_ticks >= 4);  // (a short launch would only pay for the upkeep)
+    const bool use_cert = CERT && P.cert && (two || finish || n_ticks >= 4);  // (a short launch would only pay for the upkeep)
 
     // ---- prologue: HBM -> shared memory, one bulk copy per blob
     {
@@ -1591,7 +1602,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
     int noise_w = noise ? hdr[H_TICK] % P.noise_period : 0;
     const int noise_row = P.noise_radars * P.noise_objects * 3;  // doubles per tick row
     int streak_wait = 0;  // ticks to go before the next attempt at a quiet streak (after one that ended at once)
-    if (two) n_ticks = target_tick - hdr[H_TICK];
+    if (two || finish) n_ticks = target_tick - hdr[H_TICK];
     int *const c_removed = H.c_removed();  // slots the last general tick removed (bit mask, warp teams)
     for (int it = 0; it < n_ticks; it++) {
         if (CERT && use_cert && has_ccp) {

@@ -1264,10 +1264,43 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
                 cert_recompute<TEAM>(sm, ZRK_QME_I(me_ref), lane, n_slots, tick0 - 1, tick, n_te, n_me, P.dt_s, P.noise_bound, c_in, c_out,
                                      c_refc, fp, fv, true);
                 cin = c_in[lane], cout = c_out[lane], refc1 = c_refc[lane] == 1;
-                if (__syncthreads_or(bail || !(tick < cin)) != 0) break;  // still not a quiet tick
-                continue;
+                continue;  // look at this tick again
             }
-            break;
+            // Teams larger than a warp check their uncertified detections like a warp does (streak_rivals),
+            // through shared scratch instead of shuffles: every slot publishes what its tracks measure to, the
+            // uncertified detections line up in a short list, every lane tests the two tracks it holds.
+            {
+                double *const Lx = (double *)fp, *const Ly = Lx + TEAM, *const Lz = Ly + TEAM;  // (fp: 48 x TEAM bytes, see the caller)
+                double *const dl = Lz + TEAM;                                                  // [16][4] x, y, z, threshold
+                int *const dsd = (int *)(dl + 64), *const dcnt = dsd + 16;                     // [16] own track, list length
+                if (lane == 0) *dcnt = 0;  // (the scratch is shared with the window rebuild: emptied before every use)
+                if (__syncthreads_or(bail) != 0) break;
+                const bool use_p = alive || !(fl & F_HASPREV);
+                if (lane < n_slots) Lx[lane] = use_p ? px : qx, Ly[lane] = use_p ? py : qy, Lz[lane] = use_p ? pz : qz;
+                if (doubt) {
+                    const int k = atomicAdd(dcnt, 1);
+                    if (k < 16) {
+                        dl[4 * k] = nx, dl[4 * k + 1] = ny, dl[4 * k + 2] = nz, dl[4 * k + 3] = d2 * (1.0 + 1e-12);
+                        dsd[k] = seedu;
+                    }
+                }
+                __syncthreads();
+                const int nd = *dcnt;
+                bool rival = nd > 16;  // (too many: let the general tick do it)
+                for (int k = 0; k < nd && k < 16; k++) {
+                    const double cx = dl[4 * k], cy = dl[4 * k + 1], cz = dl[4 * k + 2], thr = dl[4 * k + 3];
+                    const int sd = dsd[k];
+                    if (lane < n_te && lane != sd) {
+                        const double ex = Lx[r_te] - cx, ey = Ly[r_te] - cy, ez = Lz[r_te] - cz;
+                        rival = rival || !(dot3(ex, ey, ez, ex, ey, ez) > thr);
+                    }
+                    if (lane < n_me && TEAM + lane != sd) {
+                        const double ex = Lx[r_me] - cx, ey = Ly[r_me] - cy, ez = Lz[r_me] - cz;
+                        rival = rival || !(dot3(ex, ey, ez, ex, ey, ez) > thr);
+                    }
+                }
+                if (__syncthreads_or(rival) != 0) break;
+            }
         }
         // ---- commit
         if (alive) {

@@ -27,7 +27,7 @@
  * zrk_read_state                   model attributes (pos, prev_pos, current_azimuth,
  *                                  _target_dict ...)                BaseModel.py:28-36, CCP.py:80-86
  * zrk_read_status                  exception propagation            (CCP.py:259, CCP.py:107)
- * zrk_destroy                      Python GC
+ * zrk_destroy, zrk_release_cached_memory   Python GC
  */
 #ifndef ZRK_B200_H
 #define ZRK_B200_H
@@ -317,6 +317,9 @@ int zrk_load_state(zrk_handle *h, const void *buf, size_t bytes);
  * With zrk_options.waves > 1 the launches of different waves overlap: the figure is then the sum
  * of the per-launch durations, not the elapsed time. */
 int zrk_launch_stats(zrk_handle *h, int64_t *n_launches, double *kernel_ms);
+/* Device memory of destroyed handles is kept in a memory pool of the library's own for the next handle (the
+ * device's default pool, the host application's, is never touched); this hands it back to the driver. */
+int zrk_release_cached_memory(void);
 const char *zrk_last_error(zrk_handle *h); /* h may be NULL: error of the last failed zrk_create */
 void zrk_destroy(zrk_handle *h);
 int zrk_abi_version(void);

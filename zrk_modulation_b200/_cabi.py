@@ -184,10 +184,11 @@ def declare(lib):
     lib.zrk_destroy.argtypes = [H]
     lib.zrk_destroy.restype = None
     lib.zrk_abi_version.argtypes = []
+    lib.zrk_release_cached_memory.argtypes = []
     for f in ("zrk_create", "zrk_step", "zrk_sync", "zrk_get_time", "zrk_read_status",
               "zrk_read_counts", "zrk_read_activity", "zrk_read_certified", "zrk_read_records", "zrk_log_capacity", "zrk_read_messages",
               "zrk_read_state", "zrk_device_ptr", "zrk_launch_stats", "zrk_abi_version", "zrk_state_bytes",
-              "zrk_save_state", "zrk_load_state"):
+              "zrk_save_state", "zrk_load_state", "zrk_release_cached_memory"):
         getattr(lib, f).restype = C.c_int
     return lib
 
@@ -195,4 +196,5 @@ def declare(lib):
 EXPORTED_SYMBOLS = ["zrk_create", "zrk_step", "zrk_sync", "zrk_get_time", "zrk_read_status",
                     "zrk_read_counts", "zrk_read_activity", "zrk_read_certified", "zrk_read_records", "zrk_log_capacity", "zrk_read_messages",
                     "zrk_read_state", "zrk_device_ptr", "zrk_launch_stats", "zrk_last_error",
-                    "zrk_destroy", "zrk_abi_version", "zrk_state_bytes", "zrk_save_state", "zrk_load_state"]
+                    "zrk_destroy", "zrk_abi_version", "zrk_state_bytes", "zrk_save_state", "zrk_load_state",
+                    "zrk_release_cached_memory"]

@@ -12,6 +12,7 @@ SOURCES = ["zrk_host.cu"]
 DEPS = ["zrk_host.cu", "zrk_tick.cuh", "zrk_layout.h", os.path.join("..", "..", "include", "zrk_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-fmad=false",  # no implicit FMA contraction: fp64 results must match the reference's numpy
+              "-cudart", "shared",  # link libcudart.so (torch loads the same one) instead of embedding the static runtime
               "-Xcompiler", "-fPIC", "-shared"]
 
 
@@ -31,7 +32,9 @@ def stale() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if force or stale():
-        cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+        cuda_lib = os.path.join(os.path.dirname(os.path.dirname(os.path.realpath(nvcc()))), "lib64")
+        # (a client that is not a Python process with torch loaded finds the shared runtime next to the toolkit)
+        cmd = [nvcc()] + NVCC_FLAGS + ["-Xlinker", f"-rpath={cuda_lib}"] + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
         subprocess.check_call(cmd, cwd=CSRC)
     return OUT
 

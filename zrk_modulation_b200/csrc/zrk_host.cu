@@ -221,6 +221,7 @@ struct zrk_handle {
     int *h_summary = nullptr;  // page-locked [B][ZRK_SUMMARY_WORDS], allocated while the first step runs
     double *d_tsec = nullptr;
     Params *d_self = nullptr;
+    unsigned long long cst_hash = 0;  // identity of the scenario parameters (checked by zrk_load_state)
     // Scenario waves (zrk_options.waves > 1): contiguous scenario ranges, each uploaded,
     // initialised and stepped on its own stream, so that the host-to-device copy of one wave
     // overlaps the kernels of the waves before it.
@@ -243,6 +244,12 @@ struct zrk_handle {
 #define ZRK_ROUND_BATCH 6  /* rounds queued between two looks at the pending counters */
 
 static thread_local std::string g_create_err;
+
+static unsigned long long fnv1a(const void *p, size_t n, unsigned long long h = 1469598103934665603ull) {
+    const unsigned char *c = (const unsigned char *)p;
+    for (size_t i = 0; i < n; i++) h = (h ^ c[i]) * 1099511628211ull;
+    return h;
+}
 
 #define CK(call)                                                                         \
     do {                                                                                 \
@@ -296,21 +303,53 @@ static void pinned_put(void *p, size_t bytes) {
     cudaFreeHost(p);
 }
 
-// Stream-ordered allocations from the device's default memory pool, which is told to keep
-// freed memory: creating and destroying handles in a loop then costs no cudaMalloc/cudaFree.
+// Stream-ordered allocations from a memory pool of the library's own (one per device, created on first
+// use), which keeps freed memory: creating and destroying handles in a loop then costs no cudaMalloc /
+// cudaFree, and the device's default pool — the host application's — is left as it was.
+// zrk_release_cached_memory() hands the kept memory back.
+#define ZRK_MAX_DEVICES 64
+static std::mutex g_pool_mu;
+static cudaMemPool_t g_pool[ZRK_MAX_DEVICES];
+static bool g_pool_ok[ZRK_MAX_DEVICES];
 static int pool_alloc(zrk_handle *h, void **p, size_t bytes) {
-    static thread_local int pool_ready_dev = -1;
-    if (pool_ready_dev != h->device) {
-        cudaMemPool_t pool;
-        CK(cudaDeviceGetDefaultMemPool(&pool, h->device));
-        unsigned long long keep = ~0ull;
-        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        pool_ready_dev = h->device;
+    if (h->device < 0 || h->device >= ZRK_MAX_DEVICES) return ZRK_ERR_ARG;
+    {
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        if (!g_pool_ok[h->device]) {
+            cudaMemPoolProps props{};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = h->device;
+            CK(cudaMemPoolCreate(&g_pool[h->device], &props));
+            unsigned long long keep = ~0ull;
+            CK(cudaMemPoolSetAttribute(g_pool[h->device], cudaMemPoolAttrReleaseThreshold, &keep));
+            g_pool_ok[h->device] = true;
+        }
     }
-    CK(cudaMallocAsync(p, bytes ? bytes : 1, h->stream));
+    CK(cudaMallocFromPoolAsync(p, bytes ? bytes : 1, g_pool[h->device], h->stream));
     h->allocs.push_back(*p);
     return ZRK_OK;
 }
+extern "C" int zrk_release_cached_memory(void) {
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    for (int d = 0; d < ZRK_MAX_DEVICES; d++)
+        if (g_pool_ok[d] && cudaMemPoolTrimTo(g_pool[d], 0) != cudaSuccess) return ZRK_ERR_CUDA;
+    return ZRK_OK;
+}
+
+// Every entry point runs on the handle's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
 
 template <typename T>
 static int dev_upload(zrk_handle *h, const T *src, size_t n, const T **dst) {
@@ -366,7 +405,7 @@ extern "C" void zrk_destroy(zrk_handle *h) {
         delete h;
         return;
     }
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     cudaStreamSynchronize(h->stream);
     for (auto &pr : h->pending) {
         cudaEventDestroy(pr.first);
@@ -645,6 +684,19 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
             CK(cudaStreamWaitEvent(h->stream, h->wave_done[w], 0));
         }
     }
+    {   // identity of the batch for checkpoints: everything that ends up in the parameter blobs
+        unsigned long long hh = fnv1a(&d->dt_ms, sizeof d->dt_ms);
+        auto mix = [&](const void *p, size_t n) { if (p && n) hh = fnv1a(p, n, hh); };
+        mix(d->radar_id, sizeof(int) * (size_t)B * R); mix(d->radar_pos, 8 * 3 * (size_t)B * R); mix(d->radar_par, 8 * 8 * (size_t)B * R);
+        mix(d->launcher_id, sizeof(int) * (size_t)B * L); mix(d->launcher_pos, 8 * 3 * (size_t)B * L);
+        mix(d->missile_id, sizeof(int) * (size_t)B * M); mix(d->missile_launcher, sizeof(int) * (size_t)B * M);
+        mix(d->missile_v0, 8 * (size_t)B * M); mix(d->missile_radius, 8 * (size_t)B * M);
+        mix(d->ccp_launcher_id, sizeof(int) * (size_t)B * C); mix(d->ccp_launcher_pos, 8 * 3 * (size_t)B * C);
+        mix(d->target_id, sizeof(int) * (size_t)B * T); mix(d->ccp_id, sizeof(int) * (size_t)B);
+        const int nshape[4] = {d->noise ? d->noise_period : 0, d->noise_radars, d->noise_objects, (int)(d->noise_scenario_stride != 0)};
+        mix(nshape, sizeof nshape);
+        h->cst_hash = hh;
+    }
     // small host copies used by zrk_read_messages
     h->h_radar_id.assign(d->radar_id ? d->radar_id : nullptr, d->radar_id ? d->radar_id + (size_t)B * R : nullptr);
     h->h_n_radars.resize(B);
@@ -677,7 +729,10 @@ extern "C" int zrk_create(const zrk_batch_desc *desc, const zrk_options *opt, zr
     }
     *out = nullptr;
     zrk_handle *h = new zrk_handle();
+    int caller_dev = -1;
+    if (cudaGetDevice(&caller_dev) != cudaSuccess) caller_dev = -1;
     int rc = create_impl(h, desc, opt);
+    if (caller_dev >= 0) cudaSetDevice(caller_dev);
     if (rc != ZRK_OK) {
         g_create_err = h->err;
         zrk_destroy(h);
@@ -712,6 +767,7 @@ static int get_event(zrk_handle *h, cudaEvent_t *e) {
 extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
     if (!h || n_ticks < 0) return ZRK_ERR_ARG;
     if (h->sticky_rc) return h->sticky_rc;
+    DeviceGuard dev_guard(h->device);
     CK(cudaSetDevice(h->device));
     tick_fn fn = pick_kernel(h->P.lo, h->fast);
     if (h->pending.size() > 4096) {
@@ -846,6 +902,7 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
 extern "C" int zrk_sync(zrk_handle *h) {
     if (!h) return ZRK_ERR_ARG;
     if (h->sticky_rc) return h->sticky_rc;
+    DeviceGuard dev_guard(h->device);
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     if (h->deferred) {  // zrk_create with waves did not wait for the init kernel's verdict
@@ -868,6 +925,7 @@ extern "C" int zrk_get_time(zrk_handle *h, int64_t *tick, int64_t *time_ms) {
 
 extern "C" int zrk_launch_stats(zrk_handle *h, int64_t *n_launches, double *kernel_ms) {
     if (!h) return ZRK_ERR_ARG;
+    DeviceGuard dev_guard(h->device);
     int rc = zrk_sync(h);
     if (rc) return rc;
     if (n_launches) *n_launches = h->n_launches;
@@ -901,6 +959,7 @@ static int fetch_summary(zrk_handle *h) {
 
 extern "C" int zrk_read_status(zrk_handle *h, int32_t *fault_code, int32_t *fault_tick, int32_t *n_records) {
     if (!h) return ZRK_ERR_ARG;
+    DeviceGuard dev_guard(h->device);
     int rc = fetch_summary(h);
     if (rc) return rc;
     for (int s = 0; s < h->P.lo.B; s++) {
@@ -914,6 +973,7 @@ extern "C" int zrk_read_status(zrk_handle *h, int32_t *fault_code, int32_t *faul
 
 extern "C" int zrk_read_counts(zrk_handle *h, int64_t *counts) {
     if (!h || !counts) return ZRK_ERR_ARG;
+    DeviceGuard dev_guard(h->device);
     int rc = fetch_summary(h);
     if (rc) return rc;
     for (int s = 0; s < h->P.lo.B; s++) {
@@ -925,6 +985,7 @@ extern "C" int zrk_read_counts(zrk_handle *h, int64_t *counts) {
 
 extern "C" int zrk_read_activity(zrk_handle *h, int64_t *alive_slot_ticks) {
     if (!h || !alive_slot_ticks) return ZRK_ERR_ARG;
+    DeviceGuard dev_guard(h->device);
     int rc = fetch_summary(h);
     if (rc) return rc;
     for (int s = 0; s < h->P.lo.B; s++)
@@ -934,6 +995,7 @@ extern "C" int zrk_read_activity(zrk_handle *h, int64_t *alive_slot_ticks) {
 
 extern "C" int zrk_read_certified(zrk_handle *h, int64_t *certified_ticks) {
     if (!h || !certified_ticks) return ZRK_ERR_ARG;
+    DeviceGuard dev_guard(h->device);
     int rc = fetch_summary(h);
     if (rc) return rc;
     for (int s = 0; s < h->P.lo.B; s++)
@@ -943,6 +1005,7 @@ extern "C" int zrk_read_certified(zrk_handle *h, int64_t *certified_ticks) {
 
 extern "C" int zrk_read_records(zrk_handle *h, int s0, int s1, zrk_msg *recs, int32_t *n) {
     if (!h || s0 < 0 || s1 > h->P.lo.B || s0 > s1) return ZRK_ERR_ARG;
+    DeviceGuard dev_guard(h->device);
     int rc = fetch_summary(h);
     if (rc) return rc;
     for (int s = s0; s < s1; s++) {
@@ -958,6 +1021,7 @@ extern "C" int zrk_read_records(zrk_handle *h, int s0, int s1, zrk_msg *recs, in
 extern "C" int zrk_read_messages(zrk_handle *h, int sc, int tick0, int tick1, zrk_msg *msgs, size_t cap, size_t *n_out,
                                  int32_t *ids, size_t ids_cap, size_t *n_ids_out) {
     if (!h || sc < 0 || sc >= h->P.lo.B || tick0 < 0 || tick1 < tick0) return ZRK_ERR_ARG;
+    DeviceGuard dev_guard(h->device);
     const Params &P = h->P;
     const Layout &o = P.lo;
     if ((P.log_types & ZRK_LOG_FULL) != (unsigned)ZRK_LOG_FULL) {
@@ -1047,6 +1111,7 @@ extern "C" int zrk_read_messages(zrk_handle *h, int sc, int tick0, int tick1, zr
 
 extern "C" int zrk_read_state(zrk_handle *h, const zrk_state_view *v) {
     if (!h || !v) return ZRK_ERR_ARG;
+    DeviceGuard dev_guard(h->device);
     const Params &P = h->P;
     const Layout &o = P.lo;
     const int NS = o.NS, T = o.T, M = o.M, R = o.R, L = o.L, C = o.C;
@@ -1162,7 +1227,11 @@ struct SaveHeader {
     long long tick;
     unsigned long long dyn_bytes, rec_bytes, mask_bytes;
     int B, team, log_cap, mask_ticks;
+    int abi_version, reserved;
+    unsigned long long layout_hash;  // FNV-1a of the Layout struct: every offset of the state blob
+    unsigned long long cst_hash;     // FNV-1a of the parameter blobs (radars, launchers, missiles, CCP) + dt + noise shape
 };
+
 static const unsigned long long ZRK_SAVE_MAGIC = 0x5a524b5f53415645ull;  // "ZRK_SAVE"
 
 static void save_sizes(const zrk_handle *h, SaveHeader &sh) {
@@ -1177,6 +1246,10 @@ static void save_sizes(const zrk_handle *h, SaveHeader &sh) {
     sh.team = o.team;
     sh.log_cap = P.log_cap;
     sh.mask_ticks = P.mask_ticks;
+    sh.abi_version = ZRK_ABI_VERSION;
+    sh.reserved = 0;
+    sh.layout_hash = fnv1a(&o, sizeof(Layout));
+    sh.cst_hash = h->cst_hash;
 }
 
 extern "C" int zrk_state_bytes(zrk_handle *h, size_t *bytes) {
@@ -1189,6 +1262,7 @@ extern "C" int zrk_state_bytes(zrk_handle *h, size_t *bytes) {
 
 extern "C" int zrk_save_state(zrk_handle *h, void *buf, size_t cap) {
     if (!h || !buf) return ZRK_ERR_ARG;
+    DeviceGuard dev_guard(h->device);
     SaveHeader sh;
     save_sizes(h, sh);
     if (cap < sizeof(SaveHeader) + sh.dyn_bytes + sh.rec_bytes + sh.mask_bytes) return ZRK_ERR_CAPACITY;
@@ -1207,9 +1281,18 @@ extern "C" int zrk_save_state(zrk_handle *h, void *buf, size_t cap) {
 
 extern "C" int zrk_load_state(zrk_handle *h, const void *buf, size_t bytes) {
     if (!h || !buf || bytes < sizeof(SaveHeader)) return ZRK_ERR_ARG;
+    DeviceGuard dev_guard(h->device);
     SaveHeader sh, mine;
     memcpy(&sh, buf, sizeof sh);
     save_sizes(h, mine);
+    if (sh.magic == ZRK_SAVE_MAGIC && (sh.abi_version != mine.abi_version || sh.layout_hash != mine.layout_hash)) {
+        h->err = "checkpoint was written by a different build of the library (ABI version / state layout)";
+        return ZRK_ERR_ARG;
+    }
+    if (sh.magic == ZRK_SAVE_MAGIC && sh.cst_hash != mine.cst_hash) {
+        h->err = "checkpoint belongs to a batch with different scenario parameters";
+        return ZRK_ERR_ARG;
+    }
     if (sh.magic != ZRK_SAVE_MAGIC || sh.B != mine.B || sh.team != mine.team || sh.log_cap != mine.log_cap ||
         sh.mask_ticks != mine.mask_ticks || sh.dyn_bytes != mine.dyn_bytes || sh.rec_bytes != mine.rec_bytes ||
         sh.mask_bytes != mine.mask_bytes || bytes < sizeof(SaveHeader) + sh.dyn_bytes + sh.rec_bytes + sh.mask_bytes) {
@@ -1225,11 +1308,14 @@ extern "C" int zrk_load_state(zrk_handle *h, const void *buf, size_t bytes) {
     p += sh.rec_bytes;
     if (sh.mask_bytes) CK(cudaMemcpy(h->P.masks, p, sh.mask_bytes, cudaMemcpyHostToDevice));
     h->tick = sh.tick;
+    h->round_no = 0;
+    if (h->d_pending) CK(cudaMemset(h->d_pending, 0, sizeof(int) * ZRK_ROUND_SLOTS * (h->wave_stream.empty() ? 1 : h->wave_stream.size())));
     return ensure_tsec(h, h->tick + 2);
 }
 
 extern "C" int zrk_device_ptr(zrk_handle *h, const char *name, void **ptr, size_t *bytes) {
     if (!h || !name || !ptr) return ZRK_ERR_ARG;
+    DeviceGuard dev_guard(h->device);
     const Params &P = h->P;
     const Layout &o = P.lo;
     std::string n(name);

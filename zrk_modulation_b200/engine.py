@@ -28,6 +28,7 @@ class Engine:
                  waves: int = 0, certificate: bool = True, lib=None):
         self.lib = lib if lib is not None else _cabi.load()
         self.batch = batch
+        self.device = device
         self._h = C.c_void_p()
         opt = _cabi.ZrkOptions()
         opt.device = device
@@ -194,7 +195,7 @@ class Engine:
             __cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
 
         holder = _Buf()
-        t = torch.as_tensor(holder, device=torch.device("cuda", torch.cuda.current_device()))
+        t = torch.as_tensor(holder, device=torch.device("cuda", self.device))
         t._zrk_owner = (holder, self)
         return t if dtype is None else t.view(dtype)
 

@@ -113,7 +113,7 @@ def _profile_summaries(workload, ticks_per_launch):
             d = json.load(open(p))
         except ValueError:
             continue
-        if d.get("workload") == workload and abs(d.get("ticks_per_launch", 0) - ticks_per_launch) < 1e-9:
+        if d.get("workload") == workload:  # (the newest kernel version profiled on this workload)
             out.append((d.get("seq", 0), p, d))
     return [(p, d) for _, p, d in sorted(out, key=lambda t: -t[0])]
 
@@ -278,28 +278,53 @@ def run_ours(args, rank, world, local_rank):
         "target_type", "target_pos", "target_vel", "radar_id", "radar_pos", "radar_par", "launcher_id", "launcher_pos",
         "missile_id", "missile_launcher", "missile_v0", "missile_v0sq", "missile_radius", "missile_life",
         "ccp_launcher_id", "ccp_launcher_pos")) + (batch.noise.nbytes if batch.noise is not None else 0)
-    d2h = B * (16 + _cabi.ZRK_MSG_NTYPES) * 4
-    e2e_s = []
-    for i in range(args.warmup + args.steps):
+    d2h = (_cabi.ZRK_MSG_NTYPES + 4) * 8
+
+    def e2e_once(src, result="totals"):
+        """create (H2D) + step + result read-back (D2H) + destroy; returns (seconds, result)."""
         barrier()
         t0 = time.perf_counter()
-        eng = Engine(batch, device=dev, ticks_per_launch=args.ticks_per_launch, waves=args.waves,
-                     certificate=not args.no_certificate)
-        ta = time.perf_counter()
+        eng = Engine(src, device=dev, ticks_per_launch=args.ticks_per_launch, waves=args.waves, certificate=not args.no_certificate)
         eng.step(ticks)
-        c2 = eng.counts()  # per-scenario message counters + status: the step's result
+        if result == "totals":
+            out = eng.totals()           # batch totals reduced on the device: 22 words
+        elif result == "counters":
+            out = eng.counts()           # per-scenario message counters (B x 34 words)
+        else:
+            out = (eng.counts(), eng.records(0, B)[1])  # ... and every scenario's event records
+        eng.close()                      # zrk_destroy is part of the step
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        if args.verbose and rank == 0:
-            print(f"e2e step {i}: create {1e3 * (ta - t0):.1f} ms, step+read {1e3 * (t1 - ta):.1f} ms", file=sys.stderr)
         barrier()
-        eng.close()
+        return t1 - t0, out
+
+    e2e_s = []
+    for i in range(args.warmup + args.steps):
+        dt, tot = e2e_once(batch)
         if i >= args.warmup:
-            e2e_s.append(t1 - t0)
+            e2e_s.append(dt)
     t_e2e = torch.tensor([sum(e2e_s)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    assert np.array_equal(c2, counts), "end-to-end run disagrees with the device-resident run"
+    from zrk_modulation_b200.distributed import local_stats as _ls
+    assert np.array_equal(tot, _ls(counts, fc)), "end-to-end run disagrees with the device-resident run"
+    # less friendly variants of the same step, one run each (after a warm-up): inputs in pageable memory;
+    # per-scenario counters as the result; counters + every scenario's event records
+    variants = {}
+    if not args.no_variants:
+        pageable, _ = make_batch(args.workload, rank, pinned=False)
+        rec_bytes = None
+        for name, src, res in (("pageable_inputs", pageable, "totals"), ("per_scenario_counters", batch, "counters"),
+                               ("counters_and_event_records", batch, "records")):
+            e2e_once(src, res)
+            dt, out = e2e_once(src, res)
+            tv = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+            variants[name] = {"seconds": float(tv.item()),
+                              "d2h_bytes_per_step": {"totals": d2h, "counters": B * (16 + _cabi.ZRK_MSG_NTYPES) * 4,
+                                                     "records": B * (16 + _cabi.ZRK_MSG_NTYPES) * 4 * 2 + B * 48 * 70}[res]}
+        del pageable
 
     # ---- final statistics gather: the one collective of the path (NCCL all-reduce over NVLink)
     from zrk_modulation_b200.distributed import describe_stats, gather_stats, local_stats
@@ -307,6 +332,47 @@ def run_ours(args, rank, world, local_rank):
     stats = gather_stats(dev_stats, device=torch.device("cuda", dev))
     alive_all, units_all = (int(x) for x in gather_stats(torch.tensor([alive_ticks, units_done], dtype=torch.int64),
                                                         device=torch.device("cuda", dev)))
+
+    # ---- the other BASELINE shapes, short device-resident legs (config 3, config 4; config 2 does not shard: N = 1 only)
+    others = {}
+    if not args.no_variants and args.workload == "c5":
+        for name in ("c3", "c4") + (("c2",) if world == 1 else ()):
+            ob, oticks = make_batch(name, rank, pinned=False)
+            oB, oNS = ob.n_scenarios, ob.n_slots
+            ms_l, osteps = [], 2
+            for i in range(1 + osteps):
+                eng = Engine(ob, device=dev, certificate=not args.no_certificate)
+                eng.sync()
+                flush.fill_(i & 0xff)
+                barrier()
+                n0, m0 = eng.launch_stats()
+                eng.step(oticks)
+                eng.sync()
+                n1, m1 = eng.launch_stats()
+                barrier()
+                if i >= 1:
+                    ms_l.append(m1 - m0)
+                if i == osteps:
+                    ofc, oft, _ = eng.status()
+                    ocert = int(eng.certified_ticks().sum())
+                eng.close()
+            ran = np.where((ofc & 63) != 0, np.minimum(oft.astype(np.int64) + 1, oticks), oticks)
+            tv = torch.tensor([sum(ms_l), float(oNS * ran.sum())], dtype=torch.float64, device="cuda")
+            if world > 1:
+                tmax = tv[:1].clone()
+                dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                dist.all_reduce(tv[1:], op=dist.ReduceOp.SUM)
+                tv[0] = tmax[0]
+            oms, ounits = float(tv[0].item()), float(tv[1].item())
+            oval = ounits * osteps / (oms * 1e-3)
+            peak, _ = measured_peak_gbs()
+            others[name] = {"config": describe(name, world), "value": oval, "unit": "object-updates/s", "steps": osteps, "warmup": 1,
+                            "ms_per_step": oms / osteps, "scenario_ticks_per_s": oval / oNS,
+                            "certified_tick_fraction": ocert / float(oB * oticks),
+                            "roofline": {"bound": "hbm", "achieved": oval / world * BYTES_PER_OBJECT_UPDATE / 1e9, "peak": peak,
+                                         "unit": "GB/s", "frac": oval / world * BYTES_PER_OBJECT_UPDATE / 1e9 / peak},
+                            "faulted_scenarios_rank0": int(((ofc & 63) != 0).sum())}
+            del ob
 
     if rank == 0:
         value = units_all * args.steps / (total_ms * 1e-3)
@@ -327,12 +393,15 @@ def run_ours(args, rank, world, local_rank):
             "certified_tick_fraction": cert_ticks / float(B * ticks),  # rank 0's shard: ticks whose link_object scan was proven away
             "e2e": {"value": e2e_value, "unit": "object-updates/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t_e2e.item()) / args.steps * 1e3,
-                    "waves": args.waves},
+                    "waves": args.waves,
+                    "timed_region": "zrk_create from pinned host arrays (H2D) + zrk_step + zrk_read_totals (D2H) + zrk_destroy",
+                    "variants": {k: dict(v, value=units_all / v["seconds"], ms_per_step=v["seconds"] * 1e3)
+                                 for k, v in variants.items()}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": profiled_traffic(args.workload, ticks_per_launch), "peak_source": peak_src,
-                         "kernel": "zrk_tick_kernel",
+                         "kernel": "zrk_streak_kernel + zrk_tick_kernel (two-kernel stepping: all launches of the step)",
                          "bytes_per_object_update": BYTES_PER_OBJECT_UPDATE,
                          "real_bound": profiled(args.workload, ticks_per_launch, "issue_active_pct",
                                                 "instruction issue / dependent latency, not HBM"),
@@ -351,6 +420,8 @@ def run_ours(args, rank, world, local_rank):
             line["issue_roofline"] = {"bound": "issue", "achieved": ach_issue / 1e9, "peak": peak_issue / 1e9, "unit": "G warp-instr/s",
                                       "frac": ach_issue / peak_issue, "warp_instructions_per_scenario_tick": wi["warp_instructions_per_scenario_tick"],
                                       "source": wi["source"], "sms": sms, "sm_mhz": clocks["sm_mhz"]}
+        if others:
+            line["other_workloads"] = others
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             v, n, tk, dt = cpu_reference_throughput(args.workload, 1024, cores, min(ticks, 250))
@@ -375,6 +446,7 @@ def main():
     ap.add_argument("--waves", type=int, default=8,
                     help="scenario waves of the end-to-end leg (zrk_options.waves): the H2D copy of one wave overlaps the kernels of the others")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the extra end-to-end variants and the other workloads")
     ap.add_argument("--no-certificate", action="store_true", help="A/B: always run CCP.link_object's scan (ZRK_OPT_NO_CERTIFICATE)")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()

@@ -21,7 +21,7 @@
  * zrk_sync                         (run_simulation returning)       Manager.py:111
  * zrk_get_time                     Timer.get_time                   Timer.py:20-22
  * zrk_read_messages                Manager.give_messages            Manager.py:60-70
- * zrk_read_counts                  sum(len(messages))               main.py:171
+ * zrk_read_counts, zrk_read_totals sum(len(messages))               main.py:171
  * zrk_read_activity                sum(len(ActiveObjectsMessage.active_objects))  AirEnv.py:50-53
  * zrk_read_certified               (diagnostic: ticks on which CCP.link_object's scan, CCP.py:171-219, was proven away)
  * zrk_read_state                   model attributes (pos, prev_pos, current_azimuth,
@@ -286,6 +286,10 @@ int zrk_get_time(zrk_handle *h, int64_t *tick, int64_t *time_ms);
 int zrk_read_status(zrk_handle *h, int32_t *fault_code, int32_t *fault_tick, int32_t *n_records);
 /* Messages emitted so far per scenario and type: counts[B][ZRK_MSG_NTYPES]. */
 int zrk_read_counts(zrk_handle *h, int64_t *counts);
+/* Batch totals, reduced on the device (a read-back of ZRK_MSG_NTYPES + 4 words instead of B x ZRK_MSG_NTYPES):
+ * totals[0 .. ZRK_MSG_NTYPES) messages per type over all scenarios (main.py:171 summed over the batch), then the
+ * number of scenarios that faulted, with ZRK_FAULT_ATTRIBUTE_ERROR_CCP259, with ZRK_FAULT_KEY_ERROR_CCP107, in all. */
+int zrk_read_totals(zrk_handle *h, int64_t *totals);
 /* Per scenario: alive air objects summed over the ticks started so far, i.e. the total length of
  * the active_objects lists AirEnv.step published (AirEnv.py:50-53); divided by slots x ticks it is
  * the active-slot fraction of the run.  Counted modulo 2^32. */

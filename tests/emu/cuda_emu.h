@@ -161,6 +161,11 @@ inline int atomicAdd(int *p, int v) {
     *p = o + v;
     return o;
 }
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
+    unsigned long long o = *p;
+    *p = o + v;
+    return o;
+}
 inline int atomicExch(int *p, int v) {
     int o = *p;
     *p = v;

@@ -168,6 +168,7 @@ def declare(lib):
     lib.zrk_read_status.argtypes = [H, _pi32, _pi32, _pi32]
     lib.zrk_read_counts.argtypes = [H, C.POINTER(C.c_int64)]
     lib.zrk_read_activity.argtypes = [H, C.POINTER(C.c_int64)]
+    lib.zrk_read_totals.argtypes = [H, C.POINTER(C.c_int64)]
     lib.zrk_read_certified.argtypes = [H, C.POINTER(C.c_int64)]
     lib.zrk_read_records.argtypes = [H, C.c_int, C.c_int, C.POINTER(ZrkMsg), _pi32]
     lib.zrk_log_capacity.argtypes = [H]
@@ -186,7 +187,7 @@ def declare(lib):
     lib.zrk_abi_version.argtypes = []
     lib.zrk_release_cached_memory.argtypes = []
     for f in ("zrk_create", "zrk_step", "zrk_sync", "zrk_get_time", "zrk_read_status",
-              "zrk_read_counts", "zrk_read_activity", "zrk_read_certified", "zrk_read_records", "zrk_log_capacity", "zrk_read_messages",
+              "zrk_read_counts", "zrk_read_totals", "zrk_read_activity", "zrk_read_certified", "zrk_read_records", "zrk_log_capacity", "zrk_read_messages",
               "zrk_read_state", "zrk_device_ptr", "zrk_launch_stats", "zrk_abi_version", "zrk_state_bytes",
               "zrk_save_state", "zrk_load_state", "zrk_release_cached_memory"):
         getattr(lib, f).restype = C.c_int
@@ -194,7 +195,7 @@ def declare(lib):
 
 
 EXPORTED_SYMBOLS = ["zrk_create", "zrk_step", "zrk_sync", "zrk_get_time", "zrk_read_status",
-                    "zrk_read_counts", "zrk_read_activity", "zrk_read_certified", "zrk_read_records", "zrk_log_capacity", "zrk_read_messages",
+                    "zrk_read_counts", "zrk_read_totals", "zrk_read_activity", "zrk_read_certified", "zrk_read_records", "zrk_log_capacity", "zrk_read_messages",
                     "zrk_read_state", "zrk_device_ptr", "zrk_launch_stats", "zrk_last_error",
                     "zrk_destroy", "zrk_abi_version", "zrk_state_bytes", "zrk_save_state", "zrk_load_state",
                     "zrk_release_cached_memory"]

@@ -196,6 +196,33 @@ __global__ void zrk_summary_kernel(const Params P, int *out) {
     out[i] = w < H_WORDS ? ((const int *)(sm + o.hot.hdr))[w] : ((const int *)(sm + o.hot.counts))[w - H_WORDS];
 }
 
+// Batch totals for a caller that does not need per-scenario counters: message totals per type, then
+// scenarios faulted / with AttributeError / with KeyError / in all (the statistics vector the ranks of a
+// multi-GPU job all-reduce).  One thread per scenario, block partial sums in shared memory.
+#define ZRK_TOTALS_WORDS (ZRK_MSG_NTYPES + 4)
+__global__ void zrk_totals_kernel(const Params P, unsigned long long *out) {
+    ZRK_SMEM_DECL;
+    unsigned long long *part = (unsigned long long *)zrk_smem;  // [ZRK_TOTALS_WORDS]
+    const Layout &o = P.lo;
+    for (int i = threadIdx.x; i < ZRK_TOTALS_WORDS; i += blockDim.x) part[i] = 0;
+    __syncthreads();
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < o.B) {
+        const unsigned char *sm = P.dyn + (size_t)b * o.dyn_bytes;
+        const unsigned *cnt = (const unsigned *)(sm + o.hot.counts);
+        const int fault = ((const int *)(sm + o.hot.hdr))[H_FAULT] & 63;
+        for (int t = 0; t < ZRK_MSG_NTYPES; t++)
+            if (cnt[t]) atomicAdd(&part[t], (unsigned long long)cnt[t]);
+        if (fault) atomicAdd(&part[ZRK_MSG_NTYPES], 1ull);
+        if (fault == ZRK_FAULT_ATTRIBUTE_ERROR_CCP259) atomicAdd(&part[ZRK_MSG_NTYPES + 1], 1ull);
+        if (fault == ZRK_FAULT_KEY_ERROR_CCP107) atomicAdd(&part[ZRK_MSG_NTYPES + 2], 1ull);
+        atomicAdd(&part[ZRK_MSG_NTYPES + 3], 1ull);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ZRK_TOTALS_WORDS; i += blockDim.x)
+        if (part[i]) atomicAdd(&out[i], part[i]);
+}
+
 // ------------------------------------------------------------------ handle
 
 struct zrk_handle {
@@ -217,6 +244,7 @@ struct zrk_handle {
     int grid = 0, block = 0;
     // host copies kept for reconstruction
     std::vector<int> h_radar_id, h_n_radars, h_airenv_id;
+    unsigned long long *d_totals = nullptr, *h_totals = nullptr;  // zrk_read_totals
     int *d_summary = nullptr;
     int *h_summary = nullptr;  // page-locked [B][ZRK_SUMMARY_WORDS], allocated while the first step runs
     double *d_tsec = nullptr;
@@ -420,6 +448,7 @@ extern "C" void zrk_destroy(zrk_handle *h) {
     if (!h->wave_stream.empty()) cudaEventDestroy(h->fork_ev);
     pinned_put(h->pin_err, sizeof(int));
     pinned_put(h->h_pending, sizeof(int) * 64);
+    pinned_put(h->h_totals, sizeof(unsigned long long) * ZRK_TOTALS_WORDS);
     pinned_put(h->h_summary, (size_t)h->P.lo.B * ZRK_SUMMARY_WORDS * sizeof(int));
     for (void *p : h->allocs) cudaFreeAsync(p, h->stream);
     cudaStreamSynchronize(h->stream);
@@ -980,6 +1009,25 @@ extern "C" int zrk_read_counts(zrk_handle *h, int64_t *counts) {
         const unsigned *c = (const unsigned *)(h->h_summary + (size_t)s * ZRK_SUMMARY_WORDS + H_WORDS);
         for (int t = 0; t < ZRK_MSG_NTYPES; t++) counts[(size_t)s * ZRK_MSG_NTYPES + t] = c[t];
     }
+    return ZRK_OK;
+}
+
+extern "C" int zrk_read_totals(zrk_handle *h, int64_t *totals) {
+    if (!h || !totals) return ZRK_ERR_ARG;
+    DeviceGuard dev_guard(h->device);
+    if (!h->d_totals) {
+        int rc = dev_alloc(h, (size_t)ZRK_TOTALS_WORDS, &h->d_totals, false);
+        if (rc) return rc;
+        CK(pinned_get((void **)&h->h_totals, sizeof(unsigned long long) * ZRK_TOTALS_WORDS));
+    }
+    CK(cudaMemsetAsync(h->d_totals, 0, sizeof(unsigned long long) * ZRK_TOTALS_WORDS, h->stream));
+    ZRK_LAUNCH(zrk_totals_kernel, (h->P.lo.B + 255) / 256, 256, sizeof(unsigned long long) * ZRK_TOTALS_WORDS, h->stream, h->P,
+               h->d_totals);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_totals, h->d_totals, sizeof(unsigned long long) * ZRK_TOTALS_WORDS, cudaMemcpyDeviceToHost, h->stream));
+    int rc = zrk_sync(h);
+    if (rc) return rc;
+    for (int i = 0; i < ZRK_TOTALS_WORDS; i++) totals[i] = (int64_t)h->h_totals[i];
     return ZRK_OK;
 }
 

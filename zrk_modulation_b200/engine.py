@@ -95,6 +95,13 @@ class Engine:
         self._ck(self.lib.zrk_read_counts(self._h, c.ctypes.data_as(C.POINTER(C.c_int64))))
         return c
 
+    def totals(self) -> np.ndarray:
+        """Batch totals reduced on the device (int64[NTYPES + 4]): messages per type, then scenarios faulted /
+        AttributeError / KeyError / in all — the vector distributed.local_stats builds from counts() and status()."""
+        t = np.zeros(_cabi.ZRK_MSG_NTYPES + 4, dtype=np.int64)
+        self._ck(self.lib.zrk_read_totals(self._h, t.ctypes.data_as(C.POINTER(C.c_int64))))
+        return t
+
     def alive_slot_ticks(self) -> np.ndarray:
         """Per scenario: alive air objects summed over the ticks run (the total length of the
         active_objects lists AirEnv.step published)."""

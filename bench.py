@@ -236,11 +236,18 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()
 
+    # the log the run keeps: event records + per-tick alive / visibility masks + track journal — enough to rebuild
+    # Manager.messages of any scenario (zrk_read_messages); --log events keeps the event records only
+    def log_kw(n_ticks):
+        if args.log == "events":
+            return dict(log_types=_cabi.LOG_EVENTS)
+        return dict(log_types=_cabi.LOG_EVENTS | _cabi.LOG_MASKS, mask_ticks=n_ticks + 1)
+
     # ---- device-resident pass: state already in HBM when the timed region starts
     kern_ms, launches = [], 0
     sampler = None
     for i in range(args.warmup + args.steps):
-        eng = Engine(batch, device=dev, ticks_per_launch=args.ticks_per_launch, certificate=not args.no_certificate)
+        eng = Engine(batch, device=dev, ticks_per_launch=args.ticks_per_launch, certificate=not args.no_certificate, **log_kw(ticks))
         eng.sync()
         flush.fill_(i & 0xff)  # evict the freshly written state from L2
         if i == 0 and rank == 0:  # same load during warm-up and timed steps: sample across both
@@ -284,7 +291,8 @@ def run_ours(args, rank, world, local_rank):
         """create (H2D) + step + result read-back (D2H) + destroy; returns (seconds, result)."""
         barrier()
         t0 = time.perf_counter()
-        eng = Engine(src, device=dev, ticks_per_launch=args.ticks_per_launch, waves=args.waves, certificate=not args.no_certificate)
+        eng = Engine(src, device=dev, ticks_per_launch=args.ticks_per_launch, waves=args.waves, certificate=not args.no_certificate,
+                     **log_kw(ticks))
         eng.step(ticks)
         if result == "totals":
             out = eng.totals()           # batch totals reduced on the device: 22 words
@@ -333,6 +341,29 @@ def run_ours(args, rank, world, local_rank):
     alive_all, units_all = (int(x) for x in gather_stats(torch.tensor([alive_ticks, units_done], dtype=torch.int64),
                                                         device=torch.device("cuda", dev)))
 
+    # ---- what the masks cost: the same device-resident step keeping the event records only
+    events_only = None
+    if not args.no_variants and args.log == "masks":
+        ms_l = []
+        for i in range(3):
+            eng = Engine(batch, device=dev, ticks_per_launch=args.ticks_per_launch, certificate=not args.no_certificate,
+                         log_types=_cabi.LOG_EVENTS)
+            eng.sync()
+            flush.fill_(i & 0xff)
+            barrier()
+            n0, m0 = eng.launch_stats()
+            eng.step(ticks)
+            eng.sync()
+            n1, m1 = eng.launch_stats()
+            barrier()
+            if i >= 1:
+                ms_l.append(m1 - m0)
+            eng.close()
+        tv = torch.tensor([sum(ms_l)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        events_only = {"ms_per_step": float(tv.item()) / 2, "steps": 2, "warmup": 1}
+
     # ---- the other BASELINE shapes, short device-resident legs (config 3, config 4; config 2 does not shard: N = 1 only)
     others = {}
     if not args.no_variants and args.workload == "c5":
@@ -341,7 +372,7 @@ def run_ours(args, rank, world, local_rank):
             oB, oNS = ob.n_scenarios, ob.n_slots
             ms_l, osteps = [], 2
             for i in range(1 + osteps):
-                eng = Engine(ob, device=dev, certificate=not args.no_certificate)
+                eng = Engine(ob, device=dev, certificate=not args.no_certificate, **log_kw(oticks))
                 eng.sync()
                 flush.fill_(i & 0xff)
                 barrier()
@@ -420,6 +451,14 @@ def run_ours(args, rank, world, local_rank):
             line["issue_roofline"] = {"bound": "issue", "achieved": ach_issue / 1e9, "peak": peak_issue / 1e9, "unit": "G warp-instr/s",
                                       "frac": ach_issue / peak_issue, "warp_instructions_per_scenario_tick": wi["warp_instructions_per_scenario_tick"],
                                       "source": wi["source"], "sms": sms, "sm_mhz": clocks["sm_mhz"]}
+        R_ = WORKLOADS[args.workload][2]
+        line["log"] = {"mode": args.log,
+                       "kept": "event records + per-tick alive / per-radar visibility masks + track journal: Manager.messages of any "
+                               "scenario is rebuilt from them (zrk_read_messages)" if args.log == "masks" else "event records only",
+                       "mask_bytes_per_step": int(B * ticks * (1 + max(1, R_)) * ((NS + 31) // 32) * 4) if args.log == "masks" else 0}
+        if events_only:
+            events_only["value"] = units_all / (events_only["ms_per_step"] * 1e-3)
+            line["log"]["without_masks"] = events_only
         if others:
             line["other_workloads"] = others
         if world == 1 and not args.no_cpu_baseline:
@@ -445,6 +484,8 @@ def main():
     ap.add_argument("--ticks-per-launch", type=int, default=0)
     ap.add_argument("--waves", type=int, default=8,
                     help="scenario waves of the end-to-end leg (zrk_options.waves): the H2D copy of one wave overlaps the kernels of the others")
+    ap.add_argument("--log", default="masks", choices=["masks", "events"],
+                    help="masks (default): event records + per-tick masks + track journal, every message rebuildable; events: event records only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra end-to-end variants and the other workloads")
     ap.add_argument("--no-certificate", action="store_true", help="A/B: always run CCP.link_object's scan (ZRK_OPT_NO_CERTIFICATE)")

@@ -123,6 +123,13 @@ enum zrk_rc {
     (ZRK_TYPE_BIT(ZRK_MSG_CCP_UPDATE_TARGET) | ZRK_TYPE_BIT(ZRK_MSG_DRAW_OBJECTS) |               \
      ZRK_TYPE_BIT(ZRK_MSG_MISSILE_POS))
 #define ZRK_LOG_MASKS 0x80000000u /* keep per-tick alive + per-radar visibility masks */
+/* Private record type 30, the "track journal": one record per association of a detection with a track other
+ * than the one that followed its slot (flag = 0 new track / 1 _target_dict / 2 _missile_dict, sender = AirEnv
+ * slot, receiver = entry index, a = object id, b = launch commanded).  Switched on together with ZRK_LOG_MASKS;
+ * zrk_read_messages replays it to rebuild CCP_UPDATE_TARGET / DRAW_OBJECTS / MISSILE_POS when those are not
+ * stored as records; zrk_read_records never returns it. */
+#define ZRK_REC_TRACK 30
+#define ZRK_LOG_TRACKS 0x40000000u
 #define ZRK_LOG_FULL (ZRK_LOG_EVENTS | ZRK_LOG_BULK | ZRK_LOG_MASKS)
 
 /*
@@ -303,7 +310,11 @@ int zrk_read_certified(zrk_handle *h, int64_t *certified_ticks);
 int zrk_read_records(zrk_handle *h, int s0, int s1, zrk_msg *recs, int32_t *n);
 int zrk_log_capacity(zrk_handle *h);
 /* The full message list of one scenario for ticks [tick0, tick1), in the reference's order
- * (Manager.py:41-58), with ACTIVE/ALL/FOUND rebuilt from the masks.  Needs ZRK_LOG_FULL.
+ * (Manager.py:41-58).  Needs ZRK_LOG_MASKS and a mask history (zrk_options.mask_ticks) covering the run so far.
+ * ACTIVE/ALL/FOUND are always rebuilt from the masks; with ZRK_LOG_FULL the other bulk types come from their
+ * records, with ZRK_LOG_EVENTS | ZRK_LOG_MASKS (the mode that scales: 8 + 4 R bytes per scenario-tick) MISSILE_POS,
+ * CCP_UPDATE_TARGET and DRAW_OBJECTS are rebuilt on the host from the masks, the closed-form trajectories
+ * (AirObject.py:23-25), the noise table and a replay of the event records + track journal — the same messages, bit for bit.
  * Returns ZRK_ERR_CAPACITY (and the needed sizes) if a buffer is too small. */
 int zrk_read_messages(zrk_handle *h, int scenario, int tick0, int tick1, zrk_msg *msgs, size_t cap,
                       size_t *n, int32_t *ids, size_t ids_cap, size_t *n_ids);

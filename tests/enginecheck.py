@@ -9,12 +9,16 @@ from zrk_modulation_b200.engine import Engine
 
 
 def check_batch_full(batch, n_ticks, lib=None, ticks_per_launch=0, exact_only=False, scenarios=None,
-                     step_chunks=None):
-    """Bit-exact comparison of all messages + state of the given scenarios (default: all)."""
+                     step_chunks=None, rebuilt=False):
+    """Bit-exact comparison of all messages + state of the given scenarios (default: all).
+    rebuilt: the log that scales — event records + masks + track journal only (the quiet streak and the
+    certificate run), bulk messages rebuilt on the host by zrk_read_messages."""
+    from zrk_modulation_b200 import LOG_EVENTS, LOG_MASKS
     B = batch.n_scenarios
     scenarios = range(B) if scenarios is None else scenarios
-    cap = (3 * batch.n_slots + 16 + 4 * batch.max_radars) * n_ticks + 64
-    with Engine(batch, log_types=LOG_FULL, log_capacity=cap, mask_ticks=n_ticks + 1,
+    # (rebuilt: events + track journal; dense scenarios change tracks all the time, give them room)
+    cap = 64 * batch.n_slots + 512 if rebuilt else (3 * batch.n_slots + 16 + 4 * batch.max_radars) * n_ticks + 64
+    with Engine(batch, log_types=(LOG_EVENTS | LOG_MASKS) if rebuilt else LOG_FULL, log_capacity=cap, mask_ticks=n_ticks + 1,
                 ticks_per_launch=ticks_per_launch, exact_only=exact_only, lib=lib) as eng:
         if step_chunks:
             for k in step_chunks:

@@ -559,8 +559,12 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
     P.dt_s = (double)d->dt_ms / 1000.0;
     P.range_step = ZRK_POSSIBLE_TARGET_RADIUS * P.dt_s;
     P.log_types = opt ? opt->log_types : (unsigned)ZRK_LOG_EVENTS;
+    if (P.log_types & ZRK_LOG_MASKS) P.log_types |= ZRK_LOG_TRACKS;  // the track journal goes with the masks
     int cap = opt ? opt->log_capacity : 0;
-    if (cap <= 0) cap = 2 * C + M * (6 + R) + 4;  // every ZRK_LOG_EVENTS record a scenario can ever emit
+    if (cap <= 0) {
+        cap = 2 * C + M * (6 + R) + 4;  // every ZRK_LOG_EVENTS record a scenario can ever emit
+        if (P.log_types & ZRK_LOG_TRACKS) cap += 8 * (T + M) + 64;  // + room for the track journal (an overflow is reported per scenario)
+    }
     P.log_cap = cap;
     P.mask_words = (lo.NS + 31) / 32;
     if (P.mask_words < 1) P.mask_words = 1;
@@ -1060,9 +1064,240 @@ extern "C" int zrk_read_records(zrk_handle *h, int s0, int s1, zrk_msg *recs, in
         const int *hdr = h->h_summary + (size_t)s * ZRK_SUMMARY_WORDS;
         if (n) n[s - s0] = std::min(hdr[H_NREC], h->P.log_cap);
     }
-    if (recs && s1 > s0)
+    if (recs && s1 > s0) {
         CK(cudaMemcpy(recs, h->P.rec + (size_t)s0 * h->P.log_cap, (size_t)(s1 - s0) * h->P.log_cap * sizeof(zrk_msg),
                       cudaMemcpyDeviceToHost));
+        if (h->P.log_types & ZRK_LOG_TRACKS)  // the track journal is private: squeeze it out
+            for (int s = s0; s < s1; s++) {
+                zrk_msg *r = recs + (size_t)(s - s0) * h->P.log_cap;
+                const int nr = std::min(h->h_summary[(size_t)s * ZRK_SUMMARY_WORDS + H_NREC], h->P.log_cap);
+                int k = 0;
+                for (int i = 0; i < nr; i++)
+                    if (r[i].type != ZRK_REC_TRACK) r[k++] = r[i];
+                if (n) n[s - s0] = k;
+            }
+    }
+    return ZRK_OK;
+}
+
+// ------------------------------------------------------------------ messages rebuilt on the host
+//
+// The log that scales: per scenario-tick the device keeps 1 + R mask words (who is in AirEnv's list, whom
+// each radar saw) and, per scenario, the rare event records plus the track journal.  Everything else the
+// reference stores in Manager.messages (Manager.py:41-58) follows from those:
+//   MISSILE_POS        one per active missile per tick, in slot order (Missile.py:183-184)
+//   ACTIVE/ALL/FOUND   the lists behind the masks (AirEnv.py:50-53, Radar.py:155-174)
+//   CCP_UPDATE_TARGET  one per detection whose track is followed (CCP.py:350-357)
+//   DRAW_OBJECTS       tracked missiles seen, tracked targets seen, everything else (CCP.py:237-284), with the
+//                      object's position of that tick: Trajectory.get_pos (AirObject.py:23-25) plus the noise of
+//                      every radar that saw it, in radar order (Radar.py:138-142) — the same fp64 operations
+// The CCP's dicts are replayed from tick 0: LAUNCHED_MISSILE records (add_missile, CCP.py:102-109),
+// LAUNCH_COMMAND records (following) and the track journal (every association other than "own track").
+static int rebuild_messages(zrk_handle *h, int sc, int tick0, int tick1, std::vector<zrk_msg> &out, std::vector<int32_t> &pool) {
+    const Params &P = h->P;
+    const Layout &o = P.lo;
+    const HotOff &ho = o.hot;
+    std::vector<unsigned char> dyn, cst((size_t)o.cst_bytes);
+    int rc = fetch_dyn(h, sc, sc + 1, dyn);
+    if (rc) return rc;
+    CK(cudaMemcpy(cst.data(), P.cst + (size_t)sc * o.cst_bytes, cst.size(), cudaMemcpyDeviceToHost));
+    const int *hdr = (const int *)(dyn.data() + ho.hdr), *sid = (const int *)(dyn.data() + ho.sid),
+              *sflags = (const int *)(dyn.data() + ho.sflags);
+    const double *txy = (const double *)(dyn.data() + ho.txy), *tzt = (const double *)(dyn.data() + ho.tzt),
+                 *vxy = (const double *)(dyn.data() + ho.vxy), *qzw = (const double *)(dyn.data() + ho.qzw);
+    const int *chdr = (const int *)(cst.data() + o.c_hdr), *c_rad_id = (const int *)(cst.data() + o.c_rad_id);
+    const int nR = chdr[C_NR], ccp_id = chdr[C_CCP_ID], airenv_id = chdr[C_AIRENV_ID];
+    const bool has_ccp = ccp_id != ZRK_NONE;
+    const int n_slots = hdr[H_NSLOTS], TEAM = o.team;
+    const int fault = hdr[H_FAULT] & 63, fault_tick = hdr[H_FAULT_TICK];
+    const int done = hdr[H_TICK] + (fault ? 1 : 0);  // the faulting tick's messages exist too
+    if (hdr[H_FAULT] & ZRK_FAULT_LOG_OVERFLOW) {
+        h->err = "record log overflow: raise zrk_options.log_capacity";
+        return ZRK_ERR_CAPACITY;
+    }
+    if (tick1 > done) tick1 = done;
+    if (tick1 <= tick0) return ZRK_OK;
+    if (done > P.mask_ticks) {  // the dicts are replayed from tick 0
+        h->err = "mask history ring is shorter than the run: raise zrk_options.mask_ticks";
+        return ZRK_ERR_CAPACITY;
+    }
+    const int nrec = std::min(hdr[H_NREC], P.log_cap);
+    std::vector<zrk_msg> rec(nrec ? nrec : 1);
+    if (nrec) CK(cudaMemcpy(rec.data(), P.rec + (size_t)sc * P.log_cap, (size_t)nrec * sizeof(zrk_msg), cudaMemcpyDeviceToHost));
+    // mask rows of this scenario, ticks [0, tick1): one strided copy
+    const int W = P.mask_words, rows = (1 + o.RP) * W;
+    std::vector<unsigned> masks((size_t)tick1 * rows);
+    CK(cudaMemcpy2D(masks.data(), rows * sizeof(unsigned), P.masks + (size_t)sc * rows, (size_t)o.B * rows * sizeof(unsigned),
+                    rows * sizeof(unsigned), tick1, cudaMemcpyDeviceToHost));
+    // the scenario's noise table
+    std::vector<double> noise;
+    const size_t nrow = (size_t)P.noise_radars * P.noise_objects * 3;
+    if (P.noise) {
+        noise.resize((size_t)P.noise_period * nrow);
+        CK(cudaMemcpy(noise.data(), P.noise + (size_t)sc * P.noise_stride, noise.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    auto slot_of_id = [&](int id) {
+        for (int k = 0; k < n_slots; k++)
+            if (sid[k] == id) return k;
+        return -1;
+    };
+    // the CCP's dicts (CCP.py:80-81), as the device keeps them: key, slot the entry's object sits in, ...
+    std::vector<int> te_key, te_ref, te_follow, te_mid, me_key, me_ref, own(n_slots > 0 ? n_slots : 1, -1);
+    std::vector<int> rf(n_slots > 0 ? n_slots : 1);
+    int ri = 0, det_prev = 0;
+    for (int t = 0; t < tick1; t++) {
+        const bool emit = t >= tick0;
+        const size_t first = out.size();
+        const unsigned *m = masks.data() + (size_t)t * rows;
+        auto bit = [&](const unsigned *row, int k) { return (row[k >> 5] >> (k & 31)) & 1u; };
+        auto push = [&](const zrk_msg &x) { if (emit) out.push_back(x); };
+        auto list_msg = [&](int type, int sender, int receiver, const unsigned *bits) {
+            if (!emit) return;
+            zrk_msg x{};
+            x.tick = t; x.type = (uint8_t)type; x.relevance = 1; x.sender = sender; x.receiver = receiver;
+            x.a = (int32_t)pool.size();
+            int cnt = 0;
+            for (int k = 0; k < n_slots; k++)
+                if (bit(bits, k)) { pool.push_back(sid[k]); cnt++; }
+            x.b = cnt;
+            out.push_back(x);
+        };
+        // this tick's records, by phase
+        const int r0 = ri;
+        while (ri < nrec && rec[ri].tick == t) ri++;
+        const int r1 = ri;
+        const double now_s = (double)((long long)t * P.dt_ms) / 1000.0;
+        // AirEnv.step: per active missile (slot order) MISSILE_POS, then its MISSILE_DETONATE if it has one
+        int det_now = 0;
+        for (int k = 0; k < n_slots; k++) {
+            if (!bit(m, k) || !(sflags[k] & F_MISSILE)) continue;
+            zrk_msg x{};
+            x.tick = t; x.type = ZRK_MSG_MISSILE_POS; x.relevance = 1; x.sender = sid[k]; x.receiver = ZRK_NONE; x.a = sid[k]; x.b = ZRK_NONE;
+            push(x);
+            for (int i = r0; i < r1; i++)
+                if (rec[i].type == ZRK_MSG_MISSILE_DETONATE && rec[i].a == sid[k]) { push(rec[i]); det_now++; }
+        }
+        list_msg(ZRK_MSG_ACTIVE_OBJECTS, airenv_id, ZRK_NONE, m);
+        // radars: ALL_OBJECTS, FOUND_OBJECTS, one DESTROYED_MISSILE per detonation of the previous tick
+        int di = r0;
+        for (int r = 0; r < nR; r++) {
+            list_msg(ZRK_MSG_ALL_OBJECTS, c_rad_id[r], ZRK_CCP_ID, m);
+            list_msg(ZRK_MSG_FOUND_OBJECTS, c_rad_id[r], ZRK_CCP_ID, m + (1 + r) * W);
+            for (int k = 0; k < det_prev; k++) {
+                while (di < r1 && rec[di].type != ZRK_MSG_DESTROYED_MISSILE) di++;
+                if (di < r1) push(rec[di++]);
+            }
+        }
+        // launchers and the CCP's bookkeeping, in emission order; LAUNCHED_MISSILE feeds add_missile (CCP.py:102-109)
+        bool key_fault = false;
+        for (int i = r0; i < r1; i++) {
+            const int ty = rec[i].type;
+            if (ty == ZRK_MSG_MISSILE_DETONATE || ty == ZRK_MSG_DESTROYED_MISSILE || ty == ZRK_MSG_LAUNCH_COMMAND ||
+                ty == ZRK_REC_TRACK || ty == ZRK_MSG_CCP_UPDATE_TARGET || ty == ZRK_MSG_DRAW_OBJECTS || ty == ZRK_MSG_MISSILE_POS)
+                continue;
+            push(rec[i]);
+        }
+        if (has_ccp)
+            for (int i = r0; i < r1 && !key_fault; i++) {
+                if (rec[i].type != ZRK_MSG_LAUNCHED_MISSILE) continue;
+                const int m_id = rec[i].a, tid = rec[i].b, ms = slot_of_id(m_id);
+                size_t e = 0;
+                while (e < me_key.size() && me_key[e] != m_id) e++;
+                if (e == me_key.size()) { me_key.push_back(m_id); me_ref.push_back(ms); } else { me_ref[e] = ms; }
+                if (ms >= 0) own[ms] = TEAM + (int)e;
+                size_t q = 0;
+                while (q < te_key.size() && te_key[q] != tid) q++;
+                if (q == te_key.size()) { key_fault = true; break; }  // KeyError (CCP.py:107): the run ends here
+                te_mid[q] = m_id;
+            }
+        if (has_ccp && !key_fault && !(fault == ZRK_FAULT_KEY_ERROR_CCP107 && t == fault_tick)) {
+            // positions of this tick: Trajectory.get_pos + the noise of every radar that saw the object, in radar order
+            auto pos_of = [&](int k, double *p) {
+                const double dtm = now_s - tzt[2 * k + 1];
+                p[0] = txy[2 * k] + vxy[2 * k] * dtm;
+                p[1] = txy[2 * k + 1] + vxy[2 * k + 1] * dtm;
+                p[2] = tzt[2 * k] + qzw[2 * k + 1] * dtm;
+                if (!noise.empty()) {
+                    const int st = sflags[k] >> F_STATIC_SHIFT;
+                    for (int r = 0; r < nR; r++)
+                        if (bit(m + (1 + r) * W, k)) {
+                            const double *q = noise.data() + (size_t)(t % P.noise_period) * nrow + ((size_t)r * P.noise_objects + st) * 3;
+                            p[0] += q[0]; p[1] += q[1]; p[2] += q[2];
+                        }
+                }
+            };
+            for (int k = 0; k < n_slots; k++) {
+                rf[k] = -1;
+                for (int r = 0; r < nR && rf[k] < 0; r++)
+                    if (bit(m + (1 + r) * W, k)) rf[k] = r;
+            }
+            // detections in processing order: FOUND_OBJECTS messages in radar order, each object once (CCP.py:406-429)
+            for (int r = 0; r < nR; r++)
+                for (int k = 0; k < n_slots; k++) {
+                    if (rf[k] != r) continue;
+                    const zrk_msg *trk = nullptr, *cmd = nullptr;
+                    for (int i = r0; i < r1; i++) {
+                        if (rec[i].type == ZRK_REC_TRACK && rec[i].sender == k) trk = &rec[i];
+                        if (rec[i].type == ZRK_MSG_LAUNCH_COMMAND && rec[i].a == sid[k]) cmd = &rec[i];
+                    }
+                    int cls, e;
+                    if (trk) {
+                        cls = trk->flag;
+                        e = trk->receiver;
+                    } else {  // the detection re-acquired the track of its own slot
+                        cls = own[k] >= TEAM ? 2 : 1;
+                        e = own[k] >= TEAM ? own[k] - TEAM : own[k];
+                        if (own[k] < 0) { h->err = "rebuild_messages: a detection without a track and without a journal entry"; return ZRK_ERR_ARG; }
+                    }
+                    if (cls == 1) {
+                        const bool following = te_follow[e] != 0;
+                        if (cmd) {
+                            push(*cmd);
+                            te_follow[e] = 1;
+                        } else if (following) {
+                            zrk_msg x{};
+                            x.tick = t; x.type = ZRK_MSG_CCP_UPDATE_TARGET; x.relevance = 1; x.sender = ccp_id; x.receiver = c_rad_id[r];
+                            x.a = sid[k]; x.b = te_mid[e];
+                            push(x);
+                        }
+                        te_ref[e] = k;
+                        own[k] = e;
+                    } else if (cls == 2) {
+                        me_ref[e] = k;
+                        own[k] = TEAM + e;
+                    } else {  // new_target + add_target (CCP.py:322-330, :88-93)
+                        if (cmd) push(*cmd);
+                        if ((size_t)e >= te_key.size()) { te_key.resize(e + 1, 0); te_ref.resize(e + 1, -1); te_follow.resize(e + 1, 0); te_mid.resize(e + 1, ZRK_NONE); }
+                        te_key[e] = sid[k]; te_ref[e] = k; te_follow[e] = cmd ? 1 : 0; te_mid[e] = ZRK_NONE;
+                        own[k] = e;
+                    }
+                }
+            // send_objects_to_GUI (CCP.py:237-284)
+            auto draw = [&](int k, int type, int vis) {
+                zrk_msg x{};
+                x.tick = t; x.type = ZRK_MSG_DRAW_OBJECTS; x.relevance = 1; x.flag = (uint8_t)vis; x.sender = ccp_id; x.receiver = ZRK_MANAGER_ID;
+                x.a = sid[k]; x.b = type;
+                pos_of(k, x.xyz);
+                push(x);
+            };
+            bool attr_fault = false;
+            for (size_t e = 0; e < me_key.size(); e++)
+                if (me_ref[e] >= 0 && bit(m, me_ref[e]) && rf[me_ref[e]] >= 0) draw(me_ref[e], ZRK_ZUR, 1);
+            for (size_t e = 0; e < te_key.size() && !attr_fault; e++) {
+                const int k = te_ref[e];
+                if (k < 0 || !bit(m, k) || rf[k] < 0) continue;
+                if (sflags[k] & F_MISSILE) { attr_fault = true; break; }  // 'Missile' object has no attribute 'type' (CCP.py:259)
+                draw(k, (sflags[k] >> F_TTYPE_SHIFT) & 3, 1);
+            }
+            if (!attr_fault && nR > 0)
+                for (int k = 0; k < n_slots; k++)
+                    if (bit(m, k) && rf[k] < 0) draw(k, (sflags[k] & F_MISSILE) ? ZRK_ZUR : ((sflags[k] >> F_TTYPE_SHIFT) & 3), 0);
+        }
+        // Manager.add_message keeps each tick stably sorted by -relevance (Manager.py:56-58)
+        if (emit)
+            std::stable_sort(out.begin() + first, out.end(), [](const zrk_msg &a, const zrk_msg &b) { return a.relevance > b.relevance; });
+        det_prev = det_now;
+    }
     return ZRK_OK;
 }
 
@@ -1072,9 +1307,21 @@ extern "C" int zrk_read_messages(zrk_handle *h, int sc, int tick0, int tick1, zr
     DeviceGuard dev_guard(h->device);
     const Params &P = h->P;
     const Layout &o = P.lo;
-    if ((P.log_types & ZRK_LOG_FULL) != (unsigned)ZRK_LOG_FULL) {
-        h->err = "zrk_read_messages needs a handle created with ZRK_LOG_FULL";
+    if (!(P.log_types & ZRK_LOG_MASKS) || (P.log_types & ZRK_LOG_EVENTS) != (unsigned)ZRK_LOG_EVENTS) {
+        h->err = "zrk_read_messages needs a handle created with ZRK_LOG_EVENTS | ZRK_LOG_MASKS (or ZRK_LOG_FULL)";
         return ZRK_ERR_UNSUPPORTED;
+    }
+    if ((P.log_types & ZRK_LOG_BULK) != (unsigned)ZRK_LOG_BULK) {  // bulk types are not stored: rebuild them
+        std::vector<zrk_msg> out;
+        std::vector<int32_t> pool;
+        int rc = rebuild_messages(h, sc, tick0, tick1, out, pool);
+        if (rc) return rc;
+        if (n_out) *n_out = out.size();
+        if (n_ids_out) *n_ids_out = pool.size();
+        if (out.size() > cap || pool.size() > ids_cap) return ZRK_ERR_CAPACITY;
+        if (msgs && !out.empty()) memcpy(msgs, out.data(), out.size() * sizeof(zrk_msg));
+        if (ids && !pool.empty()) memcpy(ids, pool.data(), pool.size() * sizeof(int32_t));
+        return ZRK_OK;
     }
     std::vector<unsigned char> dyn;
     int rc = fetch_dyn(h, sc, sc + 1, dyn);
@@ -1142,8 +1389,9 @@ extern "C" int zrk_read_messages(zrk_handle *h, int sc, int tick0, int tick1, zr
             for (int k = 0; k < det_prev && ri < nrec && rec[ri].tick == t && rec[ri].type == ZRK_MSG_DESTROYED_MISSILE; k++)
                 out.push_back(rec[ri++]);
         }
-        // launchers and CCP, in emission order
-        while (ri < nrec && rec[ri].tick == t) out.push_back(rec[ri++]);
+        // launchers and CCP, in emission order (the private track journal is not a message)
+        for (; ri < nrec && rec[ri].tick == t; ri++)
+            if (rec[ri].type != ZRK_REC_TRACK) out.push_back(rec[ri]);
         // Manager.add_message keeps each tick stably sorted by -relevance (Manager.py:56-58)
         std::stable_sort(out.begin() + first, out.end(),
                          [](const zrk_msg &a, const zrk_msg &b) { return a.relevance > b.relevance; });

@@ -1198,7 +1198,7 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
         unsigned *mrow = nullptr;
         if (P.masks) {
             mrow = P.masks + ((size_t)(tick % P.mask_ticks) * o.B + b) * (size_t)((1 + o.RP) * P.mask_words);
-            if ((lane & 31) == 0 && (lane >> 5) < P.mask_words) mrow[lane >> 5] = TEAM == 32 ? alive_mask : __ballot_sync(ZRK_FULL, alive);
+            if ((lane & 31) == 0 && (lane >> 5) < P.mask_words) mrow[lane >> 5] = alive_mask;  // (this warp's 32 slots)
         }
         for (int r = 0; r < nR; r++) {
             const double *par_r = c_rad_par + RAD_PAR_STRIDE * r;
@@ -2171,6 +2171,18 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                         put_rec(P, rec, nrec + r_wr, tick, mtype, 0, ccp_id, ZRK_CST_I(c_cl_id)[ok - 1], det_id(), det_radar(), dpx, dpy, dpz);
                     else
                         put_rec(P, rec, nrec + r_wr, tick, mtype, 0, ccp_id, det_radar(), det_id(), old_mid, 0, 0, 0);
+                }
+                // Track journal (ZRK_LOG_TRACKS): every association that is not "the detection re-acquired the track
+                // of its own slot" — from these and the event records the host replays the CCP's two dicts and rebuilds
+                // the per-tick CCP_UPDATE_TARGET / DRAW_OBJECTS messages without their ever being stored (zrk_host.cu).
+                if (logged(P, ZRK_REC_TRACK)) {
+                    const bool trk = fin && !(cls != 0 && claim == seed && seed_own);
+                    int n_trk;
+                    const int r_trk = tm.rank(trk, n_trk);
+                    if (trk)
+                        put_rec(P, rec, nrec + n_wr + r_trk, tick, ZRK_REC_TRACK, cls, slot, cls == 0 ? (claim >= 0 ? claim : n_te + r_app) : cand,
+                                det_id(), ok != 0, 0, 0, 0);
+                    n_wr += n_trk;
                 }
                 if (fin) {
                     if (cls == 1) {  // old_target (CCP.py:332-359)

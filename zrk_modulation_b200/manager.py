@@ -175,8 +175,12 @@ class BatchedManager(ScenarioView):
         self.time = Timer()
         self.time.set_dt(batch.dt_ms)
         self.modules: List = []
+        # log: "rebuilt" (what "auto" picks) keeps event records + per-tick masks + the track journal — 8 + 4 R bytes
+        # per scenario-tick, any batch size — and Manager.messages is rebuilt from them on access, message for
+        # message what the reference stores (Manager.py:41-58); "full" stores every message as a record (small
+        # batches only); "events" keeps no masks: counts, status and event records, no Manager.messages.
         if log == "auto":
-            log = "full" if batch.n_scenarios <= 64 else "events"
+            log = "rebuilt"
         if max_ticks is None:
             max_ticks = max(1, int(max(batch.n_ticks(s) for s in range(batch.n_scenarios))))
         self.max_ticks = max_ticks
@@ -184,6 +188,9 @@ class BatchedManager(ScenarioView):
         if log == "full":
             cap = (3 * batch.n_slots + 16 + 4 * batch.max_radars) * max_ticks + 64
             self.engine = Engine(batch, log_types=_cabi.LOG_FULL, log_capacity=cap, mask_ticks=max_ticks + 1,
+                                 ticks_per_launch=ticks_per_launch, device=device, lib=lib)
+        elif log == "rebuilt":
+            self.engine = Engine(batch, log_types=_cabi.LOG_EVENTS | _cabi.LOG_MASKS, mask_ticks=max_ticks + 1,
                                  ticks_per_launch=ticks_per_launch, device=device, lib=lib)
         else:
             self.engine = Engine(batch, log_types=_cabi.LOG_EVENTS, ticks_per_launch=ticks_per_launch,
@@ -289,9 +296,9 @@ class BatchedManager(ScenarioView):
         return views
 
     def _materialise(self, s: int, tick0: int, tick1: int) -> List[List[BaseMessage]]:
-        if self.log != "full":
-            raise RuntimeError("this BatchedManager keeps only the event log; create it with log='full' "
-                               "to materialise Manager.messages")
+        if self.log == "events":
+            raise RuntimeError("this BatchedManager keeps only the event log; create it with log='rebuilt' (the default) "
+                               "or log='full' to materialise Manager.messages")
         msgs, ids = self.engine.messages(s, tick0, tick1)
         objs = self._object_views(s)
         dt = self.batch.dt_ms

@@ -717,19 +717,6 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
             CK(cudaStreamWaitEvent(h->stream, h->wave_done[w], 0));
         }
     }
-    {   // identity of the batch for checkpoints: everything that ends up in the parameter blobs
-        unsigned long long hh = fnv1a(&d->dt_ms, sizeof d->dt_ms);
-        auto mix = [&](const void *p, size_t n) { if (p && n) hh = fnv1a(p, n, hh); };
-        mix(d->radar_id, sizeof(int) * (size_t)B * R); mix(d->radar_pos, 8 * 3 * (size_t)B * R); mix(d->radar_par, 8 * 8 * (size_t)B * R);
-        mix(d->launcher_id, sizeof(int) * (size_t)B * L); mix(d->launcher_pos, 8 * 3 * (size_t)B * L);
-        mix(d->missile_id, sizeof(int) * (size_t)B * M); mix(d->missile_launcher, sizeof(int) * (size_t)B * M);
-        mix(d->missile_v0, 8 * (size_t)B * M); mix(d->missile_radius, 8 * (size_t)B * M);
-        mix(d->ccp_launcher_id, sizeof(int) * (size_t)B * C); mix(d->ccp_launcher_pos, 8 * 3 * (size_t)B * C);
-        mix(d->target_id, sizeof(int) * (size_t)B * T); mix(d->ccp_id, sizeof(int) * (size_t)B);
-        const int nshape[4] = {d->noise ? d->noise_period : 0, d->noise_radars, d->noise_objects, (int)(d->noise_scenario_stride != 0)};
-        mix(nshape, sizeof nshape);
-        h->cst_hash = hh;
-    }
     // small host copies used by zrk_read_messages
     h->h_radar_id.assign(d->radar_id ? d->radar_id : nullptr, d->radar_id ? d->radar_id + (size_t)B * R : nullptr);
     h->h_n_radars.resize(B);
@@ -1547,6 +1534,22 @@ static void save_sizes(const zrk_handle *h, SaveHeader &sh) {
     sh.layout_hash = fnv1a(&o, sizeof(Layout));
     sh.cst_hash = h->cst_hash;
 }
+// identity of the batch for checkpoints: the parameter blobs (radars, launchers, missiles, CCP), the time step and the
+// shape of the noise table.  Computed from the device copy the first time a checkpoint is written or read.
+static int ensure_cst_hash(zrk_handle *h) {
+    if (h->cst_hash) return ZRK_OK;
+    int rc = zrk_sync(h);
+    if (rc) return rc;
+    const Layout &o = h->P.lo;
+    std::vector<unsigned char> cst((size_t)o.B * o.cst_bytes);
+    CK(cudaMemcpy(cst.data(), h->P.cst, cst.size(), cudaMemcpyDeviceToHost));
+    unsigned long long hh = fnv1a(&h->P.dt_ms, sizeof h->P.dt_ms);
+    const int nshape[4] = {h->P.noise ? h->P.noise_period : 0, h->P.noise_radars, h->P.noise_objects, (int)(h->P.noise_stride != 0)};
+    hh = fnv1a(nshape, sizeof nshape, hh);
+    hh = fnv1a(cst.data(), cst.size(), hh);
+    h->cst_hash = hh ? hh : 1;
+    return ZRK_OK;
+}
 
 extern "C" int zrk_state_bytes(zrk_handle *h, size_t *bytes) {
     if (!h || !bytes) return ZRK_ERR_ARG;
@@ -1559,6 +1562,10 @@ extern "C" int zrk_state_bytes(zrk_handle *h, size_t *bytes) {
 extern "C" int zrk_save_state(zrk_handle *h, void *buf, size_t cap) {
     if (!h || !buf) return ZRK_ERR_ARG;
     DeviceGuard dev_guard(h->device);
+    {
+        int rc0 = ensure_cst_hash(h);
+        if (rc0) return rc0;
+    }
     SaveHeader sh;
     save_sizes(h, sh);
     if (cap < sizeof(SaveHeader) + sh.dyn_bytes + sh.rec_bytes + sh.mask_bytes) return ZRK_ERR_CAPACITY;
@@ -1578,6 +1585,10 @@ extern "C" int zrk_save_state(zrk_handle *h, void *buf, size_t cap) {
 extern "C" int zrk_load_state(zrk_handle *h, const void *buf, size_t bytes) {
     if (!h || !buf || bytes < sizeof(SaveHeader)) return ZRK_ERR_ARG;
     DeviceGuard dev_guard(h->device);
+    {
+        int rc0 = ensure_cst_hash(h);
+        if (rc0) return rc0;
+    }
     SaveHeader sh, mine;
     memcpy(&sh, buf, sizeof sh);
     save_sizes(h, mine);

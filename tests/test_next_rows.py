@@ -103,3 +103,24 @@ def test_zero_copy_torch_view_of_the_summary(request):
         assert int(t[:, 0].min()) <= 50  # H_TICK
         raw = eng.torch_view("dyn")
         assert raw.dtype == torch.uint8 and raw.numel() == eng.device_ptr("dyn")[1]
+
+
+def test_checkpoint_of_another_batch_is_refused(request):
+    """zrk_load_state checks the ABI version, the state layout and a checksum of the scenario parameters
+    (same shape, different radar -> refused)."""
+    import emu_lib
+    from zrk_modulation_b200.engine import Engine, ZrkError
+    lib = emu_lib.load()
+    a = synthetic_batch(3, 6, n_radars=1, n_launchers=1, missiles_per_launcher=2, seed0=5)
+    b = synthetic_batch(3, 6, n_radars=1, n_launchers=1, missiles_per_launcher=2, seed0=5)
+    b.radar_par[:, 0, 2] = 12345.0  # another max_distance
+    with Engine(a, lib=lib) as ea, Engine(b, lib=lib) as eb:
+        ea.step(10)
+        buf = ea.save_state()
+        with pytest.raises(ZrkError):
+            eb.load_state(buf)
+        ea.load_state(buf)  # its own checkpoint is fine
+        bad = buf.copy()
+        bad[56:60] = 99  # the ABI version field (after magic, tick, three sizes, four ints)
+        with pytest.raises(ZrkError):
+            ea.load_state(bad)

@@ -210,3 +210,100 @@ class Engine:
         p, sz = C.c_void_p(), C.c_size_t()
         self._ck(self.lib.zrk_device_ptr(self._h, name.encode(), C.byref(p), C.byref(sz)))
         return p.value, sz.value
+
+
+class ShardedEngine:
+    """One Engine per GPU of this process, each owning a contiguous block of the batch's scenarios
+    (distributed.shard_range): the single-process counterpart of the one-rank-per-GPU layout.  Scenarios never
+    interact (each is its own Manager object graph, main.py:35-149), so the devices exchange nothing: a step is
+    issued to all of them at once (one host thread per device: zrk_step blocks while it alternates its kernels)
+    and per-scenario reads go to the device that owns the scenario; batch totals are summed on the host."""
+
+    def __init__(self, batch: Batch, devices, threads: bool = True, **kw):
+        from concurrent.futures import ThreadPoolExecutor
+        from .distributed import shard_range
+        self.batch = batch
+        self.devices = list(devices)
+        if not self.devices:
+            raise ValueError("no devices")
+        n = len(self.devices)
+        self.ranges = [shard_range(batch.n_scenarios, r, n) for r in range(n)]
+        # threads=False issues the calls one device after the other (a library that is not thread-safe)
+        self._pool = ThreadPoolExecutor(max_workers=n if threads else 1)
+        self.log_types = kw.get("log_types", _cabi.LOG_EVENTS)
+        self.engines = list(self._pool.map(
+            lambda a: Engine(batch.shard(*a[1]), device=a[0], **kw) if a[1][1] > a[1][0] else None,
+            zip(self.devices, self.ranges)))
+
+    def _each(self, fn):
+        live = [e for e in self.engines if e is not None]
+        return list(self._pool.map(fn, live))
+
+    def _owner(self, s: int):
+        for e, (s0, s1) in zip(self.engines, self.ranges):
+            if s0 <= s < s1:
+                return e, s - s0
+        raise IndexError(s)
+
+    def close(self):
+        self._each(lambda e: e.close())
+        self._pool.shutdown(wait=True)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def step(self, n_ticks: int = 1):
+        self._each(lambda e: e.step(n_ticks))
+
+    def sync(self):
+        self._each(lambda e: e.sync())
+
+    def time(self):
+        return next(e for e in self.engines if e is not None).time()
+
+    def _cat(self, parts):
+        return np.concatenate(parts, axis=0)
+
+    def status(self):
+        parts = self._each(lambda e: e.status())
+        return tuple(self._cat([p[i] for p in parts]) for i in range(3))
+
+    def counts(self) -> np.ndarray:
+        return self._cat(self._each(lambda e: e.counts()))
+
+    def totals(self) -> np.ndarray:
+        return np.sum(self._each(lambda e: e.totals()), axis=0)
+
+    def alive_slot_ticks(self) -> np.ndarray:
+        return self._cat(self._each(lambda e: e.alive_slot_ticks()))
+
+    def certified_ticks(self) -> np.ndarray:
+        return self._cat(self._each(lambda e: e.certified_ticks()))
+
+    def state(self):
+        parts = self._each(lambda e: e.state())
+        return {k: self._cat([p[k] for p in parts]) for k in parts[0]}
+
+    def messages(self, scenario: int, tick0: int = 0, tick1: Optional[int] = None):
+        e, i = self._owner(scenario)
+        return e.messages(i, tick0, tick1)
+
+    def records(self, s0: int = 0, s1: Optional[int] = None):
+        s1 = self.batch.n_scenarios if s1 is None else s1
+        recs, ns = [], []
+        for e, (a, b) in zip(self.engines, self.ranges):
+            lo, hi = max(a, s0), min(b, s1)
+            if e is not None and hi > lo:
+                r, n = e.records(lo - a, hi - a)
+                recs.append(r)
+                ns.append(n)
+        cap = max(r.shape[1] for r in recs)
+        recs = [np.pad(r, ((0, 0), (0, cap - r.shape[1]))) for r in recs]
+        return self._cat(recs), self._cat(ns)
+
+    def launch_stats(self):
+        parts = self._each(lambda e: e.launch_stats())
+        return sum(p[0] for p in parts), max(p[1] for p in parts)

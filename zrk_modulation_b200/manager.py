@@ -170,7 +170,7 @@ class BatchedManager(ScenarioView):
     """Drop-in for `Manager` (Manager.py:9-140) over a batch of scenarios on one GPU."""
 
     def __init__(self, batch: Batch, log: str = "auto", device: int = 0, ticks_per_launch: int = 0,
-                 max_ticks: Optional[int] = None, lib=None):
+                 max_ticks: Optional[int] = None, lib=None, devices=None):
         self.batch = batch
         self.time = Timer()
         self.time.set_dt(batch.dt_ms)
@@ -185,16 +185,24 @@ class BatchedManager(ScenarioView):
             max_ticks = max(1, int(max(batch.n_ticks(s) for s in range(batch.n_scenarios))))
         self.max_ticks = max_ticks
         self.log = log
+        # devices: None = the one GPU `device`; a list of ordinals or "all" = this process drives every one of them,
+        # each owning a contiguous block of scenarios (ShardedEngine) — main.run_simulation_from_config is one
+        # process too (main.py:151-174); the one-rank-per-GPU layout of bench.py needs no change here
+        if devices == "all":
+            import torch
+            devices = list(range(torch.cuda.device_count()))
         if log == "full":
             cap = (3 * batch.n_slots + 16 + 4 * batch.max_radars) * max_ticks + 64
-            self.engine = Engine(batch, log_types=_cabi.LOG_FULL, log_capacity=cap, mask_ticks=max_ticks + 1,
-                                 ticks_per_launch=ticks_per_launch, device=device, lib=lib)
+            kw = dict(log_types=_cabi.LOG_FULL, log_capacity=cap, mask_ticks=max_ticks + 1)
         elif log == "rebuilt":
-            self.engine = Engine(batch, log_types=_cabi.LOG_EVENTS | _cabi.LOG_MASKS, mask_ticks=max_ticks + 1,
-                                 ticks_per_launch=ticks_per_launch, device=device, lib=lib)
+            kw = dict(log_types=_cabi.LOG_EVENTS | _cabi.LOG_MASKS, mask_ticks=max_ticks + 1)
         else:
-            self.engine = Engine(batch, log_types=_cabi.LOG_EVENTS, ticks_per_launch=ticks_per_launch,
-                                 device=device, lib=lib)
+            kw = dict(log_types=_cabi.LOG_EVENTS)
+        if devices is not None and len(devices) > 1:
+            from .engine import ShardedEngine
+            self.engine = ShardedEngine(batch, devices, threads=lib is None, ticks_per_launch=ticks_per_launch, lib=lib, **kw)
+        else:
+            self.engine = Engine(batch, ticks_per_launch=ticks_per_launch, device=devices[0] if devices else device, lib=lib, **kw)
         self._status = None
         self._counts = None
         self._objects: Dict[int, Dict[int, AirObjectView]] = {}

@@ -88,6 +88,20 @@ class Batch:
     def n_slots(self) -> int:
         return self.max_targets + self.max_missiles
 
+    def shard(self, s0: int, s1: int) -> "Batch":
+        """Scenarios [s0, s1) as a Batch of their own (array views; a shared noise table stays shared)."""
+        kw = {}
+        for f, v in vars(self).items():
+            if f == "_keep":
+                continue
+            if f == "noise":
+                kw[f] = v if v is None or v.ndim == 4 else np.ascontiguousarray(v[s0:s1])
+            elif isinstance(v, np.ndarray):
+                kw[f] = np.ascontiguousarray(v[s0:s1])
+            else:
+                kw[f] = v
+        return Batch(**kw)
+
     def dims(self):
         return (self.n_scenarios, self.n_slots, self.max_radars, self.max_missiles,
                 self.max_launchers, self.max_ccp_launchers)

@@ -17,12 +17,13 @@ MARKS = [("helpers (dot3, pymod, tsec)", None), ("radar_sees", "SectorRadar.find
          ("put_rec", "record log"), ("missile_solve", "Missile._calculate_trajectory_params"),
          ("views", "shared-memory views"), ("calc_range/link_exact", "CCP.link_object"),
          ("link_eval", "State of the squared-domain scan"), ("link_d2 (fp64 pair distance)", "double link_d2("), ("link scan (fp32 filter + loop)", "fp32 pre-filter of the scan"),
-         ("serial_section", "lane 0 alone: launchers"), ("kernel prologue", "the kernel"),
+         ("association certificate", "---- association certificate"), ("quiet streak", "---- quiet streak"),
+         ("serial_section", "lane 0 alone: launchers"), ("kernel prologue", "---- the kernel"),
          ("tick head", "for (int it = 0; it < n_ticks; it++)"), ("AirEnv.step", "AirEnv.step (AirEnv.py:26-53)"),
          ("Missile.step", "Missile.step, status 'active'"), ("radar loop", "SectorRadar.step for every radar"),
          ("sector sweep + serial call", "lane 0: sector sweep"), ("CCP link arrays + order", "CombatControlPoint.step, detections"),
          ("CCP rounds", "int lo_rank = 0;"), ("send_objects_to_GUI", "send_objects_to_GUI (CCP.py:237-284)"),
-         ("tick end", "if (nrec > P.log_cap)")]
+         ("tick end", "if (nrec > P.log_cap)"), ("streak kernel wrapper", "---- the streak kernel")]
 
 
 def ncu(rep, *args):
@@ -47,6 +48,7 @@ def main():
             "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
             "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
             "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
             "sass__inst_executed_local_loads", "sass__inst_executed_local_stores"]
     u = dict(zip(hdr, units))
     for k in want:

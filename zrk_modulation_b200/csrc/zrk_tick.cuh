@@ -1075,6 +1075,18 @@ __device__ ZRK_NOINLINE bool streak_rivals(unsigned dmask, int lane, bool use_p,
     }
     return __ballot_sync(ZRK_FULL, rival) != 0;
 }
+// The sectors the radars will look at next tick (Radar.py:96-117), computed by one lane while the others
+// finish this tick: written to the OTHER of two scratch copies, which everybody switches to after the vote
+// that commits the tick — a sweeping radar then costs a streak tick no barrier of its own.  Out of line.
+__device__ ZRK_NOINLINE void streak_sweep_next(const double *cur, double *nxt, const double *c_rad_par, int nR) {
+    for (int r = 0; r < nR; r++) {
+        const double *q = c_rad_par + RAD_PAR_STRIDE * r;
+        double caz = cur[2 * r], cel = cur[2 * r + 1];
+        if (q[10] == 0.0) radar_move(q, caz, cel);
+        nxt[2 * r] = caz;
+        nxt[2 * r + 1] = cel;
+    }
+}
 // move_to_next_sector_circular for the radars of a streak tick that sweep (Radar.py:96-117): out of line
 template <int TEAM>
 __device__ ZRK_NOINLINE void streak_sweep(double *rc, const double *c_rad_par, int nR, int lane) {
@@ -1093,7 +1105,8 @@ __device__ ZRK_NOINLINE void streak_sweep(double *rc, const double *c_rad_par, i
 }
 template <int TEAM, int MPB>
 __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, const unsigned char *cs, int lane, int b,
-                                            int max_ticks, int noise_w, float4 *fp, float4 *fv) {
+                                            int max_ticks, int noise_w, float4 *fp, float4 *fv, double *dscr) {
+    // dscr: 32 doubles of scratch (two copies of the sweep state of up to 8 radars)
     // sm: the scenario's state blob, cs: its parameter blob — in shared memory (the tick kernel) or in
     // global memory (the streak kernel: a streak touches each word once at its beginning and its end).
     // Inlined into its kernel: P is then the kernel parameter, read from the constant bank.
@@ -1163,10 +1176,18 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
     const unsigned alive_mask = __ballot_sync(ZRK_FULL, alive), msl_mask = __ballot_sync(ZRK_FULL, msl);
     const double *noise = P.noise ? P.noise + (size_t)b * P.noise_stride + (fl >> F_STATIC_SHIFT) * 3 : nullptr;
     const int noise_row = P.noise_radars * P.noise_objects * 3;
-    const double *rad_cur = ZRK_QME_D(rad_cur), *c_rad_pos = (const double *)(cs + o.c_rad_pos),
-                 *c_rad_par = (const double *)(cs + o.c_rad_par);
+    const double *rad_cur = ZRK_QME_D(rad_cur);
+    const double *const c_rad_pos = (const double *)(cs + o.c_rad_pos), *const c_rad_par = (const double *)(cs + o.c_rad_par);
     bool sweeping = false;
     for (int r = 0; r < nR; r++) sweeping = sweeping || c_rad_par[RAD_PAR_STRIDE * r + 10] == 0.0;
+    // sweeping radars: the sweep state lives in two scratch copies during the streak (see streak_sweep_next)
+    const bool sweep_db = sweeping && nR <= 8;
+    int rcp = 0;
+    if (sweep_db) {
+        if (lane < 2 * nR) dscr[lane] = rad_cur[lane];
+        team_barrier<TEAM>();
+        rad_cur = dscr;
+    }
     int n_q = 0, n_upd = 0;
     bool looked = false;  // the windows have been rebuilt during this streak's first tick
     double now_s = tick_seconds(P, tick);
@@ -1222,6 +1243,7 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
                 if ((lane & 31) == 0 && (lane >> 5) < P.mask_words) mrow[(1 + r) * P.mask_words + (lane >> 5)] = bal;
             }
         }
+        if (sweep_db && lane == 0) streak_sweep_next(rad_cur, dscr + 16 * (rcp ^ 1), c_rad_par, nR);
         // CombatControlPoint.step: the own track, exactly as link_d2 / link_eval measure it
         const bool det = alive && rf >= 0;
         bool upd_msg = false, doubt = false;
@@ -1313,13 +1335,20 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
         }
         period = per;
         n_upd += __popc(__ballot_sync(ZRK_FULL, upd_msg));
-        if (ZRK_RARE(sweeping)) streak_sweep<TEAM>(ZRK_QME_D(rad_cur), c_rad_par, nR, lane);
+        if (sweep_db) {
+            if (TEAM == 32) __syncwarp();  // (a larger team's vote was a barrier already)
+            rcp ^= 1;
+            rad_cur = dscr + 16 * rcp;
+        } else if (ZRK_RARE(sweeping)) {
+            streak_sweep<TEAM>(ZRK_QME_D(rad_cur), c_rad_par, nR, lane);
+        }
         tick++;
         n_q++;
         now_s = now_next;
         if (++noise_w == P.noise_period) noise_w = 0;
     }
     if (n_q) {  // the state the general tick expects, and the messages of the committed ticks
+        if (sweep_db && lane < 2 * nR) ZRK_QME_D(rad_cur)[lane] = rad_cur[lane];
         if (alive) {
             H.qxy()[lane] = make_double2(qx, qy);
             H.qzw()[lane].x = qz;
@@ -1674,7 +1703,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
             if (hdr[H_DETN0 + prv0] == 0 && hdr[H_MBN0 + prv0] == 0 && hdr[H_CCP_INIT] && !(hdr[H_FAULT] & 63) &&
                 !(P.log_types & ZRK_LOG_BULK)) {
                 const int nq = quiet_streak<TEAM, MPB>(P, sm, sm + o.dyn_bytes, lane, b, n_ticks - it, noise_w, (float4 *)lxy,
-                                                       (float4 *)lzd);
+                                                       (float4 *)lzd, (double *)tm.wscr);
                 if (nq) {
                     it += nq;
                     if (it >= n_ticks) break;
@@ -2332,7 +2361,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
 #ifndef ZRK_STREAK_MINB
 #define ZRK_STREAK_MINB 5 /* resident CTAs per SM the register allocation is bounded for */
 #endif
-#define ZRK_STREAK_SMEM (ZRK_STREAK_WARPS * 2 * 32 * 16)
+#define ZRK_STREAK_SMEM (ZRK_STREAK_WARPS * (2 * 32 * 16 + 32 * 8))
 template <int MPB>
 __global__ void __launch_bounds__(32 * ZRK_STREAK_WARPS, ZRK_STREAK_MINB) zrk_streak_kernel(const Params P, int b_first, int b_end, int target_tick,
                                                                                            const int *work) {
@@ -2358,7 +2387,8 @@ __global__ void __launch_bounds__(32 * ZRK_STREAK_WARPS, ZRK_STREAK_MINB) zrk_st
     int done = 0;
     if (fit) {
         const int noise_w = P.noise ? tick % P.noise_period : 0;
-        done = quiet_streak<32, MPB>(P, sm, cs, lane, b, target_tick - tick, noise_w, scratch + (2 * w) * 32, scratch + (2 * w + 1) * 32);
+        done = quiet_streak<32, MPB>(P, sm, cs, lane, b, target_tick - tick, noise_w, scratch + (2 * w) * 32, scratch + (2 * w + 1) * 32,
+                                     (double *)(scratch + 2 * ZRK_STREAK_WARPS * 32) + 32 * w);
     }
     if (tick + done < target_tick && lane == 0) {
         // the tick kernel's turn.  A streak that ended before its first tick doubles the number of ticks the

@@ -859,6 +859,39 @@ __device__ __forceinline__ void team_barrier() {
         __syncthreads();
     }
 }
+// The fp64 solve of one pair of the certificate: b = p_j - p_i and u = v_j - v_i at `tick`, sp = |v_i| + |v_j|.
+// Merges the window of ticks (from tick_now on) in which the two are within R of each other into [best_in, best_out].
+__device__ __forceinline__ void cert_solve(double bx, double by, double bz, double ux, double uy, double uz, double sp, int tick,
+                                           int tick_now, double dt_s, double nb, int &best_in, int &best_out) {
+    const double R = (sp * dt_s * 1.000000001 + 6.0 * nb + 1.0) * 1.000001;
+    const double a = dot3(ux, uy, uz, ux, uy, uz), bq = dot3(bx, by, bz, ux, uy, uz);
+    const double c = dot3(bx, by, bz, bx, by, bz) - R * R;
+    const double disc = bq * bq - a * c;
+    if (c > 0 && (bq >= 0 || disc < 0)) return;  // never within R of each other from now on
+    int kin = 0, kout = ZRK_CERT_NEVER;          // (also what every NaN ends up with)
+    if (a > 0 && disc >= 0) {
+        // within R for tau in [tin, tout]; tick + k is tau = k dt away (the clock table deviates from
+        // that by rounding only, which the 1e-9 relative + 1e-6 absolute allowance swallows)
+        const double sq = sqrt(disc), ia = 1.0 / (a * dt_s);
+        const double qo = (-bq + sq) * ia * 1.000000001 + 1e-6;
+        if (qo < 1e9) kout = tick + (int)qo;  // the last tick inside
+        if (c > 0) {                          // approaching: tin is ahead; ticks k < tin / dt are outside
+            const double qi = (-bq - sq) * ia * 0.999999999 - 1e-6;
+            kin = ZRK_CERT_NEVER;
+            if (qi < 1e9) kin = tick + (qi > 0 ? (int)qi + 1 : 0);
+            if (!(qi >= -1.0)) kin = 0;  // (NaN)
+        }
+    }
+    if (kin > ZRK_CERT_NEVER) kin = ZRK_CERT_NEVER;
+    if (kout > ZRK_CERT_NEVER) kout = ZRK_CERT_NEVER;
+    if (kout < tick_now) return;  // (positions of an older tick: this window has already passed)
+    if (kin < best_in) {
+        best_in = kin;
+        best_out = kout;
+    } else if (kin == best_in && kout > best_out) {
+        best_out = kout;
+    }
+}
 // One pair of the certificate: slot `lane` (exact position / velocity pi, zi, vi, viz; fp32 images fpi, fvi)
 // against slot j, whose tracks measure to the fp32 image pj and move with vj; the positions are those of
 // `tick`, the answer is wanted from tick_now on.  Merges the window in
@@ -901,34 +934,7 @@ __device__ __forceinline__ bool cert_pair(const Hot<TEAM> &H, int j, float4 pj, 
         ux = -vi.x, uy = -vi.y, uz = -viz;
         spj = 0.0;
     }
-    const double R = ((spi + spj) * dt_s * 1.000000001 + 6.0 * nb + 1.0) * 1.000001;
-    const double a = dot3(ux, uy, uz, ux, uy, uz), bq = dot3(bx, by, bz, ux, uy, uz);
-    const double c = dot3(bx, by, bz, bx, by, bz) - R * R;
-    const double disc = bq * bq - a * c;
-    if (c > 0 && (bq >= 0 || disc < 0)) return true;  // never within R of each other from now on
-    int kin = 0, kout = ZRK_CERT_NEVER;                // (also what every NaN ends up with)
-    if (a > 0 && disc >= 0) {
-        // within R for tau in [tin, tout]; tick + k is tau = k dt away (the clock table deviates from
-        // that by rounding only, which the 1e-9 relative + 1e-6 absolute allowance swallows)
-        const double sq = sqrt(disc), ia = 1.0 / (a * dt_s);
-        const double qo = (-bq + sq) * ia * 1.000000001 + 1e-6;
-        if (qo < 1e9) kout = tick + (int)qo;  // the last tick inside
-        if (c > 0) {                          // approaching: tin is ahead; ticks k < tin / dt are outside
-            const double qi = (-bq - sq) * ia * 0.999999999 - 1e-6;
-            kin = ZRK_CERT_NEVER;
-            if (qi < 1e9) kin = tick + (qi > 0 ? (int)qi + 1 : 0);
-            if (!(qi >= -1.0)) kin = 0;  // (NaN)
-        }
-    }
-    if (kin > ZRK_CERT_NEVER) kin = ZRK_CERT_NEVER;
-    if (kout > ZRK_CERT_NEVER) kout = ZRK_CERT_NEVER;
-    if (kout < tick_now) return true;  // (positions of an older tick: this window has already passed)
-    if (kin < best_in) {
-        best_in = kin;
-        best_out = kout;
-    } else if (kin == best_in && kout > best_out) {
-        best_out = kout;
-    }
+    cert_solve(bx, by, bz, ux, uy, uz, spi + spj, tick, tick_now, dt_s, nb, best_in, best_out);
     return true;
 }
 // this slot as the others see it: where its tracks measure to (+ its speed), and how that moves
@@ -1054,21 +1060,29 @@ __device__ ZRK_NOINLINE void cert_removed(unsigned char *sm, int lane, int fl, u
 template <int TEAM>
 __device__ ZRK_NOINLINE bool streak_rivals(unsigned dmask, int lane, bool use_p, double px, double py, double pz, double qx,
                                            double qy, double qz, int r_te, int r_me, int n_te, int n_me, double nx, double ny,
-                                           double nz, double d2, int seedu) {
+                                           double nz, double d2, int seedu, int key) {
     const double ax = use_p ? px : qx, ay = use_p ? py : qy, az = use_p ? pz : qz;
     const double tx = __shfl_sync(ZRK_FULL, ax, r_te), ty = __shfl_sync(ZRK_FULL, ay, r_te), tz = __shfl_sync(ZRK_FULL, az, r_te);
     const double mx = __shfl_sync(ZRK_FULL, ax, r_me), my = __shfl_sync(ZRK_FULL, ay, r_me), mz = __shfl_sync(ZRK_FULL, az, r_me);
+    // link_object passes over the tracks already updated this tick (upd_time == now, CCP.py:195 / :208), and detections
+    // are taken in the order of `key` (first radar that saw the slot, then slot; -1 = not seen): a track that is the
+    // own track of a slot seen earlier than d has been re-acquired by that slot's detection when d's turn comes — by
+    // induction over the order, every earlier detection being certified or passing this very check — and is no
+    // candidate for d.
+    const int kt = __shfl_sync(ZRK_FULL, key, r_te), km = __shfl_sync(ZRK_FULL, key, r_me);
+    const int ot = __shfl_sync(ZRK_FULL, seedu, r_te), om = __shfl_sync(ZRK_FULL, seedu, r_me);
+    const int gone_te = (kt >= 0 && ot == lane) ? kt : ZRK_IMAX, gone_me = (km >= 0 && om == TEAM + lane) ? km : ZRK_IMAX;
     bool rival = false;
     for (unsigned mm = dmask; mm; mm &= mm - 1) {
         const int d = __ffs(mm) - 1;
         const double cx = __shfl_sync(ZRK_FULL, nx, d), cy = __shfl_sync(ZRK_FULL, ny, d), cz = __shfl_sync(ZRK_FULL, nz, d);
         const double thr = __shfl_sync(ZRK_FULL, d2, d) * (1.0 + 1e-12);
-        const int sd = __shfl_sync(ZRK_FULL, seedu, d);
-        if (lane < n_te && lane != sd) {
+        const int sd = __shfl_sync(ZRK_FULL, seedu, d), kd = __shfl_sync(ZRK_FULL, key, d);
+        if (lane < n_te && lane != sd && !(gone_te < kd)) {
             const double ex = tx - cx, ey = ty - cy, ez = tz - cz;
             rival = rival || !(dot3(ex, ey, ez, ex, ey, ez) > thr);
         }
-        if (lane < n_me && TEAM + lane != sd) {
+        if (lane < n_me && TEAM + lane != sd && !(gone_me < kd)) {
             const double ex = mx - cx, ey = my - cy, ez = mz - cz;
             rival = rival || !(dot3(ex, ey, ez, ex, ey, ez) > thr);
         }
@@ -1103,6 +1117,67 @@ __device__ ZRK_NOINLINE void streak_sweep(double *rc, const double *c_rad_par, i
     }
     team_barrier<TEAM>();
 }
+// AirEnv.py:33-40 inside a streak (warp teams): the slots of `rm` were removed at the start of this tick and stay frozen
+// where their tracks measure to (their prev_pos, in q).  Merges the pairs with them into this lane's window, as
+// cert_removed does on the state a general tick leaves; the lane's own position is that of tick_pos.  Rare: out of line.
+__device__ ZRK_NOINLINE void streak_frozen(unsigned rm, bool alive, double px, double py, double pz, double qx, double qy, double qz,
+                                           double vx, double vy, double vz, double speed, int tick_pos, double dt_s, double nb, int &cin,
+                                           int &cout) {
+    for (unsigned mm = rm; mm; mm &= mm - 1) {
+        const int j = __ffs(mm) - 1;
+        const double fx = __shfl_sync(ZRK_FULL, qx, j), fy = __shfl_sync(ZRK_FULL, qy, j), fz = __shfl_sync(ZRK_FULL, qz, j);
+        if (alive)
+            cert_solve(fx - px, fy - py, fz - pz, -vx, -vy, -vz, fabs(speed) + 0.0, tick_pos, tick_pos + 1, dt_s, nb, cin, cout);
+    }
+}
+// What a streak tick of a warp team leaves behind when missiles detonate on it (Missile._detonate, Missile.py:135-160:
+// the MISSILE_DETONATE record, the list AirEnv.step and the radars read next tick) and when they detonated on the
+// tick before (Radar.py:193-203: one DESTROYED_MISSILE per radar and detonation; the list is consumed).  det: how this
+// lane's missile detonates now (0 no, 1 at its target, 2 end of life), det_mask: the lanes with det != 0; was / prev:
+// the same for the tick before.  Called once the tick is committed.  Rare: out of line.
+template <int TEAM, int MPB>
+__device__ ZRK_NOINLINE void streak_events(const Params *Pg, unsigned char *sm, const unsigned char *cs, int b, int lane, int tick, int det,
+                                           unsigned det_mask, int was, unsigned prev, int tg, int m, int nR) {
+    const Params &P = *Pg;
+    const Layout &o = P.lo;
+    Hot<TEAM> H;
+    H.sm = sm;
+    int *const hdr = H.hdr();
+    const int MP = MPB ? MPB : o.MP, par = tick & 1, prv = par ^ 1;
+    zrk_msg *rec = P.rec + (size_t)b * P.log_cap;
+    int nrec = hdr[H_NREC];
+    const unsigned lt = (1u << lane) - 1u;
+    const int n_det = __popc(det_mask), n_prev = __popc(prev);
+    __syncwarp();  // everybody has read the cursor
+    if (det) {
+        const int r_det = __popc(det_mask & lt), my_id = H.sid()[lane], det_tid = det == 1 ? H.sid()[tg] : ZRK_NONE;
+        if (logged(P, ZRK_MSG_MISSILE_DETONATE))
+            put_rec(P, rec, nrec + r_det, tick, ZRK_MSG_MISSILE_DETONATE, det == 2, my_id, ZRK_NONE, my_id, det_tid, 0, 0, 0);
+        ZRK_COLD_I(det_mid)[par * MP + r_det] = my_id;
+        ZRK_COLD_I(det_tid)[par * MP + r_det] = det_tid;
+        ZRK_COLD_I(det_flag)[par * MP + r_det] = det == 2;
+        ZRK_COLD_I(m_status)[m] = ST_DETONATED;
+    }
+    if (logged(P, ZRK_MSG_MISSILE_DETONATE)) nrec += n_det;
+    if (nR && logged(P, ZRK_MSG_DESTROYED_MISSILE)) {
+        if ((prev >> lane) & 1u) {
+            const int k = __popc(prev & lt), my_id = H.sid()[lane];
+            const int *c_rad_id = (const int *)(cs + o.c_rad_id);
+            for (int r = 0; r < nR; r++)
+                put_rec(P, rec, nrec + r * n_prev + k, tick, ZRK_MSG_DESTROYED_MISSILE, was == 2, c_rad_id[r], ZRK_CCP_ID, my_id, ZRK_NONE,
+                        0, 0, 0);
+        }
+        nrec += nR * n_prev;
+    }
+    if (lane == 0) {
+        unsigned *cnt = H.counts();
+        hdr[H_NREC] = nrec;
+        hdr[H_DETN0 + par] = n_det;
+        hdr[H_DETN0 + prv] = 0;
+        cnt[ZRK_MSG_MISSILE_DETONATE] += (unsigned)n_det;
+        if (nR) cnt[ZRK_MSG_DESTROYED_MISSILE] += (unsigned)(nR * n_prev);
+    }
+}
 template <int TEAM, int MPB>
 __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, const unsigned char *cs, int lane, int b,
                                             int max_ticks, int noise_w, float4 *fp, float4 *fv, double *dscr) {
@@ -1122,8 +1197,8 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
     const int nR = chdr[C_NR], T = o.T, tick_limit = chdr[C_TICK_LIMIT], n_slots = hdr[H_NSLOTS];
     int tick = hdr[H_TICK];
     const bool nolaunch = hdr[H_FREECAP] <= 0;
-    const int fl = lane < n_slots ? H.sflags()[lane] : 0;
-    const bool alive = (fl & F_ALIVE) != 0, msl = alive && (fl & F_MISSILE);
+    int fl = lane < n_slots ? H.sflags()[lane] : 0;
+    bool alive = (fl & F_ALIVE) != 0, msl = alive && (fl & F_MISSILE);
     // lanes the streak cannot carry at all
     bool bail0 = (fl & F_PENDING) != 0 || (alive && !(fl & F_HASPREV)) || (TEAM > 32 && msl);
     double px = 0, py = 0, pz = 0, qx = 0, qy = 0, qz = 0, sx = 0, sy = 0, sz = 0, t0 = 0, vx = 0, vy = 0, vz = 0, speed = 0;
@@ -1160,7 +1235,6 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
     }
     int cin = c_in[lane], cout = c_out[lane];
     bool refc1 = c_refc[lane] == 1;
-    const int tick0 = tick;  // shared memory keeps the state of tick0 - 1 for as long as the streak lasts
     const double dm = fabs(speed) * P.dt_s * 1.000000001 + 2.0 * P.noise_bound + 1e-3, dm2 = dm * dm;
     // a missile in flight: no detonation as long as it stays surely outside its radius of its target
     int m = 0, tg = 0;
@@ -1173,7 +1247,7 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
         r2hi = r * r * (1.0 + 1e-15);
         if (!(r >= 0.0) || tg < 0 || tg >= n_slots) bail0 = true;
     }
-    const unsigned alive_mask = __ballot_sync(ZRK_FULL, alive), msl_mask = __ballot_sync(ZRK_FULL, msl);
+    unsigned alive_mask = __ballot_sync(ZRK_FULL, alive), msl_mask = __ballot_sync(ZRK_FULL, msl);
     const double *noise = P.noise ? P.noise + (size_t)b * P.noise_stride + (fl >> F_STATIC_SHIFT) * 3 : nullptr;
     const int noise_row = P.noise_radars * P.noise_objects * 3;
     const double *rad_cur = ZRK_QME_D(rad_cur);
@@ -1188,220 +1262,302 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
         team_barrier<TEAM>();
         rad_cur = dscr;
     }
-    int n_q = 0, n_upd = 0;
-    bool looked = false;  // the windows have been rebuilt during this streak's first tick
+    // The streak runs in segments: the blob holds the state of the tick before the segment's first one; a segment ends
+    // when the streak does, or (again) when windows that have passed are to be rebuilt — from the blob, which therefore
+    // has to be brought up to date first.
+    int n_done = 0;            // ticks committed by the segments before this one
+    int n_look = 0;            // no window rebuild before this tick (teams of a warp)
+    bool looked = false;       // (larger teams: the windows have been rebuilt once during this streak)
+    bool again;
+    // detonations of the last committed tick (warp teams): the lanes of the missiles, how this lane's missile went
+    // (1 at its target, 2 end of life), and the slots AirEnv.step removes because of them at the start of the next tick
+    unsigned prev_det = 0, prev_rm = 0;
+    int was = 0;
     double now_s = tick_seconds(P, tick);
-    while (n_q < max_ticks) {
-        if (tick_limit >= 0 && tick >= tick_limit) break;
-        const double now_next = tick_seconds(P, tick + 1);
-        bool bail = bail0;
-        // AirObject.step (AirObject.py:39-42): the new position; the old one becomes prev_pos at commit
-        double nx = px, ny = py, nz = pz;
-        if (alive) {
-            const double dtm = now_s - t0;
-            nx = sx + vx * dtm;
-            ny = sy + vy * dtm;
-            nz = sz + vz * dtm;
-        }
-        // Missile.step (Missile.py:162-193): target's position of this tick, before any radar touches it
-        double per = period;
-        if (TEAM == 32 && msl_mask) {
-            const double tx = __shfl_sync(ZRK_FULL, nx, tg), ty = __shfl_sync(ZRK_FULL, ny, tg), tz = __shfl_sync(ZRK_FULL, nz, tg);
-            if (msl) {
-                const double ex = tx - nx, ey = ty - ny, ez = tz - nz;
-                if (!(dot3(ex, ey, ez, ex, ey, ez) > r2hi)) bail = true;  // (may be) within the radius: detonation
-                per = period - P.dt_s;
-                if (!(per > 0)) bail = true;  // self-detonation
+    do {
+        again = false;
+        int n_q = 0, n_upd = 0;
+        int acc_alive = 0, acc_msl = 0;  // alive objects / missiles summed over the segment's ticks, beyond n_q x the final counts
+        const bool alive0 = alive, msl0 = msl;
+        const int fl0 = fl;
+        bool cw_dirty = false;
+        unsigned rm = 0;  // the slots removed at the start of the tick under way (not committed yet)
+        updt = -1;
+        while (n_done + n_q < max_ticks) {
+            if (tick_limit >= 0 && tick >= tick_limit) break;
+            const double now_next = tick_seconds(P, tick + 1);
+            bool bail = bail0;
+            if (TEAM == 32 && ZRK_RARE(prev_det)) {
+                // AirEnv.step (AirEnv.py:33-40): the objects last tick's MISSILE_DETONATE messages name are gone
+                rm = prev_rm & alive_mask;
+                alive = alive && !((rm >> lane) & 1u);
+                msl = msl && alive;
+                alive_mask &= ~rm;
+                msl_mask = __ballot_sync(ZRK_FULL, msl);
+                if (rm) {
+                    streak_frozen(rm, alive, px, py, pz, qx, qy, qz, vx, vy, vz, speed, tick - 1, P.dt_s, P.noise_bound, cin, cout);
+                    cw_dirty = true;
+                }
             }
-        }
-        // SectorRadar.step (Radar.py:144-205)
-        int rf = -1;
-        unsigned *mrow = nullptr;
-        if (P.masks) {
-            mrow = P.masks + ((size_t)(tick % P.mask_ticks) * o.B + b) * (size_t)((1 + o.RP) * P.mask_words);
-            if ((lane & 31) == 0 && (lane >> 5) < P.mask_words) mrow[lane >> 5] = alive_mask;  // (this warp's 32 slots)
-        }
-        for (int r = 0; r < nR; r++) {
-            const double *par_r = c_rad_par + RAD_PAR_STRIDE * r;
-            bool vis = false;
+            // AirObject.step (AirObject.py:39-42): the new position; the old one becomes prev_pos at commit
+            double nx = px, ny = py, nz = pz;
             if (alive) {
-                const double caz = rad_cur[2 * r], cel = rad_cur[2 * r + 1];
-                const double dx = nx - c_rad_pos[3 * r], dy = ny - c_rad_pos[3 * r + 1], dz = nz - c_rad_pos[3 * r + 2];
-                vis = radar_sees<true>(dx, dy, dz, par_r, caz, caz + par_r[3], cel, cel + par_r[4]);
-                if (vis) {  // smooth_objects (Radar.py:138-142)
-                    if (noise) {
-                        const double *q = noise + (size_t)noise_w * noise_row + (size_t)r * P.noise_objects * 3;
-                        nx += q[0];
-                        ny += q[1];
-                        nz += q[2];
+                const double dtm = now_s - t0;
+                nx = sx + vx * dtm;
+                ny = sy + vy * dtm;
+                nz = sz + vz * dtm;
+            }
+            // Missile.step (Missile.py:162-193): target's position of this tick, before any radar touches it
+            double per = period;
+            int det = 0;
+            unsigned det_mask = 0;
+            if (TEAM == 32 && msl_mask) {
+                const double tx = __shfl_sync(ZRK_FULL, nx, tg), ty = __shfl_sync(ZRK_FULL, ny, tg), tz = __shfl_sync(ZRK_FULL, nz, tg);
+                if (msl) {
+                    const double ex = tx - nx, ey = ty - ny, ez = tz - nz;
+                    const double d2m = dot3(ex, ey, ez, ex, ey, ez);
+                    per = period - P.dt_s;
+                    if (ZRK_RARE(!(d2m > r2hi))) {  // (may be) within the radius: the reference's own test decides
+                        if (sqrt(d2m) <= ((const double *)(cs + o.c_m_radius))[m]) {
+                            det = 1;
+                            per = period;
+                        }
                     }
-                    if (rf < 0) rf = r;
+                    if (ZRK_RARE(!(per > 0)) && !det) {  // end of life (a NaN period: the general tick's business)
+                        if (per <= 0)
+                            det = 2;
+                        else
+                            bail = true;
+                    }
+                }
+                det_mask = __ballot_sync(ZRK_FULL, det != 0);
+            }
+            if (TEAM == 32 && ZRK_RARE((det_mask | prev_det) != 0)) {
+                // the records of this tick have to fit (otherwise the general tick is the one to report the overflow)
+                const int need = (logged(P, ZRK_MSG_MISSILE_DETONATE) ? __popc(det_mask) : 0) +
+                                 (logged(P, ZRK_MSG_DESTROYED_MISSILE) ? nR * __popc(prev_det) : 0);
+                if (need && hdr[H_NREC] + need > P.log_cap) bail = true;
+            }
+            // SectorRadar.step (Radar.py:144-205)
+            int rf = -1;
+            unsigned *mrow = nullptr;
+            if (P.masks) {
+                mrow = P.masks + ((size_t)(tick % P.mask_ticks) * o.B + b) * (size_t)((1 + o.RP) * P.mask_words);
+                if ((lane & 31) == 0 && (lane >> 5) < P.mask_words) mrow[lane >> 5] = alive_mask;  // (this warp's 32 slots)
+            }
+            for (int r = 0; r < nR; r++) {
+                const double *par_r = c_rad_par + RAD_PAR_STRIDE * r;
+                bool vis = false;
+                if (alive) {
+                    const double caz = rad_cur[2 * r], cel = rad_cur[2 * r + 1];
+                    const double dx = nx - c_rad_pos[3 * r], dy = ny - c_rad_pos[3 * r + 1], dz = nz - c_rad_pos[3 * r + 2];
+                    vis = radar_sees<true>(dx, dy, dz, par_r, caz, caz + par_r[3], cel, cel + par_r[4]);
+                    if (vis) {  // smooth_objects (Radar.py:138-142)
+                        if (noise) {
+                            const double *q = noise + (size_t)noise_w * noise_row + (size_t)r * P.noise_objects * 3;
+                            nx += q[0];
+                            ny += q[1];
+                            nz += q[2];
+                        }
+                        if (rf < 0) rf = r;
+                    }
+                }
+                if (mrow) {
+                    const unsigned bal = __ballot_sync(ZRK_FULL, vis);
+                    if ((lane & 31) == 0 && (lane >> 5) < P.mask_words) mrow[(1 + r) * P.mask_words + (lane >> 5)] = bal;
                 }
             }
-            if (mrow) {
-                const unsigned bal = __ballot_sync(ZRK_FULL, vis);
-                if ((lane & 31) == 0 && (lane >> 5) < P.mask_words) mrow[(1 + r) * P.mask_words + (lane >> 5)] = bal;
+            if (sweep_db && lane == 0) streak_sweep_next(rad_cur, dscr + 16 * (rcp ^ 1), c_rad_par, nR);
+            // CombatControlPoint.step: the own track, exactly as link_d2 / link_eval measure it
+            const bool det_ = alive && rf >= 0;
+            bool upd_msg = false, doubt = false;
+            double d2 = 0;
+            if (det_) {
+                const double ex = px - nx, ey = py - ny, ez = pz - nz;
+                d2 = dot3(ex, ey, ez, ex, ey, ez);
+                double lo, hi;
+                calc_range(speed, now_s - upds, P.range_step, lo, hi);
+                const double EPS = 4e-15;
+                const double l2 = lo * lo, h2 = hi * hi;
+                const bool in_sure = d2 >= l2 * (1.0 + EPS) && d2 <= h2 * (1.0 - EPS);
+                // (a Missile followed by a target track is the reference's AttributeError, CCP.py:259)
+                const bool hard = !(seed_ok && in_sure && (follow || nolaunch)) || (msl && !is_me);
+                doubt = !(tick < cin && refc1 && d2 <= dm2);
+                bail = bail || hard;
+                upd_msg = !is_me && follow;
             }
-        }
-        if (sweep_db && lane == 0) streak_sweep_next(rad_cur, dscr + 16 * (rcp ^ 1), c_rad_par, nR);
-        // CombatControlPoint.step: the own track, exactly as link_d2 / link_eval measure it
-        const bool det = alive && rf >= 0;
-        bool upd_msg = false, doubt = false;
-        double d2 = 0;
-        if (det) {
-            const double ex = px - nx, ey = py - ny, ez = pz - nz;
-            d2 = dot3(ex, ey, ez, ex, ey, ez);
-            double lo, hi;
-            calc_range(speed, now_s - upds, P.range_step, lo, hi);
-            const double EPS = 4e-15;
-            const double l2 = lo * lo, h2 = hi * hi;
-            const bool in_sure = d2 >= l2 * (1.0 + EPS) && d2 <= h2 * (1.0 - EPS);
-            // (a Missile followed by a target track is the reference's AttributeError, CCP.py:259)
-            const bool hard = !(seed_ok && in_sure && (follow || nolaunch)) || (msl && !is_me);
-            doubt = !(tick < cin && refc1 && d2 <= dm2);
-            bail = bail || hard;
-            upd_msg = !is_me && follow;
-        }
-        if (TEAM == 32) {
-            if (__ballot_sync(ZRK_FULL, bail) != 0) break;
-            const unsigned dmask = __ballot_sync(ZRK_FULL, doubt);
-            if (ZRK_RARE(dmask)) {
-                if (streak_rivals<TEAM>(dmask, lane, alive || !(fl & F_HASPREV), px, py, pz, qx, qy, qz, r_te, r_me, n_te, n_me, nx, ny,
-                                        nz, d2, seedu))
+            if (TEAM == 32) {
+                if (__ballot_sync(ZRK_FULL, bail) != 0) break;
+                const unsigned dmask = __ballot_sync(ZRK_FULL, doubt);
+                if (ZRK_RARE(dmask)) {
+                    if (streak_rivals<TEAM>(dmask, lane, alive || !(fl & F_HASPREV), px, py, pz, qx, qy, qz, r_te, r_me, n_te, n_me, nx, ny,
+                                            nz, d2, seedu, det_ ? (rf << 8) | lane : -1))
+                        break;
+                    // a window that has passed keeps its slot uncertified: end the segment, rebuild the windows and look
+                    // at this tick again
+                    if (tick >= n_look && __ballot_sync(ZRK_FULL, doubt && cout < tick) != 0) {
+                        again = true;
+                        break;
+                    }
+                }
+            } else if (__syncthreads_or(bail || doubt) != 0) {
+                if (((tick & 15) == 0 || (n_done + n_q == 0 && !looked)) && __syncthreads_or(!bail && doubt && cout < tick) != 0) {  // (as above)
+                    again = true;
                     break;
-                // a window that has passed keeps its slot uncertified: rebuild the windows (on the streak's
-                // first tick, then every 16th at most) from the state shared memory still holds, and look at
-                // this tick again
-                if ((tick & 15) == 0 && !looked && __ballot_sync(ZRK_FULL, doubt && cout < tick) != 0) {
-                    looked = true;  // (once per streak: the next one starts from the rebuilt windows anyway)
-                    cert_recompute<TEAM>(sm, ZRK_QME_I(me_ref), lane, n_slots, tick0 - 1, tick, n_te, n_me, P.dt_s, P.noise_bound, c_in,
-                                         c_out, c_refc, fp, fv, true);
-                    cin = c_in[lane], cout = c_out[lane], refc1 = c_refc[lane] == 1;
-                    continue;
+                }
+                // Teams larger than a warp check their uncertified detections like a warp does (streak_rivals),
+                // through shared scratch instead of shuffles: every slot publishes what its tracks measure to, the
+                // uncertified detections line up in a short list, every lane tests the two tracks it holds.
+                {
+                    double *const Lx = (double *)fp, *const Ly = Lx + TEAM, *const Lz = Ly + TEAM;  // (fp: 48 x TEAM bytes, see the caller)
+                    double *const dl = Lz + TEAM;                                                  // [16][4] x, y, z, threshold
+                    int *const dsd = (int *)(dl + 64), *const dcnt = dsd + 16;                     // [16] own track, list length
+                    if (lane == 0) *dcnt = 0;  // (the scratch is shared with the window rebuild: emptied before every use)
+                    if (__syncthreads_or(bail) != 0) break;
+                    const bool use_p = alive || !(fl & F_HASPREV);
+                    if (lane < n_slots) Lx[lane] = use_p ? px : qx, Ly[lane] = use_p ? py : qy, Lz[lane] = use_p ? pz : qz;
+                    if (doubt) {
+                        const int k = atomicAdd(dcnt, 1);
+                        if (k < 16) {
+                            dl[4 * k] = nx, dl[4 * k + 1] = ny, dl[4 * k + 2] = nz, dl[4 * k + 3] = d2 * (1.0 + 1e-12);
+                            dsd[k] = seedu;
+                        }
+                    }
+                    __syncthreads();
+                    const int nd = *dcnt;
+                    bool rival = nd > 16;  // (too many: let the general tick do it)
+                    for (int k = 0; k < nd && k < 16; k++) {
+                        const double cx = dl[4 * k], cy = dl[4 * k + 1], cz = dl[4 * k + 2], thr = dl[4 * k + 3];
+                        const int sd = dsd[k];
+                        if (lane < n_te && lane != sd) {
+                            const double ex = Lx[r_te] - cx, ey = Ly[r_te] - cy, ez = Lz[r_te] - cz;
+                            rival = rival || !(dot3(ex, ey, ez, ex, ey, ez) > thr);
+                        }
+                        if (lane < n_me && TEAM + lane != sd) {
+                            const double ex = Lx[r_me] - cx, ey = Ly[r_me] - cy, ez = Lz[r_me] - cz;
+                            rival = rival || !(dot3(ex, ey, ez, ex, ey, ez) > thr);
+                        }
+                    }
+                    if (__syncthreads_or(rival) != 0) break;
                 }
             }
-        } else if (__syncthreads_or(bail || doubt) != 0) {
-            if (((tick & 15) == 0 || (n_q == 0 && !looked)) && __syncthreads_or(!bail && doubt && cout < tick) != 0) {  // (as above)
-                looked = true;
-                cert_recompute<TEAM>(sm, ZRK_QME_I(me_ref), lane, n_slots, tick0 - 1, tick, n_te, n_me, P.dt_s, P.noise_bound, c_in, c_out,
-                                     c_refc, fp, fv, true);
-                cin = c_in[lane], cout = c_out[lane], refc1 = c_refc[lane] == 1;
-                continue;  // look at this tick again
+            // ---- commit
+            if (TEAM == 32 && ZRK_RARE((det_mask | prev_det) != 0)) {
+                streak_events<TEAM, MPB>(P.self, sm, cs, b, lane, tick, det, det_mask, was, prev_det, tg, m, nR);
+                if (rm) {  // what left at the start of this tick had been counted as present on the n_q ticks before it
+                    acc_alive += n_q * __popc(rm);
+                    acc_msl += n_q * __popc(__ballot_sync(ZRK_FULL, ((rm >> lane) & 1u) && (fl & F_MISSILE)));
+                    if ((rm >> lane) & 1u) fl &= ~F_ALIVE;
+                    rm = 0;
+                }
+                // the slots AirEnv.step will remove next tick: the missiles and what they hit
+                prev_rm = det_mask;
+                for (unsigned mm = det_mask; mm; mm &= mm - 1) {
+                    const int d = __ffs(mm) - 1;
+                    const int dk = __shfl_sync(ZRK_FULL, det, d), dt_ = __shfl_sync(ZRK_FULL, tg, d);
+                    if (dk == 1) prev_rm |= 1u << dt_;
+                }
+                prev_det = det_mask;
+                was = det;
             }
-            // Teams larger than a warp check their uncertified detections like a warp does (streak_rivals),
-            // through shared scratch instead of shuffles: every slot publishes what its tracks measure to, the
-            // uncertified detections line up in a short list, every lane tests the two tracks it holds.
-            {
-                double *const Lx = (double *)fp, *const Ly = Lx + TEAM, *const Lz = Ly + TEAM;  // (fp: 48 x TEAM bytes, see the caller)
-                double *const dl = Lz + TEAM;                                                  // [16][4] x, y, z, threshold
-                int *const dsd = (int *)(dl + 64), *const dcnt = dsd + 16;                     // [16] own track, list length
-                if (lane == 0) *dcnt = 0;  // (the scratch is shared with the window rebuild: emptied before every use)
-                if (__syncthreads_or(bail) != 0) break;
-                const bool use_p = alive || !(fl & F_HASPREV);
-                if (lane < n_slots) Lx[lane] = use_p ? px : qx, Ly[lane] = use_p ? py : qy, Lz[lane] = use_p ? pz : qz;
-                if (doubt) {
-                    const int k = atomicAdd(dcnt, 1);
-                    if (k < 16) {
-                        dl[4 * k] = nx, dl[4 * k + 1] = ny, dl[4 * k + 2] = nz, dl[4 * k + 3] = d2 * (1.0 + 1e-12);
-                        dsd[k] = seedu;
+            if (alive) {
+                qx = px, qy = py, qz = pz;
+                px = nx, py = ny, pz = nz;
+            }
+            if (det_) {
+                upds = now_s;
+                updt = tick;
+            }
+            period = per;
+            n_upd += __popc(__ballot_sync(ZRK_FULL, upd_msg));
+            if (sweep_db) {
+                if (TEAM == 32) __syncwarp();  // (a larger team's vote was a barrier already)
+                rcp ^= 1;
+                rad_cur = dscr + 16 * rcp;
+            } else if (ZRK_RARE(sweeping)) {
+                streak_sweep<TEAM>(ZRK_QME_D(rad_cur), c_rad_par, nR, lane);
+            }
+            tick++;
+            n_q++;
+            now_s = now_next;
+            if (++noise_w == P.noise_period) noise_w = 0;
+        }
+        if (TEAM == 32 && ZRK_RARE(rm)) {  // the tick under way was not committed: neither is its removal
+            alive = alive || ((rm >> lane) & 1u);
+            msl = alive && (fl & F_MISSILE);
+            alive_mask |= rm;
+            msl_mask = __ballot_sync(ZRK_FULL, msl);
+        }
+        if (n_q) {  // the state the general tick expects, and the messages of the committed ticks
+            if (sweep_db && lane < 2 * nR) ZRK_QME_D(rad_cur)[lane] = rad_cur[lane];
+            if (alive0) {
+                H.qxy()[lane] = make_double2(qx, qy);
+                H.qzw()[lane].x = qz;
+                H.pxy()[lane] = make_double2(px, py);
+                H.pzs()[lane].x = pz;
+            }
+            if (TEAM == 32 && fl != fl0) H.sflags()[lane] = fl;
+            if (TEAM == 32 && cw_dirty) {
+                c_in[lane] = cin;
+                c_out[lane] = cout;
+            }
+            if (updt >= 0) {
+                if (is_me) {
+                    ZRK_QME_I(me_upd)[e] = updt;
+                    ZRK_QME_D(me_upds)[e] = upds;
+                } else {
+                    H.te_upd()[e] = updt;
+                    H.te_upds()[e] = upds;
+                }
+            }
+            if (msl0) ZRK_COLD_D(m_period)[m] = period;
+            if (TEAM == 32) {
+                if (lane == 0) {
+                    const int na = n_q * __popc(alive_mask) + acc_alive;
+                    unsigned *cnt = H.counts();
+                    hdr[H_TICK] = tick;
+                    hdr[H_FAST] += n_q;
+                    hdr[H_ALIVE] += na;
+                    cnt[ZRK_MSG_ACTIVE_OBJECTS] += (unsigned)n_q;
+                    cnt[ZRK_MSG_MISSILE_POS] += (unsigned)(n_q * __popc(msl_mask) + acc_msl);
+                    cnt[ZRK_MSG_CCP_UPDATE_TARGET] += (unsigned)n_upd;
+                    if (nR) {
+                        cnt[ZRK_MSG_ALL_OBJECTS] += (unsigned)(n_q * nR);
+                        cnt[ZRK_MSG_FOUND_OBJECTS] += (unsigned)(n_q * nR);
+                        cnt[ZRK_MSG_DRAW_OBJECTS] += (unsigned)na;
                     }
                 }
-                __syncthreads();
-                const int nd = *dcnt;
-                bool rival = nd > 16;  // (too many: let the general tick do it)
-                for (int k = 0; k < nd && k < 16; k++) {
-                    const double cx = dl[4 * k], cy = dl[4 * k + 1], cz = dl[4 * k + 2], thr = dl[4 * k + 3];
-                    const int sd = dsd[k];
-                    if (lane < n_te && lane != sd) {
-                        const double ex = Lx[r_te] - cx, ey = Ly[r_te] - cy, ez = Lz[r_te] - cz;
-                        rival = rival || !(dot3(ex, ey, ez, ex, ey, ez) > thr);
-                    }
-                    if (lane < n_me && TEAM + lane != sd) {
-                        const double ex = Lx[r_me] - cx, ey = Ly[r_me] - cy, ez = Lz[r_me] - cz;
-                        rival = rival || !(dot3(ex, ey, ez, ex, ey, ez) > thr);
-                    }
-                }
-                if (__syncthreads_or(rival) != 0) break;
-            }
-        }
-        // ---- commit
-        if (alive) {
-            qx = px, qy = py, qz = pz;
-            px = nx, py = ny, pz = nz;
-        }
-        if (det) {
-            upds = now_s;
-            updt = tick;
-        }
-        period = per;
-        n_upd += __popc(__ballot_sync(ZRK_FULL, upd_msg));
-        if (sweep_db) {
-            if (TEAM == 32) __syncwarp();  // (a larger team's vote was a barrier already)
-            rcp ^= 1;
-            rad_cur = dscr + 16 * rcp;
-        } else if (ZRK_RARE(sweeping)) {
-            streak_sweep<TEAM>(ZRK_QME_D(rad_cur), c_rad_par, nR, lane);
-        }
-        tick++;
-        n_q++;
-        now_s = now_next;
-        if (++noise_w == P.noise_period) noise_w = 0;
-    }
-    if (n_q) {  // the state the general tick expects, and the messages of the committed ticks
-        if (sweep_db && lane < 2 * nR) ZRK_QME_D(rad_cur)[lane] = rad_cur[lane];
-        if (alive) {
-            H.qxy()[lane] = make_double2(qx, qy);
-            H.qzw()[lane].x = qz;
-            H.pxy()[lane] = make_double2(px, py);
-            H.pzs()[lane].x = pz;
-        }
-        if (updt >= 0) {
-            if (is_me) {
-                ZRK_QME_I(me_upd)[e] = updt;
-                ZRK_QME_D(me_upds)[e] = upds;
             } else {
-                H.te_upd()[e] = updt;
-                H.te_upds()[e] = upds;
-            }
-        }
-        if (msl) ZRK_COLD_D(m_period)[m] = period;
-        if (TEAM == 32) {
-            if (lane == 0) {
-                const int na = __popc(alive_mask);
-                unsigned *cnt = H.counts();
-                hdr[H_TICK] = tick;
-                hdr[H_FAST] += n_q;
-                hdr[H_ALIVE] += n_q * na;
-                cnt[ZRK_MSG_ACTIVE_OBJECTS] += (unsigned)n_q;
-                cnt[ZRK_MSG_MISSILE_POS] += (unsigned)(n_q * __popc(msl_mask));
-                cnt[ZRK_MSG_CCP_UPDATE_TARGET] += (unsigned)n_upd;
-                if (nR) {
-                    cnt[ZRK_MSG_ALL_OBJECTS] += (unsigned)(n_q * nR);
-                    cnt[ZRK_MSG_FOUND_OBJECTS] += (unsigned)(n_q * nR);
-                    cnt[ZRK_MSG_DRAW_OBJECTS] += (unsigned)(n_q * na);
+                if ((lane & 31) == 0) {
+                    const int na = __popc(alive_mask);
+                    if (na) atomicAdd(&hdr[H_ALIVE], n_q * na);
+                    if (n_upd) atomicAdd((int *)&H.counts()[ZRK_MSG_CCP_UPDATE_TARGET], n_upd);
+                    if (nR && na) atomicAdd((int *)&H.counts()[ZRK_MSG_DRAW_OBJECTS], n_q * na);
                 }
-            }
-        } else {
-            if ((lane & 31) == 0) {
-                const int na = __popc(alive_mask);
-                if (na) atomicAdd(&hdr[H_ALIVE], n_q * na);
-                if (n_upd) atomicAdd((int *)&H.counts()[ZRK_MSG_CCP_UPDATE_TARGET], n_upd);
-                if (nR && na) atomicAdd((int *)&H.counts()[ZRK_MSG_DRAW_OBJECTS], n_q * na);
-            }
-            if (lane == 0) {
-                unsigned *cnt = H.counts();
-                hdr[H_TICK] = tick;
-                hdr[H_FAST] += n_q;
-                cnt[ZRK_MSG_ACTIVE_OBJECTS] += (unsigned)n_q;
-                if (nR) {
-                    cnt[ZRK_MSG_ALL_OBJECTS] += (unsigned)(n_q * nR);
-                    cnt[ZRK_MSG_FOUND_OBJECTS] += (unsigned)(n_q * nR);
+                if (lane == 0) {
+                    unsigned *cnt = H.counts();
+                    hdr[H_TICK] = tick;
+                    hdr[H_FAST] += n_q;
+                    cnt[ZRK_MSG_ACTIVE_OBJECTS] += (unsigned)n_q;
+                    if (nR) {
+                        cnt[ZRK_MSG_ALL_OBJECTS] += (unsigned)(n_q * nR);
+                        cnt[ZRK_MSG_FOUND_OBJECTS] += (unsigned)(n_q * nR);
+                    }
                 }
             }
         }
-    }
-    team_barrier<TEAM>();
-    return n_q;
+        n_done += n_q;
+        team_barrier<TEAM>();
+        if (again) {
+            // the windows that have passed, rebuilt from the state just written (that of tick - 1)
+            looked = true;
+            n_look = tick + 4;
+            cert_recompute<TEAM>(sm, ZRK_QME_I(me_ref), lane, n_slots, tick - 1, tick, n_te, n_me, P.dt_s, P.noise_bound, c_in, c_out, c_refc,
+                                 fp, fv, true);
+            cin = c_in[lane], cout = c_out[lane], refc1 = c_refc[lane] == 1;
+        }
+    } while (again);
+    return n_done;
 #undef ZRK_QME_I
 #undef ZRK_QME_D
 }

@@ -24,6 +24,7 @@
 #include "cuda_emu.h"
 #define ZRK_SMEM_DECL unsigned char *zrk_smem = zrk_emu::dyn_smem()
 #define ZRK_LD_EARLY(p) (*(p))
+#define ZRK_ST_GLOBAL(p, v) (*(p) = (v))
 #define ZRK_NOINLINE __attribute__((noinline))
 #else
 #include <cuda_runtime.h>
@@ -36,10 +37,20 @@ __device__ __forceinline__ double zrk_ld_early(const double *p) {
     return v;
 }
 #define ZRK_LD_EARLY(p) zrk_ld_early(p)
+// a store the compiler knows to be to global memory (the pointer came out of a structure: it would be a generic one)
+__device__ __forceinline__ void zrk_st_global(unsigned *p, unsigned v) { asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+#define ZRK_ST_GLOBAL(p, v) zrk_st_global(p, v)
 #define ZRK_NOINLINE __noinline__
 #endif
 
 #include <math.h>
+
+// the base of the dynamic shared memory (for code that is handed an offset instead of a pointer, so that its accesses
+// are shared-memory instructions rather than generic ones)
+__device__ __forceinline__ unsigned char *zrk_smem_base() {
+    ZRK_SMEM_DECL;
+    return zrk_smem;
+}
 
 // branch hints: the rare side is moved out of the straight-line code (the hot loop has to stay
 // within the instruction cache)
@@ -121,44 +132,52 @@ __device__ __forceinline__ float atan2_deg_approx(float y, float x) {
     return r * 57.29577951f;
 }
 
+// The pre-filter itself: 1 = surely visible, 0 = surely not, -1 = not decided here.  p8 / p9: squared-range bracket
+// around max_distance^2 (radar_par[8], [9]).
+__device__ __forceinline__ int radar_fast(double dx, double dy, double dz, double p8, double p9, double az_lo, double az_hi,
+                                          double el_lo, double el_hi) {
+    const float M = 1e-2f;  // decision margin in degrees, 10x the approximation error
+    const double d2 = dot3(dx, dy, dz, dx, dy, dz);
+    if (d2 > p9) return 0;  // certainly farther than max_distance
+    bool sure_in = d2 > 0.0 && d2 <= p8, sure_out = false, ok = true;  // (an object AT the radar: arcsin(0/0) is NaN, exact path)
+    const float fx = (float)dx, fy = (float)dy, fz = (float)dz;
+    // azimuth % 360 lies in [0, 360]: a sector covering all of it needs no angle at all
+    if (!(az_lo <= 0.0 && az_hi >= 360.0)) {
+        float az = atan2_deg_approx(fy, fx);
+        if (az < 0.f) az += 360.f;
+        const float a0 = (float)az_lo, a1 = (float)az_hi;
+        ok = ok && az > M && az < 360.f - M && fabsf(a0) < 1e4f && fabsf(a1) < 1e4f;  // away from the % wrap
+        sure_in = sure_in && az > a0 + M && az < a1 - M;
+        sure_out = sure_out || az < a0 - M || az > a1 + M;
+    }
+    if (el_lo == 0.0 && el_hi == 90.0) {
+        // the upper hemisphere: degrees(arcsin(dz / d)) % 180 lies in [0, 90] iff dz >= 0 (a negative angle maps
+        // beyond 90).  Decided here unless dz is within 1e-3 of zero relative to the horizontal range
+        // (elevation within 0.06 deg of the horizon) or straight overhead (within 0.06 deg of 90).
+        const float hz = sqrt_fast(fmaf(fy, fy, fx * fx));
+        ok = ok && fabsf(fz) > 1e-3f * hz && hz > 1e-3f * fabsf(fz);
+        sure_in = sure_in && fz > 0.f;
+        sure_out = sure_out || fz < 0.f;
+    } else if (!(el_lo <= 0.0 && el_hi >= 180.0)) {
+        float el = atan2_deg_approx(fz, sqrt_fast(fmaf(fy, fy, fx * fx)));  // == asin(dz / distance), well conditioned
+        if (el < 0.f) el += 180.f;
+        const float e0 = (float)el_lo, e1 = (float)el_hi;
+        ok = ok && el > M && el < 180.f - M && fabsf(e0) < 1e4f && fabsf(e1) < 1e4f;
+        sure_in = sure_in && el > e0 + M && el < e1 - M;
+        sure_out = sure_out || el < e0 - M || el > e1 + M;
+    }
+    if (ZRK_OFTEN(ok)) {
+        if (sure_out) return 0;
+        if (ZRK_OFTEN(sure_in)) return 1;
+    }
+    return -1;
+}
 template <bool FAST>
 __device__ __forceinline__ bool radar_sees(double dx, double dy, double dz, const double *par, double az_lo,
                                            double az_hi, double el_lo, double el_hi) {
     if (FAST) {
-        const float M = 1e-2f;  // decision margin in degrees, 10x the approximation error
-        const double d2 = dot3(dx, dy, dz, dx, dy, dz);
-        if (d2 > par[9]) return false;  // certainly farther than max_distance
-        bool sure_in = d2 > 0.0 && d2 <= par[8], sure_out = false, ok = true;  // (an object AT the radar: arcsin(0/0) is NaN, exact path)
-        const float fx = (float)dx, fy = (float)dy, fz = (float)dz;
-        // azimuth % 360 lies in [0, 360]: a sector covering all of it needs no angle at all
-        if (!(az_lo <= 0.0 && az_hi >= 360.0)) {
-            float az = atan2_deg_approx(fy, fx);
-            if (az < 0.f) az += 360.f;
-            const float a0 = (float)az_lo, a1 = (float)az_hi;
-            ok = ok && az > M && az < 360.f - M && fabsf(a0) < 1e4f && fabsf(a1) < 1e4f;  // away from the % wrap
-            sure_in = sure_in && az > a0 + M && az < a1 - M;
-            sure_out = sure_out || az < a0 - M || az > a1 + M;
-        }
-        if (el_lo == 0.0 && el_hi == 90.0) {
-            // the upper hemisphere: degrees(arcsin(dz / d)) % 180 lies in [0, 90] iff dz >= 0 (a negative angle maps
-            // beyond 90).  Decided here unless dz is within 1e-3 of zero relative to the horizontal range
-            // (elevation within 0.06 deg of the horizon) or straight overhead (within 0.06 deg of 90).
-            const float hz = sqrt_fast(fmaf(fy, fy, fx * fx));
-            ok = ok && fabsf(fz) > 1e-3f * hz && hz > 1e-3f * fabsf(fz);
-            sure_in = sure_in && fz > 0.f;
-            sure_out = sure_out || fz < 0.f;
-        } else if (!(el_lo <= 0.0 && el_hi >= 180.0)) {
-            float el = atan2_deg_approx(fz, sqrt_fast(fmaf(fy, fy, fx * fx)));  // == asin(dz / distance), well conditioned
-            if (el < 0.f) el += 180.f;
-            const float e0 = (float)el_lo, e1 = (float)el_hi;
-            ok = ok && el > M && el < 180.f - M && fabsf(e0) < 1e4f && fabsf(e1) < 1e4f;
-            sure_in = sure_in && el > e0 + M && el < e1 - M;
-            sure_out = sure_out || el < e0 - M || el > e1 + M;
-        }
-        if (ZRK_OFTEN(ok)) {
-            if (sure_out) return false;
-            if (ZRK_OFTEN(sure_in)) return true;
-        }
+        const int v = radar_fast(dx, dy, dz, par[8], par[9], az_lo, az_hi, el_lo, el_hi);
+        if (ZRK_OFTEN(v >= 0)) return v != 0;
     }
     return radar_sees_exact(dx, dy, dz, par[2], az_lo, az_hi, el_lo, el_hi);
 }
@@ -1117,6 +1136,147 @@ __device__ ZRK_NOINLINE void streak_sweep(double *rc, const double *c_rad_par, i
     }
     team_barrier<TEAM>();
 }
+// A lane's share of the streak's state.  The careful tick of quiet_streak works on it where it lies; lean_run (warp
+// teams) pulls what a plain tick needs into registers for as many ticks as it can run.
+struct StreakLane {
+    double sx, sy, sz, vx, vy, vz, t0;  // Trajectory (a slot that is gone: s = p, v = 0)
+    double px, py, pz, qx, qy, qz;      // pos, prev_pos
+    double upds, speed, period, dm2, r2hi, now_s;
+    const double *noise;                // this slot's column of the noise table, row 0
+    int tg, updt, tick, n_q, n_upd, noise_w, mt;
+    int cinl, cout, n_look, r_te, r_me, seedu;  // lean_run's rival check: the window (cinl: 0 unless exactly one track follows the slot), the tracks this lane holds
+};
+// what lean_run needs besides, the same for all lanes of the warp: in shared memory behind the radar records
+struct LeanArgs {
+    double dt_s, range_step;
+    const double *tsec;
+    unsigned *mbase;       // the scenario's words in mask row 0, or null
+    long long mstride;     // words from one tick's mask row to the next
+    int mask_ticks, mask_words, noise_row, n_obj3, noise_period, nR, n_te, n_me;
+};
+#define ZRK_RREC 10        /* doubles per radar record of the lean loop */
+#define ZRK_RREC_RADARS 8  /* radars the lean loop has room for */
+#define ZRK_RREC_DOUBLES (ZRK_RREC * ZRK_RREC_RADARS + 16)
+#define ZRK_LEAN_ALIVE 1u
+#define ZRK_LEAN_MSL 2u
+#define ZRK_LEAN_TRACK_OK 4u
+#define ZRK_LEAN_UPDL 8u
+#define ZRK_LEAN_HASPREV 16u
+// The plain ticks of a streak (warp teams, radars that do not sweep): no detonation or removal under way, every
+// visibility decided by the pre-filter, every detection re-acquiring its own track within the bounds the certificate
+// relies on — certified, or (the uncertified ones) checked against every track by streak_rivals.  A function of its own
+// so that its loop holds nothing in registers but what such a tick needs.  Runs ticks L.tick .. lean_end - 1 and stops
+// before the first one that is not plain, leaving nothing of it behind (the careful tick of quiet_streak redoes it).
+// The arithmetic is that of the careful tick, operation for operation.
+template <int TEAM>
+__device__ ZRK_NOINLINE bool streak_rivals(unsigned dmask, int lane, bool use_p, double px, double py, double pz, double qx,
+                                           double qy, double qz, int r_te, int r_me, int n_te, int n_me, double nx, double ny,
+                                           double nz, double d2, int seedu, int key);
+__device__ ZRK_NOINLINE void lean_run(StreakLane *Lp, int rrec_off, int lane, unsigned flags, unsigned alive_mask, unsigned msl_mask,
+                                      int lean_end) {
+    ZRK_SMEM_DECL;
+    const double *const rrec = (const double *)(zrk_smem + rrec_off);
+    const LeanArgs &A = *(const LeanArgs *)(rrec + ZRK_RREC * ZRK_RREC_RADARS);
+    const bool alive = flags & ZRK_LEAN_ALIVE, msl = flags & ZRK_LEAN_MSL, track_ok = flags & ZRK_LEAN_TRACK_OK, updl = flags & ZRK_LEAN_UPDL;
+    const double sx = Lp->sx, sy = Lp->sy, sz = Lp->sz, vx = Lp->vx, vy = Lp->vy, vz = Lp->vz, t0 = Lp->t0;
+    double px = Lp->px, py = Lp->py, pz = Lp->pz, qx = Lp->qx, qy = Lp->qy, qz = Lp->qz;
+    double upds = Lp->upds, period = Lp->period, now_s = Lp->now_s;
+    const double dm2 = Lp->dm2, r2hi = Lp->r2hi;
+    const double *const noise = Lp->noise;
+    const int tg = Lp->tg, nR = A.nR, cinl = Lp->cinl;
+    int updt = Lp->updt, tick = Lp->tick, n_upd = 0, noise_w = Lp->noise_w, mt = Lp->mt;
+    const int tick_in = tick;
+    const double dt_m = msl ? A.dt_s : 0.0, range_step = A.range_step;
+    const double *tsec = A.tsec + tick + 1;
+    // (the arguments are copied out of shared memory: the stores below could alias it as far as the compiler knows)
+    unsigned *const mbase = A.mbase;
+    const long long mstride = A.mstride;
+    const int mask_ticks = A.mask_ticks, mask_words = A.mask_words, noise_row = A.noise_row, n_obj3 = A.n_obj3, noise_period = A.noise_period;
+    const bool has_masks = mbase != nullptr, writer = has_masks && lane == 0;
+    unsigned *mrow = mbase + (long long)mt * mstride;
+    const double *nq = noise + (size_t)noise_w * noise_row;
+#pragma unroll 1
+    do {
+        const double now_nx = ZRK_LD_EARLY(tsec);
+        const double dtm = now_s - t0;
+        double nx = sx + vx * dtm, ny = sy + vy * dtm, nz = sz + vz * dtm;  // AirObject.step (a lane that is gone: s = p, v = 0)
+        bool odd = false;
+        double per = period;
+        if (msl_mask) {  // Missile.step: nothing but the clock of a missile that stays outside its radius
+            const double tx = __shfl_sync(ZRK_FULL, nx, tg), ty = __shfl_sync(ZRK_FULL, ny, tg), tz = __shfl_sync(ZRK_FULL, nz, tg);
+            const double ex = tx - nx, ey = ty - ny, ez = tz - nz;
+            per = period - dt_m;
+            odd = msl && (!(dot3(ex, ey, ez, ex, ey, ez) > r2hi) || !(per > 0));
+        }
+        if (writer) ZRK_ST_GLOBAL(mrow, alive_mask);
+        int rf = -1;
+        for (int r = 0; r < nR; r++) {  // SectorRadar.step
+            const double *w = rrec + ZRK_RREC * r;
+            const double dx = nx - w[0], dy = ny - w[1], dz = nz - w[2];
+            int v;
+            if (w[9] != 0.0) {
+                // all of the azimuth, the upper hemisphere: radar_fast for that sector, without its detours
+                const double d2 = dot3(dx, dy, dz, dx, dy, dz);
+                const float fx = (float)dx, fy = (float)dy, fz = (float)dz;
+                const float hz = sqrt_fast(fmaf(fy, fy, fx * fx));
+                const bool ok = fabsf(fz) > 1e-3f * hz && hz > 1e-3f * fabsf(fz);
+                v = (d2 > w[4]) ? 0 : (!ok ? -1 : (fz < 0.f ? 0 : ((d2 > 0.0 && d2 <= w[3] && fz > 0.f) ? 1 : -1)));
+            } else {
+                v = radar_fast(dx, dy, dz, w[3], w[4], w[5], w[6], w[7], w[8]);
+            }
+            odd = odd || (alive && v < 0);
+            const bool vis = alive && v > 0;
+            if (vis) {  // smooth_objects
+                const double *q = nq + r * n_obj3;
+                nx += ZRK_LD_EARLY(q);
+                ny += ZRK_LD_EARLY(q + 1);
+                nz += ZRK_LD_EARLY(q + 2);
+                if (rf < 0) rf = r;
+            }
+            if (has_masks) {
+                const unsigned bal = __ballot_sync(ZRK_FULL, vis);
+                if (writer) ZRK_ST_GLOBAL(mrow + (1 + r) * mask_words, bal);
+            }
+        }
+        const bool seen = rf >= 0;
+        // CombatControlPoint.step: the own track as link_d2 measures it.  track_ok includes that its hi bound lies beyond
+        // dm whatever d_t is, and with d_t < range_step its lo bound is 0: d2 <= dm2 then puts d2 surely inside.
+        const double ex = px - nx, ey = py - ny, ez = pz - nz;
+        const double d2 = dot3(ex, ey, ez, ex, ey, ez);
+        const bool fine = track_ok && d2 <= dm2 && now_s - upds < range_step;
+        odd = odd || (seen && !fine);
+        if (__ballot_sync(ZRK_FULL, odd) != 0) break;  // (nothing of this tick is kept)
+        const unsigned dmask = __ballot_sync(ZRK_FULL, seen && !(tick < cinl));
+        if (ZRK_RARE(dmask)) {
+            // detections that are not certified: no other track as near as the own one?  (A window that has passed
+            // is the careful tick's business: it has them rebuilt.)
+            if (tick >= Lp->n_look && __ballot_sync(ZRK_FULL, seen && !(tick < cinl) && Lp->cout < tick) != 0) break;
+            if (streak_rivals<32>(dmask, lane, alive || !(flags & ZRK_LEAN_HASPREV), px, py, pz, qx, qy, qz, Lp->r_te, Lp->r_me, A.n_te, A.n_me,
+                                  nx, ny, nz, d2, Lp->seedu, seen ? (rf << 8) | lane : -1))
+                break;
+        }
+        if (alive) {
+            qx = px, qy = py, qz = pz;
+            px = nx, py = ny, pz = nz;
+        }
+        if (seen) {
+            upds = now_s;
+            updt = tick;
+        }
+        period = per;
+        n_upd += __popc(__ballot_sync(ZRK_FULL, seen && updl));
+        tick++;
+        tsec++;
+        now_s = now_nx;
+        nq += noise_row;
+        if (++noise_w == noise_period) noise_w = 0, nq = noise;
+        mrow += mstride;
+        if (++mt == mask_ticks) mt = 0, mrow = mbase;
+    } while (tick < lean_end);
+    Lp->px = px, Lp->py = py, Lp->pz = pz, Lp->qx = qx, Lp->qy = qy, Lp->qz = qz;
+    Lp->upds = upds, Lp->period = period, Lp->now_s = now_s;
+    Lp->updt = updt, Lp->n_q += tick - tick_in, Lp->tick = tick, Lp->n_upd += n_upd, Lp->noise_w = noise_w, Lp->mt = mt;
+}
 // AirEnv.py:33-40 inside a streak (warp teams): the slots of `rm` were removed at the start of this tick and stay frozen
 // where their tracks measure to (their prev_pos, in q).  Merges the pairs with them into this lane's window, as
 // cert_removed does on the state a general tick leaves; the lane's own position is that of tick_pos.  Rare: out of line.
@@ -1180,8 +1340,9 @@ __device__ ZRK_NOINLINE void streak_events(const Params *Pg, unsigned char *sm, 
 }
 template <int TEAM, int MPB>
 __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, const unsigned char *cs, int lane, int b,
-                                            int max_ticks, int noise_w, float4 *fp, float4 *fv, double *dscr) {
+                                            int max_ticks, int noise_w0, float4 *fp, float4 *fv, double *dscr, double *rrec = nullptr) {
     // dscr: 32 doubles of scratch (two copies of the sweep state of up to 8 radars)
+    // rrec: ZRK_RREC_DOUBLES of shared scratch for the lean loop's radar records (warp teams), or null: no lean loop
     // sm: the scenario's state blob, cs: its parameter blob — in shared memory (the tick kernel) or in
     // global memory (the streak kernel: a streak touches each word once at its beginning and its end).
     // Inlined into its kernel: P is then the kernel parameter, read from the constant bank.
@@ -1195,13 +1356,19 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
     int *const c_in = H.c_in(), *const c_out = H.c_out(), *const c_refc = H.c_refc();
     const int *chdr = (const int *)(cs + o.c_hdr);
     const int nR = chdr[C_NR], T = o.T, tick_limit = chdr[C_TICK_LIMIT], n_slots = hdr[H_NSLOTS];
-    int tick = hdr[H_TICK];
+    StreakLane L;
+    double &px = L.px, &py = L.py, &pz = L.pz, &qx = L.qx, &qy = L.qy, &qz = L.qz, &sx = L.sx, &sy = L.sy, &sz = L.sz, &t0 = L.t0;
+    double &vx = L.vx, &vy = L.vy, &vz = L.vz, &speed = L.speed, &upds = L.upds, &period = L.period, &r2hi = L.r2hi, &now_s = L.now_s;
+    int &tick = L.tick, &tg = L.tg, &updt = L.updt, &n_q = L.n_q, &n_upd = L.n_upd, &noise_w = L.noise_w, &mt = L.mt;
+    tick = hdr[H_TICK];
+    noise_w = noise_w0;
+    mt = P.masks ? tick % P.mask_ticks : 0;
     const bool nolaunch = hdr[H_FREECAP] <= 0;
     int fl = lane < n_slots ? H.sflags()[lane] : 0;
     bool alive = (fl & F_ALIVE) != 0, msl = alive && (fl & F_MISSILE);
     // lanes the streak cannot carry at all
     bool bail0 = (fl & F_PENDING) != 0 || (alive && !(fl & F_HASPREV)) || (TEAM > 32 && msl);
-    double px = 0, py = 0, pz = 0, qx = 0, qy = 0, qz = 0, sx = 0, sy = 0, sz = 0, t0 = 0, vx = 0, vy = 0, vz = 0, speed = 0;
+    px = 0, py = 0, pz = 0, qx = 0, qy = 0, qz = 0, sx = 0, sy = 0, sz = 0, t0 = 0, vx = 0, vy = 0, vz = 0, speed = 0;
     if (lane < n_slots) {
         const double2 a = H.pxy()[lane], c = H.pzs()[lane];
         px = a.x, py = a.y, pz = c.x, speed = c.y;
@@ -1215,13 +1382,15 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
         sx = s0.x, sy = s0.y, sz = s1.x, t0 = s1.y;
         vx = v.x, vy = v.y;
     }
+    if (TEAM == 32 && !alive) sx = px, sy = py, sz = pz, vx = 0.0, vy = 0.0, vz = 0.0;  // as a trajectory: it stays where it is
     // tracks number `lane` of the two dicts: the slots they follow (fixed during a streak)
     const int n_te = hdr[H_NTE], n_me = hdr[H_NME];
     const int r_te = lane < n_te ? H.te_ref()[lane] : 0, r_me = lane < n_me ? ZRK_QME_I(me_ref)[lane] : 0;
     // the own track
     bool seed_ok = false, is_me = false, follow = false;
-    int e = 0, updt = -1, seedu = -1;
-    double upds = 0;
+    int e = 0, seedu = -1;
+    updt = -1;
+    upds = 0;
     if (alive) {
         const int seed = H.own()[lane];
         seedu = seed;
@@ -1236,9 +1405,11 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
     int cin = c_in[lane], cout = c_out[lane];
     bool refc1 = c_refc[lane] == 1;
     const double dm = fabs(speed) * P.dt_s * 1.000000001 + 2.0 * P.noise_bound + 1e-3, dm2 = dm * dm;
+    L.dm2 = dm2;
     // a missile in flight: no detonation as long as it stays surely outside its radius of its target
-    int m = 0, tg = 0;
-    double period = 0, r2hi = 0;
+    int m = 0;
+    tg = 0;
+    period = 0, r2hi = 0;
     if (msl) {
         m = (fl >> F_STATIC_SHIFT) - T;
         tg = ZRK_COLD_I(m_target)[m];
@@ -1249,6 +1420,7 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
     }
     unsigned alive_mask = __ballot_sync(ZRK_FULL, alive), msl_mask = __ballot_sync(ZRK_FULL, msl);
     const double *noise = P.noise ? P.noise + (size_t)b * P.noise_stride + (fl >> F_STATIC_SHIFT) * 3 : nullptr;
+    L.noise = noise;
     const int noise_row = P.noise_radars * P.noise_objects * 3;
     const double *rad_cur = ZRK_QME_D(rad_cur);
     const double *const c_rad_pos = (const double *)(cs + o.c_rad_pos), *const c_rad_par = (const double *)(cs + o.c_rad_par);
@@ -1262,6 +1434,39 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
         team_barrier<TEAM>();
         rad_cur = dscr;
     }
+    // The lean loop (warp teams, radars that do not sweep): the plain ticks of a streak — no detonation or removal under
+    // way, every detection certified, every visibility decided by the pre-filter — run in a loop of their own that holds
+    // nothing but what such a tick needs; a tick it cannot commit is left untouched for the careful tick below it.
+    // Per radar: position, the squared-range bracket, the sector (ZRK_RREC doubles, in shared memory).
+    const bool lean = TEAM == 32 && rrec != nullptr && !sweeping && nR <= ZRK_RREC_RADARS && noise != nullptr;
+    if (TEAM == 32 && lean) {
+        if (lane < nR) {
+            const double *q = c_rad_par + RAD_PAR_STRIDE * lane;
+            double *w = rrec + ZRK_RREC * lane;
+            const double caz = rad_cur[2 * lane], cel = rad_cur[2 * lane + 1];
+            w[0] = c_rad_pos[3 * lane], w[1] = c_rad_pos[3 * lane + 1], w[2] = c_rad_pos[3 * lane + 2];
+            w[3] = q[8], w[4] = q[9];
+            w[5] = caz, w[6] = caz + q[3], w[7] = cel, w[8] = cel + q[4];
+            w[9] = (w[5] <= 0.0 && w[6] >= 360.0 && w[7] == 0.0 && w[8] == 90.0) ? 1.0 : 0.0;  // all of the azimuth, the upper hemisphere
+        }
+        if (lane == 0) {
+            LeanArgs &A = *(LeanArgs *)(rrec + ZRK_RREC * ZRK_RREC_RADARS);
+            const long long roww = (long long)(1 + o.RP) * P.mask_words;
+            A.dt_s = P.dt_s, A.range_step = P.range_step, A.tsec = P.tsec;
+            A.mbase = P.masks ? P.masks + (long long)b * roww : nullptr;
+            A.mstride = (long long)o.B * roww;
+            A.mask_ticks = P.masks ? P.mask_ticks : 1, A.mask_words = P.mask_words, A.noise_row = noise_row, A.n_obj3 = P.noise_objects * 3;
+            A.noise_period = P.noise_period, A.nR = nR, A.n_te = n_te, A.n_me = n_me;
+        }
+        __syncwarp();
+
+    }
+    // what never changes for a lane during a streak, folded: its own track is where it should be and nothing can be
+    // launched at it; its re-acquisitions are reported (CCP_UPDATE_TARGET)
+    const bool track_ok = seed_ok && (follow || nolaunch) && !(msl && !is_me), updl = !is_me && follow;
+    // (lean_run: the upper end of calc_range, speed (d_t + range_step) with d_t >= one tick, lies beyond dm by a wide margin)
+    const bool hi_far = speed >= 0.0 && speed * P.range_step > 2.0 * P.noise_bound + 1.0 + speed * P.dt_s * 1e-6;
+    int lean_end = 0;  // the lean loop runs the ticks before this one (0: find out)
     // The streak runs in segments: the blob holds the state of the tick before the segment's first one; a segment ends
     // when the streak does, or (again) when windows that have passed are to be rebuilt — from the blob, which therefore
     // has to be brought up to date first.
@@ -1273,10 +1478,10 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
     // (1 at its target, 2 end of life), and the slots AirEnv.step removes because of them at the start of the next tick
     unsigned prev_det = 0, prev_rm = 0;
     int was = 0;
-    double now_s = tick_seconds(P, tick);
+    now_s = tick_seconds(P, tick);
     do {
         again = false;
-        int n_q = 0, n_upd = 0;
+        n_q = 0, n_upd = 0;
         int acc_alive = 0, acc_msl = 0;  // alive objects / missiles summed over the segment's ticks, beyond n_q x the final counts
         const bool alive0 = alive, msl0 = msl;
         const int fl0 = fl;
@@ -1285,6 +1490,26 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
         updt = -1;
         while (n_done + n_q < max_ticks) {
             if (tick_limit >= 0 && tick >= tick_limit) break;
+            if (TEAM == 32 && lean && !prev_det) {
+                if (lean_end == 0) {
+                    // the end of the streak; the end of the clock table
+                    lean_end = tick + (max_ticks - n_done - n_q);
+                    if (tick_limit >= 0 && lean_end > tick_limit) lean_end = tick_limit;
+                    if (lean_end > P.tsec_n - 1) lean_end = P.tsec_n - 1;
+                    if (__ballot_sync(ZRK_FULL, bail0) != 0) lean_end = -1;
+                    L.cinl = refc1 ? cin : 0, L.cout = cout, L.n_look = n_look, L.r_te = r_te, L.r_me = r_me, L.seedu = seedu;
+                }
+                if (tick < lean_end) {
+                    lean_run(&L, (int)((unsigned char *)rrec - zrk_smem_base()), lane,
+                             (alive ? ZRK_LEAN_ALIVE : 0u) | (msl ? ZRK_LEAN_MSL : 0u) | (track_ok && hi_far ? ZRK_LEAN_TRACK_OK : 0u) | (updl ? ZRK_LEAN_UPDL : 0u) |
+                                 ((fl & F_HASPREV) ? ZRK_LEAN_HASPREV : 0u),
+                             alive_mask, msl_mask, lean_end);
+                    if (tick >= lean_end) {
+                        lean_end = 0;
+                        continue;  // (the loop's own conditions decide what comes next)
+                    }
+                }
+            }
             const double now_next = tick_seconds(P, tick + 1);
             bool bail = bail0;
             if (TEAM == 32 && ZRK_RARE(prev_det)) {
@@ -1297,6 +1522,7 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
                 if (rm) {
                     streak_frozen(rm, alive, px, py, pz, qx, qy, qz, vx, vy, vz, speed, tick - 1, P.dt_s, P.noise_bound, cin, cout);
                     cw_dirty = true;
+                    lean_end = 0;
                 }
             }
             // AirObject.step (AirObject.py:39-42): the new position; the old one becomes prev_pos at commit
@@ -1342,7 +1568,7 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
             int rf = -1;
             unsigned *mrow = nullptr;
             if (P.masks) {
-                mrow = P.masks + ((size_t)(tick % P.mask_ticks) * o.B + b) * (size_t)((1 + o.RP) * P.mask_words);
+                mrow = P.masks + ((size_t)mt * o.B + b) * (size_t)((1 + o.RP) * P.mask_words);  // (mt = tick % P.mask_ticks)
                 if ((lane & 31) == 0 && (lane >> 5) < P.mask_words) mrow[lane >> 5] = alive_mask;  // (this warp's 32 slots)
             }
             for (int r = 0; r < nR; r++) {
@@ -1447,7 +1673,10 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
                 if (rm) {  // what left at the start of this tick had been counted as present on the n_q ticks before it
                     acc_alive += n_q * __popc(rm);
                     acc_msl += n_q * __popc(__ballot_sync(ZRK_FULL, ((rm >> lane) & 1u) && (fl & F_MISSILE)));
-                    if ((rm >> lane) & 1u) fl &= ~F_ALIVE;
+                    if ((rm >> lane) & 1u) {
+                        fl &= ~F_ALIVE;
+                        sx = px, sy = py, sz = pz, vx = 0.0, vy = 0.0, vz = 0.0;
+                    }
                     rm = 0;
                 }
                 // the slots AirEnv.step will remove next tick: the missiles and what they hit
@@ -1481,8 +1710,10 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
             n_q++;
             now_s = now_next;
             if (++noise_w == P.noise_period) noise_w = 0;
+            if (P.masks && ++mt == P.mask_ticks) mt = 0;
         }
         if (TEAM == 32 && ZRK_RARE(rm)) {  // the tick under way was not committed: neither is its removal
+            lean_end = 0;
             alive = alive || ((rm >> lane) & 1u);
             msl = alive && (fl & F_MISSILE);
             alive_mask |= rm;
@@ -1555,6 +1786,7 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
             cert_recompute<TEAM>(sm, ZRK_QME_I(me_ref), lane, n_slots, tick - 1, tick, n_te, n_me, P.dt_s, P.noise_bound, c_in, c_out, c_refc,
                                  fp, fv, true);
             cin = c_in[lane], cout = c_out[lane], refc1 = c_refc[lane] == 1;
+            lean_end = 0;
         }
     } while (again);
     return n_done;
@@ -2517,7 +2749,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
 #ifndef ZRK_STREAK_MINB
 #define ZRK_STREAK_MINB 5 /* resident CTAs per SM the register allocation is bounded for */
 #endif
-#define ZRK_STREAK_SMEM (ZRK_STREAK_WARPS * (2 * 32 * 16 + 32 * 8))
+#define ZRK_STREAK_SMEM (ZRK_STREAK_WARPS * (2 * 32 * 16 + 32 * 8 + ZRK_RREC_DOUBLES * 8))
 template <int MPB>
 __global__ void __launch_bounds__(32 * ZRK_STREAK_WARPS, ZRK_STREAK_MINB) zrk_streak_kernel(const Params P, int b_first, int b_end, int target_tick,
                                                                                            const int *work) {
@@ -2544,7 +2776,8 @@ __global__ void __launch_bounds__(32 * ZRK_STREAK_WARPS, ZRK_STREAK_MINB) zrk_st
     if (fit) {
         const int noise_w = P.noise ? tick % P.noise_period : 0;
         done = quiet_streak<32, MPB>(P, sm, cs, lane, b, target_tick - tick, noise_w, scratch + (2 * w) * 32, scratch + (2 * w + 1) * 32,
-                                     (double *)(scratch + 2 * ZRK_STREAK_WARPS * 32) + 32 * w);
+                                     (double *)(scratch + 2 * ZRK_STREAK_WARPS * 32) + 32 * w,
+                                     (double *)(scratch + 2 * ZRK_STREAK_WARPS * 32) + 32 * ZRK_STREAK_WARPS + ZRK_RREC_DOUBLES * w);
     }
     if (tick + done < target_tick && lane == 0) {
         // the tick kernel's turn.  A streak that ended before its first tick doubles the number of ticks the

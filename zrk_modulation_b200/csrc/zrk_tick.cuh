@@ -859,11 +859,13 @@ __device__ __forceinline__ bool link_f32_ok(float x, float y, float z) {
 // position link_object measures a track to is the tracked object's previous position
 // (CCP.py:181-183).  So for the detection of slot i at tick t, with c(.) the noise-free positions:
 //     distance to its own track     = |p_i(t) - p_i(t-1)|               <= |v_i| dt + 2 nb
-//     distance to a track on slot j >= |c_j(t) - c_i(t)| - |v_j| dt - 2 nb   (j moving)
+//     distance to a track on slot j >= |c_j(t-1) - c_i(t)| - 2 nb           (j moving: it measures to p_j(t-1) = c_j(t-1) + noise)
 //                                   >= |F_j - c_i(t)| - nb                   (j removed or not yet born: frozen at F_j)
-// and the own track is strictly the nearest whenever |c_j(t) - c_i(t)| > R_ij = (|v_i| + |v_j|) dt + 6 nb
-// + slack for every other slot j (the extra 2 nb: the quadratic below starts from the current noisy
-// positions).  cert_recompute solves |dp + dv tau| <= R_ij for every j in fp64 and keeps, per slot,
+// So the own track is strictly the nearest
+// whenever |c_j(t-1) - c_i(t)| > R_i = |v_i| dt + 6 nb + slack for every other slot j (2 nb for the own track, 2 nb for
+// the pair, 2 nb because the quadratic below starts from the current noisy positions); for a slot that is gone,
+// c_j(t-1) is the point F_j it is frozen at.  cert_recompute solves |dp + dv tau| <= R_i with dp one tick of v_j behind
+// the slots' current distance, for every j in fp64, and keeps, per slot,
 // the first window of ticks [cin, cout] in which some pair is that close: the slot is "certified"
 // while tick < cin and looks again once tick > cout.  Anything that changes the picture — a launch,
 // a birth, a removal, a track changing hands or being created — clears all windows (x_cflag); ticks
@@ -923,9 +925,9 @@ __device__ __forceinline__ bool cert_pair(const Hot<TEAM> &H, int j, float4 pj, 
                                           double2 zi, double2 vi, double viz, int tick, int tick_now, double dt_s, double nb,
                                           float fdt, float fnb, int &best_in, int &best_out) {
     {   // fp32: never within R of each other from now on?
-        const float bx = pj.x - fpi.x, by = pj.y - fpi.y, bz = pj.z - fpi.z;
+        const float bx = fmaf(-vj.x, fdt, pj.x) - fpi.x, by = fmaf(-vj.y, fdt, pj.y) - fpi.y, bz = fmaf(-vj.z, fdt, pj.z) - fpi.z;
         const float ux = vj.x - fvi.x, uy = vj.y - fvi.y, uz = vj.z - fvi.z;
-        const float R = fmaf(fpi.w + pj.w, fdt, fnb) * 1.0001f;
+        const float R = fmaf(fpi.w, fdt, fnb) * 1.0001f;
         const float a = fmaf(uz, uz, fmaf(uy, uy, ux * ux)), bq = fmaf(bz, uz, fmaf(by, uy, bx * ux));
         const float p2 = fmaf(bz, bz, fmaf(by, by, bx * bx)), c = fmaf(-R, R, p2);
         const float b2 = bq * bq;
@@ -937,9 +939,10 @@ __device__ __forceinline__ bool cert_pair(const Hot<TEAM> &H, int j, float4 pj, 
     if (flj & F_ALIVE) {
         if (!(flj & F_HASPREV)) return false;  // (its first tick: its tracks still measure to an older position)
         const double2 pj2 = H.pxy()[j], zj = H.pzs()[j], vj2 = H.vxy()[j];
-        bx = pj2.x - pi.x, by = pj2.y - pi.y, bz = zj.x - zi.x;
-        ux = vj2.x - vi.x, uy = vj2.y - vi.y, uz = H.qzw()[j].y - viz;
-        spj = fabs(zj.y);
+        const double vjz = H.qzw()[j].y;
+        bx = (pj2.x - vj2.x * dt_s) - pi.x, by = (pj2.y - vj2.y * dt_s) - pi.y, bz = (zj.x - vjz * dt_s) - zi.x;  // (one tick behind)
+        ux = vj2.x - vi.x, uy = vj2.y - vi.y, uz = vjz - viz;
+        spj = 0.0;
     } else {
         double fx, fy, fz;
         if (flj & F_PENDING) {  // on the launcher until NEW_MISSILE is consumed (its track measures to pos)
@@ -1198,6 +1201,7 @@ __device__ ZRK_NOINLINE void lean_run(StreakLane *Lp, int rrec_off, int lane, un
 #pragma unroll 1
     do {
         const double now_nx = ZRK_LD_EARLY(tsec);
+        double z0 = ZRK_LD_EARLY(nq), z1 = ZRK_LD_EARLY(nq + 1), z2 = ZRK_LD_EARLY(nq + 2);  // the first radar's noise, in flight early
         const double dtm = now_s - t0;
         double nx = sx + vx * dtm, ny = sy + vy * dtm, nz = sz + vz * dtm;  // AirObject.step (a lane that is gone: s = p, v = 0)
         bool odd = false;
@@ -1227,10 +1231,13 @@ __device__ ZRK_NOINLINE void lean_run(StreakLane *Lp, int rrec_off, int lane, un
             odd = odd || (alive && v < 0);
             const bool vis = alive && v > 0;
             if (vis) {  // smooth_objects
-                const double *q = nq + r * n_obj3;
-                nx += ZRK_LD_EARLY(q);
-                ny += ZRK_LD_EARLY(q + 1);
-                nz += ZRK_LD_EARLY(q + 2);
+                if (r) {
+                    const double *q = nq + r * n_obj3;
+                    z0 = ZRK_LD_EARLY(q), z1 = ZRK_LD_EARLY(q + 1), z2 = ZRK_LD_EARLY(q + 2);
+                }
+                nx += z0;
+                ny += z1;
+                nz += z2;
                 if (rf < 0) rf = r;
             }
             if (has_masks) {
@@ -2055,51 +2062,67 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
     if (two || finish) n_ticks = target_tick - hdr[H_TICK];
     int *const c_removed = H.c_removed();  // slots the last general tick removed (bit mask, warp teams)
     for (int it = 0; it < n_ticks; it++) {
+        // Is the next tick one for a quiet streak (in the streak kernel under two-kernel stepping, in place otherwise)?
+        bool to_streak = false;
         if (CERT && use_cert && has_ccp) {
+            const int prv0 = (hdr[H_TICK] & 1) ^ 1;
+            bool calm = hdr[H_DETN0 + prv0] == 0 && hdr[H_MBN0 + prv0] == 0 && hdr[H_CCP_INIT] && !(hdr[H_FAULT] & 63) &&
+                        !(P.log_types & ZRK_LOG_BULK);
+            if (calm) {  // ... and no object is waiting to be born or was born on the last tick (a streak would end at once)
+                const int f = lane < hdr[H_NSLOTS] ? H.sflags()[lane] : 0;
+                calm = !tm.any((f & F_PENDING) != 0 || ((f & F_ALIVE) && !(f & F_HASPREV)));
+            }
+            if (two)
+                to_streak = calm && it > ((*c_flag >> CF_HOLD_SHIFT) & 127);
+            else
+                to_streak = --streak_wait < 0 && calm;
             // Certificate upkeep, on the state the last tick left (positions of tick H_TICK - 1): after an
             // event every window is rebuilt; after tracks changed hands the reference counts; after a removal
-            // the pairs with the removed slots are merged in.
+            // the pairs with the removed slots are merged in.  Only a streak looks at the windows, so the upkeep
+            // waits until one is about to begin (a removal that is not merged in on the spot costs a full rebuild then).
             const int cf = *c_flag & (CF_WINDOWS | CF_TRACKS);
             const unsigned removed_carry = (unsigned)*c_removed;
             if (ZRK_RARE(cf != 0 || removed_carry != 0)) {
-                const int tprev = hdr[H_TICK] - 1, ns = hdr[H_NSLOTS];
-                if (cf & CF_WINDOWS) {
-                    cert_recompute<TEAM>(sm, ZRK_ME_I(me_ref), lane, ns, tprev, tprev + 1, hdr[H_NTE], hdr[H_NME], P.dt_s,
-                                         P.noise_bound, c_in, c_out, c_refc, (float4 *)lxy, (float4 *)lzd);
-                } else {
-                    if (cf) cert_recount<TEAM>(sm, ZRK_ME_I(me_ref), lane, hdr[H_NTE], hdr[H_NME], c_refc);
-                    if (removed_carry)
-                        cert_removed<TEAM>(sm, lane, lane < ns ? H.sflags()[lane] : 0, removed_carry, tprev, P.dt_s, P.noise_bound,
-                                           c_in, c_out);
-                }
-                tm.sync();  // everybody has read the flags
-                if (lane == 0) {
-                    *c_flag &= ~(CF_WINDOWS | CF_TRACKS);
-                    *c_removed = 0;
+                if (to_streak) {
+                    const int tprev = hdr[H_TICK] - 1, ns = hdr[H_NSLOTS];
+                    if (cf & CF_WINDOWS) {
+                        cert_recompute<TEAM>(sm, ZRK_ME_I(me_ref), lane, ns, tprev, tprev + 1, hdr[H_NTE], hdr[H_NME], P.dt_s,
+                                             P.noise_bound, c_in, c_out, c_refc, (float4 *)lxy, (float4 *)lzd);
+                    } else {
+                        if (cf) cert_recount<TEAM>(sm, ZRK_ME_I(me_ref), lane, hdr[H_NTE], hdr[H_NME], c_refc);
+                        if (removed_carry)
+                            cert_removed<TEAM>(sm, lane, lane < ns ? H.sflags()[lane] : 0, removed_carry, tprev, P.dt_s, P.noise_bound,
+                                               c_in, c_out);
+                    }
+                    tm.sync();  // everybody has read the flags
+                    if (lane == 0) {
+                        *c_flag &= ~(CF_WINDOWS | CF_TRACKS);
+                        *c_removed = 0;
+                    }
+                } else if (removed_carry) {
+                    tm.sync();
+                    if (lane == 0) {
+                        *c_flag |= CF_WINDOWS;
+                        *c_removed = 0;
+                    }
                 }
             }
         }
         if (two) {  // hand the scenario back to the streak kernel as soon as its next tick is one for it
-            const int prv0 = (hdr[H_TICK] & 1) ^ 1;
-            if (it > ((*c_flag >> CF_HOLD_SHIFT) & 127) && use_cert && has_ccp && hdr[H_DETN0 + prv0] == 0 && hdr[H_MBN0 + prv0] == 0 && hdr[H_CCP_INIT] &&
-                !(hdr[H_FAULT] & 63) && !(P.log_types & ZRK_LOG_BULK)) {
+            if (to_streak) {
                 if (lane == 0) *c_flag &= ~CF_GENERAL;
                 break;
             }
-        } else if (CERT && use_cert && has_ccp && --streak_wait < 0) {
-            const int prv0 = (hdr[H_TICK] & 1) ^ 1;
-            if (hdr[H_DETN0 + prv0] == 0 && hdr[H_MBN0 + prv0] == 0 && hdr[H_CCP_INIT] && !(hdr[H_FAULT] & 63) &&
-                !(P.log_types & ZRK_LOG_BULK)) {
-                const int nq = quiet_streak<TEAM, MPB>(P, sm, sm + o.dyn_bytes, lane, b, n_ticks - it, noise_w, (float4 *)lxy,
-                                                       (float4 *)lzd, (double *)tm.wscr);
-                if (nq) {
-                    it += nq;
-                    if (it >= n_ticks) break;
-                    if (noise) noise_w = (noise_w + nq) % P.noise_period;
-                    now_next = tick_seconds(P, hdr[H_TICK]);
-                } else {
-                    streak_wait = 3;
-                }
+        } else if (to_streak) {
+            const int nq = quiet_streak<TEAM, MPB>(P, sm, sm + o.dyn_bytes, lane, b, n_ticks - it, noise_w, (float4 *)lxy, (float4 *)lzd,
+                                                   (double *)tm.wscr);
+            if (nq) {
+                it += nq;
+                if (it >= n_ticks) break;
+                if (noise) noise_w = (noise_w + nq) % P.noise_period;
+                now_next = tick_seconds(P, hdr[H_TICK]);
+            } else {
+                streak_wait = 3;
             }
         }
         const int tick = hdr[H_TICK];

@@ -2114,8 +2114,11 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
                 break;
             }
         } else if (to_streak) {
+            // (the lean loop's records of a warp team go where the fp32 images, the claims and the detection list of a
+            // general tick are: ZRK_RREC_DOUBLES x 8 bytes, free between ticks)
+            static_assert(XS.x_wscr - XS.x_lf >= ZRK_RREC_DOUBLES * 8 || TEAM != 32 || !MPB, "no room for the lean loop's records");
             const int nq = quiet_streak<TEAM, MPB>(P, sm, sm + o.dyn_bytes, lane, b, n_ticks - it, noise_w, (float4 *)lxy, (float4 *)lzd,
-                                                   (double *)tm.wscr);
+                                                   (double *)tm.wscr, (TEAM == 32 && MPB) ? (double *)lf : nullptr);
             if (nq) {
                 it += nq;
                 if (it >= n_ticks) break;
@@ -2362,7 +2365,7 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
             // the rare eventful tick only, and what it costs then is the code it has to fetch, not the
             // arithmetic: it scans with link_exact (a small loop) rather than the unrolled fp32 sweep.  (Under
             // two-kernel stepping every warp of this kernel runs general ticks: the sweep's code stays cached.)
-            const bool scan_fast = FAST && !(TEAM == 32 && use_cert && !two);
+            const bool scan_fast = FAST && !(TEAM == 32 && use_cert && !two && !finish);  // (finish: the scenarios left are the ones with general tick after general tick)
             // what link_object measures to, per entry: prev_pos of the tracked object (or pos
             // for a missile whose prev_pos is None) and d_t = now - upd_time
             // the hash grid pays off once a scan is long; warp-sized scenarios scan their few entries directly

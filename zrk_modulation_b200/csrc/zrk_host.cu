@@ -400,8 +400,8 @@ static int dev_alloc(zrk_handle *h, size_t n, T **dst, bool zero) {
     return ZRK_OK;
 }
 
-typedef void (*tick_fn)(const Params, int, int, int, int, int *, const int *, int *);
-typedef void (*streak_fn)(const Params, int, int, int, const int *);
+typedef void (*tick_fn)(const Params, int, int, int, int, int *, const int *, int *, const int *);
+typedef void (*streak_fn)(const Params, int, int, int, const int *, const int *);
 
 template <int TEAM, int TPC, int MPB>
 static tick_fn pick_fast(bool fast) {
@@ -821,24 +821,30 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
                 if (n_work[w] == 0) continue;
                 const int b0 = n_waves > 1 ? h->wave_b[w] : 0, b1 = n_waves > 1 ? h->wave_b[w + 1] : h->P.lo.B;
                 cudaStream_t ws = n_waves > 1 ? h->wave_stream[w] : h->stream;
-                const int *wl = n_work[w] < 0 ? nullptr : h->d_work + (size_t)cur[w] * h->P.lo.B + b0;
-                int *wl_out = h->d_work + (size_t)(cur[w] ^ 1) * h->P.lo.B + b0;
-                const int f0 = wl ? 0 : b0, f1 = wl ? n_work[w] : b1;  // index range of the launch
+                // Every round leaves the list of the scenarios still pending (device-side compaction through the round's
+                // pending counter) in the worklist buffer the next round reads; the host only learns its length after
+                // the batch, so the grids of a batch are sized for the last length it knows and the kernels look the
+                // real one up (work_n).
+                const int f0 = n_work[w] < 0 ? b0 : 0, f1 = n_work[w] < 0 ? b1 : n_work[w];  // index range of the launches
                 for (int r = 0; r < ZRK_ROUND_BATCH; r++) {
                     cudaEvent_t e0, e1;
                     int rc;
                     if ((rc = get_event(h, &e0)) || (rc = get_event(h, &e1))) return rc;
+                    const bool listed = n_work[w] >= 0 || r > 0;  // (the first round of a step looks at the whole range)
+                    const int *wl = listed ? h->d_work + (size_t)cur[w] * h->P.lo.B + b0 : nullptr;
+                    int *wl_out = h->d_work + (size_t)(cur[w] ^ 1) * h->P.lo.B + b0;
+                    int *pend = h->d_pending + (size_t)w * ZRK_ROUND_SLOTS + h->round_no + r;
+                    const int *wn = r > 0 ? pend - 1 : nullptr;  // (r = 0: the host knows the length)
+                    const int g0 = listed ? 0 : f0, g1 = listed ? (n_work[w] < 0 ? b1 - b0 : n_work[w]) : f1;
                     CK(cudaEventRecord(e0, ws));
-                    ZRK_LAUNCH(sf, (f1 - f0 + ZRK_STREAK_WARPS - 1) / ZRK_STREAK_WARPS, 32 * ZRK_STREAK_WARPS, ZRK_STREAK_SMEM, ws, h->P,
-                               f0, f1, target, wl);
-                    // (only the batch's last round writes the next worklist)
-                    ZRK_LAUNCH(fn, (f1 - f0 + tpc - 1) / tpc, h->block, h->smem_bytes, ws, h->P, 0, f0, f1, target,
-                               h->d_pending + (size_t)w * ZRK_ROUND_SLOTS + h->round_no + r, wl,
-                               r == ZRK_ROUND_BATCH - 1 ? wl_out : (int *)nullptr);
+                    ZRK_LAUNCH(sf, (g1 - g0 + ZRK_STREAK_WARPS - 1) / ZRK_STREAK_WARPS, 32 * ZRK_STREAK_WARPS, ZRK_STREAK_SMEM, ws, h->P,
+                               g0, g1, target, wl, wn);
+                    ZRK_LAUNCH(fn, (g1 - g0 + tpc - 1) / tpc, h->block, h->smem_bytes, ws, h->P, 0, g0, g1, target, pend, wl, wl_out, wn);
                     CK(cudaGetLastError());
                     CK(cudaEventRecord(e1, ws));
                     h->pending.push_back({e0, e1});
                     h->n_launches += 2;
+                    cur[w] ^= 1;
                 }
                 CK(cudaMemcpyAsync(h->h_pending + w, h->d_pending + (size_t)w * ZRK_ROUND_SLOTS + h->round_no + ZRK_ROUND_BATCH - 1,
                                    sizeof(int), cudaMemcpyDeviceToHost, ws));
@@ -851,7 +857,6 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
                 cudaStream_t ws = n_waves > 1 ? h->wave_stream[w] : h->stream;
                 CK(cudaStreamSynchronize(ws));
                 n_work[w] = h->h_pending[w];
-                cur[w] ^= 1;
                 const int span = (n_waves > 1 ? h->wave_b[w + 1] - h->wave_b[w] : h->P.lo.B);
                 if (n_work[w] > 0 && n_work[w] <= span / 64) {
                     // the tail: a few scenarios with many rounds still to go (one tick per round, in the worst
@@ -862,7 +867,7 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
                     if ((rc = get_event(h, &e0)) || (rc = get_event(h, &e1))) return rc;
                     CK(cudaEventRecord(e0, ws));
                     ZRK_LAUNCH(fn, (n_work[w] + tpc - 1) / tpc, h->block, h->smem_bytes, ws, h->P, 0, 0, n_work[w], target, (int *)nullptr,
-                               (const int *)(h->d_work + (size_t)cur[w] * h->P.lo.B + b0), (int *)nullptr);
+                               (const int *)(h->d_work + (size_t)cur[w] * h->P.lo.B + b0), (int *)nullptr, (const int *)nullptr);
                     CK(cudaGetLastError());
                     CK(cudaEventRecord(e1, ws));
                     h->pending.push_back({e0, e1});
@@ -901,7 +906,7 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
             if ((rc = get_event(h, &e0)) || (rc = get_event(h, &e1))) return rc;
             CK(cudaEventRecord(e0, ws));
             ZRK_LAUNCH(fn, (b1 - b0 + tpc - 1) / tpc, h->block, h->smem_bytes, ws, h->P, k, b0, b1, -1, (int *)nullptr,
-                       (const int *)nullptr, (int *)nullptr);
+                       (const int *)nullptr, (int *)nullptr, (const int *)nullptr);
             CK(cudaGetLastError());
             CK(cudaEventRecord(e1, ws));
             h->pending.push_back({e0, e1});

@@ -1982,11 +1982,12 @@ constexpr int min_blocks(int threads) { return threads <= 32 ? ZRK_MINB_TINY : t
 // (zrk_streak_kernel below) cannot — of the scenarios flagged CF_GENERAL, until each of them is fit for a
 // streak again or has reached target_tick — and counts in *pending the scenarios still short of target_tick.
 // work (two-kernel stepping, may be null): the scenarios to look at, n = b_end - b_first of them, instead of
-// [b_first, b_end); work_out (may be null): the scenarios still pending are appended here, at the index
+// [b_first, b_end) — work_n (may be null): where the device keeps the length of that list, when the host only knows an
+// upper bound of it; work_out (may be null): the scenarios still pending are appended here, at the index
 // the pending counter hands out.
 template <int TEAM, int TPC, bool FAST, int MPB>
 __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int b_first, int b_end, int target_tick, int *pending,
-                                                const int *work, int *work_out) {
+                                                const int *work, int *work_out, const int *work_n) {
     ZRK_SMEM_DECL;
     const Layout &o = P.lo;
     constexpr ScratchOff XS = scratch_off(TEAM, MPB ? MPB : 2);
@@ -2006,7 +2007,10 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
     // (target_tick >= 0 without a pending counter: "finish" — run the listed scenarios up to target_tick
     // in this one launch, quiet streaks included; the host's way to end the tail of a step)
     const bool finish = TEAM == 32 && target_tick >= 0 && pending == nullptr;
-    if ((two || finish) && work) b = work[b - b_first];
+    if ((two || finish) && work) {
+        if (work_n && b - b_first >= *work_n) return;  // (the list is shorter than the grid that was sized for it)
+        b = work[b - b_first];
+    }
     if (two) {  // is there anything for this kernel to do?  (three words of the scenario's header, before any staging)
         const unsigned char *g = P.dyn + (size_t)b * o.dyn_bytes;
         const int *gh = (const int *)(g + Hot<TEAM>::O.hdr);
@@ -2778,14 +2782,17 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
 #define ZRK_STREAK_SMEM (ZRK_STREAK_WARPS * (2 * 32 * 16 + 32 * 8 + ZRK_RREC_DOUBLES * 8))
 template <int MPB>
 __global__ void __launch_bounds__(32 * ZRK_STREAK_WARPS, ZRK_STREAK_MINB) zrk_streak_kernel(const Params P, int b_first, int b_end, int target_tick,
-                                                                                           const int *work) {
+                                                                                           const int *work, const int *work_n) {
     const Layout &o = P.lo;
     ZRK_SMEM_DECL;  // ZRK_STREAK_SMEM bytes: per warp, two rows of fp32 images for a window rebuild inside a streak
     float4 *const scratch = (float4 *)zrk_smem;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int b = b_first + blockIdx.x * ZRK_STREAK_WARPS + w;
     if (b >= b_end) return;
-    if (work) b = work[b - b_first];  // (the scenarios the last look at the batch found pending)
+    if (work) {  // (the scenarios the last round found pending; work_n: how many, if the host only knows an upper bound)
+        if (work_n && b - b_first >= *work_n) return;
+        b = work[b - b_first];
+    }
     unsigned char *sm = P.dyn + (size_t)b * o.dyn_bytes;
     const unsigned char *cs = P.cst + (size_t)b * o.cst_bytes;
     Hot<32> H;

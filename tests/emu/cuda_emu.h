@@ -211,6 +211,24 @@ inline unsigned __reduce_max_sync(unsigned, unsigned v) {
     zrk_emu::barrier_wait(w.bar, 32);
     return m;
 }
+inline unsigned __reduce_or_sync(unsigned, unsigned v) {
+    zrk_emu::Warp &w = zrk_emu::my_warp();
+    w.vals[zrk_emu::my_lane()] = v;
+    zrk_emu::barrier_wait(w.bar, 32);
+    unsigned m = 0;
+    for (int i = 0; i < 32; i++) m |= (unsigned)w.vals[i];
+    zrk_emu::barrier_wait(w.bar, 32);
+    return m;
+}
+inline int __reduce_add_sync(unsigned, int v) {
+    zrk_emu::Warp &w = zrk_emu::my_warp();
+    w.vals[zrk_emu::my_lane()] = (uint64_t)(int64_t)v;
+    zrk_emu::barrier_wait(w.bar, 32);
+    int m = 0;
+    for (int i = 0; i < 32; i++) m += (int)(int64_t)w.vals[i];
+    zrk_emu::barrier_wait(w.bar, 32);
+    return m;
+}
 inline unsigned __float_as_uint(float f) { unsigned i; memcpy(&i, &f, 4); return i; }
 inline float __uint_as_float(unsigned i) { float f; memcpy(&f, &i, 4); return f; }
 inline unsigned __match_any_sync(unsigned, int v) {

@@ -25,6 +25,7 @@
 #define ZRK_SMEM_DECL unsigned char *zrk_smem = zrk_emu::dyn_smem()
 #define ZRK_LD_EARLY(p) (*(p))
 #define ZRK_ST_GLOBAL(p, v) (*(p) = (v))
+#define ZRK_ST_MASK(p, v) (*(p) = (v))
 #define ZRK_NOINLINE __attribute__((noinline))
 #else
 #include <cuda_runtime.h>
@@ -40,6 +41,9 @@ __device__ __forceinline__ double zrk_ld_early(const double *p) {
 // a store the compiler knows to be to global memory (the pointer came out of a structure: it would be a generic one)
 __device__ __forceinline__ void zrk_st_global(unsigned *p, unsigned v) { asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 #define ZRK_ST_GLOBAL(p, v) zrk_st_global(p, v)
+// the same for a word nothing in the storing code reads back (a mask row): values the code holds in registers stay there
+__device__ __forceinline__ void zrk_st_mask(unsigned *p, unsigned v) { asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v)); }
+#define ZRK_ST_MASK(p, v) zrk_st_mask(p, v)
 #define ZRK_NOINLINE __noinline__
 #endif
 
@@ -1284,6 +1288,143 @@ __device__ ZRK_NOINLINE void lean_run(StreakLane *Lp, int rrec_off, int lane, un
     Lp->upds = upds, Lp->period = period, Lp->now_s = now_s;
     Lp->updt = updt, Lp->n_q += tick - tick_in, Lp->tick = tick, Lp->n_upd += n_upd, Lp->noise_w = noise_w, Lp->mt = mt;
 }
+// The lean loop for the commonest shape — ONE radar that looks at all of the azimuth and the upper hemisphere (rrec[9]) —
+// two ticks per pass.  A tick's own arithmetic depends on the tick before only through the position its track measures to
+// (prev_pos), the track's update time and the missile clock, so the two ticks of a pass are computed side by side in
+// straight-line, branch-free code (the scheduler interleaves their dependent fp64 chains) and settled by ONE vote
+// (a 4-bit OR reduction: either tick odd, either tick holding an uncertified detection); nothing is stored — mask rows
+// included — before the tick it belongs to is committed.  The arithmetic is that of lean_run / the careful tick,
+// operation for operation; the pre-filter's horizon / zenith guard compares squares instead of taking a root (it only
+// ever decides what is far from both).  Stops before the first tick that is not plain, or with fewer than two ticks to go.
+__device__ __forceinline__ void lean_run1(StreakLane *Lp, int rrec_off, int lane, unsigned flags, unsigned alive_mask, unsigned msl_mask, int lean_end) {
+    ZRK_SMEM_DECL;
+    const double *const rrec = (const double *)(zrk_smem + rrec_off);
+    const LeanArgs &A = *(const LeanArgs *)(rrec + ZRK_RREC * ZRK_RREC_RADARS);
+    const bool alive = flags & ZRK_LEAN_ALIVE, msl = flags & ZRK_LEAN_MSL, track_ok = flags & ZRK_LEAN_TRACK_OK, updl = flags & ZRK_LEAN_UPDL;
+    const double sx = Lp->sx, sy = Lp->sy, sz = Lp->sz, vx = Lp->vx, vy = Lp->vy, vz = Lp->vz, t0 = Lp->t0;
+    double px = Lp->px, py = Lp->py, pz = Lp->pz, qx = Lp->qx, qy = Lp->qy, qz = Lp->qz;
+    double upds = Lp->upds, period = Lp->period, now_s = Lp->now_s;
+    const double dm2 = Lp->dm2, r2hi = Lp->r2hi;
+    const double rx = rrec[0], ry = rrec[1], rz = rrec[2], r2in = rrec[3], r2out = rrec[4];
+    const double *const noise = Lp->noise;
+    const int tg = Lp->tg, cinl = Lp->cinl;
+    int updt = Lp->updt, tick = Lp->tick, cnt = 0, noise_w = Lp->noise_w, mt = Lp->mt;
+    const int tick_in = tick;
+    const double dt_m = msl ? A.dt_s : 0.0, range_step = A.range_step;
+    const double *tsec = A.tsec + tick + 1;
+    unsigned *const mbase = A.mbase;
+    const long long mstride = A.mstride;
+    const int mask_ticks = A.mask_ticks, mask_words = A.mask_words, noise_row = A.noise_row, noise_period = A.noise_period;
+    const bool has_masks = mbase != nullptr, writer = has_masks && lane == 0;
+#pragma unroll 1
+    while (tick + 2 <= lean_end) {
+        const int wb = noise_w + 1 == noise_period ? 0 : noise_w + 1, mb = mt + 1 == mask_ticks ? 0 : mt + 1;
+        const double *const na = noise + (long long)noise_w * noise_row, *const nb = noise + (long long)wb * noise_row;
+        const double now_b = ZRK_LD_EARLY(tsec), now_c = ZRK_LD_EARLY(tsec + 1);
+        const double a0 = ZRK_LD_EARLY(na), a1 = ZRK_LD_EARLY(na + 1), a2 = ZRK_LD_EARLY(na + 2);
+        const double b0 = ZRK_LD_EARLY(nb), b1 = ZRK_LD_EARLY(nb + 1), b2 = ZRK_LD_EARLY(nb + 2);
+        // AirObject.step of both ticks (a lane that is gone: s = p, v = 0)
+        const double dta = now_s - t0, dtb = now_b - t0;
+        double ax = sx + vx * dta, ay = sy + vy * dta, az = sz + vz * dta;
+        double bx = sx + vx * dtb, by = sy + vy * dtb, bz = sz + vz * dtb;
+        // Missile.step: nothing but the clock of a missile that stays outside its radius
+        const double per_a = period - dt_m, per_b = per_a - dt_m;
+        bool odd_a = false, odd_b = false;
+        if (msl_mask) {
+            const double tax = __shfl_sync(ZRK_FULL, ax, tg), tay = __shfl_sync(ZRK_FULL, ay, tg), taz = __shfl_sync(ZRK_FULL, az, tg);
+            const double tbx = __shfl_sync(ZRK_FULL, bx, tg), tby = __shfl_sync(ZRK_FULL, by, tg), tbz = __shfl_sync(ZRK_FULL, bz, tg);
+            const double eax = tax - ax, eay = tay - ay, eaz = taz - az, ebx = tbx - bx, eby = tby - by, ebz = tbz - bz;
+            odd_a = msl & (!(dot3(eax, eay, eaz, eax, eay, eaz) > r2hi) | !(per_a > 0));
+            odd_b = msl & (!(dot3(ebx, eby, ebz, ebx, eby, ebz) > r2hi) | !(per_b > 0));
+        }
+        // SectorRadar.step: radar_fast for that sector.  sure: decided here (beyond the outer bracket, or clear of the
+        // horizon and the zenith); vis: inside the inner bracket and above the horizon
+        bool vis_a, vis_b;
+        {
+            const double dx = ax - rx, dy = ay - ry, dz = az - rz;
+            const double d2 = dot3(dx, dy, dz, dx, dy, dz);
+            const float fx = (float)dx, fy = (float)dy, fz = (float)dz;
+            const float h2 = fmaf(fy, fy, fx * fx), z2 = fz * fz;
+            const bool ok = (z2 > 1e-6f * h2) & (h2 > 1e-6f * z2), far = d2 > r2out;
+            vis_a = alive & !far & ok & (fz > 0.f) & (d2 > 0.0) & (d2 <= r2in);
+            odd_a = odd_a | (alive & !far & !(ok & ((fz < 0.f) | vis_a)));
+        }
+        {
+            const double dx = bx - rx, dy = by - ry, dz = bz - rz;
+            const double d2 = dot3(dx, dy, dz, dx, dy, dz);
+            const float fx = (float)dx, fy = (float)dy, fz = (float)dz;
+            const float h2 = fmaf(fy, fy, fx * fx), z2 = fz * fz;
+            const bool ok = (z2 > 1e-6f * h2) & (h2 > 1e-6f * z2), far = d2 > r2out;
+            vis_b = alive & !far & ok & (fz > 0.f) & (d2 > 0.0) & (d2 <= r2in);
+            odd_b = odd_b | (alive & !far & !(ok & ((fz < 0.f) | vis_b)));
+        }
+        // smooth_objects
+        ax += vis_a ? a0 : 0.0, ay += vis_a ? a1 : 0.0, az += vis_a ? a2 : 0.0;
+        bx += vis_b ? b0 : 0.0, by += vis_b ? b1 : 0.0, bz += vis_b ? b2 : 0.0;
+        // CombatControlPoint.step: the own track as link_d2 measures it (see lean_run); tick b measures to what tick a leaves
+        const double eax = px - ax, eay = py - ay, eaz = pz - az;
+        const double d2a = dot3(eax, eay, eaz, eax, eay, eaz);
+        const double mx = alive ? ax : px, my = alive ? ay : py, mz = alive ? az : pz;
+        const double ebx = mx - bx, eby = my - by, ebz = mz - bz;
+        const double d2b = dot3(ebx, eby, ebz, ebx, eby, ebz);
+        const double upd_b = vis_a ? now_s : upds;
+        const bool fine_a = track_ok & (d2a <= dm2) & (now_s - upds < range_step);
+        const bool fine_b = track_ok & (d2b <= dm2) & (now_b - upd_b < range_step);
+        odd_a = odd_a | (vis_a & !fine_a);
+        odd_b = odd_b | (vis_b & !fine_b);
+        const bool unc_a = vis_a & !(tick < cinl), unc_b = vis_b & !(tick + 1 < cinl);
+        const unsigned r = __reduce_or_sync(ZRK_FULL, (odd_a ? 1u : 0u) | (odd_b ? 2u : 0u) | (unc_a ? 4u : 0u) | (unc_b ? 8u : 0u));
+        if (ZRK_RARE(r != 0)) {
+            // not two plain ticks: tick a on its own; the next pass looks at tick b again, as its first tick
+            if (r & 1u) break;  // (nothing of tick a is kept)
+            if (r & 4u) {
+                // detections that are not certified: no other track as near as the own one?  (A window that has passed
+                // is the careful tick's business: it has them rebuilt.)
+                if (tick >= Lp->n_look && __ballot_sync(ZRK_FULL, unc_a && Lp->cout < tick) != 0) break;
+                if (streak_rivals<32>(__ballot_sync(ZRK_FULL, unc_a), lane, alive || !(flags & ZRK_LEAN_HASPREV), px, py, pz, qx, qy, qz, Lp->r_te,
+                                      Lp->r_me, A.n_te, A.n_me, ax, ay, az, d2a, Lp->seedu, vis_a ? lane : -1))
+                    break;
+            }
+            if (has_masks) {
+                const unsigned bal = __ballot_sync(ZRK_FULL, vis_a);
+                if (writer) {
+                    unsigned *mrow = mbase + (long long)mt * mstride;
+                    ZRK_ST_MASK(mrow, alive_mask);
+                    ZRK_ST_MASK(mrow + mask_words, bal);
+                }
+            }
+            if (alive) qx = px, qy = py, qz = pz, px = ax, py = ay, pz = az;
+            if (vis_a) upds = now_s, updt = tick;
+            period = per_a;
+            cnt += vis_a && updl;
+            tick++, tsec++, now_s = now_b, noise_w = wb, mt = mb;
+            continue;
+        }
+        // both ticks are plain: commit them
+        if (has_masks) {
+            const unsigned bal_a = __ballot_sync(ZRK_FULL, vis_a), bal_b = __ballot_sync(ZRK_FULL, vis_b);
+            if (writer) {
+                unsigned *mra = mbase + (long long)mt * mstride, *mrb = mbase + (long long)mb * mstride;
+                ZRK_ST_MASK(mra, alive_mask);
+                ZRK_ST_MASK(mra + mask_words, bal_a);
+                ZRK_ST_MASK(mrb, alive_mask);
+                ZRK_ST_MASK(mrb + mask_words, bal_b);
+            }
+        }
+        if (alive) qx = ax, qy = ay, qz = az, px = bx, py = by, pz = bz;
+        if (vis_a) upds = now_s, updt = tick;
+        if (vis_b) upds = now_b, updt = tick + 1;
+        period = per_b;
+        cnt += (vis_a && updl) + (vis_b && updl);
+        tick += 2, tsec += 2, now_s = now_c;
+        noise_w = wb + 1 == noise_period ? 0 : wb + 1;
+        mt = mb + 1 == mask_ticks ? 0 : mb + 1;
+    }
+    const int n_upd = __reduce_add_sync(ZRK_FULL, cnt);
+    Lp->px = px, Lp->py = py, Lp->pz = pz, Lp->qx = qx, Lp->qy = qy, Lp->qz = qz;
+    Lp->upds = upds, Lp->period = period, Lp->now_s = now_s;
+    Lp->updt = updt, Lp->n_q += tick - tick_in, Lp->tick = tick, Lp->n_upd += n_upd, Lp->noise_w = noise_w, Lp->mt = mt;
+}
 // AirEnv.py:33-40 inside a streak (warp teams): the slots of `rm` were removed at the start of this tick and stay frozen
 // where their tracks measure to (their prev_pos, in q).  Merges the pairs with them into this lane's window, as
 // cert_removed does on the state a general tick leaves; the lane's own position is that of tick_pos.  Rare: out of line.
@@ -1363,10 +1504,10 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
     int *const c_in = H.c_in(), *const c_out = H.c_out(), *const c_refc = H.c_refc();
     const int *chdr = (const int *)(cs + o.c_hdr);
     const int nR = chdr[C_NR], T = o.T, tick_limit = chdr[C_TICK_LIMIT], n_slots = hdr[H_NSLOTS];
-    StreakLane L;
-    double &px = L.px, &py = L.py, &pz = L.pz, &qx = L.qx, &qy = L.qy, &qz = L.qz, &sx = L.sx, &sy = L.sy, &sz = L.sz, &t0 = L.t0;
-    double &vx = L.vx, &vy = L.vy, &vz = L.vz, &speed = L.speed, &upds = L.upds, &period = L.period, &r2hi = L.r2hi, &now_s = L.now_s;
-    int &tick = L.tick, &tg = L.tg, &updt = L.updt, &n_q = L.n_q, &n_upd = L.n_upd, &noise_w = L.noise_w, &mt = L.mt;
+    // (the lane's state in plain variables: the record lean_run works on is filled in around its call only, so that
+    // the careful tick below does not go through local memory for every value)
+    double px, py, pz, qx, qy, qz, sx, sy, sz, t0, vx, vy, vz, speed, upds, period, r2hi, now_s;
+    int tick, tg, updt, n_q, n_upd, noise_w, mt;
     tick = hdr[H_TICK];
     noise_w = noise_w0;
     mt = P.masks ? tick % P.mask_ticks : 0;
@@ -1412,7 +1553,6 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
     int cin = c_in[lane], cout = c_out[lane];
     bool refc1 = c_refc[lane] == 1;
     const double dm = fabs(speed) * P.dt_s * 1.000000001 + 2.0 * P.noise_bound + 1e-3, dm2 = dm * dm;
-    L.dm2 = dm2;
     // a missile in flight: no detonation as long as it stays surely outside its radius of its target
     int m = 0;
     tg = 0;
@@ -1427,7 +1567,6 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
     }
     unsigned alive_mask = __ballot_sync(ZRK_FULL, alive), msl_mask = __ballot_sync(ZRK_FULL, msl);
     const double *noise = P.noise ? P.noise + (size_t)b * P.noise_stride + (fl >> F_STATIC_SHIFT) * 3 : nullptr;
-    L.noise = noise;
     const int noise_row = P.noise_radars * P.noise_objects * 3;
     const double *rad_cur = ZRK_QME_D(rad_cur);
     const double *const c_rad_pos = (const double *)(cs + o.c_rad_pos), *const c_rad_par = (const double *)(cs + o.c_rad_par);
@@ -1504,13 +1643,26 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
                     if (tick_limit >= 0 && lean_end > tick_limit) lean_end = tick_limit;
                     if (lean_end > P.tsec_n - 1) lean_end = P.tsec_n - 1;
                     if (__ballot_sync(ZRK_FULL, bail0) != 0) lean_end = -1;
-                    L.cinl = refc1 ? cin : 0, L.cout = cout, L.n_look = n_look, L.r_te = r_te, L.r_me = r_me, L.seedu = seedu;
                 }
                 if (tick < lean_end) {
-                    lean_run(&L, (int)((unsigned char *)rrec - zrk_smem_base()), lane,
-                             (alive ? ZRK_LEAN_ALIVE : 0u) | (msl ? ZRK_LEAN_MSL : 0u) | (track_ok && hi_far ? ZRK_LEAN_TRACK_OK : 0u) | (updl ? ZRK_LEAN_UPDL : 0u) |
-                                 ((fl & F_HASPREV) ? ZRK_LEAN_HASPREV : 0u),
-                             alive_mask, msl_mask, lean_end);
+                    const unsigned lflags = (alive ? ZRK_LEAN_ALIVE : 0u) | (msl ? ZRK_LEAN_MSL : 0u) | (track_ok && hi_far ? ZRK_LEAN_TRACK_OK : 0u) |
+                                            (updl ? ZRK_LEAN_UPDL : 0u) | ((fl & F_HASPREV) ? ZRK_LEAN_HASPREV : 0u);
+                    const int rrec_off = (int)((unsigned char *)rrec - zrk_smem_base());
+                    StreakLane L;
+                    L.sx = sx, L.sy = sy, L.sz = sz, L.vx = vx, L.vy = vy, L.vz = vz, L.t0 = t0;
+                    L.px = px, L.py = py, L.pz = pz, L.qx = qx, L.qy = qy, L.qz = qz;
+                    L.upds = upds, L.speed = speed, L.period = period, L.dm2 = dm2, L.r2hi = r2hi, L.now_s = now_s;
+                    L.noise = noise;
+                    L.tg = tg, L.updt = updt, L.tick = tick, L.n_q = n_q, L.n_upd = n_upd, L.noise_w = noise_w, L.mt = mt;
+                    L.cinl = refc1 ? cin : 0, L.cout = cout, L.n_look = n_look, L.r_te = r_te, L.r_me = r_me, L.seedu = seedu;
+                    if (nR == 1 && rrec[9] != 0.0 && tick + 2 <= lean_end) {  // one radar, the upper hemisphere: two ticks per pass
+                        lean_run1(&L, rrec_off, lane, lflags, alive_mask, msl_mask, lean_end);
+                    } else {
+                        lean_run(&L, rrec_off, lane, lflags, alive_mask, msl_mask, lean_end);
+                    }
+                    px = L.px, py = L.py, pz = L.pz, qx = L.qx, qy = L.qy, qz = L.qz;
+                    upds = L.upds, period = L.period, now_s = L.now_s;
+                    updt = L.updt, n_q = L.n_q, tick = L.tick, n_upd = L.n_upd, noise_w = L.noise_w, mt = L.mt;
                     if (tick >= lean_end) {
                         lean_end = 0;
                         continue;  // (the loop's own conditions decide what comes next)
@@ -1582,9 +1734,17 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
                 const double *par_r = c_rad_par + RAD_PAR_STRIDE * r;
                 bool vis = false;
                 if (alive) {
-                    const double caz = rad_cur[2 * r], cel = rad_cur[2 * r + 1];
-                    const double dx = nx - c_rad_pos[3 * r], dy = ny - c_rad_pos[3 * r + 1], dz = nz - c_rad_pos[3 * r + 2];
-                    vis = radar_sees<true>(dx, dy, dz, par_r, caz, caz + par_r[3], cel, cel + par_r[4]);
+                    if (TEAM == 32 && lean) {
+                        // (the radar records of the lean loop, in shared memory: the same values, no trip to the parameter blob)
+                        const double *w = rrec + ZRK_RREC * r;
+                        const double dx = nx - w[0], dy = ny - w[1], dz = nz - w[2];
+                        const int v = radar_fast(dx, dy, dz, w[3], w[4], w[5], w[6], w[7], w[8]);
+                        vis = ZRK_OFTEN(v >= 0) ? v != 0 : radar_sees_exact(dx, dy, dz, par_r[2], w[5], w[6], w[7], w[8]);
+                    } else {
+                        const double caz = rad_cur[2 * r], cel = rad_cur[2 * r + 1];
+                        const double dx = nx - c_rad_pos[3 * r], dy = ny - c_rad_pos[3 * r + 1], dz = nz - c_rad_pos[3 * r + 2];
+                        vis = radar_sees<true>(dx, dy, dz, par_r, caz, caz + par_r[3], cel, cel + par_r[4]);
+                    }
                     if (vis) {  // smooth_objects (Radar.py:138-142)
                         if (noise) {
                             const double *q = noise + (size_t)noise_w * noise_row + (size_t)r * P.noise_objects * 3;

@@ -482,7 +482,7 @@ def main():
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--ticks", type=int, default=0)
     ap.add_argument("--ticks-per-launch", type=int, default=0)
-    ap.add_argument("--waves", type=int, default=1,
+    ap.add_argument("--waves", type=int, default=8,
                     help="scenario waves of the end-to-end leg (zrk_options.waves): the H2D copy of one wave overlaps the kernels of the others")
     ap.add_argument("--log", default="masks", choices=["masks", "events"],
                     help="masks (default): event records + per-tick masks + track journal, every message rebuildable; events: event records only")

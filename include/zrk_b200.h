@@ -237,9 +237,10 @@ typedef struct zrk_options {
     int32_t mask_ticks;        /* ticks of mask history to keep when ZRK_LOG_MASKS (ring if smaller than the run) */
     int32_t ticks_per_launch;  /* ticks fused into one kernel launch; 0 = library default */
     uint32_t flags;            /* ZRK_OPT_* */
-    int32_t waves;             /* > 1: split the batch into that many contiguous scenario ranges ("waves"), each uploaded,
-                                  initialised and stepped on its own CUDA stream, so that the host-to-device copy of a
-                                  wave overlaps the kernels of the waves before it.  zrk_create then returns without
+    int32_t waves;             /* > 1: split the batch into that many contiguous scenario ranges ("waves"), each uploaded
+                                  and initialised on its own CUDA stream, where the first kernels of the first zrk_step
+                                  are queued as well, so that the host-to-device copy of a wave overlaps the kernels of
+                                  the waves before it (later launches run over the whole batch).  zrk_create then returns without
                                   waiting: the arrays of the zrk_batch_desc must stay valid and unchanged until the first
                                   call that synchronises (zrk_sync or any zrk_read_*), and a per-scenario validation
                                   error is reported by that call (and by every call after it) instead of zrk_create.

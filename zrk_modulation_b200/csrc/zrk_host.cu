@@ -256,6 +256,7 @@ struct zrk_handle {
     std::vector<cudaStream_t> wave_stream;  // empty = everything on `stream`
     std::vector<int> wave_b;                // wave w covers scenarios [wave_b[w], wave_b[w + 1])
     std::vector<cudaEvent_t> wave_done;
+    bool stepped = false;  // zrk_step has run (the waves' streams matter to the first step only)
     cudaEvent_t fork_ev{};
     int *pin_err = nullptr;   // pinned: the init kernel's verdict when zrk_create did not wait for it
     bool deferred = false;    // that verdict has not been looked at yet
@@ -807,84 +808,81 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
         // the host looks at the pending counters after every few rounds.
         const int target = (int)(h->tick + n_ticks);
         streak_fn sf = pick_streak(h->P.lo);
-        // per wave: how many scenarios the last batch left pending (-1: all of the wave's range, no worklist yet),
-        // and which of the two worklist buffers holds them
-        std::vector<int> n_work(n_waves, -1), cur(n_waves, 0);
+        const int B = h->P.lo.B;
+        cudaStream_t ms = h->stream;
+        // Scenario waves: the first round after zrk_create runs wave by wave on the waves' streams, where their uploads
+        // and init kernels are queued (the copy of one wave overlaps the kernels of the waves before it); all waves
+        // append to ONE worklist, and every later round runs over the whole batch on the main stream.
+        bool fork_first = n_waves > 1 && !h->stepped;
+        h->stepped = true;
+        // how many scenarios the last batch of rounds left pending (-1: the whole batch, no worklist yet), and which of
+        // the two worklist buffers holds them
+        int n_work = -1, cur = 0;
         for (;;) {
             if (h->round_no + ZRK_ROUND_BATCH > ZRK_ROUND_SLOTS) {
-                for (int w = 0; w < n_waves; w++)
-                    CK(cudaMemsetAsync(h->d_pending + (size_t)w * ZRK_ROUND_SLOTS, 0, sizeof(int) * ZRK_ROUND_SLOTS,
-                                       n_waves > 1 ? h->wave_stream[w] : h->stream));
+                CK(cudaMemsetAsync(h->d_pending, 0, sizeof(int) * ZRK_ROUND_SLOTS, ms));
                 h->round_no = 0;
+                fork_first = false;  // (the waves' streams are not ordered behind this memset)
             }
-            for (int w = 0; w < n_waves; w++) {
-                if (n_work[w] == 0) continue;
-                const int b0 = n_waves > 1 ? h->wave_b[w] : 0, b1 = n_waves > 1 ? h->wave_b[w + 1] : h->P.lo.B;
-                cudaStream_t ws = n_waves > 1 ? h->wave_stream[w] : h->stream;
-                // Every round leaves the list of the scenarios still pending (device-side compaction through the round's
-                // pending counter) in the worklist buffer the next round reads; the host only learns its length after
-                // the batch, so the grids of a batch are sized for the last length it knows and the kernels look the
-                // real one up (work_n).
-                const int f0 = n_work[w] < 0 ? b0 : 0, f1 = n_work[w] < 0 ? b1 : n_work[w];  // index range of the launches
-                for (int r = 0; r < ZRK_ROUND_BATCH; r++) {
+            // Every round leaves the list of the scenarios still pending (device-side compaction through the round's
+            // pending counter) in the worklist buffer the next round reads; the host only learns its length after
+            // the batch, so the grids of a batch are sized for the last length it knows and the kernels look the
+            // real one up (work_n).
+            for (int r = 0; r < ZRK_ROUND_BATCH; r++) {
+                const bool listed = n_work >= 0 || r > 0;  // (the first round of a step looks at the whole range)
+                const int *wl = listed ? h->d_work + (size_t)cur * B : nullptr;
+                int *wl_out = h->d_work + (size_t)(cur ^ 1) * B;
+                int *pend = h->d_pending + h->round_no + r;
+                const int *wn = r > 0 ? pend - 1 : nullptr;  // (r = 0: the host knows the length)
+                const int g1 = n_work < 0 ? B : n_work;      // index range of the launches: [0, g1)
+                const int n_parts = !listed && fork_first ? n_waves : 1;
+                for (int w = 0; w < n_parts; w++) {
+                    const int p0 = n_parts > 1 ? h->wave_b[w] : 0, p1 = n_parts > 1 ? h->wave_b[w + 1] : g1;
+                    cudaStream_t ws = n_parts > 1 ? h->wave_stream[w] : ms;
                     cudaEvent_t e0, e1;
                     int rc;
                     if ((rc = get_event(h, &e0)) || (rc = get_event(h, &e1))) return rc;
-                    const bool listed = n_work[w] >= 0 || r > 0;  // (the first round of a step looks at the whole range)
-                    const int *wl = listed ? h->d_work + (size_t)cur[w] * h->P.lo.B + b0 : nullptr;
-                    int *wl_out = h->d_work + (size_t)(cur[w] ^ 1) * h->P.lo.B + b0;
-                    int *pend = h->d_pending + (size_t)w * ZRK_ROUND_SLOTS + h->round_no + r;
-                    const int *wn = r > 0 ? pend - 1 : nullptr;  // (r = 0: the host knows the length)
-                    const int g0 = listed ? 0 : f0, g1 = listed ? (n_work[w] < 0 ? b1 - b0 : n_work[w]) : f1;
                     CK(cudaEventRecord(e0, ws));
-                    ZRK_LAUNCH(sf, (g1 - g0 + ZRK_STREAK_WARPS - 1) / ZRK_STREAK_WARPS, 32 * ZRK_STREAK_WARPS, ZRK_STREAK_SMEM, ws, h->P,
-                               g0, g1, target, wl, wn);
-                    ZRK_LAUNCH(fn, (g1 - g0 + tpc - 1) / tpc, h->block, h->smem_bytes, ws, h->P, 0, g0, g1, target, pend, wl, wl_out, wn);
+                    ZRK_LAUNCH(sf, (p1 - p0 + ZRK_STREAK_WARPS - 1) / ZRK_STREAK_WARPS, 32 * ZRK_STREAK_WARPS, ZRK_STREAK_SMEM, ws, h->P, p0, p1,
+                               target, wl, wn);
+                    ZRK_LAUNCH(fn, (p1 - p0 + tpc - 1) / tpc, h->block, h->smem_bytes, ws, h->P, 0, p0, p1, target, pend, wl, wl_out, wn);
                     CK(cudaGetLastError());
                     CK(cudaEventRecord(e1, ws));
                     h->pending.push_back({e0, e1});
                     h->n_launches += 2;
-                    cur[w] ^= 1;
+                    if (n_parts > 1) {
+                        CK(cudaEventRecord(h->wave_done[w], ws));
+                        CK(cudaStreamWaitEvent(ms, h->wave_done[w], 0));
+                    }
                 }
-                CK(cudaMemcpyAsync(h->h_pending + w, h->d_pending + (size_t)w * ZRK_ROUND_SLOTS + h->round_no + ZRK_ROUND_BATCH - 1,
-                                   sizeof(int), cudaMemcpyDeviceToHost, ws));
+                cur ^= 1;
             }
+            fork_first = false;
+            CK(cudaMemcpyAsync(h->h_pending, h->d_pending + h->round_no + ZRK_ROUND_BATCH - 1, sizeof(int), cudaMemcpyDeviceToHost, ms));
             h->round_no += ZRK_ROUND_BATCH;
             h->n_rounds += ZRK_ROUND_BATCH;
-            bool more = false;
-            for (int w = 0; w < n_waves; w++) {
-                if (n_work[w] == 0) continue;
-                cudaStream_t ws = n_waves > 1 ? h->wave_stream[w] : h->stream;
-                CK(cudaStreamSynchronize(ws));
-                n_work[w] = h->h_pending[w];
-                const int span = (n_waves > 1 ? h->wave_b[w + 1] - h->wave_b[w] : h->P.lo.B);
-                if (n_work[w] > 0 && n_work[w] <= span / 64) {
-                    // the tail: a few scenarios with many rounds still to go (one tick per round, in the worst
-                    // case) are finished by one launch of the tick kernel on its own
-                    const int b0 = n_waves > 1 ? h->wave_b[w] : 0;
-                    cudaEvent_t e0, e1;
-                    int rc;
-                    if ((rc = get_event(h, &e0)) || (rc = get_event(h, &e1))) return rc;
-                    CK(cudaEventRecord(e0, ws));
-                    ZRK_LAUNCH(fn, (n_work[w] + tpc - 1) / tpc, h->block, h->smem_bytes, ws, h->P, 0, 0, n_work[w], target, (int *)nullptr,
-                               (const int *)(h->d_work + (size_t)cur[w] * h->P.lo.B + b0), (int *)nullptr, (const int *)nullptr);
-                    CK(cudaGetLastError());
-                    CK(cudaEventRecord(e1, ws));
-                    h->pending.push_back({e0, e1});
-                    h->n_launches++;
-                    n_work[w] = 0;
-                }
-                more = more || n_work[w] != 0;
+            CK(cudaStreamSynchronize(ms));
+            n_work = h->h_pending[0];
+            if (n_work > 0 && n_work <= B / 64) {
+                // the tail: a few scenarios with many rounds still to go (one tick per round, in the worst
+                // case) are finished by one launch of the tick kernel on its own
+                cudaEvent_t e0, e1;
+                int rc;
+                if ((rc = get_event(h, &e0)) || (rc = get_event(h, &e1))) return rc;
+                CK(cudaEventRecord(e0, ms));
+                ZRK_LAUNCH(fn, (n_work + tpc - 1) / tpc, h->block, h->smem_bytes, ms, h->P, 0, 0, n_work, target, (int *)nullptr,
+                           (const int *)(h->d_work + (size_t)cur * B), (int *)nullptr, (const int *)nullptr);
+                CK(cudaGetLastError());
+                CK(cudaEventRecord(e1, ms));
+                h->pending.push_back({e0, e1});
+                h->n_launches++;
+                n_work = 0;
             }
             if (h->pending.size() > 2048) {
                 int rc = resolve_events(h);
                 if (rc) return rc;
             }
-            if (!more) break;
-        }
-        for (int w = 0; w < n_waves && n_waves > 1; w++) {
-            CK(cudaEventRecord(h->wave_done[w], h->wave_stream[w]));
-            CK(cudaStreamWaitEvent(h->stream, h->wave_done[w], 0));
+            if (n_work == 0) break;
         }
         h->tick += n_ticks;
         if (!h->h_summary)

@@ -40,6 +40,7 @@ class Engine:
         opt.waves = waves  # > 1: upload / init / step in scenario waves on separate streams (see zrk_options.waves)
         self.log_types = log_types
         desc = batch.desc()
+        self._desc = desc  # (waves: the arrays it points to are read until the first sync)
         rc = self.lib.zrk_create(C.byref(desc), C.byref(opt), C.byref(self._h))
         if rc != 0:
             msg = self.lib.zrk_last_error(None)

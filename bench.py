@@ -293,24 +293,31 @@ def run_ours(args, rank, world, local_rank):
         t0 = time.perf_counter()
         eng = Engine(src, device=dev, ticks_per_launch=args.ticks_per_launch, waves=args.waves, certificate=not args.no_certificate,
                      **log_kw(ticks))
+        ta = time.perf_counter()
         eng.step(ticks)
+        tb = time.perf_counter()
         if result == "totals":
             out = eng.totals()           # batch totals reduced on the device: 22 words
         elif result == "counters":
             out = eng.counts()           # per-scenario message counters (B x 34 words)
         else:
             out = (eng.counts(), eng.records(0, B)[1])  # ... and every scenario's event records
+        tc = time.perf_counter()
         eng.close()                      # zrk_destroy is part of the step
         torch.cuda.synchronize()
         t1 = time.perf_counter()
+        e2e_parts.append((ta - t0, tb - ta, tc - tb, t1 - tc))  # host-side time in create / step / read / destroy
         barrier()
         return t1 - t0, out
+
+    e2e_parts = []
 
     e2e_s = []
     for i in range(args.warmup + args.steps):
         dt, tot = e2e_once(batch)
         if i >= args.warmup:
             e2e_s.append(dt)
+    e2e_breakdown = [round(float(np.mean([p[k] for p in e2e_parts[args.warmup:]])) * 1e3, 3) for k in range(4)]
     t_e2e = torch.tensor([sum(e2e_s)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
@@ -425,6 +432,7 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "object-updates/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t_e2e.item()) / args.steps * 1e3,
                     "waves": args.waves,
+                    "host_ms": dict(zip(("create", "step", "read", "destroy"), e2e_breakdown)),  # rank 0, where the host thread spends the step
                     "timed_region": "zrk_create from pinned host arrays (H2D) + zrk_step + zrk_read_totals (D2H) + zrk_destroy",
                     "variants": {k: dict(v, value=units_all / v["seconds"], ms_per_step=v["seconds"] * 1e3)
                                  for k, v in variants.items()}},

@@ -256,6 +256,9 @@ struct zrk_handle {
     std::vector<cudaStream_t> wave_stream;  // empty = everything on `stream`
     std::vector<int> wave_b;                // wave w covers scenarios [wave_b[w], wave_b[w + 1])
     std::vector<cudaEvent_t> wave_done;
+    bool defer_zero = false;                         // zrk_create: dev_alloc(zero) only notes the buffer ...
+    std::vector<std::pair<void *, size_t>> zero_list;  // ... and the memsets are queued after the last host synchronisation
+    cudaEvent_t alloc_ev = nullptr;
     bool stepped = false;  // zrk_step has run (the waves' streams matter to the first step only)
     cudaEvent_t fork_ev{};
     int *pin_err = nullptr;   // pinned: the init kernel's verdict when zrk_create did not wait for it
@@ -396,7 +399,12 @@ static int dev_alloc(zrk_handle *h, size_t n, T **dst, bool zero) {
     void *p = nullptr;
     int rc = pool_alloc(h, &p, (n ? n : 1) * sizeof(T));
     if (rc) return rc;
-    if (zero) CK(cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), h->stream));
+    if (zero) {
+        if (h->defer_zero)
+            h->zero_list.push_back({p, (n ? n : 1) * sizeof(T)});  // (zrk_create: queued once nothing has to wait for them)
+        else
+            CK(cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), h->stream));
+    }
     *dst = (T *)p;
     return ZRK_OK;
 }
@@ -447,6 +455,7 @@ extern "C" void zrk_destroy(zrk_handle *h) {
     }
     for (auto e : h->wave_done) cudaEventDestroy(e);
     if (!h->wave_stream.empty()) cudaEventDestroy(h->fork_ev);
+    if (h->alloc_ev) cudaEventDestroy(h->alloc_ev);
     pinned_put(h->pin_err, sizeof(int));
     pinned_put(h->h_pending, sizeof(int) * 64);
     pinned_put(h->h_totals, sizeof(unsigned long long) * ZRK_TOTALS_WORDS);
@@ -596,6 +605,7 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
         size_t per_scenario;  // bytes
     };
     std::vector<Field> fields;
+    h->defer_zero = true;
 #define UP(field, n)                                                                                   \
     if (d->field && (size_t)(n) != 0) {                                                                             \
         void *q_ = nullptr;                                                                            \
@@ -689,12 +699,21 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
         }
     }
 
-    // upload + init, wave by wave
+    // upload + init, wave by wave.  The buffers the init kernel fills are zeroed now, after the last host
+    // synchronisation above (nothing waited for the memsets); a wave's copies only need the allocations, its init
+    // kernel the memsets as well.
     if (n_waves > 1) {
         CK(pinned_get((void **)&h->pin_err, sizeof(int)));
         *h->pin_err = 0;
+        CK(cudaEventCreateWithFlags(&h->alloc_ev, cudaEventDisableTiming));
+        CK(cudaEventRecord(h->alloc_ev, h->stream));  // the allocations above
+    }
+    h->defer_zero = false;
+    for (auto &z : h->zero_list) CK(cudaMemsetAsync(z.first, 0, z.second, h->stream));
+    h->zero_list.clear();
+    if (n_waves > 1) {
         CK(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
-        CK(cudaEventRecord(h->fork_ev, h->stream));  // allocations and memsets above
+        CK(cudaEventRecord(h->fork_ev, h->stream));  // ... and the memsets
         for (int w = 0; w < n_waves; w++) {
             cudaStream_t ws;
             cudaEvent_t ev;
@@ -702,7 +721,7 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
             h->wave_stream.push_back(ws);
             CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             h->wave_done.push_back(ev);
-            CK(cudaStreamWaitEvent(ws, h->fork_ev, 0));
+            CK(cudaStreamWaitEvent(ws, h->alloc_ev, 0));
         }
     }
     for (int w = 0; w < n_waves; w++) {
@@ -711,6 +730,7 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
         for (const Field &f : fields)
             CK(cudaMemcpyAsync(f.dst + (size_t)b0 * f.per_scenario, f.src + (size_t)b0 * f.per_scenario,
                                (size_t)(b1 - b0) * f.per_scenario, cudaMemcpyHostToDevice, ws));
+        if (n_waves > 1) CK(cudaStreamWaitEvent(ws, h->fork_ev, 0));
         ZRK_LAUNCH(zrk_init_kernel, (b1 - b0 + ZRK_INIT_BLOCK / 32 - 1) / (ZRK_INIT_BLOCK / 32), ZRK_INIT_BLOCK, 0, ws, P, dd, derr, b0, b1);
         CK(cudaGetLastError());
         if (n_waves > 1) {

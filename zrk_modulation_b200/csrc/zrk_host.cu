@@ -266,6 +266,8 @@ struct zrk_handle {
     int sticky_rc = ZRK_OK;   // a deferred create error: every later call returns it
     // two-kernel stepping (warp teams with the certificate): rounds of streak kernel + tick kernel
     bool two_kernel = false;
+    int *d_queue = nullptr;    // [ZRK_ROUND_SLOTS + 64] the work-queue counters of the streak kernel's launches (one per round; + one per wave)
+    int n_sms = 0;
     int *d_pending = nullptr;  // [waves][ZRK_ROUND_SLOTS] scenarios still short of the target after a round
     int *h_pending = nullptr;  // pinned [waves]
     int *d_work = nullptr;     // [2][B] worklists: the scenarios a batch of rounds found pending (per wave: its own range)
@@ -410,7 +412,7 @@ static int dev_alloc(zrk_handle *h, size_t n, T **dst, bool zero) {
 }
 
 typedef void (*tick_fn)(const Params, int, int, int, int, int *, const int *, int *, const int *);
-typedef void (*streak_fn)(const Params, int, int, int, const int *, const int *);
+typedef void (*streak_fn)(const Params, int, int, int, const int *, const int *, int *);
 
 template <int TEAM, int TPC, int MPB>
 static tick_fn pick_fast(bool fast) {
@@ -694,6 +696,8 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
         h->two_kernel = lo.team == 32 && P.cert && h->fast && !(env && atoi(env) == 0);
         if (h->two_kernel) {
             if ((rc = dev_alloc(h, (size_t)n_waves * ZRK_ROUND_SLOTS, &h->d_pending, true)) != ZRK_OK) return rc;
+            if ((rc = dev_alloc(h, (size_t)ZRK_ROUND_SLOTS + 64, &h->d_queue, true)) != ZRK_OK) return rc;
+            CK(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, h->device));
             CK(pinned_get((void **)&h->h_pending, sizeof(int) * 64));
             if ((rc = dev_alloc(h, (size_t)2 * B, &h->d_work, false)) != ZRK_OK) return rc;
         }
@@ -841,6 +845,7 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
         for (;;) {
             if (h->round_no + ZRK_ROUND_BATCH > ZRK_ROUND_SLOTS) {
                 CK(cudaMemsetAsync(h->d_pending, 0, sizeof(int) * ZRK_ROUND_SLOTS, ms));
+                CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int) * (ZRK_ROUND_SLOTS + 64), ms));
                 h->round_no = 0;
                 fork_first = false;  // (the waves' streams are not ordered behind this memset)
             }
@@ -863,8 +868,10 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
                     int rc;
                     if ((rc = get_event(h, &e0)) || (rc = get_event(h, &e1))) return rc;
                     CK(cudaEventRecord(e0, ws));
-                    ZRK_LAUNCH(sf, (p1 - p0 + ZRK_STREAK_WARPS - 1) / ZRK_STREAK_WARPS, 32 * ZRK_STREAK_WARPS, ZRK_STREAK_SMEM, ws, h->P, p0, p1,
-                               target, wl, wn);
+                    // (persistent: at most the CTAs the SMs hold at once; every warp draws scenarios from the launch's queue)
+                    const int s_ctas = std::min((p1 - p0 + ZRK_STREAK_WARPS - 1) / ZRK_STREAK_WARPS, std::max(h->n_sms, 1) * ZRK_STREAK_MINB);
+                    ZRK_LAUNCH(sf, s_ctas, 32 * ZRK_STREAK_WARPS, ZRK_STREAK_SMEM, ws, h->P, p0, p1, target, wl, wn,
+                               h->d_queue + (n_parts > 1 ? ZRK_ROUND_SLOTS + w : h->round_no + r));
                     ZRK_LAUNCH(fn, (p1 - p0 + tpc - 1) / tpc, h->block, h->smem_bytes, ws, h->P, 0, p0, p1, target, pend, wl, wl_out, wn);
                     CK(cudaGetLastError());
                     CK(cudaEventRecord(e1, ws));
@@ -1640,6 +1647,7 @@ extern "C" int zrk_load_state(zrk_handle *h, const void *buf, size_t bytes) {
     h->tick = sh.tick;
     h->round_no = 0;
     if (h->d_pending) CK(cudaMemset(h->d_pending, 0, sizeof(int) * ZRK_ROUND_SLOTS * (h->wave_stream.empty() ? 1 : h->wave_stream.size())));
+    if (h->d_queue) CK(cudaMemset(h->d_queue, 0, sizeof(int) * (ZRK_ROUND_SLOTS + 64)));
     return ensure_tsec(h, h->tick + 2);
 }
 

@@ -2940,19 +2940,10 @@ __global__ void ZRK_KERNEL_ATTR zrk_tick_kernel(const Params P, int n_ticks, int
 #define ZRK_STREAK_MINB 4 /* resident CTAs per SM the register allocation is bounded for: 128 registers (the lean loop spills at 96: 36.3 vs 35.7 ms per c5 step) */
 #endif
 #define ZRK_STREAK_SMEM (ZRK_STREAK_WARPS * (2 * 32 * 16 + 32 * 8 + ZRK_RREC_DOUBLES * 8))
+// One scenario's turn in the streak kernel (warp w of the CTA, scratch: the CTA's shared memory).
 template <int MPB>
-__global__ void __launch_bounds__(32 * ZRK_STREAK_WARPS, ZRK_STREAK_MINB) zrk_streak_kernel(const Params P, int b_first, int b_end, int target_tick,
-                                                                                           const int *work, const int *work_n) {
+__device__ __forceinline__ void streak_scenario(const Params &P, int b, int target_tick, int w, int lane, float4 *scratch) {
     const Layout &o = P.lo;
-    ZRK_SMEM_DECL;  // ZRK_STREAK_SMEM bytes: per warp, two rows of fp32 images for a window rebuild inside a streak
-    float4 *const scratch = (float4 *)zrk_smem;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int b = b_first + blockIdx.x * ZRK_STREAK_WARPS + w;
-    if (b >= b_end) return;
-    if (work) {  // (the scenarios the last round found pending; work_n: how many, if the host only knows an upper bound)
-        if (work_n && b - b_first >= *work_n) return;
-        b = work[b - b_first];
-    }
     unsigned char *sm = P.dyn + (size_t)b * o.dyn_bytes;
     const unsigned char *cs = P.cst + (size_t)b * o.cst_bytes;
     Hot<32> H;
@@ -2979,6 +2970,28 @@ __global__ void __launch_bounds__(32 * ZRK_STREAK_WARPS, ZRK_STREAK_MINB) zrk_st
         int hold = (f >> CF_HOLD_SHIFT) & 127;
         hold = fit && done == 0 ? (hold ? (hold * 2 > 64 ? 64 : hold * 2) : 1) : (done >= 4 ? 0 : hold);
         *H.c_flag() = (f & ((1 << CF_HOLD_SHIFT) - 1)) | (hold << CF_HOLD_SHIFT) | CF_GENERAL;
+    }
+}
+// The kernel is persistent: the grid is sized for the SMs, and every warp draws scenarios from a queue (*queue: a
+// counter the host has zeroed) until it is empty — streaks differ in length by two orders of magnitude, and a warp that
+// is done early would otherwise leave its slot idle until the slowest warp of its CTA has finished.
+// The scenarios: [b_first, b_end), or — work given — the entries [0, b_end - b_first) of that list (work_n, may be null:
+// where the device keeps the length of the list, when the host only knows an upper bound of it).
+template <int MPB>
+__global__ void __launch_bounds__(32 * ZRK_STREAK_WARPS, ZRK_STREAK_MINB) zrk_streak_kernel(const Params P, int b_first, int b_end, int target_tick,
+                                                                                           const int *work, const int *work_n, int *queue) {
+    ZRK_SMEM_DECL;  // ZRK_STREAK_SMEM bytes: per warp, two rows of fp32 images for a window rebuild inside a streak
+    float4 *const scratch = (float4 *)zrk_smem;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int n = b_end - b_first;
+    if (work && work_n && *work_n < n) n = *work_n;
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(queue, 1);
+        i = __shfl_sync(ZRK_FULL, i, 0);
+        if (i >= n) break;
+        streak_scenario<MPB>(P, work ? work[i] : b_first + i, target_tick, w, lane, scratch);
+        __syncwarp();  // (the warp's scratch is the next scenario's)
     }
 }
 

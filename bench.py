@@ -211,6 +211,31 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_host_thread(local_rank, local_world):
+    """Pins this rank's host thread to its own share of the cores next to its GPU (NVML's CPU affinity of the device =
+    the GPU's NUMA node), so that eight ranks feeding eight GPUs neither migrate nor share cores while they enqueue
+    the copies and launches of a step.  Returns what was done (for the bench line), or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        near = sorted(c for c in os.sched_getaffinity(0) if (mask[c // 64] >> (c % 64)) & 1)
+        if not near:
+            return None
+        # the ranks whose GPUs share this core set split it evenly
+        same = [r for r in range(local_world)
+                if list(pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(r), words)) == list(mask)]
+        per = max(1, len(near) // max(1, len(same)))
+        k = same.index(local_rank) if local_rank in same else 0
+        mine = near[k * per:(k + 1) * per] or near
+        os.sched_setaffinity(0, mine)
+        return {"cores": [mine[0], mine[-1]], "n": len(mine), "of_gpu_node": len(near)}
+    except Exception as e:  # no NVML, fewer devices than ranks, a restricted cpuset ...
+        return {"error": str(e)[:80]}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -221,6 +246,7 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = local_rank
+    host_binding = bind_host_thread(local_rank, world) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
     _cabi.load()
@@ -431,7 +457,7 @@ def run_ours(args, rank, world, local_rank):
             "certified_tick_fraction": cert_ticks / float(B * ticks),  # rank 0's shard: ticks whose link_object scan was proven away
             "e2e": {"value": e2e_value, "unit": "object-updates/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t_e2e.item()) / args.steps * 1e3,
-                    "waves": args.waves,
+                    "waves": args.waves, "host_binding": host_binding,
                     "host_ms": dict(zip(("create", "step", "read", "destroy"), e2e_breakdown)),  # rank 0, where the host thread spends the step
                     "timed_region": "zrk_create from pinned host arrays (H2D) + zrk_step + zrk_read_totals (D2H) + zrk_destroy",
                     "variants": {k: dict(v, value=units_all / v["seconds"], ms_per_step=v["seconds"] * 1e3)

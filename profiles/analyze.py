@@ -17,7 +17,11 @@ MARKS = [("helpers (dot3, pymod, tsec)", None), ("radar_sees", "SectorRadar.find
          ("put_rec", "record log"), ("missile_solve", "Missile._calculate_trajectory_params"),
          ("views", "shared-memory views"), ("calc_range/link_exact", "CCP.link_object"),
          ("link_eval", "State of the squared-domain scan"), ("link_d2 (fp64 pair distance)", "double link_d2("), ("link scan (fp32 filter + loop)", "fp32 pre-filter of the scan"),
-         ("association certificate", "---- association certificate"), ("quiet streak", "---- quiet streak"),
+         ("association certificate", "---- association certificate"), ("streak: rival check, sweep", "---- quiet streak"),
+         ("streak: lean loop, one tick per pass", "struct StreakLane {"), ("streak: lean loop, two ticks per pass", "// The lean loop for the commonest shape"),
+         ("streak: frozen slots, event records", "// AirEnv.py:33-40 inside a streak"),
+         ("streak: entry (state from the blob)", "__device__ __forceinline__ int quiet_streak("),
+         ("streak: careful tick", "const double now_next = tick_seconds(P, tick + 1);"), ("streak: commit, write-back", "// ---- commit"),
          ("serial_section", "lane 0 alone: launchers"), ("kernel prologue", "---- the kernel"),
          ("tick head", "for (int it = 0; it < n_ticks; it++)"), ("AirEnv.step", "AirEnv.step (AirEnv.py:26-53)"),
          ("Missile.step", "Missile.step, status 'active'"), ("radar loop", "SectorRadar.step for every radar"),
@@ -82,13 +86,13 @@ def main():
                 pass
     tot = sum(a[0] for a in agg.values()) or 1
     ts = sum(a[1] for a in agg.values()) or 1
-    print("\nregion                          inst%   stall-samples%")
+    print("\nregion                                  inst%   stall-samples%")
     for (name, a), (_, b) in zip(marks[:-1], marks[1:]):
         i = sum(v[0] for (f, l), v in agg.items() if f == "zrk_tick.cuh" and a <= l < b)
         s = sum(v[1] for (f, l), v in agg.items() if f == "zrk_tick.cuh" and a <= l < b)
-        print(f"{name:30s} {100 * i / tot:6.1f} {100 * s / ts:8.1f}")
+        print(f"{name:38s} {100 * i / tot:6.1f} {100 * s / ts:8.1f}")
     i = sum(v[0] for (f, l), v in agg.items() if f != "zrk_tick.cuh")
-    print(f"{'other files (intrinsics, libm)':30s} {100 * i / tot:6.1f}")
+    print(f"{'other files (intrinsics, libm)':38s} {100 * i / tot:6.1f}")
 
 
 if __name__ == "__main__":

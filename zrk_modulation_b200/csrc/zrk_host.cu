@@ -834,6 +834,8 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
         streak_fn sf = pick_streak(h->P.lo);
         const int B = h->P.lo.B;
         cudaStream_t ms = h->stream;
+        static const int round_batch = getenv("ZRK_ROUND_BATCH") ? std::max(1, atoi(getenv("ZRK_ROUND_BATCH"))) : ZRK_ROUND_BATCH;
+        static const int tail_div = getenv("ZRK_TAIL_DIV") ? std::max(1, atoi(getenv("ZRK_TAIL_DIV"))) : 64;
         // Scenario waves: the first round after zrk_create runs wave by wave on the waves' streams, where their uploads
         // and init kernels are queued (the copy of one wave overlaps the kernels of the waves before it); all waves
         // append to ONE worklist, and every later round runs over the whole batch on the main stream.
@@ -843,7 +845,7 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
         // the two worklist buffers holds them
         int n_work = -1, cur = 0;
         for (;;) {
-            if (h->round_no + ZRK_ROUND_BATCH > ZRK_ROUND_SLOTS) {
+            if (h->round_no + round_batch > ZRK_ROUND_SLOTS) {
                 CK(cudaMemsetAsync(h->d_pending, 0, sizeof(int) * ZRK_ROUND_SLOTS, ms));
                 CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int) * (ZRK_ROUND_SLOTS + 64), ms));
                 h->round_no = 0;
@@ -853,7 +855,7 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
             // pending counter) in the worklist buffer the next round reads; the host only learns its length after
             // the batch, so the grids of a batch are sized for the last length it knows and the kernels look the
             // real one up (work_n).
-            for (int r = 0; r < ZRK_ROUND_BATCH; r++) {
+            for (int r = 0; r < round_batch; r++) {
                 const bool listed = n_work >= 0 || r > 0;  // (the first round of a step looks at the whole range)
                 const int *wl = listed ? h->d_work + (size_t)cur * B : nullptr;
                 int *wl_out = h->d_work + (size_t)(cur ^ 1) * B;
@@ -885,12 +887,12 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
                 cur ^= 1;
             }
             fork_first = false;
-            CK(cudaMemcpyAsync(h->h_pending, h->d_pending + h->round_no + ZRK_ROUND_BATCH - 1, sizeof(int), cudaMemcpyDeviceToHost, ms));
-            h->round_no += ZRK_ROUND_BATCH;
-            h->n_rounds += ZRK_ROUND_BATCH;
+            CK(cudaMemcpyAsync(h->h_pending, h->d_pending + h->round_no + round_batch - 1, sizeof(int), cudaMemcpyDeviceToHost, ms));
+            h->round_no += round_batch;
+            h->n_rounds += round_batch;
             CK(cudaStreamSynchronize(ms));
             n_work = h->h_pending[0];
-            if (n_work > 0 && n_work <= B / 64) {
+            if (n_work > 0 && n_work <= B / tail_div) {
                 // the tail: a few scenarios with many rounds still to go (one tick per round, in the worst
                 // case) are finished by one launch of the tick kernel on its own
                 cudaEvent_t e0, e1;

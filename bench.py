@@ -250,7 +250,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
     _cabi.load()
-    batch, ticks = make_batch(args.workload, rank, pinned=True)
+    batch, ticks = make_batch(args.workload, rank + args.shard_offset, pinned=True)
     if args.ticks:
         ticks = args.ticks
     B, NS = batch.n_scenarios, batch.n_slots
@@ -353,7 +353,7 @@ def run_ours(args, rank, world, local_rank):
     # per-scenario counters as the result; counters + every scenario's event records
     variants = {}
     if not args.no_variants:
-        pageable, _ = make_batch(args.workload, rank, pinned=False)
+        pageable, _ = make_batch(args.workload, rank + args.shard_offset, pinned=False)
         rec_bytes = None
         for name, src, res in (("pageable_inputs", pageable, "totals"), ("per_scenario_counters", batch, "counters"),
                                ("counters_and_event_records", batch, "records")):
@@ -523,6 +523,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra end-to-end variants and the other workloads")
     ap.add_argument("--no-certificate", action="store_true", help="A/B: always run CCP.link_object's scan (ZRK_OPT_NO_CERTIFICATE)")
+    ap.add_argument("--shard-offset", type=int, default=0, help="run the scenario shard of rank + this (to look at another rank's data on one GPU)")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

@@ -15,6 +15,7 @@
 #endif
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -337,6 +338,60 @@ static void pinned_put(void *p, size_t bytes) {
     cudaFreeHost(p);
 }
 
+// Streams and events are kept for the next handle of the process as well (a handle created per step creates nine
+// streams and some forty events otherwise): idle ones, per device; a stream is only put back once it has drained.
+#define ZRK_STREAMS_KEEP 80
+#define ZRK_EVENTS_KEEP 512
+#define ZRK_CACHE_DEVICES 64
+static std::vector<cudaStream_t> g_streams_free[ZRK_CACHE_DEVICES];
+static std::vector<cudaEvent_t> g_events_free[ZRK_CACHE_DEVICES][2];  // [device][timing?]
+static cudaError_t stream_get(int dev, cudaStream_t *st) {
+    if (dev >= 0 && dev < ZRK_CACHE_DEVICES) {
+        std::lock_guard<std::mutex> g(g_pinned_mu);
+        auto &v = g_streams_free[dev];
+        if (!v.empty()) {
+            *st = v.back();
+            v.pop_back();
+            return cudaSuccess;
+        }
+    }
+    return cudaStreamCreateWithFlags(st, cudaStreamNonBlocking);
+}
+static void stream_put(int dev, cudaStream_t st) {  // (the caller has synchronised it)
+    if (dev >= 0 && dev < ZRK_CACHE_DEVICES) {
+        std::lock_guard<std::mutex> g(g_pinned_mu);
+        if (g_streams_free[dev].size() < ZRK_STREAMS_KEEP) {
+            g_streams_free[dev].push_back(st);
+            return;
+        }
+    }
+    cudaStreamDestroy(st);
+}
+static cudaError_t event_get(int dev, bool timing, cudaEvent_t *e) {
+    if (dev >= 0 && dev < ZRK_CACHE_DEVICES) {
+        std::lock_guard<std::mutex> g(g_pinned_mu);
+        auto &v = g_events_free[dev][timing ? 1 : 0];
+        if (!v.empty()) {
+            *e = v.back();
+            v.pop_back();
+            return cudaSuccess;
+        }
+    }
+    return timing ? cudaEventCreate(e) : cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+}
+static void event_put(int dev, bool timing, cudaEvent_t e) {  // (whatever it was recorded on has completed)
+    if (!e) return;
+    if (dev >= 0 && dev < ZRK_CACHE_DEVICES) {
+        std::lock_guard<std::mutex> g(g_pinned_mu);
+        auto &v = g_events_free[dev][timing ? 1 : 0];
+        if (v.size() < ZRK_EVENTS_KEEP) {
+            v.push_back(e);
+            return;
+        }
+    }
+    cudaEventDestroy(e);
+}
+
 // Stream-ordered allocations from a memory pool of the library's own (one per device, created on first
 // use), which keeps freed memory: creating and destroying handles in a loop then costs no cudaMalloc /
 // cudaFree, and the device's default pool — the host application's — is left as it was.
@@ -366,6 +421,17 @@ static int pool_alloc(zrk_handle *h, void **p, size_t bytes) {
     return ZRK_OK;
 }
 extern "C" int zrk_release_cached_memory(void) {
+    {
+        std::lock_guard<std::mutex> g(g_pinned_mu);
+        for (int d = 0; d < ZRK_CACHE_DEVICES; d++) {
+            for (auto st : g_streams_free[d]) cudaStreamDestroy(st);
+            g_streams_free[d].clear();
+            for (int k = 0; k < 2; k++) {
+                for (auto e : g_events_free[d][k]) cudaEventDestroy(e);
+                g_events_free[d][k].clear();
+            }
+        }
+    }
     std::lock_guard<std::mutex> g(g_pool_mu);
     for (int d = 0; d < ZRK_MAX_DEVICES; d++)
         if (g_pool_ok[d] && cudaMemPoolTrimTo(g_pool[d], 0) != cudaSuccess) return ZRK_ERR_CUDA;
@@ -446,25 +512,23 @@ extern "C" void zrk_destroy(zrk_handle *h) {
     }
     DeviceGuard dev_guard(h->device);
     cudaStreamSynchronize(h->stream);
+    for (auto ws : h->wave_stream) cudaStreamSynchronize(ws);
     for (auto &pr : h->pending) {
-        cudaEventDestroy(pr.first);
-        cudaEventDestroy(pr.second);
+        event_put(h->device, true, pr.first);
+        event_put(h->device, true, pr.second);
     }
-    for (auto e : h->free_events) cudaEventDestroy(e);
-    for (auto ws : h->wave_stream) {
-        cudaStreamSynchronize(ws);
-        cudaStreamDestroy(ws);
-    }
-    for (auto e : h->wave_done) cudaEventDestroy(e);
-    if (!h->wave_stream.empty()) cudaEventDestroy(h->fork_ev);
-    if (h->alloc_ev) cudaEventDestroy(h->alloc_ev);
+    for (auto e : h->free_events) event_put(h->device, true, e);
+    for (auto ws : h->wave_stream) stream_put(h->device, ws);
+    for (auto e : h->wave_done) event_put(h->device, false, e);
+    if (!h->wave_stream.empty()) event_put(h->device, false, h->fork_ev);
+    event_put(h->device, false, h->alloc_ev);
     pinned_put(h->pin_err, sizeof(int));
     pinned_put(h->h_pending, sizeof(int) * 64);
     pinned_put(h->h_totals, sizeof(unsigned long long) * ZRK_TOTALS_WORDS);
     pinned_put(h->h_summary, (size_t)h->P.lo.B * ZRK_SUMMARY_WORDS * sizeof(int));
     for (void *p : h->allocs) cudaFreeAsync(p, h->stream);
     cudaStreamSynchronize(h->stream);
-    cudaStreamDestroy(h->stream);
+    stream_put(h->device, h->stream);
     delete h;
 }
 
@@ -513,7 +577,17 @@ static int init_verdict(zrk_handle *h, int herr) {
     return ZRK_OK;
 }
 
+// ZRK_TRACE_HOST=1: where the host thread spends zrk_create (microseconds since its start, to stderr)
+struct HostTrace {
+    bool on = getenv("ZRK_TRACE_HOST") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char *what) const {
+        if (on) fprintf(stderr, "zrk_create %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
+
 static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options *opt) {
+    HostTrace trace;
     if (d->abi_version != ZRK_ABI_VERSION) {
         h->err = "zrk_batch_desc.abi_version mismatch";
         return ZRK_ERR_ARG;
@@ -562,7 +636,7 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
         return ZRK_ERR_ARG;
     }
     CK(cudaSetDevice(h->device));
-    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(stream_get(h->device, &h->stream));
     h->has_stream = true;
     h->hd = *d;
     Params &P = h->P;
@@ -597,6 +671,7 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
         n_waves = (int)h->wave_b.size() - 1;
     }
 
+    trace.mark("layout, stream");
     DevDesc dd{};
     dd.B = B; dd.T = T; dd.R = R; dd.L = L; dd.M = M; dd.C = C;
     int rc;
@@ -626,6 +701,7 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
     UP(ccp_launcher_id, C); UP(ccp_launcher_pos, (size_t)C * 3);
 #undef UP
     const size_t n_desc_allocs = h->allocs.size();
+    trace.mark("description allocations");
     if (d->noise) {
         P.noise_period = d->noise_period;
         P.noise_radars = d->noise_radars;
@@ -663,6 +739,7 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
         size_t n = (size_t)P.mask_ticks * B * (1 + lo.RP) * P.mask_words;
         if ((rc = dev_alloc(h, n, &P.masks, true)) != ZRK_OK) return rc;
     }
+    trace.mark("noise upload + bound, state allocations");
     int *derr = nullptr;
     if ((rc = dev_alloc(h, 1, &derr, true)) != ZRK_OK) return rc;
     if ((rc = dev_alloc(h, (size_t)B * ZRK_SUMMARY_WORDS, &h->d_summary, false)) != ZRK_OK) return rc;
@@ -690,7 +767,9 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
         if (pct < 8) pct = 8;
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
+    trace.mark("kernel attributes");
     if ((rc = ensure_tsec(h, 1024)) != ZRK_OK) return rc;
+    trace.mark("clock table + params (2 syncs)");
     {
         const char *env = getenv("ZRK_TWO_KERNEL");
         h->two_kernel = lo.team == 32 && P.cert && h->fast && !(env && atoi(env) == 0);
@@ -703,27 +782,28 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
         }
     }
 
+    trace.mark("round buffers");
     // upload + init, wave by wave.  The buffers the init kernel fills are zeroed now, after the last host
     // synchronisation above (nothing waited for the memsets); a wave's copies only need the allocations, its init
     // kernel the memsets as well.
     if (n_waves > 1) {
         CK(pinned_get((void **)&h->pin_err, sizeof(int)));
         *h->pin_err = 0;
-        CK(cudaEventCreateWithFlags(&h->alloc_ev, cudaEventDisableTiming));
+        CK(event_get(h->device, false, &h->alloc_ev));
         CK(cudaEventRecord(h->alloc_ev, h->stream));  // the allocations above
     }
     h->defer_zero = false;
     for (auto &z : h->zero_list) CK(cudaMemsetAsync(z.first, 0, z.second, h->stream));
     h->zero_list.clear();
     if (n_waves > 1) {
-        CK(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+        CK(event_get(h->device, false, &h->fork_ev));
         CK(cudaEventRecord(h->fork_ev, h->stream));  // ... and the memsets
         for (int w = 0; w < n_waves; w++) {
             cudaStream_t ws;
             cudaEvent_t ev;
-            CK(cudaStreamCreateWithFlags(&ws, cudaStreamNonBlocking));
+            CK(stream_get(h->device, &ws));
             h->wave_stream.push_back(ws);
-            CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            CK(event_get(h->device, false, &ev));
             h->wave_done.push_back(ev);
             CK(cudaStreamWaitEvent(ws, h->alloc_ev, 0));
         }
@@ -742,6 +822,7 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
             CK(cudaStreamWaitEvent(h->stream, h->wave_done[w], 0));
         }
     }
+    trace.mark("streams, copies, init queued");
     // small host copies used by zrk_read_messages
     h->h_radar_id.assign(d->radar_id ? d->radar_id : nullptr, d->radar_id ? d->radar_id + (size_t)B * R : nullptr);
     h->h_n_radars.resize(B);
@@ -750,6 +831,7 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
         h->h_n_radars[b] = d->n_radars ? d->n_radars[b] : R;
         h->h_airenv_id[b] = d->airenv_id ? d->airenv_id[b] : 1;
     }
+    trace.mark("host copies of ids");
     if (n_waves > 1) {
         // do not wait: the verdict of the init kernel is looked at by the first call that synchronises
         CK(cudaMemcpyAsync(h->pin_err, derr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -805,7 +887,7 @@ static int get_event(zrk_handle *h, cudaEvent_t *e) {
         h->free_events.pop_back();
         return ZRK_OK;
     }
-    CK(cudaEventCreate(e));
+    CK(event_get(h->device, true, e));
     return ZRK_OK;
 }
 

@@ -156,3 +156,21 @@ def test_large_teams_odd_and_even_radar_counts(lib, shape):
     B, T, R, L, mpl, ticks, box = shape
     b = synthetic_batch(B, T, n_radars=R, n_launchers=L, missiles_per_launcher=mpl, seed0=7 * T, noise_period=8, box_km=box)
     check_batch_full(b, ticks, lib=lib, ticks_per_launch=3)
+
+
+def test_many_steps_of_rounds_and_waves(lib):
+    """Two-kernel stepping over more zrk_step calls than there are per-round counters (pending, work queue: 1024 slots,
+    6 per step), plain and created in scenario waves (only the first round is forked): counts and faults against
+    the oracle."""
+    from oracle import oracle as O
+    b = synthetic_batch(8, 24, n_radars=1, n_launchers=2, missiles_per_launcher=4, seed0=77000)
+    steps, per = 175, 8
+    oc, ofc, oft = O.run_batch(b, 0, b.n_scenarios, steps * per, n_threads=2)
+    for waves in (0, 2):
+        with Engine(b, waves=waves, lib=lib) as eng:
+            for _ in range(steps):
+                eng.step(per)
+            fc, ft, nr = eng.status()
+            counts = eng.counts()
+        assert np.array_equal(fc & 63, ofc) and np.array_equal(ft, oft), f"faults differ (waves={waves})"
+        assert np.array_equal(counts, oc), f"message counts differ (waves={waves})"

@@ -193,3 +193,23 @@ def test_c_abi_from_plain_c(tmp_path):
     assert [int(x) for x in out[0].split()] == list(g["counts"])
     assert out[1] == "total 685"
     assert out[2:] == ["detonate tick 11 missile 3005 target 40", "detonate tick 13 missile 4005 target 39"]
+
+
+@pytest.mark.gpu
+def test_many_steps_of_rounds_and_waves():
+    """Two-kernel stepping over many zrk_step calls: the per-round counters (pending, work queue) are used up and
+    reset on the way (1024 slots, 6 per step), and a handle created in scenario waves forks only its first round —
+    counts and faults of every scenario against the oracle either way."""
+    b = synthetic_batch(512, 24, n_radars=1, n_launchers=2, missiles_per_launcher=4, seed0=77000)
+    steps, per = 200, 8
+    oc, ofc, oft = O.run_batch(b, 0, b.n_scenarios, steps * per, n_threads=8)
+    for waves in (0, 4):
+        with Engine(b, waves=waves) as eng:
+            for _ in range(steps):
+                eng.step(per)
+            fc, ft, nr = eng.status()
+            counts = eng.counts()
+            n_launch, ms = eng.launch_stats()
+        assert np.array_equal(fc & 63, ofc) and np.array_equal(ft, oft), f"faults differ (waves={waves})"
+        assert np.array_equal(counts, oc), f"message counts differ (waves={waves})"
+        assert n_launch >= 2 * 6 * steps  # (rounds of two launches, not one launch per step)

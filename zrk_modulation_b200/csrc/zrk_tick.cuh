@@ -1503,6 +1503,14 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
     int *const hdr = H.hdr();
     int *const c_in = H.c_in(), *const c_out = H.c_out(), *const c_refc = H.c_refc();
     const int *chdr = (const int *)(cs + o.c_hdr);
+    // Everything a lane reads of its own slot is asked for at once, before any of it is looked at (every array of the
+    // hot layout has TEAM entries: a lane beyond the scenario's slots reads padding, and drops it below) — a streak that
+    // begins in HBM (the streak kernel) then waits for one round trip to memory instead of a chain of them.
+    const int fl_raw = H.sflags()[lane], own_raw = H.own()[lane];
+    const double2 ld_a = H.pxy()[lane], ld_c = H.pzs()[lane], ld_q = H.qxy()[lane], ld_w = H.qzw()[lane];
+    const double2 ld_s0 = H.txy()[lane], ld_s1 = H.tzt()[lane], ld_v = H.vxy()[lane];
+    const int te_ref_raw = H.te_ref()[lane];
+    const int cin_raw = c_in[lane], cout_raw = c_out[lane], refc_raw = c_refc[lane];
     const int nR = chdr[C_NR], T = o.T, tick_limit = chdr[C_TICK_LIMIT], n_slots = hdr[H_NSLOTS];
     // (the lane's state in plain variables: the record lean_run works on is filled in around its call only, so that
     // the careful tick below does not go through local memory for every value)
@@ -1512,35 +1520,30 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
     noise_w = noise_w0;
     mt = P.masks ? tick % P.mask_ticks : 0;
     const bool nolaunch = hdr[H_FREECAP] <= 0;
-    int fl = lane < n_slots ? H.sflags()[lane] : 0;
+    int fl = lane < n_slots ? fl_raw : 0;
     bool alive = (fl & F_ALIVE) != 0, msl = alive && (fl & F_MISSILE);
     // lanes the streak cannot carry at all
     bool bail0 = (fl & F_PENDING) != 0 || (alive && !(fl & F_HASPREV)) || (TEAM > 32 && msl);
     px = 0, py = 0, pz = 0, qx = 0, qy = 0, qz = 0, sx = 0, sy = 0, sz = 0, t0 = 0, vx = 0, vy = 0, vz = 0, speed = 0;
     if (lane < n_slots) {
-        const double2 a = H.pxy()[lane], c = H.pzs()[lane];
-        px = a.x, py = a.y, pz = c.x, speed = c.y;
-    }
-    if (lane < n_slots) {
-        const double2 q = H.qxy()[lane], w = H.qzw()[lane];
-        qx = q.x, qy = q.y, qz = w.x, vz = w.y;
+        px = ld_a.x, py = ld_a.y, pz = ld_c.x, speed = ld_c.y;
+        qx = ld_q.x, qy = ld_q.y, qz = ld_w.x, vz = ld_w.y;
     }
     if (alive) {
-        const double2 s0 = H.txy()[lane], s1 = H.tzt()[lane], v = H.vxy()[lane];
-        sx = s0.x, sy = s0.y, sz = s1.x, t0 = s1.y;
-        vx = v.x, vy = v.y;
+        sx = ld_s0.x, sy = ld_s0.y, sz = ld_s1.x, t0 = ld_s1.y;
+        vx = ld_v.x, vy = ld_v.y;
     }
     if (TEAM == 32 && !alive) sx = px, sy = py, sz = pz, vx = 0.0, vy = 0.0, vz = 0.0;  // as a trajectory: it stays where it is
     // tracks number `lane` of the two dicts: the slots they follow (fixed during a streak)
     const int n_te = hdr[H_NTE], n_me = hdr[H_NME];
-    const int r_te = lane < n_te ? H.te_ref()[lane] : 0, r_me = lane < n_me ? ZRK_QME_I(me_ref)[lane] : 0;
+    const int r_te = lane < n_te ? te_ref_raw : 0, r_me = lane < n_me ? ZRK_QME_I(me_ref)[lane] : 0;
     // the own track
     bool seed_ok = false, is_me = false, follow = false;
     int e = 0, seedu = -1;
     updt = -1;
     upds = 0;
     if (alive) {
-        const int seed = H.own()[lane];
+        const int seed = own_raw;
         seedu = seed;
         if (seed >= 0) {
             is_me = seed >= TEAM;
@@ -1550,8 +1553,8 @@ __device__ __forceinline__ int quiet_streak(const Params &P, unsigned char *sm, 
             follow = is_me || H.te_follow()[e] != 0;
         }
     }
-    int cin = c_in[lane], cout = c_out[lane];
-    bool refc1 = c_refc[lane] == 1;
+    int cin = cin_raw, cout = cout_raw;
+    bool refc1 = refc_raw == 1;
     const double dm = fabs(speed) * P.dt_s * 1.000000001 + 2.0 * P.noise_bound + 1e-3, dm2 = dm * dm;
     // a missile in flight: no detonation as long as it stays surely outside its radius of its target
     int m = 0;

@@ -497,7 +497,7 @@ def run_ours(args, rank, world, local_rank):
             line["other_workloads"] = others
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            v, n, tk, dt = cpu_reference_throughput(args.workload, 1024, cores, min(ticks, 250))
+            v, n, tk, dt = cpu_reference_throughput(args.workload, 8192, cores, min(ticks, 250))  # (c5 on 16 threads: the whole shard, ~10 s)
             line["cpu_baseline"] = {"value": v, "unit": "object-updates/s", "cores": cores, "kind": "port",
                                     "sample": f"{n} scenarios x {NS} slots x {tk} ticks in {dt:.2f}s, "
                                               f"oracle/zrk_oracle.c on {cores} host threads",

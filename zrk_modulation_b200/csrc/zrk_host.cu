@@ -1166,17 +1166,58 @@ extern "C" int zrk_read_records(zrk_handle *h, int s0, int s1, zrk_msg *recs, in
         if (n) n[s - s0] = std::min(hdr[H_NREC], h->P.log_cap);
     }
     if (recs && s1 > s0) {
-        CK(cudaMemcpy(recs, h->P.rec + (size_t)s0 * h->P.log_cap, (size_t)(s1 - s0) * h->P.log_cap * sizeof(zrk_msg),
-                      cudaMemcpyDeviceToHost));
-        if (h->P.log_types & ZRK_LOG_TRACKS)  // the track journal is private: squeeze it out
-            for (int s = s0; s < s1; s++) {
-                zrk_msg *r = recs + (size_t)(s - s0) * h->P.log_cap;
+        // The log leaves the device in chunks of whole scenarios through two page-locked buffers (a copy straight into
+        // the caller's pageable array runs at a tenth of the link's rate); while one chunk is in flight the host moves
+        // the one before it into place — each scenario's records only, the private track journal squeezed out.
+        const size_t cap = (size_t)h->P.log_cap, per = cap * sizeof(zrk_msg);
+        const int chunk_sc = (int)std::max<size_t>(1, ((size_t)8 << 20) / per);
+        const bool squeeze = (h->P.log_types & ZRK_LOG_TRACKS) != 0;
+        void *pin[2] = {nullptr, nullptr};
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        for (int k = 0; k < 2; k++) {
+            CK(pinned_get(&pin[k], (size_t)chunk_sc * per));
+            CK(event_get(h->device, false, &ev[k]));
+        }
+        auto place = [&](int c0, int c1, const zrk_msg *src) {
+            for (int s = c0; s < c1; s++) {
+                const zrk_msg *r = src + (size_t)(s - c0) * cap;
+                zrk_msg *dst = recs + (size_t)(s - s0) * cap;
                 const int nr = std::min(h->h_summary[(size_t)s * ZRK_SUMMARY_WORDS + H_NREC], h->P.log_cap);
-                int k = 0;
-                for (int i = 0; i < nr; i++)
-                    if (r[i].type != ZRK_REC_TRACK) r[k++] = r[i];
-                if (n) n[s - s0] = k;
+                if (!squeeze) {
+                    memcpy(dst, r, (size_t)nr * sizeof(zrk_msg));
+                } else {
+                    int k = 0;
+                    for (int i = 0; i < nr; i++)
+                        if (r[i].type != ZRK_REC_TRACK) dst[k++] = r[i];
+                    if (n) n[s - s0] = k;
+                }
             }
+        };
+        int rc_cuda = 0, prev0 = -1, prev1 = -1, slot = 0;
+        for (int c0 = s0; c0 < s1 && !rc_cuda; c0 += chunk_sc, slot ^= 1) {
+            const int c1 = std::min(s1, c0 + chunk_sc);
+            if (cudaMemcpyAsync(pin[slot], h->P.rec + (size_t)c0 * cap, (size_t)(c1 - c0) * per, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                cudaEventRecord(ev[slot], h->stream) != cudaSuccess)
+                rc_cuda = 1;
+            if (prev0 >= 0 && !rc_cuda) {
+                if (cudaEventSynchronize(ev[slot ^ 1]) != cudaSuccess) rc_cuda = 1;
+                else place(prev0, prev1, (const zrk_msg *)pin[slot ^ 1]);
+            }
+            prev0 = c0, prev1 = c1;
+        }
+        if (prev0 >= 0 && !rc_cuda) {
+            if (cudaEventSynchronize(ev[slot ^ 1]) != cudaSuccess) rc_cuda = 1;
+            else place(prev0, prev1, (const zrk_msg *)pin[slot ^ 1]);
+        }
+        cudaStreamSynchronize(h->stream);
+        for (int k = 0; k < 2; k++) {
+            pinned_put(pin[k], (size_t)chunk_sc * per);
+            event_put(h->device, false, ev[k]);
+        }
+        if (rc_cuda) {
+            h->err = "zrk_read_records: device-to-host copy failed";
+            return ZRK_ERR_CUDA;
+        }
     }
     return ZRK_OK;
 }

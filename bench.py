@@ -313,11 +313,14 @@ def run_ours(args, rank, world, local_rank):
         "ccp_launcher_id", "ccp_launcher_pos")) + (batch.noise.nbytes if batch.noise is not None else 0)
     d2h = (_cabi.ZRK_MSG_NTYPES + 4) * 8
 
+    # (several ranks share the host's PCIe fabric: their uploads take longer than the first round, two rounds hide them)
+    wave_rounds = args.wave_rounds or (2 if world > 1 else 1)
+
     def e2e_once(src, result="totals"):
         """create (H2D) + step + result read-back (D2H) + destroy; returns (seconds, result)."""
         barrier()
         t0 = time.perf_counter()
-        eng = Engine(src, device=dev, ticks_per_launch=args.ticks_per_launch, waves=args.waves, certificate=not args.no_certificate,
+        eng = Engine(src, device=dev, ticks_per_launch=args.ticks_per_launch, waves=args.waves, wave_rounds=wave_rounds, certificate=not args.no_certificate,
                      **log_kw(ticks))
         ta = time.perf_counter()
         eng.step(ticks)
@@ -457,7 +460,7 @@ def run_ours(args, rank, world, local_rank):
             "certified_tick_fraction": cert_ticks / float(B * ticks),  # rank 0's shard: ticks whose link_object scan was proven away
             "e2e": {"value": e2e_value, "unit": "object-updates/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t_e2e.item()) / args.steps * 1e3,
-                    "waves": args.waves, "host_binding": host_binding,
+                    "waves": args.waves, "wave_rounds": wave_rounds, "host_binding": host_binding,
                     "host_ms": dict(zip(("create", "step", "read", "destroy"), e2e_breakdown)),  # rank 0, where the host thread spends the step
                     "timed_region": "zrk_create from pinned host arrays (H2D) + zrk_step + zrk_read_totals (D2H) + zrk_destroy",
                     "variants": {k: dict(v, value=units_all / v["seconds"], ms_per_step=v["seconds"] * 1e3)
@@ -518,6 +521,7 @@ def main():
     ap.add_argument("--ticks-per-launch", type=int, default=0)
     ap.add_argument("--waves", type=int, default=8,
                     help="scenario waves of the end-to-end leg (zrk_options.waves): the H2D copy of one wave overlaps the kernels of the others")
+    ap.add_argument("--wave-rounds", type=int, default=0, help="zrk_options.wave_rounds of the end-to-end leg (0: 1 on one GPU, 2 on several)")
     ap.add_argument("--log", default="masks", choices=["masks", "events"],
                     help="masks (default): event records + per-tick masks + track journal, every message rebuildable; events: event records only")
     ap.add_argument("--no-cpu-baseline", action="store_true")

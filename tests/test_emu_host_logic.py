@@ -166,11 +166,11 @@ def test_many_steps_of_rounds_and_waves(lib):
     b = synthetic_batch(8, 24, n_radars=1, n_launchers=2, missiles_per_launcher=4, seed0=77000)
     steps, per = 175, 8
     oc, ofc, oft = O.run_batch(b, 0, b.n_scenarios, steps * per, n_threads=2)
-    for waves in (0, 2):
-        with Engine(b, waves=waves, lib=lib) as eng:
+    for waves, wr in ((0, 0), (2, 1), (4, 2)):
+        with Engine(b, waves=waves, wave_rounds=wr, lib=lib) as eng:
             for _ in range(steps):
                 eng.step(per)
             fc, ft, nr = eng.status()
             counts = eng.counts()
-        assert np.array_equal(fc & 63, ofc) and np.array_equal(ft, oft), f"faults differ (waves={waves})"
-        assert np.array_equal(counts, oc), f"message counts differ (waves={waves})"
+        assert np.array_equal(fc & 63, ofc) and np.array_equal(ft, oft), f"faults differ (waves={waves}, wave_rounds={wr})"
+        assert np.array_equal(counts, oc), f"message counts differ (waves={waves}, wave_rounds={wr})"

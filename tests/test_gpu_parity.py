@@ -203,13 +203,13 @@ def test_many_steps_of_rounds_and_waves():
     b = synthetic_batch(512, 24, n_radars=1, n_launchers=2, missiles_per_launcher=4, seed0=77000)
     steps, per = 200, 8
     oc, ofc, oft = O.run_batch(b, 0, b.n_scenarios, steps * per, n_threads=8)
-    for waves in (0, 4):
-        with Engine(b, waves=waves) as eng:
+    for waves, wr in ((0, 0), (4, 1), (8, 2)):
+        with Engine(b, waves=waves, wave_rounds=wr) as eng:
             for _ in range(steps):
                 eng.step(per)
             fc, ft, nr = eng.status()
             counts = eng.counts()
             n_launch, ms = eng.launch_stats()
-        assert np.array_equal(fc & 63, ofc) and np.array_equal(ft, oft), f"faults differ (waves={waves})"
-        assert np.array_equal(counts, oc), f"message counts differ (waves={waves})"
+        assert np.array_equal(fc & 63, ofc) and np.array_equal(ft, oft), f"faults differ (waves={waves}, wave_rounds={wr})"
+        assert np.array_equal(counts, oc), f"message counts differ (waves={waves}, wave_rounds={wr})"
         assert n_launch >= 2 * 6 * steps  # (rounds of two launches, not one launch per step)

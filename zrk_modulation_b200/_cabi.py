@@ -87,7 +87,7 @@ OPT_NO_CERTIFICATE = 2
 class ZrkOptions(C.Structure):
     _fields_ = [("device", C.c_int32), ("log_types", C.c_uint32), ("log_capacity", C.c_int32),
                 ("mask_ticks", C.c_int32), ("ticks_per_launch", C.c_int32),
-                ("flags", C.c_uint32), ("waves", C.c_int32), ("reserved", C.c_int32)]
+                ("flags", C.c_uint32), ("waves", C.c_int32), ("wave_rounds", C.c_int32)]
 
 
 STATE_FIELDS = [

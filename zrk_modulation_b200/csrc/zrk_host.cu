@@ -260,6 +260,7 @@ struct zrk_handle {
     bool defer_zero = false;                         // zrk_create: dev_alloc(zero) only notes the buffer ...
     std::vector<std::pair<void *, size_t>> zero_list;  // ... and the memsets are queued after the last host synchronisation
     cudaEvent_t alloc_ev = nullptr;
+    int wave_rounds = 1;   // zrk_options.wave_rounds
     bool stepped = false;  // zrk_step has run (the waves' streams matter to the first step only)
     cudaEvent_t fork_ev{};
     int *pin_err = nullptr;   // pinned: the init kernel's verdict when zrk_create did not wait for it
@@ -276,6 +277,7 @@ struct zrk_handle {
     long long n_rounds = 0;
 };
 #define ZRK_ROUND_SLOTS 1024
+#define ZRK_FORK_ROUNDS_MAX 4  /* zrk_options.wave_rounds: rounds of a handle's first step that can be issued wave by wave */
 #define ZRK_ROUND_BATCH 6  /* rounds queued between two looks at the pending counters */
 
 static thread_local std::string g_create_err;
@@ -659,6 +661,7 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
     h->fast = !(opt && (opt->flags & ZRK_OPT_EXACT_ONLY));
 
     // scenario waves: whole CTAs and whole init blocks per wave
+    h->wave_rounds = opt && opt->wave_rounds > 0 ? std::min((int)opt->wave_rounds, ZRK_FORK_ROUNDS_MAX) : 1;
     int n_waves = opt ? opt->waves : 0;
     if (n_waves < 1) n_waves = 1;
     if (n_waves > 64) n_waves = 64;
@@ -775,7 +778,7 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
         h->two_kernel = lo.team == 32 && P.cert && h->fast && !(env && atoi(env) == 0);
         if (h->two_kernel) {
             if ((rc = dev_alloc(h, (size_t)n_waves * ZRK_ROUND_SLOTS, &h->d_pending, true)) != ZRK_OK) return rc;
-            if ((rc = dev_alloc(h, (size_t)ZRK_ROUND_SLOTS + 64, &h->d_queue, true)) != ZRK_OK) return rc;
+            if ((rc = dev_alloc(h, (size_t)ZRK_ROUND_SLOTS + 64 * ZRK_FORK_ROUNDS_MAX, &h->d_queue, true)) != ZRK_OK) return rc;
             CK(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, h->device));
             CK(pinned_get((void **)&h->h_pending, sizeof(int) * 64));
             if ((rc = dev_alloc(h, (size_t)2 * B, &h->d_work, false)) != ZRK_OK) return rc;
@@ -917,6 +920,7 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
         const int B = h->P.lo.B;
         cudaStream_t ms = h->stream;
         static const int round_batch = getenv("ZRK_ROUND_BATCH") ? std::max(1, atoi(getenv("ZRK_ROUND_BATCH"))) : ZRK_ROUND_BATCH;
+        const int fork_rounds = std::min(h->wave_rounds, round_batch);
         static const int tail_div = getenv("ZRK_TAIL_DIV") ? std::max(1, atoi(getenv("ZRK_TAIL_DIV"))) : 64;
         // Scenario waves: the first round after zrk_create runs wave by wave on the waves' streams, where their uploads
         // and init kernels are queued (the copy of one wave overlaps the kernels of the waves before it); all waves
@@ -929,7 +933,7 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
         for (;;) {
             if (h->round_no + round_batch > ZRK_ROUND_SLOTS) {
                 CK(cudaMemsetAsync(h->d_pending, 0, sizeof(int) * ZRK_ROUND_SLOTS, ms));
-                CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int) * (ZRK_ROUND_SLOTS + 64), ms));
+                CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int) * (ZRK_ROUND_SLOTS + 64 * ZRK_FORK_ROUNDS_MAX), ms));
                 h->round_no = 0;
                 fork_first = false;  // (the waves' streams are not ordered behind this memset)
             }
@@ -938,13 +942,16 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
             // the batch, so the grids of a batch are sized for the last length it knows and the kernels look the
             // real one up (work_n).
             for (int r = 0; r < round_batch; r++) {
-                const bool listed = n_work >= 0 || r > 0;  // (the first round of a step looks at the whole range)
+                // (forked: the first zrk_options.wave_rounds rounds after zrk_create, wave by wave over the waves' ranges;
+                // the last of them writes the worklist)
+                const bool forked = fork_first && n_work < 0 && r < fork_rounds;
+                const bool listed = !forked && (n_work >= 0 || r > 0);  // (the first round of a step looks at the whole range)
                 const int *wl = listed ? h->d_work + (size_t)cur * B : nullptr;
-                int *wl_out = h->d_work + (size_t)(cur ^ 1) * B;
+                int *wl_out = forked && r < fork_rounds - 1 ? nullptr : h->d_work + (size_t)(cur ^ 1) * B;
                 int *pend = h->d_pending + h->round_no + r;
-                const int *wn = r > 0 ? pend - 1 : nullptr;  // (r = 0: the host knows the length)
-                const int g1 = n_work < 0 ? B : n_work;      // index range of the launches: [0, g1)
-                const int n_parts = !listed && fork_first ? n_waves : 1;
+                const int *wn = listed && r > 0 ? pend - 1 : nullptr;  // (r = 0: the host knows the length)
+                const int g1 = n_work < 0 ? B : n_work;                // index range of the launches: [0, g1)
+                const int n_parts = forked ? n_waves : 1;
                 for (int w = 0; w < n_parts; w++) {
                     const int p0 = n_parts > 1 ? h->wave_b[w] : 0, p1 = n_parts > 1 ? h->wave_b[w + 1] : g1;
                     cudaStream_t ws = n_parts > 1 ? h->wave_stream[w] : ms;
@@ -955,13 +962,13 @@ extern "C" int zrk_step(zrk_handle *h, int n_ticks) {
                     // (persistent: at most the CTAs the SMs hold at once; every warp draws scenarios from the launch's queue)
                     const int s_ctas = std::min((p1 - p0 + ZRK_STREAK_WARPS - 1) / ZRK_STREAK_WARPS, std::max(h->n_sms, 1) * ZRK_STREAK_MINB);
                     ZRK_LAUNCH(sf, s_ctas, 32 * ZRK_STREAK_WARPS, ZRK_STREAK_SMEM, ws, h->P, p0, p1, target, wl, wn,
-                               h->d_queue + (n_parts > 1 ? ZRK_ROUND_SLOTS + w : h->round_no + r));
+                               h->d_queue + (n_parts > 1 ? ZRK_ROUND_SLOTS + 64 * r + w : h->round_no + r));
                     ZRK_LAUNCH(fn, (p1 - p0 + tpc - 1) / tpc, h->block, h->smem_bytes, ws, h->P, 0, p0, p1, target, pend, wl, wl_out, wn);
                     CK(cudaGetLastError());
                     CK(cudaEventRecord(e1, ws));
                     h->pending.push_back({e0, e1});
                     h->n_launches += 2;
-                    if (n_parts > 1) {
+                    if (n_parts > 1 && r == fork_rounds - 1) {  // the main stream goes on after the waves' last forked round
                         CK(cudaEventRecord(h->wave_done[w], ws));
                         CK(cudaStreamWaitEvent(ms, h->wave_done[w], 0));
                     }
@@ -1772,7 +1779,7 @@ extern "C" int zrk_load_state(zrk_handle *h, const void *buf, size_t bytes) {
     h->tick = sh.tick;
     h->round_no = 0;
     if (h->d_pending) CK(cudaMemset(h->d_pending, 0, sizeof(int) * ZRK_ROUND_SLOTS * (h->wave_stream.empty() ? 1 : h->wave_stream.size())));
-    if (h->d_queue) CK(cudaMemset(h->d_queue, 0, sizeof(int) * (ZRK_ROUND_SLOTS + 64)));
+    if (h->d_queue) CK(cudaMemset(h->d_queue, 0, sizeof(int) * (ZRK_ROUND_SLOTS + 64 * ZRK_FORK_ROUNDS_MAX)));
     return ensure_tsec(h, h->tick + 2);
 }
 

@@ -25,7 +25,7 @@ class Engine:
 
     def __init__(self, batch: Batch, log_types: int = _cabi.LOG_EVENTS, log_capacity: int = 0,
                  mask_ticks: int = 0, ticks_per_launch: int = 0, device: int = 0, exact_only: bool = False,
-                 waves: int = 0, certificate: bool = True, lib=None):
+                 waves: int = 0, certificate: bool = True, lib=None, wave_rounds: int = 0):
         self.lib = lib if lib is not None else _cabi.load()
         self.batch = batch
         self.device = device
@@ -37,6 +37,7 @@ class Engine:
         opt.mask_ticks = mask_ticks
         opt.ticks_per_launch = ticks_per_launch
         opt.flags = (_cabi.OPT_EXACT_ONLY if exact_only else 0) | (0 if certificate else _cabi.OPT_NO_CERTIFICATE)
+        opt.wave_rounds = wave_rounds  # rounds of the first step issued wave by wave (see zrk_options.wave_rounds)
         opt.waves = waves  # > 1: upload / init / step in scenario waves on separate streams (see zrk_options.waves)
         self.log_types = log_types
         desc = batch.desc()

@@ -79,6 +79,9 @@ __device__ __forceinline__ double dot3(double ax, double ay, double az, double b
 }
 // Python float % for a positive modulus.
 __device__ __forceinline__ double pymod(double a, double m) {
+    // (0 < a < 2 m, what a sweeping sector's angle + step always is: fmod is a or a - m, both exact)
+    if (a > 0.0 && a < m) return a;
+    if (a >= m && a < m + m) return a - m;
     double r = fmod(a, m);
     if (r != 0.0) {
         if (r < 0.0) r += m;

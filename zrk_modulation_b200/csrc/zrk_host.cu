@@ -14,12 +14,17 @@
 #define ZRK_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
+#if defined(__linux__)
+#include <sched.h>
+#endif
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "zrk_tick.cuh"
@@ -261,6 +266,8 @@ struct zrk_handle {
     std::vector<std::pair<void *, size_t>> zero_list;  // ... and the memsets are queued after the last host synchronisation
     cudaEvent_t alloc_ev = nullptr;
     int wave_rounds = 1;   // zrk_options.wave_rounds
+    void *bounce = nullptr;  // page-locked staging of a pageable description (zrk_create), kept until the handle goes
+    size_t bounce_bytes = 0;
     bool stepped = false;  // zrk_step has run (the waves' streams matter to the first step only)
     cudaEvent_t fork_ev{};
     int *pin_err = nullptr;   // pinned: the init kernel's verdict when zrk_create did not wait for it
@@ -525,6 +532,7 @@ extern "C" void zrk_destroy(zrk_handle *h) {
     if (!h->wave_stream.empty()) event_put(h->device, false, h->fork_ev);
     event_put(h->device, false, h->alloc_ev);
     pinned_put(h->pin_err, sizeof(int));
+    pinned_put(h->bounce, h->bounce_bytes);
     pinned_put(h->h_pending, sizeof(int) * 64);
     pinned_put(h->h_totals, sizeof(unsigned long long) * ZRK_TOTALS_WORDS);
     pinned_put(h->h_summary, (size_t)h->P.lo.B * ZRK_SUMMARY_WORDS * sizeof(int));
@@ -811,12 +819,98 @@ static int create_impl(zrk_handle *h, const zrk_batch_desc *d, const zrk_options
             CK(cudaStreamWaitEvent(ws, h->alloc_ev, 0));
         }
     }
+    // A description in pageable host memory (what a caller holding numpy arrays passes) would be copied by the driver
+    // through its own staging buffer, one call at a time, at a fraction of the link's rate and with the host thread
+    // blocked.  It is staged here instead: helper threads move it, wave by wave, into one page-locked buffer (kept for
+    // the next handle of the process), and every wave's copies are queued from there as soon as the wave is in.
+    size_t desc_bytes = 0;
+    for (const Field &f : fields) desc_bytes += (size_t)B * f.per_scenario;
+    bool staged = false;
+#ifndef ZRK_EMU
+    if (!fields.empty() && desc_bytes >= ((size_t)4 << 20) && !getenv("ZRK_NO_STAGING")) {
+        cudaPointerAttributes at{};
+        size_t big = 0;
+        for (size_t i = 1; i < fields.size(); i++)
+            if (fields[i].per_scenario > fields[big].per_scenario) big = i;
+        if (cudaPointerGetAttributes(&at, fields[big].src) != cudaSuccess) cudaGetLastError();
+        else staged = at.type == cudaMemoryTypeUnregistered;
+    }
+#endif
+    struct Seg {
+        char *dst;
+        const char *src;
+        size_t n;
+        int wave;
+    };
+    std::vector<Seg> segs;
+    std::vector<std::vector<std::pair<size_t, size_t>>> wave_off((size_t)n_waves);  // per wave, per field: offset in the staging buffer
+    std::vector<std::thread> helpers;
+    std::atomic<size_t> seg_next{0};
+    std::vector<std::atomic<int>> seg_left((size_t)n_waves);
+    if (staged) {
+        CK(pinned_get(&h->bounce, desc_bytes));
+        h->bounce_bytes = desc_bytes;
+        size_t off = 0;
+        for (int w = 0; w < n_waves; w++) {
+            const int b0 = h->wave_b[w], b1 = h->wave_b[w + 1];
+            int n_seg = 0;
+            for (const Field &f : fields) {
+                const size_t n = (size_t)(b1 - b0) * f.per_scenario;
+                wave_off[(size_t)w].push_back({off, n});
+                for (size_t o2 = 0; o2 < n; o2 += (size_t)1 << 20, n_seg++)
+                    segs.push_back({(char *)h->bounce + off + o2, f.src + (size_t)b0 * f.per_scenario + o2, std::min(n - o2, (size_t)1 << 20), w});
+                off += n;
+            }
+            seg_left[(size_t)w].store(n_seg);
+        }
+        auto work = [&]() {
+            for (size_t i; (i = seg_next.fetch_add(1)) < segs.size();) {
+                memcpy(segs[i].dst, segs[i].src, segs[i].n);
+                seg_left[(size_t)segs[i].wave].fetch_sub(1, std::memory_order_release);
+            }
+        };
+        unsigned hc = std::thread::hardware_concurrency();
+#if defined(__linux__)
+        {  // (the cores this thread may run on: a rank bound to a few cores of its GPU's node gets that many helpers)
+            cpu_set_t cs;
+            CPU_ZERO(&cs);
+            if (sched_getaffinity(0, sizeof cs, &cs) == 0 && CPU_COUNT(&cs) > 0) hc = (unsigned)CPU_COUNT(&cs) + 1;
+        }
+#endif
+        const unsigned want = getenv("ZRK_STAGING_THREADS") ? (unsigned)std::max(1, atoi(getenv("ZRK_STAGING_THREADS"))) : 8u;
+        const int n_help = (int)std::min<size_t>(std::min<unsigned>(hc > 1 ? hc - 1 : 1, want), segs.size());
+        for (int t = 0; t < n_help; t++) helpers.emplace_back(work);
+    }
+    struct JoinHelpers {
+        std::vector<std::thread> &v;
+        ~JoinHelpers() {
+            for (auto &t : v)
+                if (t.joinable()) t.join();
+        }
+    } join_helpers{helpers};
     for (int w = 0; w < n_waves; w++) {
         const int b0 = h->wave_b[w], b1 = h->wave_b[w + 1];
         cudaStream_t ws = n_waves > 1 ? h->wave_stream[w] : h->stream;
-        for (const Field &f : fields)
-            CK(cudaMemcpyAsync(f.dst + (size_t)b0 * f.per_scenario, f.src + (size_t)b0 * f.per_scenario,
-                               (size_t)(b1 - b0) * f.per_scenario, cudaMemcpyHostToDevice, ws));
+        if (staged) {
+            // (this thread helps with the wave it is waiting for, then queues its copies)
+            for (size_t i; seg_left[(size_t)w].load(std::memory_order_acquire) > 0;) {
+                if ((i = seg_next.fetch_add(1)) < segs.size()) {
+                    memcpy(segs[i].dst, segs[i].src, segs[i].n);
+                    seg_left[(size_t)segs[i].wave].fetch_sub(1, std::memory_order_release);
+                } else {
+                    std::this_thread::yield();
+                }
+            }
+            size_t k = 0;
+            for (const Field &f : fields) {
+                const auto &po = wave_off[(size_t)w][k++];
+                CK(cudaMemcpyAsync(f.dst + (size_t)b0 * f.per_scenario, (const char *)h->bounce + po.first, po.second, cudaMemcpyHostToDevice, ws));
+            }
+        } else {
+            for (const Field &f : fields)
+                CK(cudaMemcpyAsync(f.dst + (size_t)b0 * f.per_scenario, f.src + (size_t)b0 * f.per_scenario,
+                                   (size_t)(b1 - b0) * f.per_scenario, cudaMemcpyHostToDevice, ws));
+        }
         if (n_waves > 1) CK(cudaStreamWaitEvent(ws, h->fork_ev, 0));
         ZRK_LAUNCH(zrk_init_kernel, (b1 - b0 + ZRK_INIT_BLOCK / 32 - 1) / (ZRK_INIT_BLOCK / 32), ZRK_INIT_BLOCK, 0, ws, P, dd, derr, b0, b1);
         CK(cudaGetLastError());

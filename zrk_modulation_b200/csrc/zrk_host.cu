@@ -1279,9 +1279,9 @@ extern "C" int zrk_read_records(zrk_handle *h, int s0, int s1, zrk_msg *recs, in
             CK(pinned_get(&pin[k], (size_t)chunk_sc * per));
             CK(event_get(h->device, false, &ev[k]));
         }
-        auto place = [&](int c0, int c1, const zrk_msg *src) {
+        auto place_part = [&](int c0, int c1, const zrk_msg *src, int c_base) {
             for (int s = c0; s < c1; s++) {
-                const zrk_msg *r = src + (size_t)(s - c0) * cap;
+                const zrk_msg *r = src + (size_t)(s - c_base) * cap;
                 zrk_msg *dst = recs + (size_t)(s - s0) * cap;
                 const int nr = std::min(h->h_summary[(size_t)s * ZRK_SUMMARY_WORDS + H_NREC], h->P.log_cap);
                 if (!squeeze) {
@@ -1293,6 +1293,15 @@ extern "C" int zrk_read_records(zrk_handle *h, int s0, int s1, zrk_msg *recs, in
                     if (n) n[s - s0] = k;
                 }
             }
+        };
+        // (the caller's array is often fresh memory: its first touch is what takes the time, and goes in parallel)
+        auto place = [&](int c0, int c1, const zrk_msg *src) {
+            const int n_thr = (c1 - c0) >= 256 ? 4 : 1, per_thr = (c1 - c0 + n_thr - 1) / n_thr;
+            std::vector<std::thread> th;
+            for (int t = 1; t < n_thr; t++)
+                th.emplace_back(place_part, std::min(c1, c0 + t * per_thr), std::min(c1, c0 + (t + 1) * per_thr), src, c0);
+            place_part(c0, std::min(c1, c0 + per_thr), src, c0);
+            for (auto &t : th) t.join();
         };
         int rc_cuda = 0, prev0 = -1, prev1 = -1, slot = 0;
         for (int c0 = s0; c0 < s1 && !rc_cuda; c0 += chunk_sc, slot ^= 1) {

@@ -313,9 +313,9 @@ def run_ours(args, rank, world, local_rank):
         "ccp_launcher_id", "ccp_launcher_pos")) + (batch.noise.nbytes if batch.noise is not None else 0)
     d2h = (_cabi.ZRK_MSG_NTYPES + 4) * 8
 
-    # (eight ranks share the host's PCIe fabric: their uploads take longer than the first round, two rounds hide them —
-    # measured: 8 GPUs 35.5 -> 34.5 ms; on 1 or 2 GPUs the smaller launches of a second forked round cost ~1.5 ms)
-    wave_rounds = args.wave_rounds or (2 if world >= 8 else 1)
+    # (many ranks share the host's PCIe fabric: their uploads take longer than the first round, two rounds hide them —
+    # measured: 8 GPUs 35.5 -> 34.5 ms, 4 GPUs 33.6 -> 33.3 ms; on 1 or 2 GPUs the smaller launches of a second forked round cost ~1.5 ms)
+    wave_rounds = args.wave_rounds or (2 if world >= 4 else 1)
 
     def e2e_once(src, result="totals"):
         """create (H2D) + step + result read-back (D2H) + destroy; returns (seconds, result)."""
@@ -522,7 +522,7 @@ def main():
     ap.add_argument("--ticks-per-launch", type=int, default=0)
     ap.add_argument("--waves", type=int, default=8,
                     help="scenario waves of the end-to-end leg (zrk_options.waves): the H2D copy of one wave overlaps the kernels of the others")
-    ap.add_argument("--wave-rounds", type=int, default=0, help="zrk_options.wave_rounds of the end-to-end leg (0: 2 on 8 GPUs, 1 on fewer)")
+    ap.add_argument("--wave-rounds", type=int, default=0, help="zrk_options.wave_rounds of the end-to-end leg (0: 2 on 4 or more GPUs, 1 on fewer)")
     ap.add_argument("--log", default="masks", choices=["masks", "events"],
                     help="masks (default): event records + per-tick masks + track journal, every message rebuildable; events: event records only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
